@@ -1,0 +1,295 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE (ctypes loader for the CPU checkers).
+
+Two libraries share one flat-array C interface (layouts in oracle/ref_driver.cpp):
+
+* ``ref``  -> oracle/_ref/libgevref.so : the reference's own gevolution.hpp /
+  tools.hpp / background.hpp compiled against the single-rank LATfield2 shim
+  (built from /root/reference in the build container; travels prebuilt to the
+  GPU box).
+* ``ora``  -> oracle/libgev_oracle.so  : the independent plain-C restatement
+  (oracle/gev_oracle.c), each function citing the reference file:line it follows.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU-baseline legs may
+import this module.  The product (gevolution-1.2_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libgevref.so")
+ORA_SO = os.path.join(HERE, "libgev_oracle.so")
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_d = C.c_double
+_i = C.c_int
+_l = C.c_long
+
+# name -> (restype, argtypes); pointers that may be NULL are declared c_void_p
+_SIGS = {
+    "fft_forward": (None, [_i, _i, _dp, _dp]),
+    "fft_backward": (None, [_i, _i, _dp, _dp]),
+    "prepareFTsource_scalar": (None, [_i, _dp, _dp, _dp, _d, _dp, _d, _d, _d]),
+    "prepareFTsource_tensor": (None, [_i, _dp, _dp, _dp, _d]),
+    "solveModifiedPoissonFT": (None, [_i, _dp, _dp, _d, _d]),
+    "projectFTscalar": (None, [_i, _dp, _dp, _i]),
+    "evolveFTvector": (None, [_i, _dp, _dp, _d]),
+    "projectFTvector": (None, [_i, _dp, _dp, _d, _d]),
+    "projectFTtensor": (None, [_i, _dp, _dp]),
+    "projection_T00": (None, [_i, _l, _dp, _dp, _d, _d, _vp, _d, _dp]),
+    "projection_T0i": (None, [_i, _l, _dp, _dp, _d, _vp, _d, _dp]),
+    "projection_Tij": (None, [_i, _l, _dp, _dp, _d, _d, _vp, _d, _dp]),
+    "scalarProjectionCIC": (None, [_i, _l, _dp, _d, _dp]),
+    "updateVel": (_d, [_i, _l, _dp, _dp, _i, _d, _vp, _vp, _vp, _i, _dp]),
+    "moveParticles": (None, [_i, _l, _dp, _dp, _i, _d, _vp, _vp, _vp, _i, _dp]),
+    "cell_index": (None, [_i, _l, _dp, _i32p, _u32p]),
+    "extractPowerSpectrum": (None, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp, _i32p, _i, _i, _i]),
+    "computeVectorDiagnostics": (None, [_i, _dp, _dp, _dp]),
+    "computeTensorDiagnostics": (None, [_i, _dp, _dp, _dp, _dp]),
+    "Hconf": (_d, [_d, _d, _dp]),
+    "rungekutta4bg": (_d, [_d, _d, _dp, _d]),
+    "particleHorizon": (_d, [_d, _d, _dp]),
+    "sim_create": (_vp, [_i, _i, _i, _dp, _dp]),
+    "sim_destroy": (None, [_vp]),
+    "sim_set_particles": (None, [_vp, _i, _l, _i64p, _dp, _dp, _d]),
+    "sim_set_field": (None, [_vp, _i, _dp]),
+    "sim_get_field": (None, [_vp, _i, _dp]),
+    "sim_num_particles": (_l, [_vp, _i]),
+    "sim_get_particles": (None, [_vp, _i, _i64p, _dp, _dp]),
+    "sim_get_state": (None, [_vp, _dp]),
+    "sim_set_state": (None, [_vp, _dp]),
+    "sim_get_timers": (None, [_vp, _dp]),
+    "sim_step": (None, [_vp]),
+}
+
+FIELD_IDS = {"phi": 0, "chi": 1, "Bi": 2, "source": 3, "Sij": 4, "scalarFT": 10, "BiFT": 11, "SijFT": 12}
+FIELD_COMPS = {"phi": 1, "chi": 1, "Bi": 3, "source": 1, "Sij": 6, "scalarFT": 1, "BiFT": 3, "SijFT": 6}
+
+
+def build(force=False):
+    """Compile the checkers (make). `_ref` is rebuilt only where /root/reference exists."""
+    args = ["make", "-C", HERE, "-s"] + (["-B"] if force else [])
+    subprocess.run(args, check=True)
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Thin, typed view of one checker library; ``prefix`` is 'ref' or 'ora'."""
+
+    def __init__(self, path, prefix):
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        self.fn = {}
+        for name, (res, args) in _SIGS.items():
+            f = getattr(self.lib, f"{prefix}_{name}", None)
+            if f is None:
+                continue
+            f.restype, f.argtypes = res, args
+            self.fn[name] = f
+        d = getattr(self.lib, f"{prefix}_describe")
+        d.restype = C.c_char_p
+        self.description = d().decode()
+
+    # ---- FFT -------------------------------------------------------------
+    def fft_forward(self, real):
+        real = np.ascontiguousarray(real, dtype=np.float64)
+        nc, N = real.shape[0], real.shape[-1]
+        out = np.zeros((nc, N, N, N // 2 + 1, 2))
+        self.fn["fft_forward"](N, nc, real, out)
+        return out
+
+    def fft_backward(self, cplx):
+        cplx = np.ascontiguousarray(cplx, dtype=np.float64)
+        nc, N = cplx.shape[0], cplx.shape[1]
+        out = np.zeros((nc, N, N, N))
+        self.fn["fft_backward"](N, nc, cplx, out)
+        return out
+
+    # ---- real-space source preparation --------------------------------------
+    def prepareFTsource_scalar(self, phi, chi, source, bgmodel, coeff, coeff2, coeff3):
+        N = phi.shape[-1]
+        out = np.zeros_like(source)
+        self.fn["prepareFTsource_scalar"](N, phi, chi, source, bgmodel, out, coeff, coeff2, coeff3)
+        return out
+
+    def prepareFTsource_tensor(self, phi, Tij, coeff):
+        N = phi.shape[-1]
+        out = np.zeros_like(Tij)
+        self.fn["prepareFTsource_tensor"](N, phi, Tij, out, coeff)
+        return out
+
+    # ---- Fourier-space kernels -----------------------------------------------
+    def solveModifiedPoissonFT(self, src, coeff, modif=0.0):
+        out = np.zeros_like(src)
+        self.fn["solveModifiedPoissonFT"](src.shape[1], src, out, coeff, modif)
+        return out
+
+    def projectFTscalar(self, SijFT, chiFT=None):
+        N = SijFT.shape[1]
+        add = 0 if chiFT is None else 1
+        out = np.zeros((1,) + SijFT.shape[1:]) if chiFT is None else chiFT.copy()
+        self.fn["projectFTscalar"](N, SijFT, out, add)
+        return out
+
+    def evolveFTvector(self, SijFT, BiFT, a2dtau):
+        out = BiFT.copy()
+        self.fn["evolveFTvector"](SijFT.shape[1], SijFT, out, a2dtau)
+        return out
+
+    def projectFTvector(self, SiFT, coeff=1.0, modif=0.0):
+        out = np.zeros_like(SiFT)
+        self.fn["projectFTvector"](SiFT.shape[1], SiFT, out, coeff, modif)
+        return out
+
+    def projectFTtensor(self, SijFT):
+        out = np.zeros_like(SijFT)
+        self.fn["projectFTtensor"](SijFT.shape[1], SijFT, out)
+        return out
+
+    # ---- projections -----------------------------------------------------------
+    def projection_T00(self, N, pos, vel, mass, a, phi=None, coeff=1.0):
+        out = np.zeros((1, N, N, N))
+        self.fn["projection_T00"](N, len(pos), pos, vel, mass, a, _opt(phi), coeff, out)
+        return out
+
+    def projection_T0i(self, N, pos, vel, mass, phi=None, coeff=1.0):
+        out = np.zeros((3, N, N, N))
+        self.fn["projection_T0i"](N, len(pos), pos, vel, mass, _opt(phi), coeff, out)
+        return out
+
+    def projection_Tij(self, N, pos, vel, mass, a, phi=None, coeff=1.0):
+        out = np.zeros((6, N, N, N))
+        self.fn["projection_Tij"](N, len(pos), pos, vel, mass, a, _opt(phi), coeff, out)
+        return out
+
+    def scalarProjectionCIC(self, N, pos, mass):
+        out = np.zeros((1, N, N, N))
+        self.fn["scalarProjectionCIC"](N, len(pos), pos, mass, out)
+        return out
+
+    # ---- kick / drift ------------------------------------------------------------
+    def updateVel(self, N, pos, vel, kind, dtau, phi, chi, Bi, nfields, params):
+        vel = vel.copy()
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        r = self.fn["updateVel"](N, len(pos), pos, vel, kind, dtau, _opt(phi), _opt(chi), _opt(Bi), nfields, params)
+        return vel, r
+
+    def moveParticles(self, N, pos, vel, kind, dtau, phi, chi, Bi, nfields, params):
+        pos = pos.copy()
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self.fn["moveParticles"](N, len(pos), pos, vel, kind, dtau, _opt(phi), _opt(chi), _opt(Bi), nfields, params)
+        return pos
+
+    def cell_index(self, N, pos):
+        cell = np.zeros(len(pos), dtype=np.int32)
+        counts = np.zeros(N * N * N, dtype=np.uint32)
+        self.fn["cell_index"](N, len(pos), pos, cell, counts)
+        return cell, counts
+
+    # ---- analysis ------------------------------------------------------------------
+    def extractPowerSpectrum(self, fldFT, numbins, symmetric=False, deconvolve=True, ktype=1):
+        N = fldFT.shape[1]
+        kbin, power, ksc, psc = (np.zeros(numbins) for _ in range(4))
+        occ = np.zeros(numbins, dtype=np.int32)
+        self.fn["extractPowerSpectrum"](N, fldFT.shape[0], int(symmetric), fldFT, kbin, power, ksc, psc, occ, numbins, int(deconvolve), ktype)
+        return kbin, power, ksc, psc, occ
+
+    def computeVectorDiagnostics(self, Bi):
+        a, b = np.zeros(1), np.zeros(1)
+        self.fn["computeVectorDiagnostics"](Bi.shape[-1], Bi, a, b)
+        return a[0], b[0]
+
+    def computeTensorDiagnostics(self, hij):
+        a, b, c = np.zeros(1), np.zeros(1), np.zeros(1)
+        self.fn["computeTensorDiagnostics"](hij.shape[-1], hij, a, b, c)
+        return a[0], b[0], c[0]
+
+    # ---- background ------------------------------------------------------------------
+    def Hconf(self, a, fourpiG, cosmo):
+        return self.fn["Hconf"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64))
+
+    def rungekutta4bg(self, a, fourpiG, cosmo, dtau):
+        return self.fn["rungekutta4bg"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64), dtau)
+
+    def particleHorizon(self, a, fourpiG, cosmo):
+        return self.fn["particleHorizon"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64))
+
+    # ---- stateful simulation -----------------------------------------------------------
+    def sim(self, N, gr_flag, vector_flag, dsettings, cosmo):
+        return Sim(self, N, gr_flag, vector_flag, dsettings, cosmo)
+
+
+class Sim:
+    """main.cpp:217-246 state + one-cycle stepping, on the CPU checker."""
+
+    def __init__(self, ora, N, gr_flag, vector_flag, dsettings, cosmo):
+        self.o, self.N = ora, N
+        self.h = ora.fn["sim_create"](N, gr_flag, vector_flag,
+                                      np.ascontiguousarray(dsettings, dtype=np.float64),
+                                      np.ascontiguousarray(cosmo, dtype=np.float64))
+
+    def close(self):
+        if self.h:
+            self.o.fn["sim_destroy"](self.h)
+            self.h = None
+
+    def set_particles(self, species, ids, pos, vel, mass):
+        self.o.fn["sim_set_particles"](self.h, species, len(ids), np.ascontiguousarray(ids, dtype=np.int64),
+                                       np.ascontiguousarray(pos), np.ascontiguousarray(vel), mass)
+
+    def set_field(self, name, data):
+        self.o.fn["sim_set_field"](self.h, FIELD_IDS[name], np.ascontiguousarray(data, dtype=np.float64))
+
+    def get_field(self, name):
+        N, nc = self.N, FIELD_COMPS[name]
+        out = np.zeros((nc, N, N, N)) if FIELD_IDS[name] < 10 else np.zeros((nc, N, N, N // 2 + 1, 2))
+        self.o.fn["sim_get_field"](self.h, FIELD_IDS[name], out)
+        return out
+
+    def get_particles(self, species=0):
+        n = self.o.fn["sim_num_particles"](self.h, species)
+        ids = np.zeros(n, dtype=np.int64)
+        pos, vel = np.zeros((n, 3)), np.zeros((n, 3))
+        self.o.fn["sim_get_particles"](self.h, species, ids, pos, vel)
+        return ids, pos, vel
+
+    def state(self):
+        s = np.zeros(9)
+        self.o.fn["sim_get_state"](self.h, s)
+        return dict(a=s[0], tau=s[1], dtau=s[2], dtau_old=s[3], cycle=int(s[4]), maxvel=(s[5], s[6]), T00hom=s[7], fourpiG=s[8])
+
+    def set_state(self, a, tau, dtau, dtau_old, cycle, maxvel=(0.0, 0.0)):
+        self.o.fn["sim_set_state"](self.h, np.array([a, tau, dtau, dtau_old, cycle, maxvel[0], maxvel[1]], dtype=np.float64))
+
+    def timers(self):
+        t = np.zeros(6)
+        self.o.fn["sim_get_timers"](self.h, t)
+        return dict(projection=t[0], gravity_solver=t[1], fft=t[2], update_q=t[3], move_particles=t[4], cycle=t[5])
+
+    def step(self):
+        self.o.fn["sim_step"](self.h)
+
+
+def load_ref():
+    """The compiled reference (None if oracle/_ref was never built here)."""
+    return Oracle(REF_SO, "ref") if os.path.exists(REF_SO) else None
+
+
+def load_ora():
+    if not os.path.exists(ORA_SO):
+        build()
+    return Oracle(ORA_SO, "ora")
+
+
+def best():
+    """Preferred checker: compiled reference when present, else the C restatement."""
+    return load_ref() or load_ora()

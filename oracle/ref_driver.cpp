@@ -1,0 +1,651 @@
+// =============================================================================
+// oracle/ref_driver.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE
+// =============================================================================
+// Builds oracle/_ref/libgevref.so: the REFERENCE's own hot-path source
+// (/root/reference/gevolution.hpp, tools.hpp, background.hpp, metadata.hpp,
+// #included by path at build time, never copied) compiled against the
+// single-rank LATfield2 shim in oracle/latfield2_shim/, behind a flat-array
+// C interface.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+// legs may load this library; the product never does.
+//
+// Flat layouts (shared with oracle/gev_oracle.c and the tests):
+//   real field    double[ncomp][N][N][N]          index [c][z][y][x], no halo
+//   Fourier field double[ncomp][N][N][N/2+1][2]   index [c][kz][ky][kx][re,im]
+//   particles     double pos[np][3], vel[np][3]   (vel = canonical momentum q/m)
+//   symmetric tensor component order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
+//
+// The time-loop restatement in ref_sim_step() follows main.cpp:372-879 call by
+// call (main.cpp itself cannot be compiled here: it needs HDF5, GSL splines,
+// the parser and the I/O modules).
+// =============================================================================
+#include <stdint.h>
+#include <stdlib.h>
+#include <chrono>
+#include <set>
+#include <vector>
+#include "LATfield2.hpp"
+#include "metadata.hpp"
+#include "tools.hpp"
+#include "background.hpp"
+#include "gevolution.hpp"
+
+using namespace std;
+using namespace LATfield2;
+
+typedef Particles<part_simple, part_simple_info, part_simple_dataType> Pcls;
+
+namespace {
+
+struct Lat
+{
+	int N;
+	Lattice lat, latFT, latPart;
+	explicit Lat(int n) : N(n)
+	{
+		int box[3] = {n, n, n};
+		lat.initialize(3, box, GRADIENT_ORDER);      // main.cpp:213
+		latFT.initializeRealFFT(lat, 0);             // main.cpp:215
+	}
+};
+
+Lat & get_lat(int N)
+{
+	static std::vector<Lat *> cache;
+	for (size_t i = 0; i < cache.size(); i++) if (cache[i]->N == N) return *cache[i];
+	cache.push_back(new Lat(N));
+	return *cache.back();
+}
+
+void load_real(Field<Real> & f, const double * flat, bool halo = true)
+{
+	Lattice & l = f.lattice();
+	const int N = l.size(0), nc = f.components();
+	const size_t V = (size_t) N * N * N;
+	for (int c = 0; c < nc; c++)
+		for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) for (int x = 0; x < N; x++)
+			f(l.indexOf(x, y, z), c) = flat[c * V + ((size_t) z * N + y) * N + x];
+	if (halo) f.updateHalo();
+}
+
+void store_real(Field<Real> & f, double * flat)
+{
+	Lattice & l = f.lattice();
+	const int N = l.size(0), nc = f.components();
+	const size_t V = (size_t) N * N * N;
+	for (int c = 0; c < nc; c++)
+		for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) for (int x = 0; x < N; x++)
+			flat[c * V + ((size_t) z * N + y) * N + x] = f(l.indexOf(x, y, z), c);
+}
+
+void load_cplx(Field<Cplx> & f, const double * flat)
+{
+	Lattice & l = f.lattice();
+	const int nx = l.size(0), N = l.size(1), nc = f.components();
+	const size_t Vk = (size_t) nx * N * N;
+	for (int c = 0; c < nc; c++)
+		for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) for (int x = 0; x < nx; x++)
+		{
+			size_t o = 2 * (c * Vk + ((size_t) z * N + y) * nx + x);
+			f(l.indexOf(x, y, z), c) = Cplx(flat[o], flat[o + 1]);
+		}
+}
+
+void store_cplx(Field<Cplx> & f, double * flat)
+{
+	Lattice & l = f.lattice();
+	const int nx = l.size(0), N = l.size(1), nc = f.components();
+	const size_t Vk = (size_t) nx * N * N;
+	for (int c = 0; c < nc; c++)
+		for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) for (int x = 0; x < nx; x++)
+		{
+			size_t o = 2 * (c * Vk + ((size_t) z * N + y) * nx + x);
+			Cplx v = f(l.indexOf(x, y, z), c);
+			flat[o] = v.real(); flat[o + 1] = v.imag();
+		}
+}
+
+void make_pcls(Pcls & p, Lat & L, long np, const double * pos, const double * vel, double mass, const int64_t * ids = NULL)
+{
+	part_simple_info info;
+	info.mass = mass; info.relativistic = 0; strcpy(info.type_name, "part_simple");
+	part_simple_dataType dt;
+	Real box[3] = {1., 1., 1.};
+	p.initialize(info, dt, &L.lat, box);
+	for (long i = 0; i < np; i++)
+	{
+		part_simple q;
+		q.ID = ids ? (long) ids[i] : i;
+		for (int l = 0; l < 3; l++) { q.pos[l] = pos[3 * i + l]; q.vel[l] = vel ? vel[3 * i + l] : 0.; }
+		p.addParticle_global(q);
+	}
+}
+
+// write particles back to flat arrays at slot ID (IDs must be 0..np-1 for this)
+void read_pcls_by_id(Pcls & p, double * pos, double * vel)
+{
+	Site x(p.lattice());
+	for (x.first(); x.test(); x.next())
+	{
+		partList<part_simple> & cell = p.field()(x);
+		for (std::list<part_simple>::iterator it = cell.parts.begin(); it != cell.parts.end(); ++it)
+			for (int l = 0; l < 3; l++)
+			{
+				if (pos) pos[3 * (*it).ID + l] = (*it).pos[l];
+				if (vel) vel[3 * (*it).ID + l] = (*it).vel[l];
+			}
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+const char * ref_describe(void)
+{
+	return "reference gevolution.hpp/tools.hpp/background.hpp (gevolution 1.2) compiled with -DFFT3D -DPHINONLINEAR "
+	       "against the single-rank LATfield2 shim (oracle/latfield2_shim)";
+}
+
+// ---- PlanFFT::execute (main.cpp:477,488,544,563,575,593) --------------------
+void ref_fft_forward(int N, int ncomp, const double * real_in, double * cplx_out)
+{
+	Lat & L = get_lat(N);
+	Field<Real> r; Field<Cplx> k;
+	r.initialize(L.lat, ncomp); k.initialize(L.latFT, ncomp);
+	PlanFFT<Cplx> plan(&r, &k);
+	load_real(r, real_in, false);
+	plan.execute(FFT_FORWARD);
+	store_cplx(k, cplx_out);
+}
+
+void ref_fft_backward(int N, int ncomp, const double * cplx_in, double * real_out)
+{
+	Lat & L = get_lat(N);
+	Field<Real> r; Field<Cplx> k;
+	r.initialize(L.lat, ncomp); k.initialize(L.latFT, ncomp);
+	PlanFFT<Cplx> plan(&r, &k);
+	load_cplx(k, cplx_in);
+	plan.execute(FFT_BACKWARD);
+	store_real(r, real_out);
+}
+
+// ---- real-space source preparation (gevolution.hpp:57,170) ------------------
+void ref_prepareFTsource_scalar(int N, const double * phi, const double * chi, const double * source, double bgmodel, double * result, double coeff, double coeff2, double coeff3)
+{
+	Lat & L = get_lat(N);
+	Field<Real> fphi(L.lat, 1), fchi(L.lat, 1), fsrc(L.lat, 1);
+	load_real(fphi, phi); load_real(fchi, chi); load_real(fsrc, source);
+	prepareFTsource<Real>(fphi, fchi, fsrc, bgmodel, fsrc, coeff, coeff2, coeff3);   // aliasing as in main.cpp:472
+	store_real(fsrc, result);
+}
+
+void ref_prepareFTsource_tensor(int N, const double * phi, const double * Tij, double * Sij, double coeff)
+{
+	Lat & L = get_lat(N);
+	Field<Real> fphi(L.lat, 1), fT;
+	fT.initialize(L.lat, 3, 3, symmetric); fT.alloc();
+	load_real(fphi, phi); load_real(fT, Tij);
+	prepareFTsource<Real>(fphi, fT, fT, coeff);                                     // aliasing as in main.cpp:539
+	store_real(fT, Sij);
+}
+
+// ---- Fourier-space kernels (gevolution.hpp:211-535) ---------------------------
+void ref_solveModifiedPoissonFT(int N, const double * src, double * pot, double coeff, double modif)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> f(L.latFT, 1);
+	load_cplx(f, src);
+	solveModifiedPoissonFT(f, f, coeff, modif);                                      // in place as in main.cpp:483
+	store_cplx(f, pot);
+}
+
+void ref_projectFTscalar(int N, const double * SijFT, double * chiFT, int add)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> S, chi(L.latFT, 1);
+	S.initialize(L.latFT, 3, 3, symmetric); S.alloc();
+	load_cplx(S, SijFT);
+	if (add) load_cplx(chi, chiFT);
+	projectFTscalar(S, chi, add);
+	store_cplx(chi, chiFT);
+}
+
+void ref_evolveFTvector(int N, const double * SijFT, double * BiFT, double a2dtau)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> S, B(L.latFT, 3);
+	S.initialize(L.latFT, 3, 3, symmetric); S.alloc();
+	load_cplx(S, SijFT); load_cplx(B, BiFT);
+	evolveFTvector(S, B, a2dtau);
+	store_cplx(B, BiFT);
+}
+
+void ref_projectFTvector(int N, const double * SiFT, double * BiFT, double coeff, double modif)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> B(L.latFT, 3);
+	load_cplx(B, SiFT);
+	projectFTvector(B, B, coeff, modif);                                             // in place as in main.cpp:580
+	store_cplx(B, BiFT);
+}
+
+void ref_projectFTtensor(int N, const double * SijFT, double * hijFT)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> S;
+	S.initialize(L.latFT, 3, 3, symmetric); S.alloc();
+	load_cplx(S, SijFT);
+	projectFTtensor(S, S);                                                           // in place as in output.hpp:263
+	store_cplx(S, hijFT);
+}
+
+// ---- particle -> mesh projections (+ the *_comm fold) --------------------------
+void ref_projection_T00(int N, long np, const double * pos, const double * vel, double mass, double a, const double * phi, double coeff, double * T00)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, vel, mass);
+	Field<Real> src(L.lat, 1), fphi(L.lat, 1);
+	if (phi) load_real(fphi, phi);
+	projection_init(&src);
+	projection_T00_project(&p, &src, a, phi ? &fphi : (Field<Real> *) NULL, coeff);
+	projection_T00_comm(&src);
+	store_real(src, T00);
+}
+
+void ref_projection_T0i(int N, long np, const double * pos, const double * vel, double mass, const double * phi, double coeff, double * T0i)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, vel, mass);
+	Field<Real> B(L.lat, 3), fphi(L.lat, 1);
+	if (phi) load_real(fphi, phi);
+	projection_init(&B);
+	projection_T0i_project(&p, &B, phi ? &fphi : (Field<Real> *) NULL, coeff);
+	projection_T0i_comm(&B);
+	store_real(B, T0i);
+}
+
+void ref_projection_Tij(int N, long np, const double * pos, const double * vel, double mass, double a, const double * phi, double coeff, double * Tij)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, vel, mass);
+	Field<Real> S, fphi(L.lat, 1);
+	S.initialize(L.lat, 3, 3, symmetric); S.alloc();
+	if (phi) load_real(fphi, phi);
+	projection_init(&S);
+	projection_Tij_project(&p, &S, a, phi ? &fphi : (Field<Real> *) NULL, coeff);
+	projection_Tij_comm(&S);
+	store_real(S, Tij);
+}
+
+void ref_scalarProjectionCIC(int N, long np, const double * pos, double mass, double * rho)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, NULL, mass);
+	Field<Real> src(L.lat, 1);
+	projection_init(&src);
+	scalarProjectionCIC_project(&p, &src);
+	scalarProjectionCIC_comm(&src);
+	store_real(src, rho);
+}
+
+// ---- kick / drift (main.cpp:775,798; callbacks gevolution.hpp:570,709,810,900) --
+// kind: 0 = update_q / update_pos (GR), 1 = *_Newton
+double ref_updateVel(int N, long np, const double * pos, double * vel, int kind, double dtau, const double * phi, const double * chi, const double * Bi, int nfields, const double * params)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, vel, 1.0);
+	Field<Real> fphi(L.lat, 1), fchi(L.lat, 1), fB(L.lat, 3);
+	if (phi) load_real(fphi, phi);
+	if (chi) load_real(fchi, chi);
+	if (Bi) load_real(fB, Bi);
+	Field<Real> * fields[3] = {&fphi, &fchi, &fB};
+	double par[2] = {params[0], params[1]};
+	double r = (kind == 0) ? p.updateVel(update_q, dtau, fields, nfields, par)
+	                       : p.updateVel(update_q_Newton, dtau, fields, nfields, par);
+	read_pcls_by_id(p, NULL, vel);
+	return r;
+}
+
+void ref_moveParticles(int N, long np, double * pos, const double * vel, int kind, double dtau, const double * phi, const double * chi, const double * Bi, int nfields, const double * params)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, vel, 1.0);
+	Field<Real> fphi(L.lat, 1), fchi(L.lat, 1), fB(L.lat, 3);
+	if (phi) load_real(fphi, phi);
+	if (chi) load_real(fchi, chi);
+	if (Bi) load_real(fB, Bi);
+	Field<Real> * fields[3] = {&fphi, &fchi, &fB};
+	double par[2] = {params[0], params[1]};
+	if (kind == 0) p.moveParticles(update_pos, dtau, fields, nfields, par);
+	else p.moveParticles(update_pos_Newton, dtau, NULL, 0, par);
+	read_pcls_by_id(p, pos, NULL);
+}
+
+// cell under which each particle is filed + per-cell counts (bit-exact contract)
+void ref_cell_index(int N, long np, const double * pos, int32_t * cell, uint32_t * counts)
+{
+	Lat & L = get_lat(N);
+	Pcls p; make_pcls(p, L, np, pos, NULL, 1.0);
+	if (counts) memset(counts, 0, sizeof(uint32_t) * (size_t) N * N * N);
+	Site x(p.lattice());
+	for (x.first(); x.test(); x.next())
+	{
+		partList<part_simple> & c = p.field()(x);
+		int32_t key = (x.coord(2) * N + x.coord(1)) * N + x.coord(0);
+		if (counts) counts[key] = (uint32_t) c.size;
+		if (cell) for (std::list<part_simple>::iterator it = c.parts.begin(); it != c.parts.end(); ++it) cell[(*it).ID] = key;
+	}
+}
+
+// ---- analysis (tools.hpp:53,364,405) -------------------------------------------
+void ref_extractPowerSpectrum(int N, int ncomp, int symm, const double * fldFT, double * kbin, double * power, double * kscatter, double * pscatter, int * occupation, int numbins, int deconvolve, int ktype)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> f;
+	if (symm) f.initialize(L.latFT, 3, 3, symmetric); else f.initialize(L.latFT, ncomp);
+	f.alloc();
+	load_cplx(f, fldFT);
+	extractPowerSpectrum(f, kbin, power, kscatter, pscatter, occupation, numbins, deconvolve != 0, ktype);
+}
+
+void ref_computeVectorDiagnostics(int N, const double * Bi, double * mdivB, double * mcurlB)
+{
+	Lat & L = get_lat(N);
+	Field<Real> B(L.lat, 3);
+	load_real(B, Bi);
+	computeVectorDiagnostics(B, *mdivB, *mcurlB);
+}
+
+void ref_computeTensorDiagnostics(int N, const double * hij, double * mdivh, double * mtraceh, double * mnormh)
+{
+	Lat & L = get_lat(N);
+	Field<Real> h;
+	h.initialize(L.lat, 3, 3, symmetric); h.alloc();
+	load_real(h, hij);
+	computeTensorDiagnostics(h, *mdivh, *mtraceh, *mnormh);
+}
+
+// ---- background (background.hpp:137,167,200) ----------------------------------
+// cosmo_in: Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h
+static cosmology make_cosmo(const double * c)
+{
+	cosmology co;
+	memset(&co, 0, sizeof(co));
+	co.Omega_cdm = c[0]; co.Omega_b = c[1]; co.Omega_m = c[2]; co.Omega_Lambda = c[3];
+	co.Omega_fld = c[4]; co.w0_fld = c[5]; co.wa_fld = c[6]; co.Omega_g = c[7]; co.Omega_ur = c[8];
+	co.Omega_rad = c[9]; co.h = c[10]; co.cs2_fld = 1.; co.num_ncdm = 0;
+	return co;
+}
+double ref_Hconf(double a, double fourpiG, const double * cosmo) { return Hconf(a, fourpiG, make_cosmo(cosmo)); }
+double ref_rungekutta4bg(double a, double fourpiG, const double * cosmo, double dtau) { rungekutta4bg(a, fourpiG, make_cosmo(cosmo), dtau); return a; }
+double ref_particleHorizon(double a, double fourpiG, const double * cosmo) { cosmology co = make_cosmo(cosmo); return particleHorizon(a, fourpiG, co); }
+
+// =============================================================================
+// Stateful single-rank simulation: state of main.cpp:217-246 + the time loop
+// =============================================================================
+struct RefSim
+{
+	int N;
+	Lat * L;
+	cosmology cosmo;
+	double boxsize, Cf, steplimit, z_in, z_relax;
+	int gr_flag, vector_flag, baryon_flag;
+	double fourpiG, a, tau, dtau, dtau_old, dx, T00hom;
+	int cycle;
+	double maxvel[2];
+	Pcls pcls_cdm, pcls_b;
+	bool have_b;
+	Field<Real> phi, source, chi, Sij, Bi;
+	Field<Cplx> scalarFT, SijFT, BiFT;
+	PlanFFT<Cplx> plan_source, plan_phi, plan_chi, plan_Sij, plan_Bi;
+	// BENCHMARK-style timers (main.cpp:71-88)
+	double projection_time, gravity_solver_time, fft_time, update_q_time, moveParts_time, cycle_time;
+};
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// settings: N, gr_flag, vector_flag(0 parabolic,1 elliptic) ; dsettings: boxsize, Cf, steplimit, z_in, z_relax
+void * ref_sim_create(int N, int gr_flag, int vector_flag, const double * dsettings, const double * cosmo)
+{
+	RefSim * s = new RefSim();
+	s->N = N; s->L = &get_lat(N);
+	s->cosmo = make_cosmo(cosmo);
+	s->boxsize = dsettings[0]; s->Cf = dsettings[1]; s->steplimit = dsettings[2]; s->z_in = dsettings[3]; s->z_relax = dsettings[4];
+	s->gr_flag = gr_flag; s->vector_flag = vector_flag; s->baryon_flag = 0; s->have_b = false;
+	Lattice & lat = s->L->lat; Lattice & latFT = s->L->latFT;
+	// main.cpp:234-246
+	s->source.initialize(lat, 1); s->phi.initialize(lat, 1); s->chi.initialize(lat, 1);
+	s->scalarFT.initialize(latFT, 1);
+	s->plan_source.initialize(&s->source, &s->scalarFT);
+	s->plan_phi.initialize(&s->phi, &s->scalarFT);
+	s->plan_chi.initialize(&s->chi, &s->scalarFT);
+	s->Sij.initialize(lat, 3, 3, symmetric); s->SijFT.initialize(latFT, 3, 3, symmetric);
+	s->plan_Sij.initialize(&s->Sij, &s->SijFT);
+	s->Bi.initialize(lat, 3); s->BiFT.initialize(latFT, 3);
+	s->plan_Bi.initialize(&s->Bi, &s->BiFT);
+	// main.cpp:278-297
+	s->dx = 1.0 / (double) N;
+	s->fourpiG = 1.5 * s->boxsize * s->boxsize / C_SPEED_OF_LIGHT / C_SPEED_OF_LIGHT;
+	s->a = 1. / (1. + s->z_in);
+	s->tau = particleHorizon(s->a, s->fourpiG, s->cosmo);
+	if (s->Cf * s->dx < s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo)) s->dtau = s->Cf * s->dx;
+	else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
+	s->dtau_old = 0.;
+	s->cycle = 0; s->T00hom = 0.;
+	s->maxvel[0] = s->maxvel[1] = 0.;
+	s->projection_time = s->gravity_solver_time = s->fft_time = s->update_q_time = s->moveParts_time = s->cycle_time = 0.;
+	return s;
+}
+
+void ref_sim_destroy(void * h) { delete (RefSim *) h; }
+
+void ref_sim_set_particles(void * h, int species, long np, const int64_t * ids, const double * pos, const double * vel, double mass)
+{
+	RefSim * s = (RefSim *) h;
+	if (species == 0) make_pcls(s->pcls_cdm, *s->L, np, pos, vel, mass, ids);
+	else { make_pcls(s->pcls_b, *s->L, np, pos, vel, mass, ids); s->have_b = true; s->baryon_flag = 1; }
+}
+
+// which: 0 phi, 1 chi, 2 Bi(3), 3 source, 4 Sij(6)  [real];  10 scalarFT, 11 BiFT(3), 12 SijFT(6) [Fourier]
+static Field<Real> * real_field(RefSim * s, int which)
+{
+	switch (which) { case 0: return &s->phi; case 1: return &s->chi; case 2: return &s->Bi; case 3: return &s->source; case 4: return &s->Sij; }
+	return NULL;
+}
+static Field<Cplx> * cplx_field(RefSim * s, int which)
+{
+	switch (which) { case 10: return &s->scalarFT; case 11: return &s->BiFT; case 12: return &s->SijFT; }
+	return NULL;
+}
+void ref_sim_set_field(void * h, int which, const double * data)
+{
+	RefSim * s = (RefSim *) h;
+	if (which < 10) load_real(*real_field(s, which), data); else load_cplx(*cplx_field(s, which), data);
+}
+void ref_sim_get_field(void * h, int which, double * data)
+{
+	RefSim * s = (RefSim *) h;
+	if (which < 10) store_real(*real_field(s, which), data); else store_cplx(*cplx_field(s, which), data);
+}
+long ref_sim_num_particles(void * h, int species) { RefSim * s = (RefSim *) h; return species == 0 ? s->pcls_cdm.numParticles() : s->pcls_b.numParticles(); }
+
+// particles out in lattice iteration order (cell-sorted, x fastest)
+void ref_sim_get_particles(void * h, int species, int64_t * ids, double * pos, double * vel)
+{
+	RefSim * s = (RefSim *) h;
+	Pcls & p = species == 0 ? s->pcls_cdm : s->pcls_b;
+	Site x(p.lattice());
+	long n = 0;
+	for (x.first(); x.test(); x.next())
+	{
+		partList<part_simple> & cell = p.field()(x);
+		for (std::list<part_simple>::iterator it = cell.parts.begin(); it != cell.parts.end(); ++it, ++n)
+		{
+			ids[n] = (*it).ID;
+			for (int l = 0; l < 3; l++) { pos[3 * n + l] = (*it).pos[l]; vel[3 * n + l] = (*it).vel[l]; }
+		}
+	}
+}
+
+// scalars: a, tau, dtau, dtau_old, cycle, maxvel0, maxvel1, T00hom, fourpiG
+void ref_sim_get_state(void * h, double * out)
+{
+	RefSim * s = (RefSim *) h;
+	out[0] = s->a; out[1] = s->tau; out[2] = s->dtau; out[3] = s->dtau_old; out[4] = s->cycle;
+	out[5] = s->maxvel[0]; out[6] = s->maxvel[1]; out[7] = s->T00hom; out[8] = s->fourpiG;
+}
+void ref_sim_set_state(void * h, const double * in)
+{
+	RefSim * s = (RefSim *) h;
+	s->a = in[0]; s->tau = in[1]; s->dtau = in[2]; s->dtau_old = in[3]; s->cycle = (int) in[4];
+	s->maxvel[0] = in[5]; s->maxvel[1] = in[6];
+}
+// timers: projection, gravity solver, thereof FFT, update momenta, move particles, cycle total
+void ref_sim_get_timers(void * h, double * out)
+{
+	RefSim * s = (RefSim *) h;
+	out[0] = s->projection_time; out[1] = s->gravity_solver_time; out[2] = s->fft_time;
+	out[3] = s->update_q_time; out[4] = s->moveParts_time; out[5] = s->cycle_time;
+}
+
+// one cycle of the main loop, outputs stripped (main.cpp:372-879)
+void ref_sim_step(void * h)
+{
+	RefSim * s = (RefSim *) h;
+	const double dx = s->dx, fourpiG = s->fourpiG;
+	cosmology & cosmo = s->cosmo;
+	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
+	Field<Real> * update_cdm_fields[3] = {&s->phi, &s->chi, &s->Bi};
+	double f_params[5];
+	Site x(s->L->lat);
+	double t0 = now_s(), t1, t2;
+
+	// main.cpp:378-411  T00
+	projection_init(&s->source);
+	if (s->gr_flag > 0)
+	{
+		projection_T00_project(&s->pcls_cdm, &s->source, a, &s->phi);
+		if (s->baryon_flag) projection_T00_project(&s->pcls_b, &s->source, a, &s->phi);
+	}
+	else
+	{
+		scalarProjectionCIC_project(&s->pcls_cdm, &s->source);
+		if (s->baryon_flag) scalarProjectionCIC_project(&s->pcls_b, &s->source);
+	}
+	projection_T00_comm(&s->source);
+
+	// main.cpp:424-436  T0i (elliptic only)
+	if (s->vector_flag == VECTOR_ELLIPTIC)
+	{
+		projection_init(&s->Bi);
+		projection_T0i_project(&s->pcls_cdm, &s->Bi, &s->phi);
+		if (s->baryon_flag) projection_T0i_project(&s->pcls_b, &s->Bi, &s->phi);
+		projection_T0i_comm(&s->Bi);
+	}
+
+	// main.cpp:438-450  Tij
+	projection_init(&s->Sij);
+	projection_Tij_project(&s->pcls_cdm, &s->Sij, a, &s->phi);
+	if (s->baryon_flag) projection_Tij_project(&s->pcls_b, &s->Sij, a, &s->phi);
+	projection_Tij_comm(&s->Sij);
+
+	t1 = now_s(); s->projection_time += t1 - t0;
+
+	if (s->gr_flag > 0)
+	{
+		// main.cpp:459-463
+		double T00hom = 0.;
+		for (x.first(); x.test(); x.next()) T00hom += s->source(x);
+		T00hom /= (double) ((long) s->N * s->N * s->N);
+		s->T00hom = T00hom;
+
+		if (dtau_old > 0.)
+		{
+			// main.cpp:472-488
+			prepareFTsource<Real>(s->phi, s->chi, s->source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), s->source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx);
+			t2 = now_s(); s->plan_source.execute(FFT_FORWARD); s->fft_time += now_s() - t2;
+			solveModifiedPoissonFT(s->scalarFT, s->scalarFT, 1. / (dx * dx), 3. * Hconf(a, fourpiG, cosmo) / dtau_old);
+			t2 = now_s(); s->plan_phi.execute(FFT_BACKWARD); s->fft_time += now_s() - t2;
+		}
+	}
+	else
+	{
+		// main.cpp:500-511
+		t2 = now_s(); s->plan_source.execute(FFT_FORWARD); s->fft_time += now_s() - t2;
+		solveModifiedPoissonFT(s->scalarFT, s->scalarFT, fourpiG / a);
+		t2 = now_s(); s->plan_phi.execute(FFT_BACKWARD); s->fft_time += now_s() - t2;
+	}
+
+	s->phi.updateHalo();   // main.cpp:518
+
+	// main.cpp:539-568  chi
+	prepareFTsource<Real>(s->phi, s->Sij, s->Sij, 2. * fourpiG * dx * dx / a);
+	t2 = now_s(); s->plan_Sij.execute(FFT_FORWARD); s->fft_time += now_s() - t2;
+	projectFTscalar(s->SijFT, s->scalarFT);
+	t2 = now_s(); s->plan_chi.execute(FFT_BACKWARD); s->fft_time += now_s() - t2;
+	s->chi.updateHalo();
+
+	// main.cpp:570-599  B
+	if (s->vector_flag == VECTOR_ELLIPTIC)
+	{
+		t2 = now_s(); s->plan_Bi.execute(FFT_FORWARD); s->fft_time += now_s() - t2;
+		projectFTvector(s->BiFT, s->BiFT, fourpiG * dx * dx);
+	}
+	else
+		evolveFTvector(s->SijFT, s->BiFT, a * a * dtau_old);
+
+	if (s->gr_flag > 0)
+	{
+		t2 = now_s(); s->plan_Bi.execute(FFT_BACKWARD); s->fft_time += now_s() - t2;
+		s->Bi.updateHalo();
+	}
+
+	t2 = now_s(); s->gravity_solver_time += t2 - t1;
+
+	// main.cpp:771-784  kick
+	f_params[0] = a;
+	f_params[1] = a * a * s->N;
+	if (s->gr_flag > 0)
+	{
+		s->maxvel[0] = s->pcls_cdm.updateVel(update_q, (dtau + dtau_old) / 2., update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);
+		if (s->baryon_flag) s->maxvel[1] = s->pcls_b.updateVel(update_q, (dtau + dtau_old) / 2., update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);
+	}
+	else
+	{
+		s->maxvel[0] = s->pcls_cdm.updateVel(update_q_Newton, (dtau + dtau_old) / 2., update_cdm_fields, 1, f_params);
+		if (s->baryon_flag) s->maxvel[1] = s->pcls_b.updateVel(update_q_Newton, (dtau + dtau_old) / 2., update_cdm_fields, 1, f_params);
+	}
+	t1 = now_s(); s->update_q_time += t1 - t2;
+
+	rungekutta4bg(a, fourpiG, cosmo, 0.5 * dtau);   // main.cpp:792
+
+	// main.cpp:794-807  drift
+	f_params[0] = a;
+	f_params[1] = a * a * s->N;
+	if (s->gr_flag > 0)
+	{
+		s->pcls_cdm.moveParticles(update_pos, dtau, update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 0), f_params);
+		if (s->baryon_flag) s->pcls_b.moveParticles(update_pos, dtau, update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 0), f_params);
+	}
+	else
+	{
+		s->pcls_cdm.moveParticles(update_pos_Newton, dtau, NULL, 0, f_params);
+		if (s->baryon_flag) s->pcls_b.moveParticles(update_pos_Newton, dtau, NULL, 0, f_params);
+	}
+	s->moveParts_time += now_s() - t1;
+
+	rungekutta4bg(a, fourpiG, cosmo, 0.5 * dtau);   // main.cpp:814
+
+	// main.cpp:816-822
+	if (s->gr_flag > 0)
+		for (int i = 0; i < 1 + s->baryon_flag; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);
+
+	s->tau += dtau;         // main.cpp:825
+	dtau_old = dtau;        // main.cpp:867
+	if (s->Cf * dx < s->steplimit / Hconf(a, fourpiG, cosmo)) dtau = s->Cf * dx;   // main.cpp:869-872
+	else dtau = s->steplimit / Hconf(a, fourpiG, cosmo);
+	s->cycle++;
+	s->cycle_time += now_s() - t0;
+}
+
+} // extern "C"
