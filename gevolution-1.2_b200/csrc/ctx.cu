@@ -1,0 +1,360 @@
+// ctx.cu -- context, field storage, ghost-plane exchange, reductions
+//
+// Replaces, for the hot path only: LATfield2 `parallel`, `Lattice`, `Field<T>`
+// storage, Field::updateHalo, projection_init and the three *_comm folds
+// (reference call sites main.cpp:152,213-246,378,411,435,450,459-463,518,568,598).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include "gevb_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gevb_set_error(const char * fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char * gevb_last_error(void) { return g_err; }
+extern "C" const char * gevb_version(void) { return "gevb 0.1 (sm_100a; hot path of gevolution 1.2)"; }
+
+extern "C" int gevb_nccl_unique_id(void * out128)
+{
+	GEVB_CHECK_ARG(out128 != NULL, "gevb_nccl_unique_id: NULL output");
+	ncclUniqueId id;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+	GEVB_TRY(gevb_nccl_load());
+	NCCL_TRY(ncclGetUniqueId(&id));
+	memcpy(out128, &id, sizeof(id));
+	return 0;
+}
+
+extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank, int nranks, const void * nccl_id)
+{
+	GEVB_CHECK_ARG(out != NULL, "gevb_ctx_create: NULL output");
+	GEVB_CHECK_ARG(ngrid >= 4 && ngrid % 2 == 0, "gevb_ctx_create: Ngrid must be even and >= 4 (got %d)", ngrid);
+	GEVB_CHECK_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "gevb_ctx_create: bad rank %d of %d", rank, nranks);
+	GEVB_CHECK_ARG(ngrid % nranks == 0, "gevb_ctx_create: Ngrid %d not divisible by %d ranks", ngrid, nranks);
+	GEVB_CHECK_ARG(nranks == 1 || ngrid / nranks >= 2, "gevb_ctx_create: slabs must be at least 2 planes thick");
+	GEVB_CHECK_ARG(nranks == 1 || nccl_id != NULL, "gevb_ctx_create: nccl_id required when nranks > 1");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) GEVB_FAIL("gevb_ctx_create: no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+	GEVB_CHECK_ARG(device >= 0 && device < ndev, "gevb_ctx_create: device %d out of range (%d devices)", device, ndev);
+	CUDA_TRY(cudaSetDevice(device));
+	gevb_ctx * c = new gevb_ctx();
+	memset(c, 0, sizeof(*c));
+	c->N = ngrid; c->nh = ngrid / 2 + 1;
+	c->device = device; c->rank = rank; c->nranks = nranks;
+	c->nzl = ngrid / nranks; c->z0 = rank * c->nzl;
+	c->nkyl = ngrid / nranks; c->ky0 = rank * c->nkyl;
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	c->num_sms = prop.multiProcessorCount;
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	// k tables, computed on the host with the reference's own expressions (gevolution.hpp:222-227)
+	std::vector<double> g(ngrid);
+	std::vector<double2> ks(ngrid);
+	for (int i = 0; i < ngrid; i++)
+	{
+		g[i] = 2. * (double) ngrid * sin(M_PI * (double) i / (double) ngrid);
+		ks[i].x = g[i] * cos(M_PI * (double) i / (double) ngrid);
+		ks[i].y = g[i] * -sin(M_PI * (double) i / (double) ngrid);
+		g[i] *= g[i];
+	}
+	CUDA_TRY(cudaMalloc(&c->d_gridk2, sizeof(double) * ngrid));
+	CUDA_TRY(cudaMalloc(&c->d_kshift, sizeof(double2) * ngrid));
+	CUDA_TRY(cudaMemcpy(c->d_gridk2, g.data(), sizeof(double) * ngrid, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(c->d_kshift, ks.data(), sizeof(double2) * ngrid, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&c->d_red, sizeof(double) * 8192));
+	CUDA_TRY(cudaMallocHost(&c->h_red, sizeof(double) * 8192));
+	if (nranks > 1)
+	{
+		ncclUniqueId id;
+		memcpy(&id, nccl_id, sizeof(id));
+		GEVB_TRY(gevb_nccl_load());
+		NCCL_TRY(ncclCommInitRank(&c->comm, nranks, id, rank));
+		c->have_comm = true;
+	}
+	*out = c;
+	return 0;
+}
+
+extern "C" int gevb_ctx_destroy(gevb_ctx * c)
+{
+	if (c == NULL) return 0;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	if (c->have_comm) ncclCommDestroy(c->comm);
+	cudaFree(c->d_gridk2); cudaFree(c->d_kshift); cudaFree(c->d_red); cudaFreeHost(c->h_red);
+	if (c->scratch) cudaFree(c->scratch);
+	if (c->scratch2) cudaFree(c->scratch2);
+	cudaStreamDestroy(c->stream);
+	delete c;
+	return 0;
+}
+
+extern "C" int gevb_ctx_sync(gevb_ctx * c)
+{
+	GEVB_CHECK_ARG(c != NULL, "gevb_ctx_sync: NULL context");
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int gevb_ctx_geometry(gevb_ctx * c, int * ngrid, int * z0, int * nzl, int * ky0, int * nkyl)
+{
+	GEVB_CHECK_ARG(c != NULL, "gevb_ctx_geometry: NULL context");
+	if (ngrid) *ngrid = c->N;
+	if (z0) *z0 = c->z0;
+	if (nzl) *nzl = c->nzl;
+	if (ky0) *ky0 = c->ky0;
+	if (nkyl) *nkyl = c->nkyl;
+	return 0;
+}
+
+extern "C" void * gevb_ctx_stream(gevb_ctx * c) { return c ? (void *) c->stream : NULL; }
+extern "C" int64_t gevb_ctx_launch_count(gevb_ctx * c) { return c ? c->launches : 0; }
+
+static int grow(void ** buf, size_t * have, size_t want)
+{
+	if (*have >= want) return 0;
+	if (*buf) CUDA_TRY(cudaFree(*buf));
+	*buf = NULL; *have = 0;
+	size_t sz = want + want / 8 + 256;
+	CUDA_TRY(cudaMalloc(buf, sz));
+	*have = sz;
+	return 0;
+}
+int gevb_ctx_scratch(gevb_ctx * c, size_t bytes, void ** out)
+{
+	// the stream may still be using the old buffer
+	if (c->scratch_bytes < bytes) CUDA_TRY(cudaStreamSynchronize(c->stream));
+	GEVB_TRY(grow(&c->scratch, &c->scratch_bytes, bytes));
+	*out = c->scratch;
+	return 0;
+}
+int gevb_ctx_scratch2(gevb_ctx * c, size_t bytes, void ** out)
+{
+	if (c->scratch2_bytes < bytes) CUDA_TRY(cudaStreamSynchronize(c->stream));
+	GEVB_TRY(grow(&c->scratch2, &c->scratch2_bytes, bytes));
+	*out = c->scratch2;
+	return 0;
+}
+
+// ---- parallel.sum / parallel.max --------------------------------------------
+static int host_allreduce(gevb_ctx * c, double * v, int n, ncclRedOp_t op)
+{
+	GEVB_CHECK_ARG(c != NULL && v != NULL && n >= 0 && n <= 4096, "gevb_parallel_*: bad arguments");
+	if (c->nranks == 1 || n == 0) return 0;
+	CUDA_TRY(cudaSetDevice(c->device));
+	memcpy(c->h_red, v, sizeof(double) * n);
+	CUDA_TRY(cudaMemcpyAsync(c->d_red + 4096, c->h_red, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+	NCCL_TRY(ncclAllReduce(c->d_red + 4096, c->d_red + 4096, n, ncclDouble, op, c->comm, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->h_red, c->d_red + 4096, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	memcpy(v, c->h_red, sizeof(double) * n);
+	return 0;
+}
+extern "C" int gevb_parallel_sum(gevb_ctx * c, double * v, int n) { return host_allreduce(c, v, n, ncclSum); }
+extern "C" int gevb_parallel_max(gevb_ctx * c, double * v, int n) { return host_allreduce(c, v, n, ncclMax); }
+
+// ---- fields ------------------------------------------------------------------
+extern "C" int gevb_field_create(gevb_ctx * c, gevb_field ** out, int kind, int ncomp, int symmetric)
+{
+	GEVB_CHECK_ARG(c != NULL && out != NULL, "gevb_field_create: NULL argument");
+	GEVB_CHECK_ARG(kind == GEVB_REAL || kind == GEVB_CPLX, "gevb_field_create: bad kind %d", kind);
+	GEVB_CHECK_ARG(ncomp >= 1 && ncomp <= 16, "gevb_field_create: bad component count %d", ncomp);
+	GEVB_CHECK_ARG(!symmetric || ncomp == 6, "gevb_field_create: symmetric fields are 3x3 (6 components)");
+	CUDA_TRY(cudaSetDevice(c->device));
+	gevb_field * f = new gevb_field();
+	f->ctx = c; f->kind = kind; f->ncomp = ncomp; f->symmetric = symmetric;
+	f->comp_stride = kind == GEVB_REAL ? c->real_comp_stride() : c->cplx_comp_stride();
+	f->bytes = f->comp_stride * ncomp * (kind == GEVB_REAL ? sizeof(double) : sizeof(double2));
+	cudaError_t e = cudaMalloc(&f->data, f->bytes);
+	if (e != cudaSuccess) { delete f; GEVB_FAIL("gevb_field_create: cudaMalloc(%zu) failed: %s", f->bytes, cudaGetErrorString(e)); }
+	CUDA_TRY(cudaMemsetAsync(f->data, 0, f->bytes, c->stream));
+	*out = f;
+	return 0;
+}
+
+extern "C" int gevb_field_destroy(gevb_field * f)
+{
+	if (f == NULL) return 0;
+	cudaSetDevice(f->ctx->device);
+	cudaStreamSynchronize(f->ctx->stream);
+	cudaFree(f->data);
+	delete f;
+	return 0;
+}
+
+extern "C" int gevb_field_components(gevb_field * f) { return f ? f->ncomp : 0; }
+extern "C" void * gevb_field_device_ptr(gevb_field * f) { return f ? (void *) f->data : NULL; }
+
+extern "C" int gevb_field_upload(gevb_field * f, const double * host)
+{
+	GEVB_CHECK_ARG(f != NULL && host != NULL, "gevb_field_upload: NULL argument");
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	if (f->kind == GEVB_REAL)
+	{
+		size_t bulk = (size_t) c->nzl * c->plane();
+		for (int k = 0; k < f->ncomp; k++)
+			CUDA_TRY(cudaMemcpyAsync(f->data + k * f->comp_stride + c->plane(), host + k * bulk, bulk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	else
+		CUDA_TRY(cudaMemcpyAsync(f->data, host, f->bytes, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int gevb_field_download(gevb_field * f, double * host)
+{
+	GEVB_CHECK_ARG(f != NULL && host != NULL, "gevb_field_download: NULL argument");
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	if (f->kind == GEVB_REAL)
+	{
+		size_t bulk = (size_t) c->nzl * c->plane();
+		for (int k = 0; k < f->ncomp; k++)
+			CUDA_TRY(cudaMemcpyAsync(host + k * bulk, f->data + k * f->comp_stride + c->plane(), bulk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	else
+		CUDA_TRY(cudaMemcpyAsync(host, f->data, f->bytes, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// projection_init (main.cpp:378,426,438): zero everything, ghost planes included
+extern "C" int gevb_projection_init(gevb_field * f)
+{
+	GEVB_CHECK_ARG(f != NULL, "projection_init: NULL field");
+	CUDA_TRY(cudaSetDevice(f->ctx->device));
+	CUDA_TRY(cudaMemsetAsync(f->data, 0, f->bytes, f->ctx->stream));
+	return 0;
+}
+
+// Field::updateHalo (main.cpp:518,568,598)
+extern "C" int gevb_field_updateHalo(gevb_field * f)
+{
+	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "updateHalo: needs a real field");
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t pl = c->plane();
+	if (c->nranks == 1)
+	{
+		for (int k = 0; k < f->ncomp; k++)
+		{
+			double * base = f->data + k * f->comp_stride;
+			CUDA_TRY(cudaMemcpyAsync(base, base + (size_t) c->nzl * pl, pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+			CUDA_TRY(cudaMemcpyAsync(base + (size_t) (c->nzl + 1) * pl, base + pl, pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		}
+		return 0;
+	}
+	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+	NCCL_TRY(ncclGroupStart());
+	for (int k = 0; k < f->ncomp; k++)
+	{
+		double * base = f->data + k * f->comp_stride;
+		NCCL_TRY(ncclSend(base + pl, pl, ncclDouble, dn, c->comm, c->stream));                          // my first bulk plane -> lower neighbour's upper ghost
+		NCCL_TRY(ncclSend(base + (size_t) c->nzl * pl, pl, ncclDouble, up, c->comm, c->stream));        // my last bulk plane  -> upper neighbour's lower ghost
+		NCCL_TRY(ncclRecv(base + (size_t) (c->nzl + 1) * pl, pl, ncclDouble, up, c->comm, c->stream));
+		NCCL_TRY(ncclRecv(base, pl, ncclDouble, dn, c->comm, c->stream));
+	}
+	NCCL_TRY(ncclGroupEnd());
+	return 0;
+}
+
+__global__ void k_fold_add(double * __restrict__ dst, const double * __restrict__ src, size_t n, int ncomp, size_t dst_stride, size_t src_stride)
+{
+	for (int k = 0; k < ncomp; k++)
+		for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+			dst[k * dst_stride + i] += src[k * src_stride + i];
+}
+
+// scalarProjectionCIC_comm / vectorProjectionCICNGP_comm / symtensorProjectionCICNGP_comm
+// (gevolution.hpp:1024,1149,1300): deposits only reach x and +1 neighbours, x/y wrap is done
+// by the deposit kernels, so the fold is one plane: upper ghost -> next rank's first bulk plane
+extern "C" int gevb_projection_comm(gevb_field * f)
+{
+	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "projection_comm: needs a real field");
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t pl = c->plane();
+	const double * src = f->data + (size_t) (c->nzl + 1) * pl;
+	size_t src_stride = f->comp_stride;
+	if (c->nranks > 1)
+	{
+		void * stage;
+		GEVB_TRY(gevb_ctx_scratch(c, pl * f->ncomp * sizeof(double), &stage));
+		const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+		NCCL_TRY(ncclGroupStart());
+		for (int k = 0; k < f->ncomp; k++)
+		{
+			NCCL_TRY(ncclSend(f->data + k * f->comp_stride + (size_t) (c->nzl + 1) * pl, pl, ncclDouble, up, c->comm, c->stream));
+			NCCL_TRY(ncclRecv((double *) stage + k * pl, pl, ncclDouble, dn, c->comm, c->stream));
+		}
+		NCCL_TRY(ncclGroupEnd());
+		src = (const double *) stage; src_stride = pl;
+	}
+	k_fold_add<<<gevb_grid(c, pl, 256), 256, 0, c->stream>>>(f->data + pl, src, pl, f->ncomp, f->comp_stride, src_stride);
+	KERNEL_CHECK(c);
+	return 0;
+}
+
+// ---- reductions ----------------------------------------------------------------
+__global__ void k_block_sum(const double * __restrict__ v, size_t n, double * __restrict__ partial)
+{
+	__shared__ double sm[32];
+	double s = 0.;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) s += v[i];
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x < 32)
+	{
+		s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.;
+		for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+		if (threadIdx.x == 0) partial[blockIdx.x] = s;
+	}
+}
+
+// sum of the local bulk of one component, then parallel.sum (main.cpp:459-463)
+extern "C" int gevb_field_sum(gevb_field * f, int comp, double * out)
+{
+	GEVB_CHECK_ARG(f != NULL && out != NULL && f->kind == GEVB_REAL, "gevb_field_sum: needs a real field");
+	GEVB_CHECK_ARG(comp >= 0 && comp < f->ncomp, "gevb_field_sum: component %d out of range", comp);
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t n = (size_t) c->nzl * c->plane();
+	int blocks = gevb_grid(c, n, 256, 4);
+	if (blocks > 2048) blocks = 2048;
+	k_block_sum<<<blocks, 256, 0, c->stream>>>(f->data + comp * f->comp_stride + c->plane(), n, c->d_red);
+	KERNEL_CHECK(c);
+	k_block_sum<<<1, 256, 0, c->stream>>>(c->d_red, blocks, c->d_red + 2048);
+	KERNEL_CHECK(c);
+	if (c->nranks > 1) NCCL_TRY(ncclAllReduce(c->d_red + 2048, c->d_red + 2048, 1, ncclDouble, ncclSum, c->comm, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->h_red, c->d_red + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	*out = c->h_red[0];
+	return 0;
+}
+
+__global__ void k_add_constant(double * __restrict__ v, size_t n, double value)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) v[i] += value;
+}
+
+extern "C" int gevb_field_add_constant(gevb_field * f, int comp, double value)
+{
+	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "gevb_field_add_constant: needs a real field");
+	GEVB_CHECK_ARG(comp >= 0 && comp < f->ncomp, "gevb_field_add_constant: component %d out of range", comp);
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t n = (size_t) c->nzl * c->plane();
+	k_add_constant<<<gevb_grid(c, n, 256), 256, 0, c->stream>>>(f->data + comp * f->comp_stride + c->plane(), n, value);
+	KERNEL_CHECK(c);
+	return 0;
+}

@@ -1,0 +1,221 @@
+// fft.cu -- PlanFFT<Cplx>::execute (main.cpp:238-246,477,488,544,563,575,593)
+//
+// Per-component 3-D r2c (forward, e^{-ikx}) / c2r (backward), unnormalised both
+// ways (manual.pdf section 4).  cuFFT does the local transforms; with more than
+// one rank the global transpose is one NCCL all-to-all per execute:
+//
+//   nranks == 1 : one batched 3-D D2Z / Z2D plan over all components.
+//   nranks  > 1 : forward  = 2-D D2Z on every local z-plane  -> pack -> all-to-all
+//                            -> unpack/transposed to [ky][kx][kz] -> 1-D Z2Z along kz
+//                 backward = 1-D Z2Z^-1 along kz (out of place) -> pack -> all-to-all
+//                            -> unpack to [z][ky][kx] -> 2-D Z2D per plane.
+//
+// The Fourier input of a backward transform is preserved (the reference keeps
+// BiFT as persistent state across steps, main.cpp:586-593): cuFFT's multi-dim
+// Z2D may overwrite its input, so it runs on a staged copy.
+#include "gevb_internal.cuh"
+
+namespace {
+
+// [c][zl][ky][kx] (2-D transformed planes)  ->  send buffer [dst rank][c][zl][ky in dst slab][kx]
+__global__ void k_pack_fwd(const double2 * __restrict__ w, double2 * __restrict__ send, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
+{
+	const size_t total = (size_t) ncomp * nzl * N * nh;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
+	{
+		int kx = (int) (i % nh); size_t r = i / nh;
+		int ky = (int) (r % N); r /= N;
+		int zl = (int) (r % nzl); int c = (int) (r / nzl);
+		int dst = ky / nkyl, kyl = ky % nkyl;
+		size_t o = ((((size_t) dst * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx;
+		send[o] = w[i];
+	}
+}
+
+// recv buffer [src rank][c][zl of src][kyl][kx]  ->  slab layout [c][kyl][kx][kz = src*nzl + zl]
+// tile transpose (kz <-> kx) through shared memory so that reads and writes are both coalesced
+__global__ void k_unpack_fwd(const double2 * __restrict__ recv, double2 * __restrict__ out, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
+{
+	__shared__ double2 tile[32][33];
+	// grid: x = kx tiles, y = kz tiles, z = c * nkyl + kyl
+	const int c = blockIdx.z / nkyl, kyl = blockIdx.z % nkyl;
+	const int kx0 = blockIdx.x * 32, kz0 = blockIdx.y * 32;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		int kz = kz0 + j, kx = kx0 + threadIdx.x;
+		if (kz < N && kx < nh)
+		{
+			int src = kz / nzl, zl = kz % nzl;
+			tile[j][threadIdx.x] = recv[((((size_t) src * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx];
+		}
+	}
+	__syncthreads();
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		int kx = kx0 + j, kz = kz0 + threadIdx.x;
+		if (kz < N && kx < nh) out[(((size_t) c * nkyl + kyl) * nh + kx) * N + kz] = tile[threadIdx.x][j];
+	}
+}
+
+// slab layout [c][kyl][kx][z]  ->  send buffer [dst rank][c][zl in dst slab][kyl][kx]   (transpose back)
+__global__ void k_pack_bwd(const double2 * __restrict__ in, double2 * __restrict__ send, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
+{
+	__shared__ double2 tile[32][33];
+	const int c = blockIdx.z / nkyl, kyl = blockIdx.z % nkyl;
+	const int kx0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		int kx = kx0 + j, z = z0 + threadIdx.x;
+		if (z < N && kx < nh) tile[j][threadIdx.x] = in[(((size_t) c * nkyl + kyl) * nh + kx) * N + z];
+	}
+	__syncthreads();
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		int z = z0 + j, kx = kx0 + threadIdx.x;
+		if (z < N && kx < nh)
+		{
+			int dst = z / nzl, zl = z % nzl;
+			send[((((size_t) dst * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx] = tile[threadIdx.x][j];
+		}
+	}
+}
+
+// recv buffer [src rank][c][zl][kyl of src][kx]  ->  [c][zl][ky = src*nkyl + kyl][kx]
+__global__ void k_unpack_bwd(const double2 * __restrict__ recv, double2 * __restrict__ w, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
+{
+	const size_t total = (size_t) ncomp * nzl * N * nh;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
+	{
+		int kx = (int) (i % nh); size_t r = i / nh;
+		int ky = (int) (r % N); r /= N;
+		int zl = (int) (r % nzl); int c = (int) (r / nzl);
+		int src = ky / nkyl, kyl = ky % nkyl;
+		w[i] = recv[((((size_t) src * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx];
+	}
+}
+
+int alltoall(gevb_ctx * c, const double2 * send, double2 * recv, size_t per_pair)
+{
+	NCCL_TRY(ncclGroupStart());
+	for (int r = 0; r < c->nranks; r++)
+	{
+		NCCL_TRY(ncclSend(send + (size_t) r * per_pair, per_pair * 2, ncclDouble, r, c->comm, c->stream));
+		NCCL_TRY(ncclRecv(recv + (size_t) r * per_pair, per_pair * 2, ncclDouble, r, c->comm, c->stream));
+	}
+	NCCL_TRY(ncclGroupEnd());
+	return 0;
+}
+
+} // namespace
+
+extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * cf)
+{
+	GEVB_CHECK_ARG(out != NULL && rf != NULL && cf != NULL, "gevb_plan_create: NULL argument");
+	GEVB_CHECK_ARG(rf->kind == GEVB_REAL && cf->kind == GEVB_CPLX, "gevb_plan_create: needs (real field, Fourier field)");
+	GEVB_CHECK_ARG(rf->ncomp == cf->ncomp, "gevb_plan_create: component counts differ (%d vs %d)", rf->ncomp, cf->ncomp);
+	GEVB_CHECK_ARG(rf->ctx == cf->ctx, "gevb_plan_create: fields belong to different contexts");
+	gevb_ctx * c = rf->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	gevb_plan * p = new gevb_plan();
+	memset(p, 0, sizeof(*p));
+	p->ctx = c; p->real_field = rf; p->cplx_field = cf; p->multi = c->nranks > 1;
+	const int N = c->N, nh = c->nh;
+	if (!p->multi)
+	{
+		int n[3] = {N, N, N};
+		int rembed[3] = {N, N, N}, kembed[3] = {N, N, nh};
+		CUFFT_TRY(cufftPlanMany(&p->fwd, 3, n, rembed, 1, (int) rf->comp_stride, kembed, 1, (int) cf->comp_stride, CUFFT_D2Z, rf->ncomp));
+		CUFFT_TRY(cufftPlanMany(&p->bwd, 3, n, kembed, 1, (int) cf->comp_stride, rembed, 1, (int) rf->comp_stride, CUFFT_Z2D, rf->ncomp));
+		CUFFT_TRY(cufftSetStream(p->fwd, c->stream));
+		CUFFT_TRY(cufftSetStream(p->bwd, c->stream));
+	}
+	else
+	{
+		int n2[2] = {N, N};
+		int rembed[2] = {N, N}, kembed[2] = {N, nh};
+		// one call per component: nzl planes, contiguous in both the real bulk and the staging buffer
+		CUFFT_TRY(cufftPlanMany(&p->fwd2d, 2, n2, rembed, 1, N * N, kembed, 1, N * nh, CUFFT_D2Z, c->nzl));
+		CUFFT_TRY(cufftPlanMany(&p->bwd2d, 2, n2, kembed, 1, N * nh, rembed, 1, N * N, CUFFT_Z2D, c->nzl));
+		int n1[1] = {N};
+		CUFFT_TRY(cufftPlanMany(&p->z1d, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, rf->ncomp * c->nkyl * nh));
+		CUFFT_TRY(cufftSetStream(p->fwd2d, c->stream));
+		CUFFT_TRY(cufftSetStream(p->bwd2d, c->stream));
+		CUFFT_TRY(cufftSetStream(p->z1d, c->stream));
+	}
+	*out = p;
+	return 0;
+}
+
+extern "C" int gevb_plan_destroy(gevb_plan * p)
+{
+	if (p == NULL) return 0;
+	cudaSetDevice(p->ctx->device);
+	cudaStreamSynchronize(p->ctx->stream);
+	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); }
+	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); }
+	delete p;
+	return 0;
+}
+
+extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
+{
+	GEVB_CHECK_ARG(p != NULL, "gevb_plan_execute: NULL plan");
+	GEVB_CHECK_ARG(direction == GEVB_FFT_FORWARD || direction == GEVB_FFT_BACKWARD, "gevb_plan_execute: bad direction %d", direction);
+	gevb_ctx * c = p->ctx;
+	gevb_field * rf = p->real_field, * cf = p->cplx_field;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int N = c->N, nh = c->nh, nc = rf->ncomp;
+	double * rbulk = rf->data + c->plane();
+	if (!p->multi)
+	{
+		if (direction == GEVB_FFT_FORWARD)
+		{
+			CUFFT_TRY(cufftExecD2Z(p->fwd, rbulk, (cufftDoubleComplex *) cf->data));
+			c->launches++;
+		}
+		else
+		{
+			void * stage;
+			GEVB_TRY(gevb_ctx_scratch2(c, cf->bytes, &stage));
+			CUDA_TRY(cudaMemcpyAsync(stage, cf->data, cf->bytes, cudaMemcpyDeviceToDevice, c->stream));
+			CUFFT_TRY(cufftExecZ2D(p->bwd, (cufftDoubleComplex *) stage, rbulk));
+			c->launches++;
+		}
+		return 0;
+	}
+	// ---- slab-decomposed transform ------------------------------------------------
+	const size_t wsites = (size_t) nc * c->nzl * N * nh;             // == nc * nkyl * nh * N
+	const size_t per_pair = (size_t) nc * c->nzl * c->nkyl * nh;
+	void * s1, * s2;
+	GEVB_TRY(gevb_ctx_scratch(c, wsites * sizeof(double2), &s1));
+	GEVB_TRY(gevb_ctx_scratch2(c, wsites * sizeof(double2), &s2));
+	double2 * A = (double2 *) s1, * B = (double2 *) s2;
+	dim3 tb(32, 8), tg((nh + 31) / 32, (N + 31) / 32, nc * c->nkyl);
+	if (direction == GEVB_FFT_FORWARD)
+	{
+		for (int k = 0; k < nc; k++)
+			CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * c->nzl * N * nh)));
+		c->launches += nc;
+		k_pack_fwd<<<gevb_grid(c, wsites, 256), 256, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
+		KERNEL_CHECK(c);
+		GEVB_TRY(alltoall(c, B, A, per_pair));
+		k_unpack_fwd<<<tg, tb, 0, c->stream>>>(A, (double2 *) cf->data, N, nh, c->nzl, c->nkyl, nc, c->nranks);
+		KERNEL_CHECK(c);
+		CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) cf->data, CUFFT_FORWARD));
+		c->launches++;
+	}
+	else
+	{
+		CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
+		c->launches++;
+		k_pack_bwd<<<tg, tb, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
+		KERNEL_CHECK(c);
+		GEVB_TRY(alltoall(c, B, A, per_pair));
+		k_unpack_bwd<<<gevb_grid(c, wsites, 256), 256, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
+		KERNEL_CHECK(c);
+		for (int k = 0; k < nc; k++)
+			CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (B + (size_t) k * c->nzl * N * nh), rbulk + k * rf->comp_stride));
+		c->launches += nc;
+	}
+	return 0;
+}

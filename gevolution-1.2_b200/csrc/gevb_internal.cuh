@@ -1,0 +1,148 @@
+// gevb_internal.cuh -- shared definitions of libgevb.so (sm_100a only)
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/gevb.h"
+
+// ---------------------------------------------------------------- errors -----
+void gevb_set_error(const char * fmt, ...);
+
+// ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
+struct GevbNccl
+{
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*GroupStart)(void);
+	ncclResult_t (*GroupEnd)(void);
+	const char * (*GetErrorString)(ncclResult_t);
+};
+GevbNccl * gevb_nccl();
+int gevb_nccl_load();
+#define ncclGetUniqueId gevb_nccl()->GetUniqueId
+#define ncclCommInitRank gevb_nccl()->CommInitRank
+#define ncclCommDestroy gevb_nccl()->CommDestroy
+#define ncclSend gevb_nccl()->Send
+#define ncclRecv gevb_nccl()->Recv
+#define ncclAllReduce gevb_nccl()->AllReduce
+#define ncclGroupStart gevb_nccl()->GroupStart
+#define ncclGroupEnd gevb_nccl()->GroupEnd
+#define ncclGetErrorString gevb_nccl()->GetErrorString
+
+#define GEVB_FAIL(...) do { gevb_set_error(__VA_ARGS__); return 1; } while (0)
+#define GEVB_CHECK_ARG(cond, ...) do { if (!(cond)) GEVB_FAIL(__VA_ARGS__); } while (0)
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) GEVB_FAIL("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(e_), cudaGetErrorString(e_)); } while (0)
+#define CUFFT_TRY(expr) do { cufftResult r_ = (expr); if (r_ != CUFFT_SUCCESS) GEVB_FAIL("%s:%d cuFFT error %d", __FILE__, __LINE__, (int) r_); } while (0)
+#define NCCL_TRY(expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) GEVB_FAIL("%s:%d NCCL error %s", __FILE__, __LINE__, ncclGetErrorString(r_)); } while (0)
+#define GEVB_TRY(expr) do { int r_ = (expr); if (r_ != 0) return r_; } while (0)
+#define KERNEL_CHECK(ctx) do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------- context ----
+struct gevb_ctx
+{
+	int N, nh;                 // lattice points per dimension, N/2+1
+	int device, rank, nranks;
+	int z0, nzl;               // z-slab of real space owned by this rank
+	int ky0, nkyl;             // ky-slab of Fourier space owned by this rank (nranks > 1)
+	int num_sms;
+	cudaStream_t stream;
+	ncclComm_t comm;
+	bool have_comm;
+	double * d_gridk2;         // (2N sin(pi i/N))^2, host-computed exactly as gevolution.hpp:224-226
+	double2 * d_kshift;        // 2N sin(pi i/N) e^{-i pi i/N}
+	void * scratch;            // grow-only device scratch (sort temp, reductions, FFT staging)
+	size_t scratch_bytes;
+	void * scratch2;
+	size_t scratch2_bytes;
+	double * d_red;            // small device reduction buffer (4096 doubles)
+	double * h_red;            // pinned mirror
+	int64_t launches;
+	size_t plane() const { return (size_t) N * N; }
+	size_t real_comp_stride() const { return (size_t) (nzl + 2) * N * N; }
+	size_t cplx_comp_stride() const { return nranks == 1 ? (size_t) N * N * nh : (size_t) nkyl * nh * N; }
+};
+
+int gevb_ctx_scratch(gevb_ctx * ctx, size_t bytes, void ** out);
+int gevb_ctx_scratch2(gevb_ctx * ctx, size_t bytes, void ** out);
+
+// ---------------------------------------------------------------- fields -----
+// real : double  [ncomp][nzl+2][N][N]   plane p = local z + 1; p = 0 and p = nzl+1 are ghost planes
+// cplx : double2 [ncomp][N (kz)][N (ky)][nh (kx)]          when nranks == 1  ("natural")
+//        double2 [ncomp][nkyl (ky)][nh (kx)][N (kz)]       when nranks  > 1  ("slab", kz fastest)
+struct gevb_field
+{
+	gevb_ctx * ctx;
+	int kind, ncomp, symmetric;
+	double * data;
+	size_t comp_stride;        // in elements (double or double2)
+	size_t bytes;
+};
+
+struct gevb_plan
+{
+	gevb_ctx * ctx;
+	gevb_field * real_field, * cplx_field;
+	cufftHandle fwd, bwd;      // nranks == 1: 3-D D2Z / Z2D batched over components
+	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
+	bool multi;
+};
+
+// ---------------------------------------------------------------- particles --
+struct gevb_pcls
+{
+	gevb_ctx * ctx;
+	double mass;
+	int64_t n, cap;
+	// cell-sorted structure of arrays; [0] is live, [1] is the sort's output buffer
+	double * x[2], * y[2], * z[2], * qx[2], * qy[2], * qz[2];
+	int64_t * id[2];
+	uint32_t * key[2];         // local cell key (zl*N + y)*N + x
+	uint32_t * perm[2];
+	int cur;
+};
+
+int gevb_pcls_reserve(gevb_pcls * p, int64_t cap);
+int gevb_pcls_sort(gevb_pcls * p, bool keys_valid, bool full_bits);
+
+// Fourier-space index decode shared by all k-kernels
+struct KLayout
+{
+	int N, nh, slab, ky0, nkyl;
+	size_t sites;              // complex sites per component on this rank
+};
+static inline KLayout make_klayout(const gevb_ctx * c)
+{
+	KLayout L;
+	L.N = c->N; L.nh = c->nh; L.slab = c->nranks > 1; L.ky0 = c->ky0; L.nkyl = c->nkyl;
+	L.sites = c->cplx_comp_stride();
+	return L;
+}
+__device__ __forceinline__ void k_decode(const KLayout & L, size_t i, int & kx, int & ky, int & kz)
+{
+	if (L.slab)
+	{
+		kz = (int) (i % L.N); size_t r = i / L.N;
+		kx = (int) (r % L.nh); ky = (int) (r / L.nh) + L.ky0;
+	}
+	else
+	{
+		kx = (int) (i % L.nh); size_t r = i / L.nh;
+		ky = (int) (r % L.N); kz = (int) (r / L.N);
+	}
+}
+
+static inline int gevb_grid(const gevb_ctx * ctx, size_t work, int block, int per_sm = 8)
+{
+	size_t want = (work + block - 1) / block;
+	size_t cap = (size_t) ctx->num_sms * per_sm;
+	if (want < 1) want = 1;
+	return (int) (want < cap ? want : cap);
+}

@@ -1,0 +1,298 @@
+// particles.cu -- cell-sorted FP64 structure-of-arrays particle storage
+//
+// Replaces LATfield2's Particles<part_simple,...> container (per-cell
+// std::list<part_simple>, reference uses at gevolution.hpp:960,977 and
+// ic_basic.hpp:1429,1990) by seven flat device arrays {x,y,z,qx,qy,qz,id}
+// kept sorted by the local cell key (zl*N + y)*N + x, cell = floor(pos/dx).
+// The integer contract (which cell a particle is filed under, particles per
+// cell) is bit-exact with the reference's floor(pos/dx) filing rule.
+#include <cub/device/device_radix_sort.cuh>
+#include "gevb_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ int cell_of(double p, double dx, int N)
+{
+	int c = (int) floor(p / dx);
+	c = c >= N ? N - 1 : c;
+	return c < 0 ? 0 : c;
+}
+
+// host AoS chunk -> SoA append, keeping only particles filed in this rank's slab
+__global__ void k_append(int64_t n, const int64_t * __restrict__ id, const double * __restrict__ pos, const double * __restrict__ vel,
+                         int N, int z0, int nzl, double dx,
+                         double * x, double * y, double * z, double * qx, double * qy, double * qz, int64_t * oid,
+                         unsigned long long * counter, int64_t cap)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const double pz = pos[3 * i + 2];
+		const int cz = cell_of(pz, dx, N);
+		if (cz < z0 || cz >= z0 + nzl) continue;
+		const unsigned long long slot = atomicAdd(counter, 1ull);
+		if ((int64_t) slot >= cap) continue;
+		x[slot] = pos[3 * i]; y[slot] = pos[3 * i + 1]; z[slot] = pz;
+		qx[slot] = vel[3 * i]; qy[slot] = vel[3 * i + 1]; qz[slot] = vel[3 * i + 2];
+		oid[slot] = id[i];
+	}
+}
+
+__global__ void k_count_local(int64_t n, const double * __restrict__ pos, int N, int z0, int nzl, double dx, unsigned long long * counter)
+{
+	unsigned long long mine = 0;
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const int cz = cell_of(pos[3 * i + 2], dx, N);
+		mine += (cz >= z0 && cz < z0 + nzl);
+	}
+	for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+	if ((threadIdx.x & 31) == 0 && mine) atomicAdd(counter, mine);
+}
+
+__global__ void k_make_keys(int64_t n, const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
+                            int N, int z0, double dx, uint32_t * __restrict__ key, uint32_t * __restrict__ perm)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const int cx = cell_of(x[i], dx, N), cy = cell_of(y[i], dx, N), cz = cell_of(z[i], dx, N) - z0;
+		key[i] = (uint32_t) ((cz * N + cy) * N + cx);
+		perm[i] = (uint32_t) i;
+	}
+}
+
+__global__ void k_iota(int64_t n, uint32_t * __restrict__ perm)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) perm[i] = (uint32_t) i;
+}
+
+__global__ void __launch_bounds__(256) k_permute(int64_t n, const uint32_t * __restrict__ perm,
+                          const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
+                          const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
+                          double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
+                          double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const uint32_t s = perm[i];
+		ox[i] = x[s]; oy[i] = y[s]; oz[i] = z[s];
+		oqx[i] = qx[s]; oqy[i] = qy[s]; oqz[i] = qz[s];
+		oid[i] = id[s];
+	}
+}
+
+__global__ void k_histogram(int64_t n, const uint32_t * __restrict__ key, uint32_t * __restrict__ counts)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) atomicAdd(counts + key[i], 1u);
+}
+
+__global__ void k_interleave3(int64_t n, const double * __restrict__ a, const double * __restrict__ b, const double * __restrict__ c, double * __restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		out[3 * i] = a[i]; out[3 * i + 1] = b[i]; out[3 * i + 2] = c[i];
+	}
+}
+
+int key_bits(const gevb_ctx * c)
+{
+	uint64_t cells = (uint64_t) c->nzl * c->N * c->N;
+	int bits = 1;
+	while ((1ull << bits) < cells) bits++;
+	return bits;
+}
+
+} // namespace
+
+extern "C" int gevb_pcls_create(gevb_ctx * c, gevb_pcls ** out, double mass)
+{
+	GEVB_CHECK_ARG(c != NULL && out != NULL, "gevb_pcls_create: NULL argument");
+	GEVB_CHECK_ARG((uint64_t) c->nzl * c->N * c->N <= (1ull << 32), "gevb_pcls_create: local slab has more than 2^32 cells");
+	gevb_pcls * p = new gevb_pcls();
+	memset(p, 0, sizeof(*p));
+	p->ctx = c; p->mass = mass;
+	*out = p;
+	return 0;
+}
+
+static void free_arrays(gevb_pcls * p)
+{
+	for (int b = 0; b < 2; b++)
+	{
+		cudaFree(p->x[b]); cudaFree(p->y[b]); cudaFree(p->z[b]); cudaFree(p->qx[b]); cudaFree(p->qy[b]); cudaFree(p->qz[b]);
+		cudaFree(p->id[b]); cudaFree(p->key[b]); cudaFree(p->perm[b]);
+		p->x[b] = p->y[b] = p->z[b] = p->qx[b] = p->qy[b] = p->qz[b] = NULL; p->id[b] = NULL; p->key[b] = p->perm[b] = NULL;
+	}
+}
+
+extern "C" int gevb_pcls_destroy(gevb_pcls * p)
+{
+	if (p == NULL) return 0;
+	cudaSetDevice(p->ctx->device);
+	cudaStreamSynchronize(p->ctx->stream);
+	free_arrays(p);
+	delete p;
+	return 0;
+}
+
+extern "C" double gevb_pcls_mass(gevb_pcls * p) { return p ? p->mass : 0.; }
+
+// grow capacity, keeping the live particles
+int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)
+{
+	if (cap <= p->cap) return 0;
+	gevb_ctx * c = p->ctx;
+	GEVB_CHECK_ARG(cap < (1ll << 32), "particles: more than 2^32 particles on one rank");
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	gevb_pcls old = *p;
+	for (int b = 0; b < 2; b++)
+	{
+		double ** arrs[6] = {&p->x[b], &p->y[b], &p->z[b], &p->qx[b], &p->qy[b], &p->qz[b]};
+		for (int a = 0; a < 6; a++) CUDA_TRY(cudaMalloc(arrs[a], sizeof(double) * cap));
+		CUDA_TRY(cudaMalloc(&p->id[b], sizeof(int64_t) * cap));
+		CUDA_TRY(cudaMalloc(&p->key[b], sizeof(uint32_t) * cap));
+		CUDA_TRY(cudaMalloc(&p->perm[b], sizeof(uint32_t) * cap));
+	}
+	if (old.n > 0)
+	{
+		const int s = old.cur, d = 0;
+		CUDA_TRY(cudaMemcpy(p->x[d], old.x[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->y[d], old.y[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->z[d], old.z[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qx[d], old.qx[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qy[d], old.qy[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qz[d], old.qz[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->id[d], old.id[s], sizeof(int64_t) * old.n, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->key[d], old.key[s], sizeof(uint32_t) * old.n, cudaMemcpyDeviceToDevice));
+	}
+	p->cur = 0; p->cap = cap;
+	free_arrays(&old);
+	return 0;
+}
+
+// restore the cell-sorted order: keys (if not already valid) -> radix sort of (key, index) -> gather
+int gevb_pcls_sort(gevb_pcls * p, bool keys_valid, bool full_bits)
+{
+	gevb_ctx * c = p->ctx;
+	if (p->n == 0) return 0;
+	const int s = p->cur, d = 1 - p->cur;
+	const double dx = 1.0 / (double) c->N;
+	const int grid = gevb_grid(c, (size_t) p->n, 256);
+	if (!keys_valid)
+		k_make_keys<<<grid, 256, 0, c->stream>>>(p->n, p->x[s], p->y[s], p->z[s], c->N, c->z0, dx, p->key[s], p->perm[s]);
+	else
+		k_iota<<<grid, 256, 0, c->stream>>>(p->n, p->perm[s]);
+	KERNEL_CHECK(c);
+	size_t temp_bytes = 0;
+	const int bits = full_bits ? 32 : key_bits(c);
+	CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, temp_bytes, p->key[s], p->key[d], p->perm[s], p->perm[d], p->n, 0, bits, c->stream));
+	void * temp;
+	GEVB_TRY(gevb_ctx_scratch(c, temp_bytes, &temp));
+	CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, p->key[s], p->key[d], p->perm[s], p->perm[d], p->n, 0, bits, c->stream));
+	c->launches += (bits + 7) / 8 + 1;
+	k_permute<<<grid, 256, 0, c->stream>>>(p->n, p->perm[d], p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+	                                       p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+	KERNEL_CHECK(c);
+	p->cur = d;
+	return 0;
+}
+
+extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const double * pos, const double * vel)
+{
+	GEVB_CHECK_ARG(p != NULL && n >= 0, "gevb_pcls_add: bad arguments");
+	if (n == 0) return 0;
+	GEVB_CHECK_ARG(id != NULL && pos != NULL && vel != NULL, "gevb_pcls_add: NULL array");
+	gevb_ctx * c = p->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const double dx = 1.0 / (double) c->N;
+	const int64_t chunk = 1 << 24;
+	unsigned long long * counter = (unsigned long long *) (c->d_red + 4000);
+	for (int64_t off = 0; off < n; off += chunk)
+	{
+		const int64_t m = (n - off < chunk) ? n - off : chunk;
+		void * stage;
+		GEVB_TRY(gevb_ctx_scratch(c, (size_t) m * 56, &stage));
+		int64_t * did = (int64_t *) stage;
+		double * dpos = (double *) (did + m), * dvel = dpos + 3 * m;
+		CUDA_TRY(cudaMemcpyAsync(did, id + off, sizeof(int64_t) * m, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(dpos, pos + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(dvel, vel + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+		// how many of this chunk are local?
+		CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
+		k_count_local<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, dpos, c->N, c->z0, c->nzl, dx, counter);
+		KERNEL_CHECK(c);
+		unsigned long long nloc = 0;
+		CUDA_TRY(cudaMemcpyAsync(&nloc, counter, sizeof(nloc), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if (nloc == 0) continue;
+		if (p->n + (int64_t) nloc > p->cap)
+		{
+			int64_t want = p->n + (int64_t) nloc;
+			if (off + m < n) want += want / 4;      // more chunks to come
+			// scratch holds the staged chunk; reserve() syncs but does not touch scratch
+			GEVB_TRY(gevb_pcls_reserve(p, want));
+		}
+		const int b = p->cur;
+		unsigned long long start = (unsigned long long) p->n;
+		CUDA_TRY(cudaMemcpyAsync(counter, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
+		k_append<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, did, dpos, dvel, c->N, c->z0, c->nzl, dx,
+			p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], counter, p->cap);
+		KERNEL_CHECK(c);
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		p->n += (int64_t) nloc;
+	}
+	GEVB_TRY(gevb_pcls_sort(p, false, false));
+	return 0;
+}
+
+extern "C" int gevb_pcls_count(gevb_pcls * p, int64_t * n_local)
+{
+	GEVB_CHECK_ARG(p != NULL && n_local != NULL, "gevb_pcls_count: NULL argument");
+	*n_local = p->n;
+	return 0;
+}
+
+extern "C" int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel)
+{
+	GEVB_CHECK_ARG(p != NULL, "gevb_pcls_download: NULL handle");
+	gevb_ctx * c = p->ctx;
+	if (p->n == 0) return 0;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int b = p->cur;
+	void * stage;
+	GEVB_TRY(gevb_ctx_scratch(c, (size_t) p->n * 24, &stage));
+	const int grid = gevb_grid(c, (size_t) p->n, 256);
+	if (id) CUDA_TRY(cudaMemcpyAsync(id, p->id[b], sizeof(int64_t) * p->n, cudaMemcpyDeviceToHost, c->stream));
+	if (pos)
+	{
+		k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->x[b], p->y[b], p->z[b], (double *) stage);
+		KERNEL_CHECK(c);
+		CUDA_TRY(cudaMemcpyAsync(pos, stage, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (vel)
+	{
+		k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->qx[b], p->qy[b], p->qz[b], (double *) stage);
+		KERNEL_CHECK(c);
+		CUDA_TRY(cudaMemcpyAsync(vel, stage, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts)
+{
+	GEVB_CHECK_ARG(p != NULL && counts != NULL, "gevb_pcls_cell_counts: NULL argument");
+	gevb_ctx * c = p->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t cells = (size_t) c->nzl * c->plane();
+	void * stage;
+	GEVB_TRY(gevb_ctx_scratch(c, cells * sizeof(uint32_t), &stage));
+	CUDA_TRY(cudaMemsetAsync(stage, 0, cells * sizeof(uint32_t), c->stream));
+	if (p->n > 0)
+	{
+		k_histogram<<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(p->n, p->key[p->cur], (uint32_t *) stage);
+		KERNEL_CHECK(c);
+	}
+	CUDA_TRY(cudaMemcpyAsync(counts, stage, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return 0;
+}

@@ -1,0 +1,288 @@
+// sim.cpp -- the reference's time loop over the device-resident drop-in surface
+//
+// C++ host side of the hot path: one cycle of gevolution 1.2's main loop
+// (main.cpp:372-879) with the output / hibernation branches stripped, written
+// against include/gevolution_b200.hpp so that it reads like the reference's own
+// loop.  Exposed through the C ABI as gevb_sim_* (include/gevb.h).
+#include <cmath>
+#include <cstring>
+#include <new>
+#define GEVB_THROW_ON_ERROR
+#include "../../include/gevolution_b200.hpp"
+#include "background.hpp"
+
+using namespace gevb200;
+
+#define VECTOR_PARABOLIC 0      // metadata.hpp:92
+#define VECTOR_ELLIPTIC 1       // metadata.hpp:93
+
+struct gevb_sim
+{
+	Lattice lat;
+	cosmology cosmo;
+	int numpts, gr_flag, vector_flag, baryon_flag, fused;
+	double boxsize, Cf, steplimit, z_in, z_relax;
+	double fourpiG, a, tau, dtau, dtau_old, dx, T00hom;
+	int cycle;
+	double maxvel[2];
+	Particles_gevolution pcls_cdm, pcls_b;
+	Field<Real> phi, source, chi, Sij, Bi;
+	Field<Cplx> scalarFT, SijFT, BiFT;
+	PlanFFT<Cplx> plan_source, plan_phi, plan_chi, plan_Sij, plan_Bi;
+	explicit gevb_sim(gevb_ctx * ctx) : lat(ctx) {}
+};
+
+extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int vector_flag, const double * ds, const double * c)
+{
+	if (out == NULL || ctx == NULL || ds == NULL || c == NULL) return 1;
+	gevb_sim * s = new (std::nothrow) gevb_sim(ctx);
+	if (s == NULL) return 1;
+	s->numpts = s->lat.size(0);
+	s->gr_flag = gr_flag; s->vector_flag = vector_flag; s->baryon_flag = 0; s->fused = 1;
+	s->boxsize = ds[0]; s->Cf = ds[1]; s->steplimit = ds[2]; s->z_in = ds[3]; s->z_relax = ds[4];
+	cosmology co = {c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10]};
+	s->cosmo = co;
+	Lattice & lat = s->lat;
+	// main.cpp:234-246
+	s->source.initialize(lat, 1);
+	s->phi.initialize(lat, 1);
+	s->chi.initialize(lat, 1);
+	s->scalarFT.initialize(lat, 1);
+	s->plan_source.initialize(&s->source, &s->scalarFT);
+	s->plan_phi.initialize(&s->phi, &s->scalarFT);
+	s->plan_chi.initialize(&s->chi, &s->scalarFT);
+	s->Sij.initialize(lat, 3, 3, symmetric);
+	s->SijFT.initialize(lat, 3, 3, symmetric);
+	s->plan_Sij.initialize(&s->Sij, &s->SijFT);
+	s->Bi.initialize(lat, 3);
+	s->BiFT.initialize(lat, 3);
+	s->plan_Bi.initialize(&s->Bi, &s->BiFT);
+	// main.cpp:278-297
+	s->dx = 1.0 / (double) s->numpts;
+	s->fourpiG = 1.5 * s->boxsize * s->boxsize / GEVB_C_SPEED_OF_LIGHT / GEVB_C_SPEED_OF_LIGHT;
+	s->a = 1. / (1. + s->z_in);
+	s->tau = particleHorizon(s->a, s->fourpiG, s->cosmo);
+	if (s->Cf * s->dx < s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo)) s->dtau = s->Cf * s->dx;
+	else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
+	s->dtau_old = 0.;
+	s->cycle = 0; s->T00hom = 0.;
+	s->maxvel[0] = s->maxvel[1] = 0.;
+	*out = s;
+	return 0;
+}
+
+extern "C" int gevb_sim_destroy(gevb_sim * s) { delete s; return 0; }
+
+extern "C" int gevb_sim_set_particles(gevb_sim * s, int species, int64_t n, const int64_t * id, const double * pos, const double * vel, double mass)
+{
+	if (s == NULL || species < 0 || species > 1) return 1;
+	part_simple_info info;
+	info.mass = mass; info.relativistic = 0; std::strcpy(info.type_name, "part_simple");
+	Particles_gevolution & p = species == 0 ? s->pcls_cdm : s->pcls_b;
+	p.initialize(info, &s->lat);
+	if (species == 1) s->baryon_flag = 1;
+	return gevb_pcls_add(p.handle(), n, id, pos, vel);
+}
+
+extern "C" gevb_field * gevb_sim_field(gevb_sim * s, int which)
+{
+	switch (which)
+	{
+		case 0: return s->phi.handle(); case 1: return s->chi.handle(); case 2: return s->Bi.handle();
+		case 3: return s->source.handle(); case 4: return s->Sij.handle();
+		case 10: return s->scalarFT.handle(); case 11: return s->BiFT.handle(); case 12: return s->SijFT.handle();
+	}
+	return NULL;
+}
+
+extern "C" gevb_pcls * gevb_sim_pcls(gevb_sim * s, int species) { return species == 0 ? s->pcls_cdm.handle() : s->pcls_b.handle(); }
+
+extern "C" int gevb_sim_set_field(gevb_sim * s, int which, const double * host)
+{
+	gevb_field * f = gevb_sim_field(s, which);
+	if (f == NULL) return 1;
+	int r = gevb_field_upload(f, host);
+	if (r == 0 && which < 10) r = gevb_field_updateHalo(f);
+	return r;
+}
+
+extern "C" int gevb_sim_get_field(gevb_sim * s, int which, double * host)
+{
+	gevb_field * f = gevb_sim_field(s, which);
+	return f ? gevb_field_download(f, host) : 1;
+}
+
+extern "C" int gevb_sim_get_state(gevb_sim * s, double * o)
+{
+	o[0] = s->a; o[1] = s->tau; o[2] = s->dtau; o[3] = s->dtau_old; o[4] = s->cycle;
+	o[5] = s->maxvel[0]; o[6] = s->maxvel[1]; o[7] = s->T00hom; o[8] = s->fourpiG;
+	return 0;
+}
+
+extern "C" int gevb_sim_set_state(gevb_sim * s, const double * in)
+{
+	s->a = in[0]; s->tau = in[1]; s->dtau = in[2]; s->dtau_old = in[3]; s->cycle = (int) in[4];
+	s->maxvel[0] = in[5]; s->maxvel[1] = in[6];
+	return 0;
+}
+
+extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused) { s->fused = fused; return 0; }
+
+static int sim_step(gevb_sim * s);
+
+// one cycle of the main loop (main.cpp:372-879 without outputs); errors come back as a status
+extern "C" int gevb_sim_step(gevb_sim * s)
+{
+	if (s == NULL || !s->pcls_cdm.initialized()) return 1;
+	try { return sim_step(s); }
+	catch (const gevb_error &) { return 1; }
+}
+
+static int sim_step(gevb_sim * s)
+{
+	const double dx = s->dx, fourpiG = s->fourpiG;
+	cosmology & cosmo = s->cosmo;
+	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
+	Field<Real> & phi = s->phi, & chi = s->chi, & source = s->source, & Sij = s->Sij, & Bi = s->Bi;
+	Field<Cplx> & scalarFT = s->scalarFT, & SijFT = s->SijFT, & BiFT = s->BiFT;
+	Particles_gevolution & pcls_cdm = s->pcls_cdm, & pcls_b = s->pcls_b;
+	Field<Real> * update_cdm_fields[3] = {&phi, &chi, &Bi};
+	double f_params[5];
+	const bool fuse = s->fused && s->gr_flag > 0;
+
+	// construct stress-energy tensor (main.cpp:378-450)
+	projection_init(&source);
+	projection_init(&Sij);
+	if (fuse)
+	{
+		// one pass over the particles deposits T00 and Tij (same sums as :385 and :439)
+		projection_T00_Tij_project(&pcls_cdm, &source, &Sij, a, &phi);
+		if (s->baryon_flag) projection_T00_Tij_project(&pcls_b, &source, &Sij, a, &phi);
+	}
+	else if (s->gr_flag > 0)
+	{
+		projection_T00_project(&pcls_cdm, &source, a, &phi);                                  // :385
+		if (s->baryon_flag) projection_T00_project(&pcls_b, &source, a, &phi);                // :387
+	}
+	else
+	{
+		scalarProjectionCIC_project(&pcls_cdm, &source);                                      // :402
+		if (s->baryon_flag) scalarProjectionCIC_project(&pcls_b, &source);                    // :404
+	}
+	projection_T00_comm(&source);                                                             // :411
+
+	if (s->vector_flag == VECTOR_ELLIPTIC)
+	{
+		projection_init(&Bi);                                                                 // :426
+		projection_T0i_project(&pcls_cdm, &Bi, &phi);                                         // :427
+		if (s->baryon_flag) projection_T0i_project(&pcls_b, &Bi, &phi);                       // :429
+		projection_T0i_comm(&Bi);                                                             // :435
+	}
+
+	if (!fuse)
+	{
+		projection_Tij_project(&pcls_cdm, &Sij, a, &phi);                                     // :439
+		if (s->baryon_flag) projection_Tij_project(&pcls_b, &Sij, a, &phi);                   // :441
+	}
+	projection_Tij_comm(&Sij);                                                                // :450
+
+	if (s->gr_flag > 0)
+	{
+		double T00hom = 0.;
+		check(gevb_field_sum(source.handle(), 0, &T00hom), "T00hom");                         // :459-462 (sum + parallel.sum)
+		T00hom /= (double) ((long) s->numpts * (long) s->numpts * (long) s->numpts);          // :463
+		s->T00hom = T00hom;
+
+		if (dtau_old > 0.)
+		{
+			prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx);   // :472
+			s->plan_source.execute(FFT_FORWARD);                                              // :477
+			solveModifiedPoissonFT(scalarFT, scalarFT, 1. / (dx * dx), 3. * Hconf(a, fourpiG, cosmo) / dtau_old);   // :483
+			s->plan_phi.execute(FFT_BACKWARD);                                                // :488
+		}
+	}
+	else
+	{
+		s->plan_source.execute(FFT_FORWARD);                                                  // :500
+		solveModifiedPoissonFT(scalarFT, scalarFT, fourpiG / a);                              // :506
+		s->plan_phi.execute(FFT_BACKWARD);                                                    // :511
+	}
+
+	phi.updateHalo();                                                                         // :518
+
+	prepareFTsource<Real>(phi, Sij, Sij, 2. * fourpiG * dx * dx / a);                         // :539
+	s->plan_Sij.execute(FFT_FORWARD);                                                         // :544
+	projectFTscalar(SijFT, scalarFT);                                                         // :558
+	s->plan_chi.execute(FFT_BACKWARD);                                                        // :563
+	chi.updateHalo();                                                                         // :568
+
+	if (s->vector_flag == VECTOR_ELLIPTIC)
+	{
+		s->plan_Bi.execute(FFT_FORWARD);                                                      // :575
+		projectFTvector(BiFT, BiFT, fourpiG * dx * dx);                                       // :580
+	}
+	else
+		evolveFTvector(SijFT, BiFT, a * a * dtau_old);                                        // :586
+
+	if (s->gr_flag > 0)
+	{
+		s->plan_Bi.execute(FFT_BACKWARD);                                                     // :593
+		Bi.updateHalo();                                                                      // :598
+	}
+
+	// cdm and baryon particle update (main.cpp:771-807)
+	f_params[0] = a;
+	f_params[1] = a * a * s->numpts;
+	if (fuse)
+	{
+		// kick uses {a, a^2 N}; the drift uses the scale factor after half a step (:792-795)
+		double a_half = a;
+		rungekutta4bg(a_half, fourpiG, cosmo, 0.5 * dtau);
+		double d_params[2] = {a_half, a_half * a_half * s->numpts};
+		const int nf_kick = (1. / a < s->z_relax + 1. ? 3 : 2), nf_drift = (1. / a_half < s->z_relax + 1. ? 3 : 0);
+		s->maxvel[0] = pcls_cdm.kickDrift(update_q, (dtau + dtau_old) / 2., nf_kick, f_params, dtau, nf_drift, d_params, update_cdm_fields);
+		if (s->baryon_flag) s->maxvel[1] = pcls_b.kickDrift(update_q, (dtau + dtau_old) / 2., nf_kick, f_params, dtau, nf_drift, d_params, update_cdm_fields);
+		a = a_half;
+	}
+	else
+	{
+		if (s->gr_flag > 0)
+		{
+			s->maxvel[0] = pcls_cdm.updateVel(update_q, (dtau + dtau_old) / 2., update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);   // :775
+			if (s->baryon_flag) s->maxvel[1] = pcls_b.updateVel(update_q, (dtau + dtau_old) / 2., update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);
+		}
+		else
+		{
+			s->maxvel[0] = pcls_cdm.updateVel(update_q_Newton, (dtau + dtau_old) / 2., update_cdm_fields, 1, f_params);   // :781
+			if (s->baryon_flag) s->maxvel[1] = pcls_b.updateVel(update_q_Newton, (dtau + dtau_old) / 2., update_cdm_fields, 1, f_params);
+		}
+
+		rungekutta4bg(a, fourpiG, cosmo, 0.5 * dtau);                                         // :792
+
+		f_params[0] = a;
+		f_params[1] = a * a * s->numpts;
+		if (s->gr_flag > 0)
+		{
+			pcls_cdm.moveParticles(update_pos, dtau, update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 0), f_params);   // :798
+			if (s->baryon_flag) pcls_b.moveParticles(update_pos, dtau, update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 0), f_params);
+		}
+		else
+		{
+			pcls_cdm.moveParticles(update_pos_Newton, dtau, NULL, 0, f_params);               // :804
+			if (s->baryon_flag) pcls_b.moveParticles(update_pos_Newton, dtau, NULL, 0, f_params);
+		}
+	}
+
+	rungekutta4bg(a, fourpiG, cosmo, 0.5 * dtau);                                             // :814
+
+	s->lat.max(s->maxvel, 1 + s->baryon_flag);                                                // :816
+	if (s->gr_flag > 0)
+		for (int i = 0; i < 1 + s->baryon_flag; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);   // :818-822
+
+	s->tau += dtau;                                                                           // :825
+	dtau_old = dtau;                                                                          // :867
+	if (s->Cf * dx < s->steplimit / Hconf(a, fourpiG, cosmo)) dtau = s->Cf * dx;              // :869-872
+	else dtau = s->steplimit / Hconf(a, fourpiG, cosmo);
+	s->cycle++;                                                                               // :874
+	return 0;
+}

@@ -1,0 +1,180 @@
+/* =============================================================================
+ * include/gevb.h -- C ABI of the B200-native gevolution hot path (libgevb.so)
+ * =============================================================================
+ * Drop-in boundary for the per-step particle-mesh path that gevolution 1.2's
+ * main.cpp time loop (main.cpp:372-879) drives.  The reference has no FFI
+ * layer: its "operator API" is the set of C++ free functions in gevolution.hpp
+ * plus the LATfield2 methods they are called with.  Every entry point below
+ * names the reference symbol (file:line) it replaces; include/gevolution_b200.hpp
+ * re-exposes them under the reference's own C++ names and signatures.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers, sizes, doubles by value; no torch types.
+ *   - every function returns 0 on success, non-zero on error (never exits);
+ *     gevb_last_error() returns the message of the last failure on this thread.
+ *   - all work is FP64 on one CUDA stream per context, asynchronous unless the
+ *     call returns a scalar or copies to host memory.
+ *   - one process drives one GPU (rank); ranks own z-slabs of the lattice:
+ *     rank r owns planes [r*N/P, (r+1)*N/P) of every real field (+1 ghost plane
+ *     below and above), the particles filed in those planes, and -- after a
+ *     forward FFT when P > 1 -- the ky-slab [r*N/P, (r+1)*N/P) of Fourier space.
+ *
+ * Host-side array layouts (what upload/download exchange)
+ *   real field      double[ncomp][nz_local][N][N]              [c][z][y][x]
+ *   Fourier field   P == 1: double[ncomp][N][N][N/2+1][2]      [c][kz][ky][kx][re,im]
+ *                   P  > 1: double[ncomp][nky_local][N][N/2+1][2]   [c][ky][kz][kx][re,im]
+ *   particles       int64 id[n], double pos[n][3], double vel[n][3]
+ *                   (vel = canonical momentum q/m, pos in box units [0,1))
+ *   symmetric 3x3 tensor component order: (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
+ * ============================================================================= */
+#ifndef GEVB_H
+#define GEVB_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gevb_ctx gevb_ctx;       /* LATfield2 `parallel` + `Lattice lat, latFT` (main.cpp:152,213-215) */
+typedef struct gevb_field gevb_field;   /* LATfield2 Field<Real> / Field<Cplx>        (main.cpp:226-245)     */
+typedef struct gevb_plan gevb_plan;     /* LATfield2 PlanFFT<Cplx>                    (main.cpp:238-246)     */
+typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>      (main.cpp:217-219)     */
+
+#define GEVB_REAL 0
+#define GEVB_CPLX 1
+
+#define GEVB_FFT_FORWARD 1              /* LATfield2 FFT_FORWARD  */
+#define GEVB_FFT_BACKWARD (-1)          /* LATfield2 FFT_BACKWARD */
+
+/* the particle callbacks main.cpp passes to updateVel / moveParticles; host
+ * function pointers cannot run on the device, so the known ones are an enum  */
+#define GEVB_UPDATE_Q 0                 /* update_q         gevolution.hpp:570 ; update_pos         :810 */
+#define GEVB_UPDATE_Q_NEWTON 1          /* update_q_Newton  gevolution.hpp:709 ; update_pos_Newton  :900 */
+
+/* ---- errors / versioning -------------------------------------------------- */
+const char * gevb_last_error(void);
+const char * gevb_version(void);
+
+/* ---- context: lattice geometry + device + communicator --------------------
+ * replaces parallel.initialize(n,m) (main.cpp:152), Lattice lat(3,box,halo)
+ * (main.cpp:213) and latFT.initializeRealFFT (main.cpp:215).
+ * nccl_id: NULL when nranks == 1, else the 128-byte ncclUniqueId produced by
+ * gevb_nccl_unique_id() on rank 0 and distributed by the host program.       */
+int gevb_nccl_unique_id(void * out128);
+int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank, int nranks, const void * nccl_id);
+int gevb_ctx_destroy(gevb_ctx * ctx);
+int gevb_ctx_sync(gevb_ctx * ctx);                         /* cudaStreamSynchronize                */
+int gevb_ctx_geometry(gevb_ctx * ctx, int * ngrid, int * z0, int * nz_local, int * ky0, int * nky_local);
+void * gevb_ctx_stream(gevb_ctx * ctx);                    /* cudaStream_t, for event timing       */
+/* kernels of this library launched on ctx since creation (bench.py gpu_launches) */
+int64_t gevb_ctx_launch_count(gevb_ctx * ctx);
+/* parallel.sum / parallel.max (main.cpp:462,816): all-reduce n doubles in place (host values) */
+int gevb_parallel_sum(gevb_ctx * ctx, double * v, int n);
+int gevb_parallel_max(gevb_ctx * ctx, double * v, int n);
+
+/* ---- fields ------------------------------------------------------------------
+ * Field::initialize(lat, ncomp) / (lat,3,3,symmetric) + alloc (main.cpp:234-245) */
+int gevb_field_create(gevb_ctx * ctx, gevb_field ** out, int kind, int ncomp, int symmetric);
+int gevb_field_destroy(gevb_field * f);
+int gevb_field_upload(gevb_field * f, const double * host);      /* bulk only; ghost planes untouched */
+int gevb_field_download(gevb_field * f, double * host);
+int gevb_field_components(gevb_field * f);
+void * gevb_field_device_ptr(gevb_field * f);
+/* projection_init(Field*) (main.cpp:378,426,438): zero all components incl. ghost planes */
+int gevb_projection_init(gevb_field * f);
+/* Field::updateHalo() (main.cpp:518,568,598): periodic ghost fill (z planes; x,y wrap is index math) */
+int gevb_field_updateHalo(gevb_field * f);
+/* scalarProjectionCIC_comm / vectorProjectionCICNGP_comm / symtensorProjectionCICNGP_comm
+ * (gevolution.hpp:1024,1149,1300; main.cpp:411,435,450): fold the upper ghost plane into
+ * the periodically next rank's first bulk plane                                            */
+int gevb_projection_comm(gevb_field * f);
+/* sum over the local bulk of one component, then parallel.sum (main.cpp:459-463) */
+int gevb_field_sum(gevb_field * f, int comp, double * out);
+/* result(x) += value on the bulk of comp (the bg_ncdm add, main.cpp:394-397) */
+int gevb_field_add_constant(gevb_field * f, int comp, double value);
+
+/* ---- FFT ---------------------------------------------------------------------
+ * PlanFFT<Cplx>(&real,&cplx) + execute(dir) (main.cpp:238-246,477,488,544,563,575,593):
+ * per-component 3-D r2c / c2r, unnormalised both ways; the Fourier input of a
+ * backward transform is preserved (BiFT is persistent state, main.cpp:586-593). */
+int gevb_plan_create(gevb_plan ** out, gevb_field * real_field, gevb_field * cplx_field);
+int gevb_plan_destroy(gevb_plan * plan);
+int gevb_plan_execute(gevb_plan * plan, int direction);
+
+/* ---- particles ---------------------------------------------------------------
+ * Particles::initialize + addParticle_global (ic_basic.hpp:1990,1429): particles
+ * whose cell lies in this rank's slab are kept, the rest ignored.  Storage is
+ * cell-sorted FP64 structure-of-arrays; cell = floor(pos/dx) per axis.          */
+int gevb_pcls_create(gevb_ctx * ctx, gevb_pcls ** out, double mass);
+int gevb_pcls_destroy(gevb_pcls * p);
+int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const double * pos, const double * vel);
+int gevb_pcls_count(gevb_pcls * p, int64_t * n_local);
+int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);   /* cell-sorted order */
+/* bit-exact contract: particles per cell of the local slab, uint32[nz_local][N][N] */
+int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts);
+double gevb_pcls_mass(gevb_pcls * p);
+
+/* ---- particle -> mesh projections (gevolution.hpp:927,1046,1173; main.cpp:385,402,427,439)
+ * phi may be NULL (no geometric correction, gevolution.hpp:949,965).  Target
+ * fields accumulate (several species project into one field); the target's
+ * ghost planes must be valid targets (projection_init zeroes them).            */
+int gevb_projection_T00_project(gevb_pcls * p, gevb_field * T00, double a, gevb_field * phi, double coeff);
+int gevb_projection_T0i_project(gevb_pcls * p, gevb_field * T0i, gevb_field * phi, double coeff);
+int gevb_projection_Tij_project(gevb_pcls * p, gevb_field * Tij, double a, gevb_field * phi, double coeff);
+int gevb_scalarProjectionCIC_project(gevb_pcls * p, gevb_field * rho);
+/* one pass over the particles for T00 and Tij together (same results as the two calls) */
+int gevb_projection_T00_Tij_project(gevb_pcls * p, gevb_field * T00, gevb_field * Tij, double a, gevb_field * phi, double coeff);
+
+/* ---- real-space source preparation (gevolution.hpp:57,170; main.cpp:472,539);
+ * result may alias source / Sij may alias Tij                                    */
+int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3);
+int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, gevb_field * Sij, double coeff);
+
+/* ---- Fourier-space kernels (gevolution.hpp:211,284,350,411,501); outputs may alias inputs */
+int gevb_solveModifiedPoissonFT(gevb_field * sourceFT, gevb_field * potFT, double coeff, double modif);
+int gevb_projectFTscalar(gevb_field * SijFT, gevb_field * chiFT, int add);
+int gevb_evolveFTvector(gevb_field * SijFT, gevb_field * BiFT, double a2dtau);
+int gevb_projectFTvector(gevb_field * SiFT, gevb_field * BiFT, double coeff, double modif);
+int gevb_projectFTtensor(gevb_field * SijFT, gevb_field * hijFT);
+
+/* ---- geodesic updates ----------------------------------------------------------
+ * Particles::updateVel(fn, dtau, fields, nfields, params) (main.cpp:775): returns
+ * sqrt(max v^2) over the LOCAL particles in *maxvel (caller reduces, main.cpp:816).
+ * Particles::moveParticles(fn, dtau, fields, nfields, params) (main.cpp:798):
+ * drift, periodic wrap, re-bin (cell-sorted order restored), slab migration.
+ * fields = {phi, chi, Bi} with valid ghost planes; params = {a, a^2 N}.         */
+int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * maxvel);
+int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params);
+/* fused kick (main.cpp:775) + drift (main.cpp:798) in one pass over the particles: positions
+ * do not change between the two reference calls, only params (a advances by rungekutta4bg,
+ * main.cpp:792), so the result equals updateVel followed by moveParticles.      */
+int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfields_kick, const double * params_kick,
+                    double dtau_drift, int nfields_drift, const double * params_drift,
+                    gevb_field * const * fields, double * maxvel);
+
+/* ---- analysis (tools.hpp:53,237): binned power spectrum incl. the final
+ * normalisation of tools.hpp:186-193 (all ranks receive the result)             */
+int gevb_extractPowerSpectrum(gevb_field * fldFT, double * kbin, double * power, double * kscatter, double * pscatter, int * occupation, int numbins, int deconvolve, int ktype);
+
+/* ---- time loop (main.cpp:372-879, outputs stripped), host side in C++ ---------
+ * dsettings: boxsize, Cf, steplimit, z_in, z_relax
+ * cosmo    : Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h */
+typedef struct gevb_sim gevb_sim;
+int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int vector_flag, const double * dsettings, const double * cosmo);
+int gevb_sim_destroy(gevb_sim * sim);
+int gevb_sim_set_particles(gevb_sim * sim, int species, int64_t n, const int64_t * id, const double * pos, const double * vel, double mass);
+int gevb_sim_set_field(gevb_sim * sim, int which, const double * host);   /* 0 phi,1 chi,2 Bi,3 source,4 Sij,10 scalarFT,11 BiFT,12 SijFT */
+int gevb_sim_get_field(gevb_sim * sim, int which, double * host);
+gevb_field * gevb_sim_field(gevb_sim * sim, int which);
+gevb_pcls * gevb_sim_pcls(gevb_sim * sim, int species);
+int gevb_sim_get_state(gevb_sim * sim, double * out9);     /* a,tau,dtau,dtau_old,cycle,maxvel0,maxvel1,T00hom,fourpiG */
+int gevb_sim_set_state(gevb_sim * sim, const double * in7);
+int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fused deposit + fused kick/drift; 0: one call per reference call */
+int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,59 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol that
+include/gevb.h declares, and refuses to work without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gevb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gevb_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(gevb):
+    L = gevb.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 55
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert missing == []
+    assert sorted(gevb.SYMBOLS) == declared, "gevb/__init__.py SYMBOLS out of sync with include/gevb.h"
+
+
+def test_version_and_error_strings(gevb):
+    L = gevb.lib()
+    assert b"gevb" in L.gevb_version()
+    assert isinstance(L.gevb_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_device(gevb):
+    L = gevb.lib()
+    h = ctypes.c_void_p()
+    assert L.gevb_ctx_create(ctypes.byref(h), 7, 0, 0, 1, None) != 0        # odd Ngrid
+    assert b"Ngrid" in L.gevb_last_error()
+    assert L.gevb_ctx_create(ctypes.byref(h), 16, 0, 0, 3, None) != 0       # not divisible
+    assert L.gevb_ctx_create(ctypes.byref(h), 16, 0, 1, 2, None) != 0       # nccl id missing
+
+
+def test_no_cpu_fallback(gevb):
+    """without a CUDA device context creation must fail loudly, not fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gevb.GevbError) as e:
+        gevb.Context(16)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """the product tree must not import, link or mention the oracle"""
+    prod = os.path.join(ROOT, "gevolution-1.2_b200")
+    for dirpath, _, files in os.walk(prod):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".py", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"

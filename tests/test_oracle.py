@@ -1,0 +1,197 @@
+"""CPU tests of the checkers themselves (run with -m "not gpu").
+
+The reference ships no tests or golden vectors, so the oracle
+is pinned three ways:
+  1. tests/golden/hotpath_N8.npz -- outputs of the reference's own gevolution.hpp
+     (compiled against the LATfield2 shim, oracle/_ref) on seeded inputs;
+  2. the compiled reference itself where oracle/_ref is present (this container);
+  3. the analytic invariants the reference's own diagnostics check
+     (tools.hpp:364-431, main.cpp:465-468).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import common
+import golden_cases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "hotpath_N8.npz")
+TOL = 1e-13   # CPU restatement vs compiled reference: same arithmetic, different summation layout
+
+
+def _compare(out, gold, tol):
+    bad = []
+    for k in gold.files:
+        a, b = np.asarray(out[k]), gold[k]
+        if k in golden_cases.EXACT:
+            if not np.array_equal(a.astype(np.int64), b.astype(np.int64)):
+                bad.append((k, "integer mismatch"))
+        else:
+            err = common.rel_linf(a, b)
+            if not err <= tol:
+                bad.append((k, err))
+    return bad
+
+
+def test_restatement_matches_golden(ora):
+    gold = np.load(GOLDEN)
+    out = golden_cases.run_cpu(ora, golden_cases.inputs(N=8))
+    assert set(gold.files) == set(out.keys())
+    assert _compare(out, gold, TOL) == []
+
+
+def test_compiled_reference_reproduces_golden(ref):
+    gold = np.load(GOLDEN)
+    out = golden_cases.run_cpu(ref, golden_cases.inputs(N=8))
+    assert _compare(out, gold, 0.0) == []
+
+
+@pytest.mark.parametrize("N", [6, 12, 16])
+def test_restatement_matches_reference_other_sizes(ora, ref, N):
+    """non-power-of-two and larger lattices, fresh seed"""
+    inp = golden_cases.inputs(N=N, seed=77 + N)
+    a, b = golden_cases.run_cpu(ora, inp), golden_cases.run_cpu(ref, inp)
+
+    class G:
+        files = list(b.keys())
+        __getitem__ = lambda self, k: b[k]
+    assert _compare(a, G(), TOL) == []
+
+
+def test_fft_matches_numpy(ora):
+    rng = np.random.default_rng(3)
+    N = 16
+    f = rng.standard_normal((2, N, N, N))
+    F = ora.fft_forward(f)
+    Fn = np.fft.rfftn(f, axes=(1, 2, 3))
+    assert common.rel_linf(common.to_cplx(F), Fn) < 1e-14
+    assert common.rel_linf(ora.fft_backward(F), f * N ** 3) < 1e-14      # unnormalised both ways
+
+
+# ---- invariants (verified against the reference's diagnostics) ----
+def Dp(f, i): return np.roll(f, -1, axis=2 - i) - f
+def Dm(f, i): return f - np.roll(f, 1, axis=2 - i)
+
+
+def test_invariant_poisson(ora):
+    rng = np.random.default_rng(1)
+    N = 16
+    src = rng.standard_normal((1, N, N, N)); src -= src.mean()
+    pot = ora.fft_backward(ora.solveModifiedPoissonFT(ora.fft_forward(src), 1.0, 0.0))[0]
+    lap = sum(Dp(Dm(pot, i), i) for i in range(3)) * N * N
+    assert np.abs(lap - src[0]).max() < 1e-12
+
+
+def test_invariant_vector_projection_divergence_free(ora):
+    rng = np.random.default_rng(2)
+    N = 16
+    B = ora.fft_backward(ora.projectFTvector(ora.fft_forward(rng.standard_normal((3, N, N, N))), 1.0))
+    mdiv, mcurl = ora.computeVectorDiagnostics(B)
+    assert mdiv < 1e-11 * np.abs(B).max() * N and mcurl > 1.0
+
+
+def test_invariant_scalar_projection_recovers_chi(ora):
+    rng = np.random.default_rng(4)
+    N = 16
+    chi = rng.standard_normal((N, N, N))
+    trace = rng.standard_normal((N, N, N))
+    idx = {(0, 0): 0, (0, 1): 1, (0, 2): 2, (1, 1): 3, (1, 2): 4, (2, 2): 5}
+    S = np.zeros((6, N, N, N))
+    for i in range(3):
+        S[idx[(i, i)]] = Dp(Dm(chi, i), i) + trace
+    for (i, j) in ((0, 1), (0, 2), (1, 2)):
+        S[idx[(i, j)]] = Dp(Dp(chi, i), j)
+    back = ora.fft_backward(ora.projectFTscalar(ora.fft_forward(S)))[0]
+    assert np.abs(back - (chi - chi.mean())).max() < 1e-12
+
+
+def test_invariant_tensor_projection_transverse_traceless(ora):
+    rng = np.random.default_rng(5)
+    N = 16
+    h = ora.fft_backward(ora.projectFTtensor(ora.fft_forward(rng.standard_normal((6, N, N, N)))))
+    mdiv, mtrace, mnorm = ora.computeTensorDiagnostics(h)
+    assert mdiv < 1e-11 * mnorm * N and mtrace < 1e-12 * mnorm
+
+
+def test_mass_conservation(ora):
+    """with phi = NULL the deposited -a^3 T^0_0 averages to Omega (main.cpp:465-468)"""
+    rng = np.random.default_rng(6)
+    N = 12
+    ids, pos, vel = common.clustered_particles(rng, N, 5000)
+    T00 = ora.projection_T00(N, pos, vel, 0.3 / len(pos), 0.1, None)
+    assert abs(T00.mean() - 0.3) < 1e-14
+    rho = ora.scalarProjectionCIC(N, pos, 0.3 / len(pos))
+    assert abs(rho.mean() - 0.3) < 1e-14
+
+
+def test_uniform_lattice_symmetry(ora):
+    """particles at cell centres, q = 0, phi = 0: T00 uniform, Tij = T0i = 0"""
+    N = 8
+    rng = np.random.default_rng(0)
+    ids, pos, vel = common.quasi_uniform_particles(rng, N, sigma=0.0)
+    vel[:] = 0.0
+    a = 0.05
+    T00 = ora.projection_T00(N, pos, vel, 0.3 / len(pos), a, np.zeros((1, N, N, N)))
+    assert np.abs(T00 - 0.3).max() < 1e-14
+    assert np.abs(ora.projection_Tij(N, pos, vel, 0.3 / len(pos), a, None)).max() == 0.0
+    assert np.abs(ora.projection_T0i(N, pos, vel, 0.3 / len(pos), None)).max() == 0.0
+
+
+def test_binning_edges(ora):
+    """cell = floor(pos/dx): positions on cell boundaries and next to the box edge"""
+    N = 8
+    dx = 1.0 / N
+    pos = np.array([[0.0, 0.0, 0.0], [dx, 2 * dx, 3 * dx], [np.nextafter(dx, 0), 0.5, 0.5],
+                    [np.nextafter(1.0, 0), np.nextafter(1.0, 0), np.nextafter(1.0, 0)], [0.999, 0.0, 0.4375]])
+    cell, counts = ora.cell_index(N, pos)
+    expect = [0, (3 * N + 2) * N + 1, (4 * N + 4) * N + 0, (7 * N + 7) * N + 7, (3 * N + 0) * N + 7]
+    assert cell.tolist() == expect and counts.sum() == len(pos)
+
+
+def test_drift_wrap_convention(ora):
+    """periodic wrap: result in [0,1); -eps maps to 0 (documented edge semantics)"""
+    N = 8
+    pos = np.array([[0.01, 0.99, 0.5], [1e-18, 0.5, 0.5]])
+    vel = np.array([[-0.05, 0.05, 0.0], [-1e-17, 0.0, 0.0]])
+    out = ora.moveParticles(N, pos, vel, 1, 1.0, None, None, None, 0, [1.0, 1.0])
+    assert np.all(out >= 0.0) and np.all(out < 1.0)
+    assert abs(out[0, 0] - 0.96) < 1e-15 and abs(out[0, 1] - 0.04) < 1e-15
+    assert out[1, 0] == 0.0
+
+
+def test_empty_particle_set(ora):
+    N = 6
+    pos = np.zeros((0, 3)); vel = np.zeros((0, 3))
+    assert np.all(ora.projection_T00(N, pos, vel, 1.0, 0.1, None) == 0.0)
+    assert np.all(ora.projection_Tij(N, pos, vel, 1.0, 0.1, None) == 0.0)
+
+
+def test_background_matches_reference(ora, ref):
+    cosmo = common.shipped_cosmology()
+    fourpiG = 1.5 * 320.0 ** 2 / 2997.92458 ** 2
+    for a in (0.0099, 0.1, 1.0):
+        assert ora.Hconf(a, fourpiG, cosmo) == ref.Hconf(a, fourpiG, cosmo)
+        assert ora.rungekutta4bg(a, fourpiG, cosmo, 0.01) == ref.rungekutta4bg(a, fourpiG, cosmo, 0.01)
+    # Omega_m + Omega_Lambda + Omega_rad = 1  =>  Hconf(1) = sqrt(2 fourpiG / 3)
+    assert abs(ora.Hconf(1.0, fourpiG, cosmo) - np.sqrt(2 * fourpiG / 3)) < 1e-15
+
+
+def test_reference_time_loop_runs(ref):
+    """two cycles of the reference's main loop on the shim: T00hom = Omega_m to O(phi), a advances"""
+    rng = np.random.default_rng(11)
+    N = 8
+    cosmo = common.shipped_cosmology()
+    sim = ref.sim(N, 1, 0, common.shipped_settings(), cosmo)
+    ids, pos, vel = common.quasi_uniform_particles(rng, N, sigma=0.1, a=1 / 101.0)
+    sim.set_particles(0, ids, pos, vel, (cosmo[0] + cosmo[1]) / len(ids))
+    phi, chi, Bi = common.metric_fields(rng, N, 1 / 101.0)
+    sim.set_field("phi", phi)
+    s0 = sim.state()
+    sim.step(); sim.step()
+    s = sim.state()
+    assert s["cycle"] == 2 and s["a"] > s0["a"] and s["dtau_old"] > 0
+    assert abs(s["T00hom"] - (cosmo[0] + cosmo[1])) < 1e-3
+    ids2, pos2, vel2 = sim.get_particles()
+    assert sorted(ids2.tolist()) == ids.tolist() and np.all((pos2 >= 0) & (pos2 < 1))
+    sim.close()
