@@ -29,6 +29,8 @@ def _check(out, ref_get, names):
                 bad.append((k, "integer mismatch"))
             continue
         tol = PCL_TOL if k.startswith(("kick", "drift")) else FIELD_TOL
+        if k in ("pk_kscatter", "pk_pscatter"):
+            tol = 1e-5      # variances by cancellation of large sums: summation-order sensitive (north_star: spectra to 1e-5)
         err = common.rel_linf(a, b)
         if not err <= tol:
             bad.append((k, float(err)))
@@ -138,7 +140,7 @@ def _compare_sims(rs, gs, N, nspecies=1):
         errs[f"cells{sp}"] = int(np.count_nonzero(rc != gc))
     r, g = rs.state(), gs.state()
     for k in ("a", "dtau", "dtau_old", "T00hom"):
-        errs["state_" + k] = abs(r[k] - g[k]) / abs(r[k])
+        errs["state_" + k] = abs(r[k] - g[k]) / abs(r[k]) if r[k] != 0 else abs(g[k])
     errs["state_tau"] = abs(r["tau"] - g["tau"]) / abs(r["tau"])
     errs["maxvel"] = abs(r["maxvel"][0] - g["maxvel"][0]) / max(abs(r["maxvel"][0]), 1e-300)
     return errs
@@ -208,4 +210,8 @@ def test_full_size_properties(gevb, ctx, N):
     p0 = gevb.Particles(c, 1.0).add(ids, pos, np.zeros_like(vel))
     p0.moveParticles(gevb.UPDATE_Q_NEWTON, 0.1, None, 0, [a, 1.0])
     i0, x0, v0 = p0.download()
-    assert np.array_equal(i0, before[0]) and np.array_equal(x0, before[1])
+    o0, ob = np.argsort(i0), np.argsort(before[0])
+    assert np.array_equal(i0[o0], before[0][ob]) and np.array_equal(x0[o0], before[1][ob])
+    k0 = np.minimum(np.floor(x0 * N).astype(np.int64), N - 1)
+    assert np.all(np.diff((k0[:, 2] * N + k0[:, 1]) * N + k0[:, 0]) >= 0), "cell-sorted order lost"
+    assert np.array_equal(p0.cell_counts(), counts)
