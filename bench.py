@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the gevolution per-step particle-mesh hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+A "step" is one cycle of the reference's main loop (main.cpp:372-879 without outputs):
+deposit T00/Tij -> metric solve (12 FFTs) -> kick -> drift -> re-bin, GR, parabolic B.
+Workload: the configuration BASELINE.json quotes the metric on -- 512^3 grid / 512^3
+particles (23.7 GB of fields + 7.5 GB of particles; fits one 180 GB B200), strong scaling
+over N z-slabs.  Synthetic data: quasi-uniform particles (one per cell, sigma = 0.05 cell,
+q ~ N(0,(1e-3 a)^2)) and smooth analytic metric fields of cosmological amplitude.
+
+`value`  : device-resident throughput (inputs in HBM when the timed region starts).
+`e2e`    : same metric through the C ABI with HOST buffers -- every step uploads the particle
+           and metric state from pinned host memory and downloads the updated state.
+`roofline`, `kernels`: per-entry-point device time over the timed region (CUDA events on the
+           library's stream) against algorithmic bytes.
+`cpu_baseline`: the reference's own gevolution.hpp (oracle/_ref, single-rank LATfield2 shim)
+           timed on the host cores on a bounded sample (smaller lattice, same path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "gevolution-1.2_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-steps/s (GR, 512^3)"
+UNIT = "particle-steps/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def local_particles(N, z0, nzl, a, seed):
+    """one particle per cell of the local slab, centre + N(0, 0.05 cell) (clipped inside the cell)"""
+    rng = np.random.default_rng(seed + 1000 * z0)
+    g = (np.arange(N) + 0.5) / N
+    gz = (np.arange(z0, z0 + nzl) + 0.5) / N
+    n = nzl * N * N
+    pos = np.empty((n, 3))
+    pos[:, 0] = np.tile(g, nzl * N)
+    pos[:, 1] = np.tile(np.repeat(g, N), nzl)
+    pos[:, 2] = np.repeat(gz, N * N)
+    disp = rng.standard_normal((n, 3))
+    disp *= 0.05 / N
+    np.clip(disp, -0.45 / N, 0.45 / N, out=disp)
+    pos += disp
+    vel = rng.standard_normal((n, 3))
+    vel *= 1e-3 * a
+    ids = np.arange(z0 * N * N, z0 * N * N + n, dtype=np.int64)
+    return ids, pos, vel
+
+
+def analytic_field(N, z0, nzl, rms, seed, ncomp=1):
+    """smooth periodic field from a few plane waves (cheap at 512^3), local slab [ncomp][nzl][N][N]"""
+    rng = np.random.default_rng(seed)
+    x = np.arange(N) / N
+    z = np.arange(z0, z0 + nzl) / N
+    out = np.zeros((ncomp, nzl, N, N))
+    for c in range(ncomp):
+        for _ in range(6):
+            k = rng.integers(1, 5, 3)
+            ph = rng.uniform(0, 2 * np.pi, 3)
+            amp = rng.standard_normal() / np.sqrt(float(k @ k))
+            out[c] += amp * (np.sin(2 * np.pi * k[2] * z + ph[2])[:, None, None] * np.sin(2 * np.pi * k[1] * x + ph[1])[None, :, None]
+                             * np.sin(2 * np.pi * k[0] * x + ph[0])[None, None, :])
+        out[c] *= rms / max(out[c].std(), 1e-300)
+    return out
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- roofline bookkeeping
+def algorithmic_bytes(N, nzl, np_local, P):
+    """SURVEY.md section 8(d) per-unit figures x local units, per launch of each entry point"""
+    V = nzl * N * N
+    Vk = (N // 2 + 1) * N * (N // P)
+    return {
+        "projection_T00_Tij_project": 48 * np_local + 64 * V,      # particles 48 r; source 8 w, Sij 48 w, phi 8 r
+        "projection_T00_project": 48 * np_local + 16 * V,
+        "projection_Tij_project": 48 * np_local + 56 * V,
+        "projection_T0i_project": 48 * np_local + 32 * V,
+        "kick_drift": 96 * np_local + 40 * V,                       # 48 r + 48 w per particle; phi, chi, B x3 read once
+        "updateVel": 72 * np_local + 40 * V,
+        "moveParticles": 72 * np_local + 40 * V,
+        "rebin_sort": 112 * np_local,                               # 56 r + 56 w per particle (out-of-place re-bin)
+        "prepareFTsource_scalar": 32 * V,
+        "prepareFTsource_tensor": 104 * V,
+        "solveModifiedPoissonFT": 32 * Vk,
+        "projectFTscalar": 112 * Vk,
+        "evolveFTvector": 192 * Vk,
+        "projectFTvector": 96 * Vk,
+        "projectFTtensor": 192 * Vk,
+        "fft_forward": 16 * V, "fft_backward": 16 * V,              # ideal: 8 r + 8 w per real site and component
+        "projection_init": 8 * V, "field_sum": 8 * V,
+    }
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu capture, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(ngrid, steps, warmup):
+    """the reference's own gevolution.hpp main-loop cycle on the host cores (oracle/_ref)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import common
+    import oracle
+    ref = oracle.load_ref()
+    kind = "reference"
+    if ref is None:
+        raise RuntimeError("oracle/_ref/libgevref.so missing (it is built in the build container and travels with the snapshot)")
+    cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
+    a0 = 1.0 / (1.0 + ds[3])
+    ids, pos, vel = local_particles(ngrid, 0, ngrid, a0, 42)
+    sim = ref.sim(ngrid, 1, 0, ds, cosmo)
+    sim.set_particles(0, ids, pos, vel, (cosmo[0] + cosmo[1]) / len(ids))
+    sim.set_field("phi", analytic_field(ngrid, 0, ngrid, 1e-5, 1))
+    sim.set_field("chi", analytic_field(ngrid, 0, ngrid, 1e-7, 2))
+    for _ in range(warmup):
+        sim.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    timers = sim.timers()
+    sim.close()
+    return dict(seconds=dt, particles=len(ids), kind=kind, timers=timers, description=ref.description)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ngrid = env_int("GEVB_REF_NGRID", 128)
+    cores = int(os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1)))
+    r = cpu_reference_run(ngrid, args.steps, args.warmup)
+    value = r["particles"] * args.steps / r["seconds"]
+    sample = (f"{args.steps} cycles of the reference main loop (gevolution.hpp compiled against the single-rank LATfield2 shim; "
+              f"MPI/LATfield2/FFTW absent) at {ngrid}^3 grid / {ngrid}^3 particles, same GR parabolic path; "
+              f"FFT lines on {cores} OpenMP threads, particle and field loops on 1 thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "GR 512^3 grid / 512^3 particles (parabolic B); CPU arm runs a bounded sample", "sample_ngrid": ngrid},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch                      # first: its bundled NCCL must be the one mapped into the process
+    import torch.distributed as dist
+    import common
+    import gevb
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [gevb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    N = args.ngrid
+    ctx = gevb.Context(N, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
+    a0 = 1.0 / (1.0 + ds[3])
+    t_setup = time.perf_counter()
+    ids, pos, vel = local_particles(N, ctx.z0, ctx.nzl, a0, 42)
+    np_local, np_total = len(ids), N ** 3
+    mass = (cosmo[0] + cosmo[1]) / np_total
+    phi = analytic_field(N, ctx.z0, ctx.nzl, 1e-5, 1)
+    chi = analytic_field(N, ctx.z0, ctx.nzl, 1e-7, 2)
+    sim = gevb.Sim(ctx, 1, 0, ds, cosmo)
+    sim.set_particles(0, ids, pos, vel, mass)
+    sim.set_field("phi", phi)
+    sim.set_field("chi", chi)
+    t_setup = time.perf_counter() - t_setup
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    for _ in range(args.warmup):
+        sim.step()
+    ctx.sync()
+    ctx.timing(True)
+    ctx.timing_read()
+    launches0 = ctx.launches
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); ctx.sync(); torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.step()
+    ev1.record(stream)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    per_class = ctx.timing_read()
+    ctx.timing(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = np_total * args.steps / (ms * 1e-3)
+    state = sim.state()
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    e2e_steps = max(1, min(args.steps, env_int("GEVB_E2E_STEPS", 2)))
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    gid, gpos, gvel = sim.pcls(0).download()
+    h_id, h_pos, h_vel = pin(gid), pin(gpos), pin(gvel)
+    h_phi, h_chi, h_bft = pin(sim.get_field("phi")), pin(sim.get_field("chi")), pin(sim.get_field("BiFT"))
+    pc = sim.pcls(0)
+    h2d = h_id.nbytes + h_pos.nbytes + h_vel.nbytes + h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
+    d2h = h_id.nbytes + h_pos.nbytes + h_vel.nbytes + h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
+
+    def e2e_step():
+        sim.set_particles(0, h_id, h_pos, h_vel, mass)          # host -> device: particle state
+        sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
+        sim.step()
+        p = sim.pcls(0)
+        n = p.count()
+        L = gevb.lib()
+        gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:n]), gevb._ptr(h_pos[:n]), gevb._ptr(h_vel[:n])), "download")
+        for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
+            gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
+
+    e2e_value = None
+    if world == 1:
+        e2e_step()                                              # warm-up (allocations)
+        ctx.sync(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        ctx.sync(); barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_value = np_total * e2e_steps / e2e_s
+    else:
+        # slab counts change as particles migrate; host buffers are sized once with head-room
+        cap = int(np_local * 1.1) + 1024
+        h_id, h_pos, h_vel = pin(np.resize(gid, cap)), pin(np.resize(gpos, (cap, 3))), pin(np.resize(gvel, (cap, 3)))
+        nloc = [len(gid)]
+
+        def e2e_step_multi():
+            n = nloc[0]
+            sim.set_particles(0, h_id[:n], h_pos[:n], h_vel[:n], mass)
+            sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
+            sim.step()
+            p = sim.pcls(0)
+            n = p.count()
+            L = gevb.lib()
+            gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:n]), gevb._ptr(h_pos[:n]), gevb._ptr(h_vel[:n])), "download")
+            for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
+                gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
+            nloc[0] = n
+        e2e_step_multi()
+        ctx.sync(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step_multi()
+        ctx.sync(); barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = np_total * e2e_steps / float(t.item())
+        hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hb)
+        h2d, d2h = int(hb[0].item()), int(hb[1].item())
+
+    # ---- roofline of the dominant own kernel ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    bytes_per = algorithmic_bytes(N, ctx.nzl, np_local, world)
+    kernels = {}
+    total_ms = sum(v[0] for v in per_class.values()) or 1.0
+    for name, (kms, cnt) in per_class.items():
+        b = bytes_per.get(name)
+        ncomp_calls = cnt
+        if name in ("fft_forward", "fft_backward"):
+            # one call transforms all components of its field: bytes are counted per call below
+            ncomp_calls = None
+        entry = {"ms_per_step": kms / args.steps, "calls_per_step": cnt / args.steps, "share": kms / total_ms}
+        if b is not None and ncomp_calls is not None:
+            gbs = b * cnt / (kms * 1e-3) / 1e9
+            entry.update({"bytes_per_launch": b, "achieved_gbs": gbs, "frac": gbs / peak})
+        kernels[name] = entry
+    # FFT: 12 component transforms per step in 6 forward + 6 backward component-units (1+6 fwd, 1+1+3 bwd + ...)
+    for name, ncomp_per_step in (("fft_forward", 7), ("fft_backward", 5)):
+        if name in kernels and per_class[name][0] > 0:
+            gbs = 16 * ctx.nzl * N * N * ncomp_per_step * args.steps / (per_class[name][0] * 1e-3) / 1e9
+            kernels[name].update({"bytes_per_launch": 16 * ctx.nzl * N * N, "achieved_gbs": gbs, "frac": gbs / peak, "note": "cuFFT; ideal 16 B per site and component"})
+    own = {k: v for k, v in kernels.items() if not k.startswith("fft_") and "frac" in v}
+    top = max(own, key=lambda k: own[k]["ms_per_step"]) if own else None
+    traffic = ncu_traffic().get(top) if top else None
+    roofline = None
+    if top:
+        roofline = {"kernel": top, "bound": "hbm", "achieved": own[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": own[top]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "ms_per_launch": own[top]["ms_per_step"] / max(own[top]["calls_per_step"], 1e-9), "share_of_step": own[top]["share"]}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ngrid_cpu = env_int("GEVB_REF_NGRID", 128)
+        cores = int(os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1)))
+        r = cpu_reference_run(ngrid_cpu, env_int("GEVB_REF_STEPS", 8), 1)
+        cpu = {"value": r["particles"] * env_int("GEVB_REF_STEPS", 8) / r["seconds"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+               "sample": f"{env_int('GEVB_REF_STEPS', 8)} cycles of the reference main loop (gevolution.hpp over the single-rank LATfield2 shim) at "
+                         f"{ngrid_cpu}^3 grid / {ngrid_cpu}^3 particles; FFT on {cores} OpenMP threads, particle and field loops on 1 thread"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"GR {N}^3 grid / {N}^3 particles, parabolic B, one cycle of main.cpp:372-879 per step (fused T00+Tij deposit, fused kick+drift, 12 FFTs)",
+                       "ngrid": N, "particles": np_total, "slabs": world, "parallelism": f"z-slab x{world}",
+                       "l2_policy": "inputs larger than L2: every pass streams >= 1 GB per rank (126 MB L2)",
+                       "e2e_steps": e2e_steps, "z": 1.0 / state["a"] - 1.0, "setup_s": t_setup},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    sim.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 512))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus == 1 and world == 1:
+            pass
+        elif world == 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus} (WORLD_SIZE is 1)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

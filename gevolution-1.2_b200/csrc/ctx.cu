@@ -93,6 +93,7 @@ extern "C" int gevb_ctx_destroy(gevb_ctx * c)
 	if (c->scratch) cudaFree(c->scratch);
 	if (c->scratch2) cudaFree(c->scratch2);
 	cudaStreamDestroy(c->stream);
+	if (c->timer) { for (size_t i = 0; i < c->timer->ev.size(); i++) cudaEventDestroy(c->timer->ev[i]); delete c->timer; }
 	delete c;
 	return 0;
 }
@@ -232,6 +233,7 @@ extern "C" int gevb_projection_init(gevb_field * f)
 {
 	GEVB_CHECK_ARG(f != NULL, "projection_init: NULL field");
 	CUDA_TRY(cudaSetDevice(f->ctx->device));
+	Timed timed_(f->ctx, CLS_INIT);
 	CUDA_TRY(cudaMemsetAsync(f->data, 0, f->bytes, f->ctx->stream));
 	return 0;
 }
@@ -242,6 +244,7 @@ extern "C" int gevb_field_updateHalo(gevb_field * f)
 	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "updateHalo: needs a real field");
 	gevb_ctx * c = f->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_HALO);
 	const size_t pl = c->plane();
 	if (c->nranks == 1)
 	{
@@ -282,6 +285,7 @@ extern "C" int gevb_projection_comm(gevb_field * f)
 	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "projection_comm: needs a real field");
 	gevb_ctx * c = f->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_COMM);
 	const size_t pl = c->plane();
 	const double * src = f->data + (size_t) (c->nzl + 1) * pl;
 	size_t src_stride = f->comp_stride;
@@ -328,6 +332,7 @@ extern "C" int gevb_field_sum(gevb_field * f, int comp, double * out)
 	GEVB_CHECK_ARG(comp >= 0 && comp < f->ncomp, "gevb_field_sum: component %d out of range", comp);
 	gevb_ctx * c = f->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_SUM);
 	const size_t n = (size_t) c->nzl * c->plane();
 	int blocks = gevb_grid(c, n, 256, 4);
 	if (blocks > 2048) blocks = 2048;

@@ -170,6 +170,7 @@ extern "C" int gevb_projection_T00_project(gevb_pcls * p, gevb_field * T00, doub
 	if (phi) GEVB_TRY(check_real(phi, 1, "projection_T00_project", "phi"));
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_T00);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;          // gevolution.hpp:945-947
 	return launch_st<true, false>(p, T00, NULL, a, phi, mass);
@@ -182,6 +183,7 @@ extern "C" int gevb_projection_Tij_project(gevb_pcls * p, gevb_field * Tij, doub
 	if (phi) GEVB_TRY(check_real(phi, 1, "projection_Tij_project", "phi"));
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_TIJ);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;          // gevolution.hpp:1191-1193
 	return launch_st<false, true>(p, NULL, Tij, a, phi, mass);
@@ -196,6 +198,7 @@ extern "C" int gevb_projection_T00_Tij_project(gevb_pcls * p, gevb_field * T00, 
 	GEVB_TRY(check_real(phi, 1, "projection_T00_Tij_project", "phi"));
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_T00_TIJ);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;
 	return launch_st<true, true>(p, T00, Tij, a, phi, mass);
@@ -207,6 +210,7 @@ extern "C" int gevb_scalarProjectionCIC_project(gevb_pcls * p, gevb_field * rho)
 	GEVB_TRY(check_real(rho, 1, "scalarProjectionCIC_project", "rho"));
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_T00);
 	const double dx = 1.0 / (double) c->N;
 	// plain CIC = T00 projection with e = 1, f = 0 and no 1/a
 	return launch_st<true, false>(p, rho, NULL, 1.0, NULL, p->mass / (dx * dx * dx));
@@ -219,6 +223,7 @@ extern "C" int gevb_projection_T0i_project(gevb_pcls * p, gevb_field * T0i, gevb
 	if (phi) GEVB_TRY(check_real(phi, 1, "projection_T0i_project", "phi"));
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_T0I);
 	if (p->n == 0) return 0;
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass;                     // gevolution.hpp:1064-1065

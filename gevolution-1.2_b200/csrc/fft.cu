@@ -164,6 +164,7 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 	gevb_ctx * c = p->ctx;
 	gevb_field * rf = p->real_field, * cf = p->cplx_field;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, direction == GEVB_FFT_FORWARD ? CLS_FFT_FWD : CLS_FFT_BWD);
 	const int N = c->N, nh = c->nh, nc = rf->ncomp;
 	double * rbulk = rf->data + c->plane();
 	if (!p->multi)

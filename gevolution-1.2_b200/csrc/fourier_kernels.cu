@@ -164,6 +164,7 @@ extern "C" int gevb_solveModifiedPoissonFT(gevb_field * sourceFT, gevb_field * p
 	GEVB_TRY(check_cplx(potFT, 1, "solveModifiedPoissonFT", "potFT"));
 	gevb_ctx * c = potFT->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_POISSON);
 	KLayout L = make_klayout(c);
 	coeff /= -((double) ((long) c->N * (long) c->N * (long) c->N));                                          // gevolution.hpp:511
 	k_poisson<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, (const double2 *) sourceFT->data, (double2 *) potFT->data, coeff, modif);
@@ -177,6 +178,7 @@ extern "C" int gevb_projectFTscalar(gevb_field * SijFT, gevb_field * chiFT, int 
 	GEVB_TRY(check_cplx(chiFT, 1, "projectFTscalar", "chiFT"));
 	gevb_ctx * c = chiFT->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FTSCALAR);
 	KLayout L = make_klayout(c);
 	k_ftscalar<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SijFT->data, SijFT->comp_stride, (double2 *) chiFT->data, add);
 	KERNEL_CHECK(c);
@@ -189,6 +191,7 @@ extern "C" int gevb_evolveFTvector(gevb_field * SijFT, gevb_field * BiFT, double
 	GEVB_TRY(check_cplx(BiFT, 3, "evolveFTvector", "BiFT"));
 	gevb_ctx * c = BiFT->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_EVOLVE);
 	KLayout L = make_klayout(c);
 	k_evolve_vector<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SijFT->data, SijFT->comp_stride, (double2 *) BiFT->data, BiFT->comp_stride, a2dtau);
 	KERNEL_CHECK(c);
@@ -201,6 +204,7 @@ extern "C" int gevb_projectFTvector(gevb_field * SiFT, gevb_field * BiFT, double
 	GEVB_TRY(check_cplx(BiFT, 3, "projectFTvector", "BiFT"));
 	gevb_ctx * c = BiFT->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FTVECTOR);
 	KLayout L = make_klayout(c);
 	k_ftvector<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SiFT->data, (double2 *) BiFT->data, BiFT->comp_stride, coeff, modif);
 	KERNEL_CHECK(c);
@@ -213,6 +217,7 @@ extern "C" int gevb_projectFTtensor(gevb_field * SijFT, gevb_field * hijFT)
 	GEVB_TRY(check_cplx(hijFT, 6, "projectFTtensor", "hijFT"));
 	gevb_ctx * c = hijFT->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FTTENSOR);
 	KLayout L = make_klayout(c);
 	k_fttensor<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SijFT->data, (double2 *) hijFT->data, hijFT->comp_stride);
 	KERNEL_CHECK(c);

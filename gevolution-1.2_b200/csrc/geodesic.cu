@@ -312,7 +312,8 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 int finish_move(gevb_pcls * p, GParams & P)
 {
 	gevb_ctx * c = p->ctx;
-	if (c->nranks == 1) return gevb_pcls_sort(p, true, false);
+	if (c->nranks == 1) { Timed timed_(c, CLS_SORT); return gevb_pcls_sort(p, true, false); }
+	Timed timed_mig_(c, CLS_MIGRATE);
 	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
 	unsigned long long * cnt = P.nsend;                 // [0,1] = my sends (down, up); [2,3] = what I receive (from up, from down)
 	NCCL_TRY(ncclGroupStart());
@@ -396,6 +397,7 @@ extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * c
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
+		Timed timed_(c, CLS_KICK);
 		k_geodesic<0><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
 		KERNEL_CHECK(c);
 	}
@@ -422,6 +424,7 @@ extern "C" int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field
 	GEVB_TRY(setup_migration(p, P));
 	if (p->n > 0)
 	{
+		Timed timed_(c, CLS_DRIFT);
 		k_geodesic<1><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
 		KERNEL_CHECK(c);
 	}
@@ -449,6 +452,7 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
+		Timed timed_(c, CLS_KICK_DRIFT);
 		k_geodesic<2><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
 		KERNEL_CHECK(c);
 	}

@@ -45,9 +45,34 @@ int gevb_nccl_load();
 #define GEVB_TRY(expr) do { int r_ = (expr); if (r_ != 0) return r_; } while (0)
 #define KERNEL_CHECK(ctx) do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
 
+// ---------------------------------------------------------------- timing (timing.cu)
+enum
+{
+	CLS_INIT = 0, CLS_T00, CLS_TIJ, CLS_T00_TIJ, CLS_T0I, CLS_COMM, CLS_SUM, CLS_PREP_SCALAR, CLS_PREP_TENSOR, CLS_FFT_FWD, CLS_FFT_BWD,
+	CLS_POISSON, CLS_FTSCALAR, CLS_EVOLVE, CLS_FTVECTOR, CLS_FTTENSOR, CLS_HALO, CLS_KICK, CLS_DRIFT, CLS_KICK_DRIFT, CLS_SORT, CLS_SPECTRUM,
+	CLS_MIGRATE, GEVB_NCLS
+};
+struct GevbTimer
+{
+	bool on = false;
+	std::vector<cudaEvent_t> ev;
+	std::vector<int> cls;
+	size_t used = 0;
+};
+struct gevb_ctx;
+void gevb_timer_begin(gevb_ctx * c, int cls);
+void gevb_timer_end(gevb_ctx * c);
+struct Timed
+{
+	gevb_ctx * c;
+	Timed(gevb_ctx * ctx, int cls) : c(ctx) { gevb_timer_begin(c, cls); }
+	~Timed() { gevb_timer_end(c); }
+};
+
 // ---------------------------------------------------------------- context ----
 struct gevb_ctx
 {
+	GevbTimer * timer;
 	int N, nh;                 // lattice points per dimension, N/2+1
 	int device, rank, nranks;
 	int z0, nzl;               // z-slab of real space owned by this rank

@@ -96,6 +96,7 @@ extern "C" int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, g
 	GEVB_CHECK_ARG(result != phi && result != chi, "prepareFTsource: result must not alias phi or chi");
 	gevb_ctx * c = phi->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_PREP_SCALAR);
 	RGeom G = {c->N, c->nzl, c->plane()};
 	k_prepare_scalar<<<gevb_grid(c, (size_t) c->nzl * c->plane(), 256), 256, 0, c->stream>>>(G, phi->data, chi->data, source->data, bgmodel, result->data, coeff, coeff2, coeff3);
 	KERNEL_CHECK(c);
@@ -109,6 +110,7 @@ extern "C" int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, g
 	GEVB_TRY(check_real(Sij, 6, "prepareFTsource", "Sij"));
 	gevb_ctx * c = phi->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_PREP_TENSOR);
 	RGeom G = {c->N, c->nzl, c->plane()};
 	k_prepare_tensor<<<gevb_grid(c, (size_t) c->nzl * c->plane(), 256), 256, 0, c->stream>>>(G, phi->data, Tij->data, Sij->data, Sij->comp_stride, coeff);
 	KERNEL_CHECK(c);

@@ -72,6 +72,7 @@ extern "C" int gevb_extractPowerSpectrum(gevb_field * f, double * kbin, double *
 	GEVB_CHECK_ARG(numbins >= 1 && numbins <= 1 << 20, "extractPowerSpectrum: bad number of bins %d", numbins);
 	gevb_ctx * c = f->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_SPECTRUM);
 	const int N = c->N;
 	// tables exactly as tools.hpp:64-106
 	std::vector<double> tab(2 * N);

@@ -27,7 +27,8 @@ FIELD_COMPS = {"phi": 1, "chi": 1, "Bi": 3, "source": 1, "Sij": 6, "scalarFT": 1
 # every symbol include/gevb.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "gevb_last_error", "gevb_version", "gevb_nccl_unique_id", "gevb_ctx_create", "gevb_ctx_destroy", "gevb_ctx_sync",
-    "gevb_ctx_geometry", "gevb_ctx_stream", "gevb_ctx_launch_count", "gevb_parallel_sum", "gevb_parallel_max",
+    "gevb_ctx_geometry", "gevb_ctx_stream", "gevb_ctx_launch_count",
+    "gevb_ctx_timing", "gevb_ctx_timing_read", "gevb_timing_num_classes", "gevb_timing_class_name", "gevb_parallel_sum", "gevb_parallel_max",
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
     "gevb_field_device_ptr", "gevb_projection_init", "gevb_field_updateHalo", "gevb_projection_comm", "gevb_field_sum",
     "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_pcls_create",
@@ -77,11 +78,16 @@ def _declare(L):
     L.gevb_sim_pcls.argtypes = [vp, i]
     L.gevb_pcls_mass.restype = d
     L.gevb_pcls_mass.argtypes = [vp]
+    L.gevb_timing_class_name.restype = C.c_char_p
+    L.gevb_timing_class_name.argtypes = [i]
+    L.gevb_timing_num_classes.restype = i
+    L.gevb_timing_num_classes.argtypes = []
     sig = {
         "gevb_nccl_unique_id": [vp],
         "gevb_ctx_create": [C.POINTER(vp), i, i, i, i, vp],
         "gevb_ctx_destroy": [vp], "gevb_ctx_sync": [vp],
         "gevb_ctx_geometry": [vp] + [C.POINTER(i)] * 5,
+        "gevb_ctx_timing": [vp, i], "gevb_ctx_timing_read": [vp, pd, C.POINTER(C.c_int64)],
         "gevb_parallel_sum": [vp, pd, i], "gevb_parallel_max": [vp, pd, i],
         "gevb_field_create": [vp, C.POINTER(vp), i, i, i],
         "gevb_field_destroy": [vp], "gevb_field_upload": [vp, vp], "gevb_field_download": [vp, vp],
@@ -159,6 +165,16 @@ class Context:
     @property
     def launches(self):
         return lib().gevb_ctx_launch_count(self.h)
+
+    def timing(self, enable):
+        _ck(lib().gevb_ctx_timing(self.h, int(enable)), "gevb_ctx_timing")
+
+    def timing_read(self):
+        """{entry point: (milliseconds, calls)} accumulated since the last read"""
+        n = lib().gevb_timing_num_classes()
+        ms, cnt = np.zeros(n), np.zeros(n, dtype=np.int64)
+        _ck(lib().gevb_ctx_timing_read(self.h, ms.ctypes.data_as(C.POINTER(C.c_double)), cnt.ctypes.data_as(C.POINTER(C.c_int64))), "gevb_ctx_timing_read")
+        return {lib().gevb_timing_class_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k] > 0}
 
     def parallel_sum(self, v):
         a, p = _darr(v)

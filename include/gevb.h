@@ -70,6 +70,12 @@ int gevb_ctx_geometry(gevb_ctx * ctx, int * ngrid, int * z0, int * nz_local, int
 void * gevb_ctx_stream(gevb_ctx * ctx);                    /* cudaStream_t, for event timing       */
 /* kernels of this library launched on ctx since creation (bench.py gpu_launches) */
 int64_t gevb_ctx_launch_count(gevb_ctx * ctx);
+/* optional per-call device timing (the reference's -DBENCHMARK timers, main.cpp:71-88, per entry point):
+ * enable, run, then read milliseconds and call counts per class since the last read            */
+int gevb_ctx_timing(gevb_ctx * ctx, int enable);
+int gevb_ctx_timing_read(gevb_ctx * ctx, double * ms, int64_t * counts);   /* arrays of gevb_timing_num_classes() */
+int gevb_timing_num_classes(void);
+const char * gevb_timing_class_name(int cls);
 /* parallel.sum / parallel.max (main.cpp:462,816): all-reduce n doubles in place (host values) */
 int gevb_parallel_sum(gevb_ctx * ctx, double * v, int n);
 int gevb_parallel_max(gevb_ctx * ctx, double * v, int n);
