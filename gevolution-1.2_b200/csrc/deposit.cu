@@ -5,133 +5,264 @@
 //   projection_Tij_project       gevolution.hpp:1173-1297
 //   scalarProjectionCIC_project  LATfield2 (main.cpp:402), plain CIC
 //
-// Particles are cell-sorted, one thread per particle, coalesced SoA loads
-// (48 B per particle).  The phi values at the eight cell corners come through
-// the read-only path (neighbouring particles share them in L1).  Contributions
-// go out as FP64 reductions (RED.ADD.F64) on the target field; x and y wrap by
-// index arithmetic, z+1 of the last local plane lands in the upper ghost plane
-// which gevb_projection_comm folds into the next rank.
+// One thread block per brick of 8^3 cells (particles are stored brick by brick
+// and, inside a brick, cell by cell -- gevb_internal.cuh).  The block owns a
+// 9^3-site shared-memory tile per target component (the brick's sites plus the
+// upper apron the CIC cloud reaches) and a 9^3 tile of phi.
+//
+//   1. every thread owns cells of the brick and accumulates the contributions of
+//      the cell's particles in registers -- exactly the reference's per-cell
+//      "localCube" accumulators (gevolution.hpp:953,1199-1200); particle loads are
+//      coalesced because consecutive threads own consecutive cells = consecutive
+//      particles.  Cells holding more than DEP_LIGHT particles hand the excess to
+//      a warp-cooperative pass (strided loads, shuffle reduction), so clustered
+//      states do not serialise on one thread.
+//   2. the per-cell sums go into the tile in eight corner phases: in one phase
+//      all threads write the same corner of their own cell, i.e. distinct sites,
+//      so the shared-memory update is a plain read-add-write, no atomics.
+//   3. the tile is flushed to the field in HBM with FP64 reductions (RED.ADD.F64),
+//      one per non-zero tile site and component -- about 5 k per brick instead of
+//      38 per particle; consecutive lanes flush consecutive sites of a row.
+//
+// x and y wrap by index arithmetic at flush time; z+1 of the last local plane
+// lands in the upper ghost plane which gevb_projection_comm folds into the next rank.
 #include "gevb_internal.cuh"
 
 namespace {
 
-struct DGeom { int N, nzl, z0; size_t plane; double dx; };
+#define DT_EDGE 9
+#define DT_SITES 729
+#define DEP_LIGHT 4
+#define DEP_THREADS 256
 
-struct Cell
+enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
+
+// accumulators per cell and tile components per projection
+__host__ __device__ constexpr int dep_nacc(int what) { return what == DEP_T00 ? 8 : what == DEP_TIJ ? 30 : what == DEP_T00_TIJ ? 38 : 12; }
+__host__ __device__ constexpr int dep_ncomp(int what) { return what == DEP_T00 ? 1 : what == DEP_TIJ ? 6 : what == DEP_T00_TIJ ? 7 : 3; }
+
+// symmetric-tensor accumulators: 24 diagonal (tii[k + 8 d], gevolution.hpp:1199) then 6 off-diagonal (tij[0..5], :1198)
+__host__ __device__ constexpr int tij_comp(int a) { return a < 24 ? (a / 8 == 0 ? 0 : a / 8 == 1 ? 3 : 5) : (a - 24 < 2 ? 1 : a - 24 < 4 ? 2 : 4); }
+__host__ __device__ constexpr int tij_corner(int a) { return a < 24 ? a % 8 : (a == 24 || a == 26 || a == 28 ? 0 : a == 25 ? 1 : a == 27 ? 2 : 4); }   // :1277-1294
+// T0i accumulators qi[0..11] (gevolution.hpp:1107-1126): component a / 4, corner from the write-back at :1129-1144
+__host__ __device__ constexpr int t0i_corner(int a)
 {
-	int x, y, zl;          // cell coordinates (zl local)
-	size_t row[2][2];      // [Z][Y] -> offset of the row start, plane index zl+1+Z
-	int xs[2];             // [X] -> wrapped x
+	return a == 0 || a == 4 || a == 8 ? 0 : a == 1 ? 2 : a == 2 ? 1 : a == 3 ? 3 : a == 5 ? 4 : a == 6 ? 1 : a == 7 ? 5 : a == 9 ? 4 : a == 10 ? 2 : 6;
+}
+// tile component and corner (4X + 2Y + Z, gevolution.hpp:953) of accumulator a
+__host__ __device__ constexpr int acc_comp(int what, int a)
+{
+	return what == DEP_T00 ? 0 : what == DEP_TIJ ? tij_comp(a) : what == DEP_T00_TIJ ? (a < 8 ? 0 : 1 + tij_comp(a - 8)) : a / 4;
+}
+__host__ __device__ constexpr int acc_corner(int what, int a)
+{
+	return what == DEP_T00 ? a : what == DEP_TIJ ? tij_corner(a) : what == DEP_T00_TIJ ? (a < 8 ? a : tij_corner(a - 8)) : t0i_corner(a);
+}
+__host__ __device__ constexpr int corner_offset(int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * DT_EDGE + (k & 1) * DT_EDGE * DT_EDGE; }
+
+struct DParams
+{
+	BrickGeom G;
+	int pow2;
+	double dx, rN, a, mass;
+	const uint32_t * cell_start;
+	const double * x, * y, * z, * qx, * qy, * qz;
+	const double * phi;
+	double * out[7];           // target component pointers in tile-component order
 };
 
-__device__ __forceinline__ Cell cell_from_key(uint32_t key, const DGeom & G)
+// contributions of one particle to the cell's accumulators
+template <int WHAT, bool HAS_PHI>
+__device__ __forceinline__ void accumulate(double * acc, const DParams & D, uint32_t i, double refx, double refy, double refz, const double * cphi)
 {
-	Cell c;
-	c.x = (int) (key % (uint32_t) G.N); uint32_t r = key / (uint32_t) G.N;
-	c.y = (int) (r % (uint32_t) G.N); c.zl = (int) (r / (uint32_t) G.N);
-	const int yp = c.y == G.N - 1 ? 0 : c.y + 1;
-	c.xs[0] = c.x; c.xs[1] = c.x == G.N - 1 ? 0 : c.x + 1;
-	#pragma unroll
-	for (int Z = 0; Z < 2; Z++)
+	double up[3], dn[3];
+	if (D.pow2)
 	{
-		c.row[Z][0] = ((size_t) (c.zl + 1 + Z) * G.N + c.y) * G.N;
-		c.row[Z][1] = ((size_t) (c.zl + 1 + Z) * G.N + yp) * G.N;
+		up[0] = (D.x[i] - refx) * D.rN; up[1] = (D.y[i] - refy) * D.rN; up[2] = (D.z[i] - refz) * D.rN;   // == / dx exactly (dx = 2^-k)
 	}
-	return c;
+	else
+	{
+		up[0] = (D.x[i] - refx) / D.dx; up[1] = (D.y[i] - refy) / D.dx; up[2] = (D.z[i] - refz) / D.dx;   // gevolution.hpp:981 / :1101 / :1231
+	}
+	dn[0] = 1.0 - up[0]; dn[1] = 1.0 - up[1]; dn[2] = 1.0 - up[2];                                          // :982
+	const double q0 = D.qx[i], q1 = D.qy[i], q2 = D.qz[i];
+	if (WHAT == DEP_T0I)
+	{
+		double w = D.mass * q0;                                                    // :1107
+		acc[0] += w * dn[1] * dn[2]; acc[1] += w * up[1] * dn[2]; acc[2] += w * dn[1] * up[2]; acc[3] += w * up[1] * up[2];       // :1109-1112
+		w = D.mass * q1;                                                           // :1114
+		acc[4] += w * dn[0] * dn[2]; acc[5] += w * up[0] * dn[2]; acc[6] += w * dn[0] * up[2]; acc[7] += w * up[0] * up[2];       // :1116-1119
+		w = D.mass * q2;                                                           // :1121
+		acc[8] += w * dn[0] * dn[1]; acc[9] += w * up[0] * dn[1]; acc[10] += w * dn[0] * up[1]; acc[11] += w * up[0] * up[1];     // :1123-1126
+		return;
+	}
+	const double qsq = q0 * q0 + q1 * q1 + q2 * q2;
+	double w[8];
+	#pragma unroll
+	for (int k = 0; k < 8; k++) w[k] = ((k & 4) ? up[0] : dn[0]) * ((k & 2) ? up[1] : dn[1]) * ((k & 1) ? up[2] : dn[2]);
+	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
+	{
+		double e = D.a, f = 0.;
+		if (HAS_PHI) { e = sqrt(qsq + D.a * D.a); f = 3. * e + qsq / e; }          // :989-991
+		#pragma unroll
+		for (int k = 0; k < 8; k++) acc[k] += w[k] * (e + f * cphi[k]);            // :995-1009 (mass applied at write-back, :1012)
+	}
+	if (WHAT == DEP_TIJ || WHAT == DEP_T00_TIJ)
+	{
+		double * t = acc + (WHAT == DEP_T00_TIJ ? 8 : 0);
+		const double e = sqrt(qsq + D.a * D.a);                                    // :1237
+		const double f = 4. + D.a * D.a / (qsq + D.a * D.a);                       // :1238
+		const double qq[3] = {q0, q1, q2};
+		double g[8];
+		#pragma unroll
+		for (int k = 0; k < 8; k++) g[k] = w[k] * (1. + f * cphi[k]);
+		#pragma unroll
+		for (int d = 0; d < 3; d++)
+		{
+			const double wd = D.mass * qq[d] * qq[d] / e;                          // :1243
+			#pragma unroll
+			for (int k = 0; k < 8; k++) t[d * 8 + k] += wd * g[k];                 // :1245-1259
+		}
+		double wo = D.mass * q0 * q1 / e;                                          // :1262
+		t[24] += wo * dn[2] * (1. + f * 0.25 * (cphi[0] + cphi[2] + cphi[4] + cphi[6]));
+		t[25] += wo * up[2] * (1. + f * 0.25 * (cphi[1] + cphi[3] + cphi[5] + cphi[7]));
+		wo = D.mass * q0 * q2 / e;                                                 // :1266
+		t[26] += wo * dn[1] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[4] + cphi[5]));
+		t[27] += wo * up[1] * (1. + f * 0.25 * (cphi[2] + cphi[3] + cphi[6] + cphi[7]));
+		wo = D.mass * q1 * q2 / e;                                                 // :1270
+		t[28] += wo * dn[0] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[2] + cphi[3]));
+		t[29] += wo * up[0] * (1. + f * 0.25 * (cphi[4] + cphi[5] + cphi[6] + cphi[7]));
+	}
 }
 
-// corner index 4X + 2Y + Z (gevolution.hpp:953)
-__device__ __forceinline__ size_t corner(const Cell & c, int X, int Y, int Z) { return c.row[Z][Y] + c.xs[X]; }
-
-__device__ __forceinline__ void red_add(double * p, double v) { atomicAdd(p, v); }
-
-template <bool DO_T00, bool DO_TIJ, bool HAS_PHI>
-__global__ void __launch_bounds__(256) k_deposit_scalar_tensor(DGeom G, int64_t n, const uint32_t * __restrict__ key,
-	const double * __restrict__ px, const double * __restrict__ py, const double * __restrict__ pz,
-	const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz,
-	const double * __restrict__ phi, double * T00, double * Tij, size_t cs, double mass, double a)
+// per-cell factors the reference applies at write-back
+template <int WHAT>
+__device__ __forceinline__ void finalize(double * acc, const DParams & D, const double * cphi)
 {
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
 	{
-		const Cell c = cell_from_key(key[i], G);
-		double up[3], dn[3];
-		up[0] = (px[i] - c.x * G.dx) / G.dx;                                  // gevolution.hpp:981 / :1231
-		up[1] = (py[i] - c.y * G.dx) / G.dx;
-		up[2] = (pz[i] - (c.zl + G.z0) * G.dx) / G.dx;                        // global cell coordinate, as xPart.coord(2)
-		dn[0] = 1.0 - up[0]; dn[1] = 1.0 - up[1]; dn[2] = 1.0 - up[2];         // :982
+		#pragma unroll
+		for (int k = 0; k < 8; k++) acc[k] *= D.mass;                              // :1012-1019
+	}
+	if (WHAT == DEP_T0I)
+	{
+		#pragma unroll
+		for (int a = 0; a < 12; a++)
+		{
+			const int k = t0i_corner(a), own = a / 4 == 0 ? 4 : a / 4 == 1 ? 2 : 1;   // the component's own axis bit
+			acc[a] *= 1. + cphi[k] + cphi[k + own];                                // :1129-1144
+		}
+	}
+}
+
+template <int WHAT, bool HAS_PHI>
+__global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
+{
+	constexpr int NACC = dep_nacc(WHAT), NCOMP = dep_ncomp(WHAT);
+	extern __shared__ double smem[];
+	double * tile = smem;                                   // [NCOMP][729]
+	double * tphi = smem + NCOMP * DT_SITES;                // [729]
+	__shared__ uint32_t heavy_first[GEVB_BRICK_CELLS], heavy_last[GEVB_BRICK_CELLS];
+	__shared__ uint16_t heavy_cell[GEVB_BRICK_CELLS];
+	__shared__ int nheavy;
+
+	const BrickGeom & G = D.G;
+	const uint32_t brick = blockIdx.x;
+	const uint32_t key0 = brick * GEVB_BRICK_CELLS;
+	if (D.cell_start[key0] == D.cell_start[key0 + GEVB_BRICK_CELLS]) return;   // empty brick
+	int x0, y0, zl0;
+	brick_origin(G, brick, x0, y0, zl0);
+
+	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES; idx += DEP_THREADS) tile[idx] = 0.;
+	if (threadIdx.x == 0) nheavy = 0;
+	for (int s = threadIdx.x; s < DT_SITES; s += DEP_THREADS)
+	{
+		double v = 0.;
+		if (HAS_PHI)
+		{
+			const int tz = s / (DT_EDGE * DT_EDGE), ty = (s / DT_EDGE) % DT_EDGE, tx = s % DT_EDGE;
+			const int plane = zl0 + tz + 1;
+			if (plane <= G.nzl + 1) v = __ldg(D.phi + ((size_t) plane * G.N + (y0 + ty) % G.N) * G.N + (x0 + tx) % G.N);
+		}
+		tphi[s] = v;
+	}
+	__syncthreads();
+
+	// ---- light pass: one thread per cell, DEP_LIGHT particles at most -------------------------
+	for (int c = threadIdx.x; c < GEVB_BRICK_CELLS; c += DEP_THREADS)
+	{
+		const int sx = c & 7, sy = (c >> 3) & 7, sz = c >> 6;
+		const int site = (sz * DT_EDGE + sy) * DT_EDGE + sx;
+		const uint32_t first = D.cell_start[key0 + c], last = D.cell_start[key0 + c + 1];
+		const uint32_t n = last - first;
+		double acc[NACC];
+		#pragma unroll
+		for (int a = 0; a < NACC; a++) acc[a] = 0.;
 		double cphi[8];
 		#pragma unroll
-		for (int k = 0; k < 8; k++) cphi[k] = HAS_PHI ? __ldg(phi + corner(c, (k >> 2) & 1, (k >> 1) & 1, k & 1)) : 0.;
-		const double q0 = qx[i], q1 = qy[i], q2 = qz[i];
-		const double q2sum = q0 * q0 + q1 * q1 + q2 * q2;
-		double w[8];
-		#pragma unroll
-		for (int k = 0; k < 8; k++) w[k] = ((k & 4) ? up[0] : dn[0]) * ((k & 2) ? up[1] : dn[1]) * ((k & 1) ? up[2] : dn[2]);
-		if (DO_T00)
+		for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];       // :967-974
+		if (n > 0)
 		{
-			double e = a, f = 0.;
-			if (HAS_PHI) { e = sqrt(q2sum + a * a); f = 3. * e + q2sum / e; }    // :989-991
-			#pragma unroll
-			for (int k = 0; k < 8; k++)
-				red_add(T00 + corner(c, (k >> 2) & 1, (k >> 1) & 1, k & 1), w[k] * (e + f * cphi[k]) * mass);   // :995-1019
-		}
-		if (DO_TIJ)
-		{
-			const double e = sqrt(q2sum + a * a);                              // :1237
-			const double f = 4. + a * a / (q2sum + a * a);                     // :1238
-			const double qq[3] = {q0, q1, q2};
-			const int diag[3] = {0, 3, 5};
-			#pragma unroll
-			for (int d = 0; d < 3; d++)
+			const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;   // referPos, :963
+			const uint32_t nl = n < DEP_LIGHT ? n : DEP_LIGHT;
+			for (uint32_t j = 0; j < nl; j++) accumulate<WHAT, HAS_PHI>(acc, D, first + j, refx, refy, refz, cphi);
+			finalize<WHAT>(acc, D, cphi);
+			if (n > DEP_LIGHT)
 			{
-				const double wd = mass * qq[d] * qq[d] / e;                    // :1243
-				#pragma unroll
-				for (int k = 0; k < 8; k++)
-					red_add(Tij + diag[d] * cs + corner(c, (k >> 2) & 1, (k >> 1) & 1, k & 1), wd * w[k] * (1. + f * cphi[k]));   // :1245-1259
+				const int h = atomicAdd(&nheavy, 1);
+				heavy_cell[h] = (uint16_t) c; heavy_first[h] = first + DEP_LIGHT; heavy_last[h] = last;
 			}
-			double wo = mass * q0 * q1 / e;                                    // :1262-1264 -> (0,1) at x and x+e2
-			red_add(Tij + 1 * cs + corner(c, 0, 0, 0), wo * dn[2] * (1. + f * 0.25 * (cphi[0] + cphi[2] + cphi[4] + cphi[6])));
-			red_add(Tij + 1 * cs + corner(c, 0, 0, 1), wo * up[2] * (1. + f * 0.25 * (cphi[1] + cphi[3] + cphi[5] + cphi[7])));
-			wo = mass * q0 * q2 / e;                                           // :1266-1268 -> (0,2) at x and x+e1
-			red_add(Tij + 2 * cs + corner(c, 0, 0, 0), wo * dn[1] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[4] + cphi[5])));
-			red_add(Tij + 2 * cs + corner(c, 0, 1, 0), wo * up[1] * (1. + f * 0.25 * (cphi[2] + cphi[3] + cphi[6] + cphi[7])));
-			wo = mass * q1 * q2 / e;                                           // :1270-1272 -> (1,2) at x and x+e0
-			red_add(Tij + 4 * cs + corner(c, 0, 0, 0), wo * dn[0] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[2] + cphi[3])));
-			red_add(Tij + 4 * cs + corner(c, 1, 0, 0), wo * up[0] * (1. + f * 0.25 * (cphi[4] + cphi[5] + cphi[6] + cphi[7])));
+		}
+		// eight corner phases: within a phase every thread updates a different site
+		#pragma unroll
+		for (int k = 0; k < 8; k++)
+		{
+			if (n > 0)
+			{
+				#pragma unroll
+				for (int a = 0; a < NACC; a++)
+					if (acc_corner(WHAT, a) == k) tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(k)] += acc[a];
+			}
+			__syncthreads();
 		}
 	}
-}
 
-template <bool HAS_PHI>
-__global__ void __launch_bounds__(256) k_deposit_T0i(DGeom G, int64_t n, const uint32_t * __restrict__ key,
-	const double * __restrict__ px, const double * __restrict__ py, const double * __restrict__ pz,
-	const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz,
-	const double * __restrict__ phi, double * T0i, size_t cs, double mass)
-{
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	// ---- heavy pass: one warp per crowded cell -------------------------------------------------
+	const int nh = nheavy;
+	for (int h = threadIdx.x >> 5; h < nh; h += DEP_THREADS / 32)
 	{
-		const Cell c = cell_from_key(key[i], G);
-		double up[3], dn[3];
-		up[0] = (px[i] - c.x * G.dx) / G.dx; up[1] = (py[i] - c.y * G.dx) / G.dx; up[2] = (pz[i] - (c.zl + G.z0) * G.dx) / G.dx;
-		dn[0] = 1.0 - up[0]; dn[1] = 1.0 - up[1]; dn[2] = 1.0 - up[2];
-		double cp[8];
+		const int c = heavy_cell[h];
+		const int sx = c & 7, sy = (c >> 3) & 7, sz = c >> 6;
+		const int site = (sz * DT_EDGE + sy) * DT_EDGE + sx;
+		double acc[NACC];
 		#pragma unroll
-		for (int k = 0; k < 8; k++) cp[k] = HAS_PHI ? __ldg(phi + corner(c, (k >> 2) & 1, (k >> 1) & 1, k & 1)) : 0.;
-		double w = mass * qx[i];                                               // :1107
-		red_add(T0i + corner(c, 0, 0, 0), w * dn[1] * dn[2] * (1. + cp[0] + cp[4]));            // :1109,:1129
-		red_add(T0i + corner(c, 0, 1, 0), w * up[1] * dn[2] * (1. + cp[2] + cp[6]));            // :1110,:1136
-		red_add(T0i + corner(c, 0, 0, 1), w * dn[1] * up[2] * (1. + cp[1] + cp[5]));            // :1111,:1139
-		red_add(T0i + corner(c, 0, 1, 1), w * up[1] * up[2] * (1. + cp[3] + cp[7]));            // :1112,:1142
-		w = mass * qy[i];                                                      // :1114
-		red_add(T0i + cs + corner(c, 0, 0, 0), w * dn[0] * dn[2] * (1. + cp[0] + cp[2]));       // :1116,:1130
-		red_add(T0i + cs + corner(c, 1, 0, 0), w * up[0] * dn[2] * (1. + cp[4] + cp[6]));       // :1117,:1133
-		red_add(T0i + cs + corner(c, 0, 0, 1), w * dn[0] * up[2] * (1. + cp[1] + cp[3]));       // :1118,:1140
-		red_add(T0i + cs + corner(c, 1, 0, 1), w * up[0] * up[2] * (1. + cp[5] + cp[7]));       // :1119,:1143
-		w = mass * qz[i];                                                      // :1121
-		red_add(T0i + 2 * cs + corner(c, 0, 0, 0), w * dn[0] * dn[1] * (1. + cp[0] + cp[1]));   // :1123,:1131
-		red_add(T0i + 2 * cs + corner(c, 1, 0, 0), w * up[0] * dn[1] * (1. + cp[4] + cp[5]));   // :1124,:1134
-		red_add(T0i + 2 * cs + corner(c, 0, 1, 0), w * dn[0] * up[1] * (1. + cp[2] + cp[3]));   // :1125,:1137
-		red_add(T0i + 2 * cs + corner(c, 1, 1, 0), w * up[0] * up[1] * (1. + cp[6] + cp[7]));   // :1126,:1144
+		for (int a = 0; a < NACC; a++) acc[a] = 0.;
+		double cphi[8];
+		#pragma unroll
+		for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];
+		const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;
+		for (uint32_t i = heavy_first[h] + (threadIdx.x & 31); i < heavy_last[h]; i += 32) accumulate<WHAT, HAS_PHI>(acc, D, i, refx, refy, refz, cphi);
+		#pragma unroll
+		for (int a = 0; a < NACC; a++)
+			for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+		finalize<WHAT>(acc, D, cphi);
+		if ((threadIdx.x & 31) == 0)
+		{
+			#pragma unroll
+			for (int a = 0; a < NACC; a++) atomicAdd(&tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(acc_corner(WHAT, a))], acc[a]);
+		}
+	}
+	__syncthreads();
+
+	// ---- flush the tile: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row
+	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES; idx += DEP_THREADS)
+	{
+		const double v = tile[idx];
+		if (v == 0.) continue;
+		const int comp = idx / DT_SITES, s = idx - comp * DT_SITES;
+		const int tz = s / (DT_EDGE * DT_EDGE), ty = (s / DT_EDGE) % DT_EDGE, tx = s % DT_EDGE;
+		const size_t off = ((size_t) (zl0 + tz + 1) * G.N + (y0 + ty) % G.N) * G.N + (x0 + tx) % G.N;
+		atomicAdd(D.out[comp] + off, v);
 	}
 }
 
@@ -143,20 +274,30 @@ int check_real(const gevb_field * f, int ncomp, const char * who, const char * n
 	return 0;
 }
 
-template <bool DO_T00, bool DO_TIJ>
-int launch_st(gevb_pcls * p, gevb_field * T00, gevb_field * Tij, double a, gevb_field * phi, double mass)
+template <int WHAT>
+int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, double mass)
 {
 	gevb_ctx * c = p->ctx;
 	if (p->n == 0) return 0;
 	const int b = p->cur;
-	DGeom G = {c->N, c->nzl, c->z0, c->plane(), 1.0 / (double) c->N};
-	const int grid = gevb_grid(c, (size_t) p->n, 256);
-	double * t00 = T00 ? T00->data : NULL; double * tij = Tij ? Tij->data : NULL;
-	size_t cs = Tij ? Tij->comp_stride : 0;
+	DParams D;
+	D.G = p->geom; D.pow2 = (c->N & (c->N - 1)) == 0;
+	D.dx = 1.0 / (double) c->N; D.rN = (double) c->N; D.a = a; D.mass = mass;
+	D.cell_start = p->cell_start;
+	D.x = p->x[b]; D.y = p->y[b]; D.z = p->z[b]; D.qx = p->qx[b]; D.qy = p->qy[b]; D.qz = p->qz[b];
+	D.phi = phi ? phi->data : NULL;
+	for (int k = 0; k < 7; k++) D.out[k] = k < dep_ncomp(WHAT) ? out[k] : NULL;
+	const size_t smem = (size_t) (dep_ncomp(WHAT) + 1) * DT_SITES * sizeof(double);
 	if (phi)
-		k_deposit_scalar_tensor<DO_T00, DO_TIJ, true><<<grid, 256, 0, c->stream>>>(G, p->n, p->key[b], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], phi->data, t00, tij, cs, mass, a);
+	{
+		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_deposit<WHAT, true><<<D.G.nbricks, DEP_THREADS, smem, c->stream>>>(D);
+	}
 	else
-		k_deposit_scalar_tensor<DO_T00, DO_TIJ, false><<<grid, 256, 0, c->stream>>>(G, p->n, p->key[b], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], NULL, t00, tij, cs, mass, a);
+	{
+		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_deposit<WHAT, false><<<D.G.nbricks, DEP_THREADS, smem, c->stream>>>(D);
+	}
 	KERNEL_CHECK(c);
 	return 0;
 }
@@ -173,7 +314,8 @@ extern "C" int gevb_projection_T00_project(gevb_pcls * p, gevb_field * T00, doub
 	Timed timed_(c, CLS_T00);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;          // gevolution.hpp:945-947
-	return launch_st<true, false>(p, T00, NULL, a, phi, mass);
+	double * out[7] = {T00->data};
+	return launch<DEP_T00>(p, out, a, phi, mass);
 }
 
 extern "C" int gevb_projection_Tij_project(gevb_pcls * p, gevb_field * Tij, double a, gevb_field * phi, double coeff)
@@ -186,7 +328,9 @@ extern "C" int gevb_projection_Tij_project(gevb_pcls * p, gevb_field * Tij, doub
 	Timed timed_(c, CLS_TIJ);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;          // gevolution.hpp:1191-1193
-	return launch_st<false, true>(p, NULL, Tij, a, phi, mass);
+	double * out[7];
+	for (int k = 0; k < 6; k++) out[k] = Tij->data + k * Tij->comp_stride;
+	return launch<DEP_TIJ>(p, out, a, phi, mass);
 }
 
 extern "C" int gevb_projection_T00_Tij_project(gevb_pcls * p, gevb_field * T00, gevb_field * Tij, double a, gevb_field * phi, double coeff)
@@ -201,7 +345,9 @@ extern "C" int gevb_projection_T00_Tij_project(gevb_pcls * p, gevb_field * T00, 
 	Timed timed_(c, CLS_T00_TIJ);
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass; mass /= a;
-	return launch_st<true, true>(p, T00, Tij, a, phi, mass);
+	double * out[7] = {T00->data};
+	for (int k = 0; k < 6; k++) out[1 + k] = Tij->data + k * Tij->comp_stride;
+	return launch<DEP_T00_TIJ>(p, out, a, phi, mass);
 }
 
 extern "C" int gevb_scalarProjectionCIC_project(gevb_pcls * p, gevb_field * rho)
@@ -213,7 +359,8 @@ extern "C" int gevb_scalarProjectionCIC_project(gevb_pcls * p, gevb_field * rho)
 	Timed timed_(c, CLS_T00);
 	const double dx = 1.0 / (double) c->N;
 	// plain CIC = T00 projection with e = 1, f = 0 and no 1/a
-	return launch_st<true, false>(p, rho, NULL, 1.0, NULL, p->mass / (dx * dx * dx));
+	double * out[7] = {rho->data};
+	return launch<DEP_T00>(p, out, 1.0, NULL, p->mass / (dx * dx * dx));
 }
 
 extern "C" int gevb_projection_T0i_project(gevb_pcls * p, gevb_field * T0i, gevb_field * phi, double coeff)
@@ -224,16 +371,9 @@ extern "C" int gevb_projection_T0i_project(gevb_pcls * p, gevb_field * T0i, gevb
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	Timed timed_(c, CLS_T0I);
-	if (p->n == 0) return 0;
 	const double dx = 1.0 / (double) c->N;
 	double mass = coeff / (dx * dx * dx); mass *= p->mass;                     // gevolution.hpp:1064-1065
-	const int b = p->cur;
-	DGeom G = {c->N, c->nzl, c->z0, c->plane(), dx};
-	const int grid = gevb_grid(c, (size_t) p->n, 256);
-	if (phi)
-		k_deposit_T0i<true><<<grid, 256, 0, c->stream>>>(G, p->n, p->key[b], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], phi->data, T0i->data, T0i->comp_stride, mass);
-	else
-		k_deposit_T0i<false><<<grid, 256, 0, c->stream>>>(G, p->n, p->key[b], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], NULL, T0i->data, T0i->comp_stride, mass);
-	KERNEL_CHECK(c);
-	return 0;
+	double * out[7];
+	for (int k = 0; k < 3; k++) out[k] = T0i->data + k * T0i->comp_stride;
+	return launch<DEP_T0I>(p, out, 1.0, phi, mass);
 }

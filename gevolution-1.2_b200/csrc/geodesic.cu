@@ -3,25 +3,33 @@
 //   Particles::updateVel + update_q / update_q_Newton        main.cpp:775; gevolution.hpp:570-678, 709-776
 //   Particles::moveParticles + update_pos / update_pos_Newton main.cpp:798; gevolution.hpp:810-871, 900-903
 //
-// One thread per particle over the cell-sorted SoA (coalesced 48 B in, 24 or
-// 48 B out).  Field gathers (phi x8, chi x8, B at 36 sites) go through the
-// read-only path: particles are cell-sorted, so a warp touches a handful of
-// rows of each field plane and neighbouring warps re-use them from L1/L2.
+// One thread block per brick of 8^3 cells (particles are stored brick by brick,
+// gevb_internal.cuh): the block stages the 10^3-site tile (one ghost layer below
+// and above) of phi, chi and B_i in shared memory with periodic wrap applied
+// once per tile, then every thread takes particles of the brick from the
+// coalesced SoA stream (48 B in, 24 or 48 B out) and gathers its ~90 stencil
+// values from shared memory at compile-time offsets.
 // The fused kernel does kick and drift in one pass: between main.cpp:775 and
 // :798 only `a` changes (rungekutta4bg, :792), positions and fields do not.
-// After a drift the new cell key is written; particles that leave the z-slab
+// After a drift the new sort key is written and histogrammed (first half of the
+// counting sort that re-files the particles); particles that leave the z-slab
 // are compacted into send buffers for the two ring neighbours (NCCL P2P).
 #include <math.h>
 #include "gevb_internal.cuh"
 
 namespace {
 
+#define TILE_EDGE 10
+#define TILE_SITES 1000
+
 struct GParams
 {
-	int N, nzl, z0, nranks;
+	BrickGeom G;
+	int nranks, pow2;
 	size_t plane, csB;
-	double dx;
+	double dx, rN;             // rN = (double) N: pos/dx == pos*rN exactly when N is a power of two
 	const double * phi, * chi, * B;
+	int nfmax;                 // how many of {phi, chi, B} the tile needs
 	// kick
 	int fn, nf_kick; double dtau_kick, a_kick, bscale_kick;
 	// drift
@@ -29,32 +37,30 @@ struct GParams
 	// particles
 	int64_t n;
 	double * x, * y, * z, * qx, * qy, * qz; int64_t * id; uint32_t * key;
+	const uint32_t * cell_start; uint32_t * cell_count;
 	unsigned long long * maxv2;          // bit pattern of the running max of v^2 (>= 0)
 	// migration
 	unsigned long long * nsend;          // [2]: down, up
-	double * sendbuf[2]; int64_t sendcap; uint32_t invalid_key;
+	double * sendbuf[2]; int64_t sendcap;
 };
 
-struct Stencil
+// scaled coordinate pos/dx (LATfield2 drivers use pos/dx; the product is bit-identical for power-of-two N)
+__device__ __forceinline__ double scaled(const GParams & P, double p) { return P.pow2 ? p * P.rN : p / P.dx; }
+__device__ __forceinline__ int cell_scaled(double s, int N)
 {
-	int xi[3], yi[3];      // wrapped x-1,x,x+1 ; y-1,y,y+1
-	int p;                 // plane index of the particle's cell (local z + 1)
-	int N; size_t plane;
-	__device__ __forceinline__ size_t at(int dx, int dy, int dz) const { return ((size_t) (p + dz) * N + yi[dy + 1]) * N + xi[dx + 1]; }
-};
-
-__device__ __forceinline__ int cell_of(double p, double dx, int N)
-{
-	int c = (int) floor(p / dx);
+	int c = (int) floor(s);
 	c = c >= N ? N - 1 : c;
 	return c < 0 ? 0 : c;
 }
 
+// T(f, i, j, k): value of tile component f at the particle's cell + (i, j, k), i, j, k in {-1, 0, 1}
+#define T(f, i, j, k) t[(f) * TILE_SITES + (k) * (TILE_EDGE * TILE_EDGE) + (j) * TILE_EDGE + (i)]
+
 // one-sided CIC gradient, gevolution.hpp:585-596 (GRADIENT_ORDER == 1)
-__device__ __forceinline__ void grad_cic(const double * __restrict__ f, const Stencil & s, const double * r, double * g)
+__device__ __forceinline__ void grad_cic(const double * t, int f, const double * r, double * g)
 {
-	const double f000 = __ldg(f + s.at(0, 0, 0)), f100 = __ldg(f + s.at(1, 0, 0)), f010 = __ldg(f + s.at(0, 1, 0)), f110 = __ldg(f + s.at(1, 1, 0));
-	const double f001 = __ldg(f + s.at(0, 0, 1)), f101 = __ldg(f + s.at(1, 0, 1)), f011 = __ldg(f + s.at(0, 1, 1)), f111 = __ldg(f + s.at(1, 1, 1));
+	const double f000 = T(f, 0, 0, 0), f100 = T(f, 1, 0, 0), f010 = T(f, 0, 1, 0), f110 = T(f, 1, 1, 0);
+	const double f001 = T(f, 0, 0, 1), f101 = T(f, 1, 0, 1), f011 = T(f, 0, 1, 1), f111 = T(f, 1, 1, 1);
 	g[0] = (1. - r[1]) * (1. - r[2]) * (f100 - f000);
 	g[1] = (1. - r[0]) * (1. - r[2]) * (f010 - f000);
 	g[2] = (1. - r[0]) * (1. - r[1]) * (f001 - f000);
@@ -70,62 +76,60 @@ __device__ __forceinline__ void grad_cic(const double * __restrict__ f, const St
 }
 
 // trilinear interpolation, gevolution.hpp:820-827
-__device__ __forceinline__ double tri_cic(const double * __restrict__ f, const Stencil & s, const double * r)
+__device__ __forceinline__ double tri_cic(const double * t, int f, const double * r)
 {
-	double v = __ldg(f + s.at(0, 0, 0)) * (1. - r[0]) * (1. - r[1]) * (1. - r[2]);
-	v += __ldg(f + s.at(1, 0, 0)) * r[0] * (1. - r[1]) * (1. - r[2]);
-	v += __ldg(f + s.at(0, 1, 0)) * (1. - r[0]) * r[1] * (1. - r[2]);
-	v += __ldg(f + s.at(1, 1, 0)) * r[0] * r[1] * (1. - r[2]);
-	v += __ldg(f + s.at(0, 0, 1)) * (1. - r[0]) * (1. - r[1]) * r[2];
-	v += __ldg(f + s.at(1, 0, 1)) * r[0] * (1. - r[1]) * r[2];
-	v += __ldg(f + s.at(0, 1, 1)) * (1. - r[0]) * r[1] * r[2];
-	v += __ldg(f + s.at(1, 1, 1)) * r[0] * r[1] * r[2];
+	double v = T(f, 0, 0, 0) * (1. - r[0]) * (1. - r[1]) * (1. - r[2]);
+	v += T(f, 1, 0, 0) * r[0] * (1. - r[1]) * (1. - r[2]);
+	v += T(f, 0, 1, 0) * (1. - r[0]) * r[1] * (1. - r[2]);
+	v += T(f, 1, 1, 0) * r[0] * r[1] * (1. - r[2]);
+	v += T(f, 0, 0, 1) * (1. - r[0]) * (1. - r[1]) * r[2];
+	v += T(f, 1, 0, 1) * r[0] * (1. - r[1]) * r[2];
+	v += T(f, 0, 1, 1) * (1. - r[0]) * r[1] * r[2];
+	v += T(f, 1, 1, 1) * r[0] * r[1] * r[2];
 	return v;
 }
 
 // update_q (gevolution.hpp:570-678) / update_q_Newton (:709-776); returns v^2/a^2
-__device__ __forceinline__ double kick(const GParams & P, const Stencil & s, const double * r, double * q)
+__device__ __forceinline__ double kick(const GParams & P, const double * t, const double * r, double * q)
 {
 	double g[3], v2;
 	if (P.fn == GEVB_UPDATE_Q)
 	{
 		v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                             // :581
 		double e2 = v2 + P.a_kick * P.a_kick;                                      // :582
-		grad_cic(P.phi, s, r, g);                                                  // :585-596
-		g[0] *= (v2 + e2) / e2; g[1] *= (v2 + e2) / e2; g[2] *= (v2 + e2) / e2;    // :613-615
-		if (P.nf_kick >= 2 && P.chi != NULL)
+		grad_cic(t, 0, r, g);                                                      // :585-596
+		const double boost = (v2 + e2) / e2;
+		g[0] *= boost; g[1] *= boost; g[2] *= boost;                               // :613-615
+		if (P.nf_kick >= 2)
 		{
-			double gc[3]; grad_cic(P.chi, s, r, gc);                               // :617-631
+			double gc[3]; grad_cic(t, 1, r, gc);                                   // :617-631
 			g[0] -= gc[0]; g[1] -= gc[1]; g[2] -= gc[2];
 		}
 		e2 = sqrt(e2);                                                             // :633
-		if (P.nf_kick >= 3 && P.B != NULL)
+		if (P.nf_kick >= 3)
 		{
-			const double * B0 = P.B, * B1 = P.B + P.csB, * B2 = P.B + 2 * P.csB;
-#define BV(Bc, a_, b_, c_) __ldg((Bc) + s.at(a_, b_, c_))
 			double pg0, pg1, pg2;
 			// :637-642
-			pg0 = ((1. - r[2]) * (BV(B1, 1, 0, 0) - BV(B1, 0, 0, 0)) + r[2] * (BV(B1, 1, 0, 1) - BV(B1, 0, 0, 1))) * q[1];
-			pg0 += ((1. - r[1]) * (BV(B2, 1, 0, 0) - BV(B2, 0, 0, 0)) + r[1] * (BV(B2, 1, 1, 0) - BV(B2, 0, 1, 0))) * q[2];
-			pg0 += (1. - r[1]) * (1. - r[2]) * ((r[0] - 1.) * BV(B0, -1, 0, 0) + (1. - 2. * r[0]) * BV(B0, 0, 0, 0) + r[0] * BV(B0, 1, 0, 0)) * q[0];
-			pg0 += r[1] * (1. - r[2]) * ((r[0] - 1.) * BV(B0, -1, 1, 0) + (1. - 2. * r[0]) * BV(B0, 0, 1, 0) + r[0] * BV(B0, 1, 1, 0)) * q[0];
-			pg0 += (1. - r[1]) * r[2] * ((r[0] - 1.) * BV(B0, -1, 0, 1) + (1. - 2. * r[0]) * BV(B0, 0, 0, 1) + r[0] * BV(B0, 1, 0, 1)) * q[0];
-			pg0 += r[1] * r[2] * ((r[0] - 1.) * BV(B0, -1, 1, 1) + (1. - 2. * r[0]) * BV(B0, 0, 1, 1) + r[0] * BV(B0, 1, 1, 1)) * q[0];
+			pg0 = ((1. - r[2]) * (T(3, 1, 0, 0) - T(3, 0, 0, 0)) + r[2] * (T(3, 1, 0, 1) - T(3, 0, 0, 1))) * q[1];
+			pg0 += ((1. - r[1]) * (T(4, 1, 0, 0) - T(4, 0, 0, 0)) + r[1] * (T(4, 1, 1, 0) - T(4, 0, 1, 0))) * q[2];
+			pg0 += (1. - r[1]) * (1. - r[2]) * ((r[0] - 1.) * T(2, -1, 0, 0) + (1. - 2. * r[0]) * T(2, 0, 0, 0) + r[0] * T(2, 1, 0, 0)) * q[0];
+			pg0 += r[1] * (1. - r[2]) * ((r[0] - 1.) * T(2, -1, 1, 0) + (1. - 2. * r[0]) * T(2, 0, 1, 0) + r[0] * T(2, 1, 1, 0)) * q[0];
+			pg0 += (1. - r[1]) * r[2] * ((r[0] - 1.) * T(2, -1, 0, 1) + (1. - 2. * r[0]) * T(2, 0, 0, 1) + r[0] * T(2, 1, 0, 1)) * q[0];
+			pg0 += r[1] * r[2] * ((r[0] - 1.) * T(2, -1, 1, 1) + (1. - 2. * r[0]) * T(2, 0, 1, 1) + r[0] * T(2, 1, 1, 1)) * q[0];
 			// :644-649
-			pg1 = ((1. - r[0]) * (BV(B2, 0, 1, 0) - BV(B2, 0, 0, 0)) + r[0] * (BV(B2, 1, 1, 0) - BV(B2, 1, 0, 0))) * q[2];
-			pg1 += ((1. - r[2]) * (BV(B0, 0, 1, 0) - BV(B0, 0, 0, 0)) + r[2] * (BV(B0, 0, 1, 1) - BV(B0, 0, 0, 1))) * q[0];
-			pg1 += (1. - r[0]) * (1. - r[2]) * ((r[1] - 1.) * BV(B1, 0, -1, 0) + (1. - 2. * r[1]) * BV(B1, 0, 0, 0) + r[1] * BV(B1, 0, 1, 0)) * q[1];
-			pg1 += r[0] * (1. - r[2]) * ((r[1] - 1.) * BV(B1, 1, -1, 0) + (1. - 2. * r[1]) * BV(B1, 1, 0, 0) + r[1] * BV(B1, 1, 1, 0)) * q[1];
-			pg1 += (1. - r[0]) * r[2] * ((r[1] - 1.) * BV(B1, 0, -1, 1) + (1. - 2. * r[1]) * BV(B1, 0, 0, 1) + r[1] * BV(B1, 0, 1, 1)) * q[1];
-			pg1 += r[0] * r[2] * ((r[1] - 1.) * BV(B1, 1, -1, 1) + (1. - 2. * r[1]) * BV(B1, 1, 0, 1) + r[1] * BV(B1, 1, 1, 1)) * q[1];
+			pg1 = ((1. - r[0]) * (T(4, 0, 1, 0) - T(4, 0, 0, 0)) + r[0] * (T(4, 1, 1, 0) - T(4, 1, 0, 0))) * q[2];
+			pg1 += ((1. - r[2]) * (T(2, 0, 1, 0) - T(2, 0, 0, 0)) + r[2] * (T(2, 0, 1, 1) - T(2, 0, 0, 1))) * q[0];
+			pg1 += (1. - r[0]) * (1. - r[2]) * ((r[1] - 1.) * T(3, 0, -1, 0) + (1. - 2. * r[1]) * T(3, 0, 0, 0) + r[1] * T(3, 0, 1, 0)) * q[1];
+			pg1 += r[0] * (1. - r[2]) * ((r[1] - 1.) * T(3, 1, -1, 0) + (1. - 2. * r[1]) * T(3, 1, 0, 0) + r[1] * T(3, 1, 1, 0)) * q[1];
+			pg1 += (1. - r[0]) * r[2] * ((r[1] - 1.) * T(3, 0, -1, 1) + (1. - 2. * r[1]) * T(3, 0, 0, 1) + r[1] * T(3, 0, 1, 1)) * q[1];
+			pg1 += r[0] * r[2] * ((r[1] - 1.) * T(3, 1, -1, 1) + (1. - 2. * r[1]) * T(3, 1, 0, 1) + r[1] * T(3, 1, 1, 1)) * q[1];
 			// :651-656
-			pg2 = ((1. - r[1]) * (BV(B0, 0, 0, 1) - BV(B0, 0, 0, 0)) + r[1] * (BV(B0, 0, 1, 1) - BV(B0, 0, 1, 0))) * q[0];
-			pg2 += ((1. - r[0]) * (BV(B1, 0, 0, 1) - BV(B1, 0, 0, 0)) + r[0] * (BV(B1, 1, 0, 1) - BV(B1, 1, 0, 0))) * q[1];
-			pg2 += (1. - r[0]) * (1. - r[1]) * ((r[2] - 1.) * BV(B2, 0, 0, -1) + (1. - 2. * r[2]) * BV(B2, 0, 0, 0) + r[2] * BV(B2, 0, 0, 1)) * q[2];
-			pg2 += r[0] * (1. - r[1]) * ((r[2] - 1.) * BV(B2, 1, 0, -1) + (1. - 2. * r[2]) * BV(B2, 1, 0, 0) + r[2] * BV(B2, 1, 0, 1)) * q[2];
-			pg2 += (1. - r[0]) * r[1] * ((r[2] - 1.) * BV(B2, 0, 1, -1) + (1. - 2. * r[2]) * BV(B2, 0, 1, 0) + r[2] * BV(B2, 0, 1, 1)) * q[2];
-			pg2 += r[0] * r[1] * ((r[2] - 1.) * BV(B2, 1, 1, -1) + (1. - 2. * r[2]) * BV(B2, 1, 1, 0) + r[2] * BV(B2, 1, 1, 1)) * q[2];
-#undef BV
+			pg2 = ((1. - r[1]) * (T(2, 0, 0, 1) - T(2, 0, 0, 0)) + r[1] * (T(2, 0, 1, 1) - T(2, 0, 1, 0))) * q[0];
+			pg2 += ((1. - r[0]) * (T(3, 0, 0, 1) - T(3, 0, 0, 0)) + r[0] * (T(3, 1, 0, 1) - T(3, 1, 0, 0))) * q[1];
+			pg2 += (1. - r[0]) * (1. - r[1]) * ((r[2] - 1.) * T(4, 0, 0, -1) + (1. - 2. * r[2]) * T(4, 0, 0, 0) + r[2] * T(4, 0, 0, 1)) * q[2];
+			pg2 += r[0] * (1. - r[1]) * ((r[2] - 1.) * T(4, 1, 0, -1) + (1. - 2. * r[2]) * T(4, 1, 0, 0) + r[2] * T(4, 1, 0, 1)) * q[2];
+			pg2 += (1. - r[0]) * r[1] * ((r[2] - 1.) * T(4, 0, 1, -1) + (1. - 2. * r[2]) * T(4, 0, 1, 0) + r[2] * T(4, 0, 1, 1)) * q[2];
+			pg2 += r[0] * r[1] * ((r[2] - 1.) * T(4, 1, 1, -1) + (1. - 2. * r[2]) * T(4, 1, 1, 0) + r[2] * T(4, 1, 1, 1)) * q[2];
 			g[0] += pg0 / P.bscale_kick / e2;                                      // :658-660
 			g[1] += pg1 / P.bscale_kick / e2;
 			g[2] += pg2 / P.bscale_kick / e2;
@@ -136,10 +140,10 @@ __device__ __forceinline__ double kick(const GParams & P, const Stencil & s, con
 	}
 	else
 	{
-		grad_cic(P.phi, s, r, g);                                                  // :719-730
-		if (P.nf_kick >= 2 && P.chi != NULL)
+		grad_cic(t, 0, r, g);                                                      // :719-730
+		if (P.nf_kick >= 2)
 		{
-			double gc[3]; grad_cic(P.chi, s, r, gc);                               // :747-761
+			double gc[3]; grad_cic(t, 1, r, gc);                                   // :747-761
 			g[0] -= gc[0]; g[1] -= gc[1]; g[2] -= gc[2];
 		}
 		v2 = 0.;
@@ -150,7 +154,7 @@ __device__ __forceinline__ double kick(const GParams & P, const Stencil & s, con
 }
 
 // update_pos (gevolution.hpp:810-871) / update_pos_Newton (:900-903)
-__device__ __forceinline__ void drift(const GParams & P, const Stencil & s, const double * r, const double * q, double * pos)
+__device__ __forceinline__ void drift(const GParams & P, const double * t, const double * r, const double * q, double * pos)
 {
 	if (P.fn != GEVB_UPDATE_Q)
 	{
@@ -161,28 +165,25 @@ __device__ __forceinline__ void drift(const GParams & P, const Stencil & s, cons
 	double v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                           // :813
 	const double e2 = v2 + P.a_drift * P.a_drift;                                  // :814
 	double ph = 0., ch = 0.;
-	if (P.nf_drift >= 1) ph = tri_cic(P.phi, s, r);                                // :820-827
-	if (P.nf_drift >= 2) ch = tri_cic(P.chi, s, r);                                // :832-839
+	if (P.nf_drift >= 1) ph = tri_cic(t, 0, r);                                    // :820-827
+	if (P.nf_drift >= 2) ch = tri_cic(t, 1, r);                                    // :832-839
 	v2 = (1. + (3. - v2 / e2) * ph - ch) / sqrt(e2);                               // :842
 	double v[3] = {q[0] * v2, q[1] * v2, q[2] * v2};                               // :844-846
 	if (P.nf_drift >= 3)
 	{
-		const double * B0 = P.B, * B1 = P.B + P.csB, * B2 = P.B + 2 * P.csB;
-#define BV(Bc, a_, b_, c_) __ldg((Bc) + s.at(a_, b_, c_))
 		double b[3];
-		b[0] = BV(B0, 0, 0, 0) * (1. - r[1]) * (1. - r[2]);                        // :852
-		b[1] = BV(B1, 0, 0, 0) * (1. - r[0]) * (1. - r[2]);                        // :853
-		b[2] = BV(B2, 0, 0, 0) * (1. - r[0]) * (1. - r[1]);                        // :854
-		b[1] += BV(B1, 1, 0, 0) * r[0] * (1. - r[2]);                              // :855
-		b[2] += BV(B2, 1, 0, 0) * r[0] * (1. - r[1]);                              // :856
-		b[0] += BV(B0, 0, 1, 0) * r[1] * (1. - r[2]);                              // :857
-		b[2] += BV(B2, 0, 1, 0) * (1. - r[0]) * r[1];                              // :858
-		b[0] += BV(B0, 0, 0, 1) * (1. - r[1]) * r[2];                              // :859
-		b[1] += BV(B1, 0, 0, 1) * (1. - r[0]) * r[2];                              // :860
-		b[1] += BV(B1, 1, 0, 1) * r[0] * r[2];                                     // :861
-		b[0] += BV(B0, 0, 1, 1) * r[1] * r[2];                                     // :862
-		b[2] += BV(B2, 1, 1, 0) * r[0] * r[1];                                     // :863
-#undef BV
+		b[0] = T(2, 0, 0, 0) * (1. - r[1]) * (1. - r[2]);                          // :852
+		b[1] = T(3, 0, 0, 0) * (1. - r[0]) * (1. - r[2]);                          // :853
+		b[2] = T(4, 0, 0, 0) * (1. - r[0]) * (1. - r[1]);                          // :854
+		b[1] += T(3, 1, 0, 0) * r[0] * (1. - r[2]);                                // :855
+		b[2] += T(4, 1, 0, 0) * r[0] * (1. - r[1]);                                // :856
+		b[0] += T(2, 0, 1, 0) * r[1] * (1. - r[2]);                                // :857
+		b[2] += T(4, 0, 1, 0) * (1. - r[0]) * r[1];                                // :858
+		b[0] += T(2, 0, 0, 1) * (1. - r[1]) * r[2];                                // :859
+		b[1] += T(3, 0, 0, 1) * (1. - r[0]) * r[2];                                // :860
+		b[1] += T(3, 1, 0, 1) * r[0] * r[2];                                       // :861
+		b[0] += T(2, 0, 1, 1) * r[1] * r[2];                                       // :862
+		b[2] += T(4, 1, 1, 0) * r[0] * r[1];                                       // :863
 		#pragma unroll
 		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * (v[l] + b[l] / P.bscale_drift);   // :865
 	}
@@ -192,6 +193,7 @@ __device__ __forceinline__ void drift(const GParams & P, const Stencil & s, cons
 		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * v[l];                 // :869
 	}
 }
+#undef T
 
 // periodic wrap into [0,1): p - floor(p), a result that rounds to 1 maps to 0 (edge semantics)
 __device__ __forceinline__ double wrap_pos(double p)
@@ -200,44 +202,74 @@ __device__ __forceinline__ double wrap_pos(double p)
 	return w >= 1.0 ? 0. : w;
 }
 
-// MODE 0: kick only, 1: drift only, 2: fused kick + drift
+__device__ __forceinline__ int wrap_index(int v, int N)
+{
+	v %= N;
+	return v < 0 ? v + N : v;
+}
+
+// MODE 0: kick only, 1: drift only, 2: fused kick + drift.  One block per brick.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_geodesic(GParams P)
 {
+	extern __shared__ double tile[];
+	const BrickGeom & G = P.G;
+	const uint32_t brick = blockIdx.x;
+	const uint32_t first = P.cell_start[brick * GEVB_BRICK_CELLS], last = P.cell_start[(brick + 1) * GEVB_BRICK_CELLS];
+	if (first == last) return;
+	int x0, y0, zl0;
+	brick_origin(G, brick, x0, y0, zl0);
+	// stage the field tiles: site (lx, ly, lz) of the tile is lattice site (x0 - 1 + lx, y0 - 1 + ly, local z = zl0 - 1 + lz)
+	{
+		const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
+		for (int idx = threadIdx.x; idx < ncomp * TILE_SITES; idx += blockDim.x)
+		{
+			const int f = idx / TILE_SITES, s = idx - f * TILE_SITES;
+			const int lz = s / (TILE_EDGE * TILE_EDGE), ly = (s / TILE_EDGE) % TILE_EDGE, lx = s % TILE_EDGE;
+			const int plane = zl0 + lz;                              // ghost-offset plane index of local z = zl0 - 1 + lz
+			double v = 0.;
+			if (plane <= G.nzl + 1)
+			{
+				const size_t off = ((size_t) plane * G.N + wrap_index(y0 - 1 + ly, G.N)) * G.N + wrap_index(x0 - 1 + lx, G.N);
+				const double * src = f == 0 ? P.phi : (f == 1 ? P.chi : P.B + (size_t) (f - 2) * P.csB);
+				v = __ldg(src + off);
+			}
+			tile[idx] = v;
+		}
+	}
+	__syncthreads();
 	double vmax = 0.;
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < P.n; i += (int64_t) gridDim.x * blockDim.x)
+	for (uint32_t i = first + threadIdx.x; i < last; i += blockDim.x)
 	{
 		double pos[3] = {P.x[i], P.y[i], P.z[i]};
 		double q[3] = {P.qx[i], P.qy[i], P.qz[i]};
 		// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
 		double r[3], ip;
-		Stencil s;
-		s.N = P.N; s.plane = P.plane;
+		const double * t;
 		{
-			const int cx = cell_of(pos[0], P.dx, P.N), cy = cell_of(pos[1], P.dx, P.N), cz = cell_of(pos[2], P.dx, P.N);
-			s.xi[1] = cx; s.xi[0] = cx == 0 ? P.N - 1 : cx - 1; s.xi[2] = cx == P.N - 1 ? 0 : cx + 1;
-			s.yi[1] = cy; s.yi[0] = cy == 0 ? P.N - 1 : cy - 1; s.yi[2] = cy == P.N - 1 ? 0 : cy + 1;
-			s.p = cz - P.z0 + 1;
-			r[0] = modf(pos[0] / P.dx, &ip); r[1] = modf(pos[1] / P.dx, &ip); r[2] = modf(pos[2] / P.dx, &ip);
+			const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
+			const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
+			r[0] = modf(sx, &ip); r[1] = modf(sy, &ip); r[2] = modf(sz, &ip);
+			t = tile + ((cz - G.z0 - zl0 + 1) * TILE_EDGE + (cy - y0 + 1)) * TILE_EDGE + (cx - x0 + 1);
 		}
 		if (MODE == 0 || MODE == 2)
 		{
-			const double v2 = kick(P, s, r, q);
+			const double v2 = kick(P, t, r, q);
 			vmax = fmax(vmax, v2);
 			P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
 		}
 		if (MODE == 1 || MODE == 2)
 		{
-			drift(P, s, r, q, pos);
+			drift(P, t, r, q, pos);
 			pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
-			const int cx = cell_of(pos[0], P.dx, P.N), cy = cell_of(pos[1], P.dx, P.N), cz = cell_of(pos[2], P.dx, P.N);
-			int zl = cz - P.z0;
-			bool leaving = false;
-			if (P.nranks > 1 && (zl < 0 || zl >= P.nzl))
+			const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
+			const int zl = cz - G.z0;
+			uint32_t key;
+			if (P.nranks > 1 && (zl < 0 || zl >= G.nzl))
 			{
 				// at most one slab per move (main.cpp:281-286): periodic distance decides the neighbour
-				const int d = (zl + P.N) % P.N;
-				const int dir = d < P.N / 2 ? 1 : 0;
+				const int d = (zl + G.N) % G.N;
+				const int dir = d < G.N / 2 ? 1 : 0;
 				const unsigned long long slot = atomicAdd(P.nsend + dir, 1ull);
 				if ((int64_t) slot < P.sendcap)
 				{
@@ -246,10 +278,15 @@ __global__ void __launch_bounds__(256) k_geodesic(GParams P)
 					sb[3 * P.sendcap + slot] = q[0]; sb[4 * P.sendcap + slot] = q[1]; sb[5 * P.sendcap + slot] = q[2];
 					sb[6 * P.sendcap + slot] = __longlong_as_double((long long) P.id[i]);
 				}
-				leaving = true;
+				key = GEVB_INVALID_KEY;
+			}
+			else
+			{
+				key = brick_key(G, cx, cy, zl);
+				atomicAdd(P.cell_count + key, 1u);                  // histogram of the counting sort (particles.cu)
 			}
 			P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
-			P.key[i] = leaving ? P.invalid_key : (uint32_t) ((zl * P.N + cy) * P.N + cx);
+			P.key[i] = key;
 		}
 	}
 	if (MODE == 0 || MODE == 2)
@@ -259,10 +296,10 @@ __global__ void __launch_bounds__(256) k_geodesic(GParams P)
 	}
 }
 
-// received particles (7 x cap SoA staging) appended behind the live ones, keys computed
+// received particles (7 x cap SoA staging) appended behind the live ones, keys computed and histogrammed
 __global__ void k_append_received(int64_t nrecv, const double * __restrict__ rb, int64_t cap, int64_t at,
                                   double * x, double * y, double * z, double * qx, double * qy, double * qz, int64_t * id, uint32_t * key,
-                                  int N, int z0, int nzl, double dx, unsigned long long * lost)
+                                  BrickGeom G, double dx, uint32_t * cell_count, unsigned long long * lost)
 {
 	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < nrecv; i += (int64_t) gridDim.x * blockDim.x)
 	{
@@ -270,10 +307,12 @@ __global__ void k_append_received(int64_t nrecv, const double * __restrict__ rb,
 		x[at + i] = px; y[at + i] = py; z[at + i] = pz;
 		qx[at + i] = rb[3 * cap + i]; qy[at + i] = rb[4 * cap + i]; qz[at + i] = rb[5 * cap + i];
 		id[at + i] = (int64_t) __double_as_longlong(rb[6 * cap + i]);
-		const int cx = cell_of(px, dx, N), cy = cell_of(py, dx, N);
-		int cz = cell_of(pz, dx, N) - z0;
-		if (cz < 0 || cz >= nzl) { atomicAdd(lost, 1ull); cz = cz < 0 ? 0 : nzl - 1; }   // moved farther than one slab: reported by the host
-		key[at + i] = (uint32_t) ((cz * N + cy) * N + cx);
+		const int cx = cell_of(px, dx, G.N), cy = cell_of(py, dx, G.N);
+		int cz = cell_of(pz, dx, G.N) - G.z0;
+		if (cz < 0 || cz >= G.nzl) { atomicAdd(lost, 1ull); cz = cz < 0 ? 0 : G.nzl - 1; }   // moved farther than one slab: reported by the host
+		const uint32_t k = brick_key(G, cx, cy, cz);
+		key[at + i] = k;
+		atomicAdd(cell_count + k, 1u);
 	}
 }
 
@@ -295,24 +334,37 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	gevb_ctx * c = p->ctx;
 	const int b = p->cur;
 	memset(&P, 0, sizeof(P));
-	P.N = c->N; P.nzl = c->nzl; P.z0 = c->z0; P.nranks = c->nranks;
-	P.plane = c->plane(); P.dx = 1.0 / (double) c->N;
+	P.G = p->geom; P.nranks = c->nranks;
+	P.pow2 = (c->N & (c->N - 1)) == 0;
+	P.plane = c->plane(); P.dx = 1.0 / (double) c->N; P.rN = (double) c->N;
 	P.phi = nfields >= 1 ? fields[0]->data : NULL;
 	P.chi = nfields >= 2 ? fields[1]->data : NULL;
 	P.B = nfields >= 3 ? fields[2]->data : NULL;
 	P.csB = nfields >= 3 ? fields[2]->comp_stride : 0;
+	P.nfmax = nfields;
 	P.n = p->n;
-	P.x = p->x[b]; P.y = p->y[b]; P.z = p->z[b]; P.qx = p->qx[b]; P.qy = p->qy[b]; P.qz = p->qz[b]; P.id = p->id[b]; P.key = p->key[b];
+	P.x = p->x[b]; P.y = p->y[b]; P.z = p->z[b]; P.qx = p->qx[b]; P.qy = p->qy[b]; P.qz = p->qz[b]; P.id = p->id[b]; P.key = p->key;
+	P.cell_start = p->cell_start; P.cell_count = p->cell_count;
 	P.maxv2 = (unsigned long long *) (c->d_red + 4008);
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
-	P.invalid_key = 0xffffffffu;
 }
 
-// after a drift: exchange slab-crossing particles with the ring neighbours, then restore the sort
+template <int MODE>
+int launch_geodesic(gevb_pcls * p, const GParams & P)
+{
+	gevb_ctx * c = p->ctx;
+	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
+	const size_t smem = (size_t) (ncomp > 0 ? ncomp : 1) * TILE_SITES * sizeof(double);
+	k_geodesic<MODE><<<P.G.nbricks, 256, smem, c->stream>>>(P);
+	KERNEL_CHECK(c);
+	return 0;
+}
+
+// after a drift: exchange slab-crossing particles with the ring neighbours, then re-file (counting sort)
 int finish_move(gevb_pcls * p, GParams & P)
 {
 	gevb_ctx * c = p->ctx;
-	if (c->nranks == 1) { Timed timed_(c, CLS_SORT); return gevb_pcls_sort(p, true, false); }
+	if (c->nranks == 1) { Timed timed_(c, CLS_SORT); return gevb_pcls_rebin(p, p->n, p->n, true); }
 	Timed timed_mig_(c, CLS_MIGRATE);
 	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
 	unsigned long long * cnt = P.nsend;                 // [0,1] = my sends (down, up); [2,3] = what I receive (from up, from down)
@@ -348,18 +400,16 @@ int finish_move(gevb_pcls * p, GParams & P)
 	const double dx = 1.0 / (double) c->N;
 	if (h[2])
 	{
-		k_append_received<<<gevb_grid(c, h[2], 256), 256, 0, c->stream>>>((int64_t) h[2], rb_up, P.sendcap, p->n, p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key[b], c->N, c->z0, c->nzl, dx, cnt + 4);
+		k_append_received<<<gevb_grid(c, h[2], 256), 256, 0, c->stream>>>((int64_t) h[2], rb_up, P.sendcap, p->n, p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4);
 		KERNEL_CHECK(c);
 	}
 	if (h[3])
 	{
-		k_append_received<<<gevb_grid(c, h[3], 256), 256, 0, c->stream>>>((int64_t) h[3], rb_dn, P.sendcap, p->n + (int64_t) h[2], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key[b], c->N, c->z0, c->nzl, dx, cnt + 4);
+		k_append_received<<<gevb_grid(c, h[3], 256), 256, 0, c->stream>>>((int64_t) h[3], rb_dn, P.sendcap, p->n + (int64_t) h[2], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4);
 		KERNEL_CHECK(c);
 	}
-	p->n += nrecv;
-	// keys of the departed are 0xffffffff: they sort to the very end and are dropped
-	GEVB_TRY(gevb_pcls_sort(p, true, true));
-	p->n -= (int64_t) (h[0] + h[1]);
+	// the departed carry GEVB_INVALID_KEY and are dropped by the scatter
+	GEVB_TRY(gevb_pcls_rebin(p, p->n + nrecv, p->n + nrecv - (int64_t) (h[0] + h[1]), true));
 	unsigned long long lost = 0;
 	CUDA_TRY(cudaMemcpyAsync(&lost, cnt + 4, sizeof(lost), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -398,8 +448,7 @@ extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * c
 	if (p->n > 0)
 	{
 		Timed timed_(c, CLS_KICK);
-		k_geodesic<0><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
-		KERNEL_CHECK(c);
+		GEVB_TRY(launch_geodesic<0>(p, P));
 	}
 	if (maxvel)
 	{
@@ -425,8 +474,7 @@ extern "C" int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field
 	if (p->n > 0)
 	{
 		Timed timed_(c, CLS_DRIFT);
-		k_geodesic<1><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
-		KERNEL_CHECK(c);
+		GEVB_TRY(launch_geodesic<1>(p, P));
 	}
 	return finish_move(p, P);
 }
@@ -453,10 +501,9 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 	if (p->n > 0)
 	{
 		Timed timed_(c, CLS_KICK_DRIFT);
-		k_geodesic<2><<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(P);
-		KERNEL_CHECK(c);
+		GEVB_TRY(launch_geodesic<2>(p, P));
 	}
-	// the max must be read before finish_move reuses the reduction slots' neighbourhood; slots are distinct
+	// the max lives in its own reduction slot, untouched by finish_move
 	GEVB_TRY(finish_move(p, P));
 	if (maxvel)
 	{

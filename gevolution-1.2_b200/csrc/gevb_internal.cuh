@@ -121,21 +121,62 @@ struct gevb_plan
 };
 
 // ---------------------------------------------------------------- particles --
+// Particle order: "brick-major cell order".  The local slab is cut into bricks of 8 x 8 x 8 cells; the sort
+// key of a particle is (brick index << 9) | (cell inside the brick), so that the particles of one brick are
+// contiguous (one thread block stages the brick's field tile in shared memory) and, inside the brick, the
+// particles of one cell are contiguous (deposits accumulate per cell).  cell_start[key] is the exclusive
+// prefix sum of the per-cell counts in key order (the counting sort's offsets), kept valid at all times.
+#define GEVB_BRICK 8
+#define GEVB_BRICK_CELLS 512
+#define GEVB_INVALID_KEY 0xffffffffu
+struct BrickGeom
+{
+	int N, nzl, z0;
+	int nbx, nby, nbz;         // bricks per dimension (last ones may be partial)
+	uint32_t nbricks, ncells;  // ncells = nbricks * 512 (cells of partial bricks that lie outside the slab stay empty)
+};
+__host__ __device__ __forceinline__ uint32_t brick_key(const BrickGeom & G, int cx, int cy, int czl)
+{
+	const uint32_t b = ((uint32_t) (czl >> 3) * G.nby + (uint32_t) (cy >> 3)) * G.nbx + (uint32_t) (cx >> 3);
+	return (b << 9) | (uint32_t) (((czl & 7) << 6) | ((cy & 7) << 3) | (cx & 7));
+}
+__host__ __device__ __forceinline__ void brick_origin(const BrickGeom & G, uint32_t brick, int & x0, int & y0, int & zl0)
+{
+	x0 = (int) (brick % G.nbx) * GEVB_BRICK; const uint32_t r = brick / G.nbx;
+	y0 = (int) (r % G.nby) * GEVB_BRICK; zl0 = (int) (r / G.nby) * GEVB_BRICK;
+}
+__host__ __device__ __forceinline__ void key_to_cell(const BrickGeom & G, uint32_t key, int & cx, int & cy, int & czl)
+{
+	brick_origin(G, key >> 9, cx, cy, czl);
+	cx += key & 7; cy += (key >> 3) & 7; czl += (key >> 6) & 7;
+}
+// cell = floor(pos/dx) clamped into the lattice (LATfield2 filing rule, reference uses at gevolution.hpp:979-983)
+__device__ __forceinline__ int cell_of(double p, double dx, int N)
+{
+	int c = (int) floor(p / dx);
+	c = c >= N ? N - 1 : c;
+	return c < 0 ? 0 : c;
+}
+
 struct gevb_pcls
 {
 	gevb_ctx * ctx;
 	double mass;
 	int64_t n, cap;
-	// cell-sorted structure of arrays; [0] is live, [1] is the sort's output buffer
+	// brick-major cell-sorted structure of arrays; [cur] is live, [1-cur] is the re-bin's output buffer
 	double * x[2], * y[2], * z[2], * qx[2], * qy[2], * qz[2];
 	int64_t * id[2];
-	uint32_t * key[2];         // local cell key (zl*N + y)*N + x
-	uint32_t * perm[2];
+	uint32_t * key;            // sort key of each live particle after a drift (input of the re-bin)
+	uint32_t * cell_count;     // [ncells + 1] histogram of keys; all zero between re-bins
+	uint32_t * cell_start;     // [ncells + 1] exclusive prefix sum; cell_start[ncells] == n
+	BrickGeom geom;
 	int cur;
 };
 
 int gevb_pcls_reserve(gevb_pcls * p, int64_t cap);
-int gevb_pcls_sort(gevb_pcls * p, bool keys_valid, bool full_bits);
+// counting sort of the first n_in live particles by p->key (entries with GEVB_INVALID_KEY are dropped);
+// hist_valid: cell_count already holds the histogram of the keys (the drift kernel accumulates it)
+int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid);
 
 // Fourier-space index decode shared by all k-kernels
 struct KLayout

@@ -1,22 +1,21 @@
-// particles.cu -- cell-sorted FP64 structure-of-arrays particle storage
+// particles.cu -- brick-major cell-sorted FP64 structure-of-arrays particle storage
 //
 // Replaces LATfield2's Particles<part_simple,...> container (per-cell
 // std::list<part_simple>, reference uses at gevolution.hpp:960,977 and
 // ic_basic.hpp:1429,1990) by seven flat device arrays {x,y,z,qx,qy,qz,id}
-// kept sorted by the local cell key (zl*N + y)*N + x, cell = floor(pos/dx).
+// kept sorted by the key (brick << 9 | cell in brick), cell = floor(pos/dx).
 // The integer contract (which cell a particle is filed under, particles per
 // cell) is bit-exact with the reference's floor(pos/dx) filing rule.
-#include <cub/device/device_radix_sort.cuh>
+//
+// Re-filing after a drift (the list splice inside LATfield2's moveParticles) is a
+// counting sort: the drift kernel accumulates the histogram of the new keys, one
+// exclusive scan gives cell_start[], one pass moves the 56-byte records to their
+// slots.  Particles move by a fraction of a cell per step, so source and
+// destination order are almost the same and both sides of the move stay coalesced.
+#include <cub/device/device_scan.cuh>
 #include "gevb_internal.cuh"
 
 namespace {
-
-__device__ __forceinline__ int cell_of(double p, double dx, int N)
-{
-	int c = (int) floor(p / dx);
-	c = c >= N ? N - 1 : c;
-	return c < 0 ? 0 : c;
-}
 
 // host AoS chunk -> SoA append, keeping only particles filed in this rank's slab
 __global__ void k_append(int64_t n, const int64_t * __restrict__ id, const double * __restrict__ pos, const double * __restrict__ vel,
@@ -49,23 +48,22 @@ __global__ void k_count_local(int64_t n, const double * __restrict__ pos, int N,
 	if ((threadIdx.x & 31) == 0 && mine) atomicAdd(counter, mine);
 }
 
-__global__ void k_make_keys(int64_t n, const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
-                            int N, int z0, double dx, uint32_t * __restrict__ key, uint32_t * __restrict__ perm)
+// keys of particles [first, first + n) from their positions, accumulated into the histogram
+__global__ void k_make_keys(BrickGeom G, int64_t first, int64_t n, const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
+                            double dx, uint32_t * __restrict__ key, uint32_t * count)
 {
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	for (int64_t i = first + blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < first + n; i += (int64_t) gridDim.x * blockDim.x)
 	{
-		const int cx = cell_of(x[i], dx, N), cy = cell_of(y[i], dx, N), cz = cell_of(z[i], dx, N) - z0;
-		key[i] = (uint32_t) ((cz * N + cy) * N + cx);
-		perm[i] = (uint32_t) i;
+		const int cx = cell_of(x[i], dx, G.N), cy = cell_of(y[i], dx, G.N), cz = cell_of(z[i], dx, G.N) - G.z0;
+		const uint32_t k = brick_key(G, cx, cy, cz);
+		key[i] = k;
+		atomicAdd(count + k, 1u);
 	}
 }
 
-__global__ void k_iota(int64_t n, uint32_t * __restrict__ perm)
-{
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) perm[i] = (uint32_t) i;
-}
-
-__global__ void __launch_bounds__(256) k_permute(int64_t n, const uint32_t * __restrict__ perm,
+// the move of the counting sort: slot = cell_start[key] + (number of particles of this cell not yet placed) - 1.
+// Counting down leaves cell_count all zero again, ready for the next histogram.
+__global__ void __launch_bounds__(256) k_scatter(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ cell_start, uint32_t * count,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
                           double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
@@ -73,16 +71,28 @@ __global__ void __launch_bounds__(256) k_permute(int64_t n, const uint32_t * __r
 {
 	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
 	{
-		const uint32_t s = perm[i];
-		ox[i] = x[s]; oy[i] = y[s]; oz[i] = z[s];
-		oqx[i] = qx[s]; oqy[i] = qy[s]; oqz[i] = qz[s];
-		oid[i] = id[s];
+		const uint32_t k = key[i];
+		if (k == GEVB_INVALID_KEY) continue;                  // left the slab (sent to a neighbour rank)
+		const double vx = x[i], vy = y[i], vz = z[i], wx = qx[i], wy = qy[i], wz = qz[i];
+		const int64_t vid = id[i];
+		const uint32_t d = __ldg(cell_start + k) + atomicSub(count + k, 1u) - 1u;
+		ox[d] = vx; oy[d] = vy; oz[d] = vz;
+		oqx[d] = wx; oqy[d] = wy; oqz[d] = wz;
+		oid[d] = vid;
 	}
 }
 
-__global__ void k_histogram(int64_t n, const uint32_t * __restrict__ key, uint32_t * __restrict__ counts)
+// per-cell counts in lattice order [zl][y][x] from the prefix sums in key order
+__global__ void k_counts_out(BrickGeom G, const uint32_t * __restrict__ cell_start, uint32_t * __restrict__ counts)
 {
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) atomicAdd(counts + key[i], 1u);
+	const size_t cells = (size_t) G.nzl * G.N * G.N;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < cells; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int cx = (int) (i % G.N); const size_t r = i / G.N;
+		const int cy = (int) (r % G.N), cz = (int) (r / G.N);
+		const uint32_t k = brick_key(G, cx, cy, cz);
+		counts[i] = cell_start[k + 1] - cell_start[k];
+	}
 }
 
 __global__ void k_interleave3(int64_t n, const double * __restrict__ a, const double * __restrict__ b, const double * __restrict__ c, double * __restrict__ out)
@@ -93,12 +103,15 @@ __global__ void k_interleave3(int64_t n, const double * __restrict__ a, const do
 	}
 }
 
-int key_bits(const gevb_ctx * c)
+void free_arrays(gevb_pcls * p)
 {
-	uint64_t cells = (uint64_t) c->nzl * c->N * c->N;
-	int bits = 1;
-	while ((1ull << bits) < cells) bits++;
-	return bits;
+	for (int b = 0; b < 2; b++)
+	{
+		cudaFree(p->x[b]); cudaFree(p->y[b]); cudaFree(p->z[b]); cudaFree(p->qx[b]); cudaFree(p->qy[b]); cudaFree(p->qz[b]);
+		cudaFree(p->id[b]);
+		p->x[b] = p->y[b] = p->z[b] = p->qx[b] = p->qy[b] = p->qz[b] = NULL; p->id[b] = NULL;
+	}
+	cudaFree(p->key); p->key = NULL;
 }
 
 } // namespace
@@ -106,22 +119,28 @@ int key_bits(const gevb_ctx * c)
 extern "C" int gevb_pcls_create(gevb_ctx * c, gevb_pcls ** out, double mass)
 {
 	GEVB_CHECK_ARG(c != NULL && out != NULL, "gevb_pcls_create: NULL argument");
-	GEVB_CHECK_ARG((uint64_t) c->nzl * c->N * c->N <= (1ull << 32), "gevb_pcls_create: local slab has more than 2^32 cells");
+	BrickGeom G;
+	G.N = c->N; G.nzl = c->nzl; G.z0 = c->z0;
+	G.nbx = G.nby = (c->N + GEVB_BRICK - 1) / GEVB_BRICK;
+	G.nbz = (c->nzl + GEVB_BRICK - 1) / GEVB_BRICK;
+	const uint64_t ncells = (uint64_t) G.nbx * G.nby * G.nbz * GEVB_BRICK_CELLS;
+	GEVB_CHECK_ARG(ncells < (1ull << 31), "gevb_pcls_create: local slab has more than 2^31 cells");
+	G.nbricks = (uint32_t) (ncells / GEVB_BRICK_CELLS); G.ncells = (uint32_t) ncells;
+	CUDA_TRY(cudaSetDevice(c->device));
 	gevb_pcls * p = new gevb_pcls();
 	memset(p, 0, sizeof(*p));
-	p->ctx = c; p->mass = mass;
+	p->ctx = c; p->mass = mass; p->geom = G;
+	const size_t bytes = ((size_t) G.ncells + 1) * sizeof(uint32_t);
+	cudaError_t e1 = cudaMalloc(&p->cell_count, bytes), e2 = cudaMalloc(&p->cell_start, bytes);
+	if (e1 != cudaSuccess || e2 != cudaSuccess)
+	{
+		cudaFree(p->cell_count); cudaFree(p->cell_start); delete p;
+		GEVB_FAIL("gevb_pcls_create: cudaMalloc of the cell tables (2 x %zu bytes) failed", bytes);
+	}
+	CUDA_TRY(cudaMemsetAsync(p->cell_count, 0, bytes, c->stream));
+	CUDA_TRY(cudaMemsetAsync(p->cell_start, 0, bytes, c->stream));
 	*out = p;
 	return 0;
-}
-
-static void free_arrays(gevb_pcls * p)
-{
-	for (int b = 0; b < 2; b++)
-	{
-		cudaFree(p->x[b]); cudaFree(p->y[b]); cudaFree(p->z[b]); cudaFree(p->qx[b]); cudaFree(p->qy[b]); cudaFree(p->qz[b]);
-		cudaFree(p->id[b]); cudaFree(p->key[b]); cudaFree(p->perm[b]);
-		p->x[b] = p->y[b] = p->z[b] = p->qx[b] = p->qy[b] = p->qz[b] = NULL; p->id[b] = NULL; p->key[b] = p->perm[b] = NULL;
-	}
 }
 
 extern "C" int gevb_pcls_destroy(gevb_pcls * p)
@@ -130,18 +149,19 @@ extern "C" int gevb_pcls_destroy(gevb_pcls * p)
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
 	free_arrays(p);
+	cudaFree(p->cell_count); cudaFree(p->cell_start);
 	delete p;
 	return 0;
 }
 
 extern "C" double gevb_pcls_mass(gevb_pcls * p) { return p ? p->mass : 0.; }
 
-// grow capacity, keeping the live particles
+// grow capacity, keeping the live particles (and their keys)
 int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)
 {
 	if (cap <= p->cap) return 0;
 	gevb_ctx * c = p->ctx;
-	GEVB_CHECK_ARG(cap < (1ll << 32), "particles: more than 2^32 particles on one rank");
+	GEVB_CHECK_ARG(cap < (1ll << 32) - 1, "particles: more than 2^32 particles on one rank");
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	gevb_pcls old = *p;
 	for (int b = 0; b < 2; b++)
@@ -149,50 +169,55 @@ int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)
 		double ** arrs[6] = {&p->x[b], &p->y[b], &p->z[b], &p->qx[b], &p->qy[b], &p->qz[b]};
 		for (int a = 0; a < 6; a++) CUDA_TRY(cudaMalloc(arrs[a], sizeof(double) * cap));
 		CUDA_TRY(cudaMalloc(&p->id[b], sizeof(int64_t) * cap));
-		CUDA_TRY(cudaMalloc(&p->key[b], sizeof(uint32_t) * cap));
-		CUDA_TRY(cudaMalloc(&p->perm[b], sizeof(uint32_t) * cap));
 	}
-	if (old.n > 0)
+	CUDA_TRY(cudaMalloc(&p->key, sizeof(uint32_t) * cap));
+	if (old.cap > 0)
 	{
+		// the live arrays may hold more than n records (received particles appended behind them)
 		const int s = old.cur, d = 0;
-		CUDA_TRY(cudaMemcpy(p->x[d], old.x[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->y[d], old.y[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->z[d], old.z[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->qx[d], old.qx[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->qy[d], old.qy[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->qz[d], old.qz[s], sizeof(double) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->id[d], old.id[s], sizeof(int64_t) * old.n, cudaMemcpyDeviceToDevice));
-		CUDA_TRY(cudaMemcpy(p->key[d], old.key[s], sizeof(uint32_t) * old.n, cudaMemcpyDeviceToDevice));
+		const size_t m = (size_t) old.cap;
+		CUDA_TRY(cudaMemcpy(p->x[d], old.x[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->y[d], old.y[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->z[d], old.z[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qx[d], old.qx[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qy[d], old.qy[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->qz[d], old.qz[s], sizeof(double) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->id[d], old.id[s], sizeof(int64_t) * m, cudaMemcpyDeviceToDevice));
+		CUDA_TRY(cudaMemcpy(p->key, old.key, sizeof(uint32_t) * m, cudaMemcpyDeviceToDevice));
 	}
 	p->cur = 0; p->cap = cap;
 	free_arrays(&old);
 	return 0;
 }
 
-// restore the cell-sorted order: keys (if not already valid) -> radix sort of (key, index) -> gather
-int gevb_pcls_sort(gevb_pcls * p, bool keys_valid, bool full_bits)
+// restore the brick-major cell order: [histogram ->] exclusive scan -> scatter
+int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 {
 	gevb_ctx * c = p->ctx;
-	if (p->n == 0) return 0;
+	const BrickGeom & G = p->geom;
 	const int s = p->cur, d = 1 - p->cur;
 	const double dx = 1.0 / (double) c->N;
-	const int grid = gevb_grid(c, (size_t) p->n, 256);
-	if (!keys_valid)
-		k_make_keys<<<grid, 256, 0, c->stream>>>(p->n, p->x[s], p->y[s], p->z[s], c->N, c->z0, dx, p->key[s], p->perm[s]);
-	else
-		k_iota<<<grid, 256, 0, c->stream>>>(p->n, p->perm[s]);
-	KERNEL_CHECK(c);
+	if (!hist_valid && n_in > 0)
+	{
+		k_make_keys<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(G, 0, n_in, p->x[s], p->y[s], p->z[s], dx, p->key, p->cell_count);
+		KERNEL_CHECK(c);
+	}
 	size_t temp_bytes = 0;
-	const int bits = full_bits ? 32 : key_bits(c);
-	CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, temp_bytes, p->key[s], p->key[d], p->perm[s], p->perm[d], p->n, 0, bits, c->stream));
+	const int items = (int) (G.ncells + 1);
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, temp_bytes, p->cell_count, p->cell_start, items, c->stream));
 	void * temp;
 	GEVB_TRY(gevb_ctx_scratch(c, temp_bytes, &temp));
-	CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, p->key[s], p->key[d], p->perm[s], p->perm[d], p->n, 0, bits, c->stream));
-	c->launches += (bits + 7) / 8 + 1;
-	k_permute<<<grid, 256, 0, c->stream>>>(p->n, p->perm[d], p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
-	                                       p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
-	KERNEL_CHECK(c);
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, p->cell_count, p->cell_start, items, c->stream));
+	c->launches += 2;
+	if (n_in > 0)
+	{
+		k_scatter<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->key, p->cell_start, p->cell_count,
+			p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+			p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+		KERNEL_CHECK(c);
+	}
 	p->cur = d;
+	p->n = n_out;
 	return 0;
 }
 
@@ -205,6 +230,7 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 	CUDA_TRY(cudaSetDevice(c->device));
 	const double dx = 1.0 / (double) c->N;
 	const int64_t chunk = 1 << 24;
+	const int64_t n_before = p->n;
 	unsigned long long * counter = (unsigned long long *) (c->d_red + 4000);
 	for (int64_t off = 0; off < n; off += chunk)
 	{
@@ -240,8 +266,9 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		p->n += (int64_t) nloc;
 	}
-	GEVB_TRY(gevb_pcls_sort(p, false, false));
-	return 0;
+	if (p->n == n_before) return 0;
+	// keys + histogram of everything (old particles included: their keys are not kept between calls)
+	return gevb_pcls_rebin(p, p->n, p->n, false);
 }
 
 extern "C" int gevb_pcls_count(gevb_pcls * p, int64_t * n_local)
@@ -286,12 +313,8 @@ extern "C" int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts)
 	const size_t cells = (size_t) c->nzl * c->plane();
 	void * stage;
 	GEVB_TRY(gevb_ctx_scratch(c, cells * sizeof(uint32_t), &stage));
-	CUDA_TRY(cudaMemsetAsync(stage, 0, cells * sizeof(uint32_t), c->stream));
-	if (p->n > 0)
-	{
-		k_histogram<<<gevb_grid(c, (size_t) p->n, 256), 256, 0, c->stream>>>(p->n, p->key[p->cur], (uint32_t *) stage);
-		KERNEL_CHECK(c);
-	}
+	k_counts_out<<<gevb_grid(c, cells, 256), 256, 0, c->stream>>>(p->geom, p->cell_start, (uint32_t *) stage);
+	KERNEL_CHECK(c);
 	CUDA_TRY(cudaMemcpyAsync(counts, stage, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return 0;

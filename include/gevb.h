@@ -112,12 +112,13 @@ int gevb_plan_execute(gevb_plan * plan, int direction);
 /* ---- particles ---------------------------------------------------------------
  * Particles::initialize + addParticle_global (ic_basic.hpp:1990,1429): particles
  * whose cell lies in this rank's slab are kept, the rest ignored.  Storage is
- * cell-sorted FP64 structure-of-arrays; cell = floor(pos/dx) per axis.          */
+ * cell-sorted FP64 structure-of-arrays (bricks of 8^3 cells, then cells inside the
+ * brick); cell = floor(pos/dx) per axis.                                      */
 int gevb_pcls_create(gevb_ctx * ctx, gevb_pcls ** out, double mass);
 int gevb_pcls_destroy(gevb_pcls * p);
 int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const double * pos, const double * vel);
 int gevb_pcls_count(gevb_pcls * p, int64_t * n_local);
-int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);   /* cell-sorted order */
+int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);   /* storage (brick-major cell) order */
 /* bit-exact contract: particles per cell of the local slab, uint32[nz_local][N][N] */
 int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts);
 double gevb_pcls_mass(gevb_pcls * p);

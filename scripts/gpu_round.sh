@@ -12,5 +12,5 @@ echo "== reference arm"; timeout 900 python bench.py --impl reference --steps 3 
 echo "== ncu launch list (same command, bounded)"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1; echo "ncu list exit $?"
 echo "== ncu full (256^3, top kernels)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_deposit|k_geodesic|k_prepare_tensor|k_evolve_vector|k_ftscalar|k_permute' -s 14 -c 8 -o $OUT/prof python bench.py --ngrid 256 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_deposit|k_geodesic|k_scatter|k_prepare_tensor' -s 8 -c 6 -o $OUT/prof python bench.py --ngrid 256 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
 ls -la $OUT
