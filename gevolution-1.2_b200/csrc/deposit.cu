@@ -5,10 +5,10 @@
 //   projection_Tij_project       gevolution.hpp:1173-1297
 //   scalarProjectionCIC_project  LATfield2 (main.cpp:402), plain CIC
 //
-// One thread block per brick of 8^3 cells (particles are stored brick by brick
-// and, inside a brick, cell by cell -- gevb_internal.cuh).  The block owns a
-// 9^3-site shared-memory tile per target component (the brick's sites plus the
-// upper apron the CIC cloud reaches) and a 9^3 tile of phi.
+// One thread block per brick of 16 x 8 x 4 cells (particles are stored brick by
+// brick and, inside a brick, cell by cell -- gevb_internal.cuh).  The block owns a
+// 17 x 9 x 5-site shared-memory tile per target component (the brick's sites plus
+// the upper apron the CIC cloud reaches) and a tile of phi of the same shape.
 //
 //   1. every thread owns cells of the brick and accumulates the contributions of
 //      the cell's particles in registers -- exactly the reference's per-cell
@@ -30,8 +30,10 @@
 
 namespace {
 
-#define DT_EDGE 9
-#define DT_SITES 729
+#define DX (GEVB_BX + 1)
+#define DY (GEVB_BY + 1)
+#define DZ (GEVB_BZ + 1)
+#define DT_SITES (DX * DY * DZ)
 #define DEP_LIGHT 4
 #define DEP_THREADS 256
 
@@ -58,7 +60,7 @@ __host__ __device__ constexpr int acc_corner(int what, int a)
 {
 	return what == DEP_T00 ? a : what == DEP_TIJ ? tij_corner(a) : what == DEP_T00_TIJ ? (a < 8 ? a : tij_corner(a - 8)) : t0i_corner(a);
 }
-__host__ __device__ constexpr int corner_offset(int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * DT_EDGE + (k & 1) * DT_EDGE * DT_EDGE; }
+__host__ __device__ constexpr int corner_offset(int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * DX + (k & 1) * DX * DY; }
 
 struct DParams
 {
@@ -73,19 +75,19 @@ struct DParams
 
 // contributions of one particle to the cell's accumulators
 template <int WHAT, bool HAS_PHI>
-__device__ __forceinline__ void accumulate(double * acc, const DParams & D, uint32_t i, double refx, double refy, double refz, const double * cphi)
+__device__ __forceinline__ void accumulate(double * acc, const DParams & D, const double * pv, double refx, double refy, double refz, const double * cphi)
 {
 	double up[3], dn[3];
 	if (D.pow2)
 	{
-		up[0] = (D.x[i] - refx) * D.rN; up[1] = (D.y[i] - refy) * D.rN; up[2] = (D.z[i] - refz) * D.rN;   // == / dx exactly (dx = 2^-k)
+		up[0] = (pv[0] - refx) * D.rN; up[1] = (pv[1] - refy) * D.rN; up[2] = (pv[2] - refz) * D.rN;      // == / dx exactly (dx = 2^-k)
 	}
 	else
 	{
-		up[0] = (D.x[i] - refx) / D.dx; up[1] = (D.y[i] - refy) / D.dx; up[2] = (D.z[i] - refz) / D.dx;   // gevolution.hpp:981 / :1101 / :1231
+		up[0] = (pv[0] - refx) / D.dx; up[1] = (pv[1] - refy) / D.dx; up[2] = (pv[2] - refz) / D.dx;      // gevolution.hpp:981 / :1101 / :1231
 	}
 	dn[0] = 1.0 - up[0]; dn[1] = 1.0 - up[1]; dn[2] = 1.0 - up[2];                                          // :982
-	const double q0 = D.qx[i], q1 = D.qy[i], q2 = D.qz[i];
+	const double q0 = pv[3], q1 = pv[4], q2 = pv[5];
 	if (WHAT == DEP_T0I)
 	{
 		double w = D.mass * q0;                                                    // :1107
@@ -155,114 +157,217 @@ __device__ __forceinline__ void finalize(double * acc, const DParams & D, const 
 	}
 }
 
+__device__ __forceinline__ void cp_async8(void * smem_dst, const void * gmem_src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void * smem_dst, const void * gmem_src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+#define DEP_CELLTAB (GEVB_BRICK_CELLS + 4)      // 513 prefix sums of a brick, padded
+#define DEP_PCAP 512                            // particles of a brick staged in shared memory (the rest is read from HBM directly)
+#define DEP_STAGE_DOUBLES (DT_SITES + 6 * DEP_PCAP + DEP_CELLTAB / 2)   // one pipeline stage: phi tile, 6 particle arrays, cell table
+
+// asynchronous copy (LDGSTS) of everything a brick's deposit reads: its slice of cell_start[], the phi tile and the
+// first DEP_PCAP particles.  For the tile a thread keeps its (tx, ty) column and walks z.
+template <bool HAS_PHI>
+__device__ __forceinline__ void stage_brick(const DParams & D, uint32_t brick, uint32_t first, uint32_t last, double * stage)
+{
+	const BrickGeom & G = D.G;
+	double * tphi = stage, * part = stage + DT_SITES;
+	uint32_t * ctab = (uint32_t *) (stage + DT_SITES + 6 * DEP_PCAP);
+	if (first == last) return;
+	const uint32_t * src = D.cell_start + (size_t) brick * GEVB_BRICK_CELLS;
+	for (int k = threadIdx.x; k <= GEVB_BRICK_CELLS; k += DEP_THREADS) cp_async4(ctab + k, src + k);
+	const uint32_t n = last - first < DEP_PCAP ? last - first : DEP_PCAP;
+	for (uint32_t k = threadIdx.x; k < n; k += DEP_THREADS)
+	{
+		cp_async8(part + k, D.x + first + k); cp_async8(part + DEP_PCAP + k, D.y + first + k); cp_async8(part + 2 * DEP_PCAP + k, D.z + first + k);
+		cp_async8(part + 3 * DEP_PCAP + k, D.qx + first + k); cp_async8(part + 4 * DEP_PCAP + k, D.qy + first + k); cp_async8(part + 5 * DEP_PCAP + k, D.qz + first + k);
+	}
+	if (HAS_PHI && threadIdx.x < DX * DY)
+	{
+		int x0, y0, zl0;
+		brick_origin(G, brick, x0, y0, zl0);
+		const int tx = threadIdx.x % DX, ty = threadIdx.x / DX;
+		const size_t gcol = (size_t) ((y0 + ty) % G.N) * G.N + (x0 + tx) % G.N;
+		#pragma unroll
+		for (int tz = 0; tz < DZ; tz++)
+		{
+			const int plane = zl0 + tz + 1;
+			if (plane > G.nzl + 1) break;                       // partial brick at the top of the slab: never read
+			cp_async8(tphi + (tz * DY + ty) * DX + tx, D.phi + (size_t) plane * G.N * G.N + gcol);
+		}
+	}
+}
+
+// particle i of the current brick: from the staged copy if it is there, else from HBM
+__device__ __forceinline__ void load_particle(const DParams & D, const double * part, uint32_t bfirst, uint32_t i, double * pv)
+{
+	const uint32_t k = i - bfirst;
+	if (k < DEP_PCAP)
+	{
+		#pragma unroll
+		for (int a = 0; a < 6; a++) pv[a] = part[a * DEP_PCAP + k];
+	}
+	else
+	{
+		pv[0] = D.x[i]; pv[1] = D.y[i]; pv[2] = D.z[i]; pv[3] = D.qx[i]; pv[4] = D.qy[i]; pv[5] = D.qz[i];
+	}
+}
+
+__device__ __forceinline__ void brick_range(const DParams & D, uint32_t b, uint32_t & first, uint32_t & last)
+{
+	first = last = 0;
+	if (b < D.G.nbricks) { first = __ldg(D.cell_start + (size_t) b * GEVB_BRICK_CELLS); last = __ldg(D.cell_start + (size_t) (b + 1) * GEVB_BRICK_CELLS); }
+}
+
+// Persistent blocks walk the bricks with stride gridDim.x in a two-stage software pipeline: while brick k is
+// accumulated and flushed, everything brick k+1 needs is in flight into the other shared-memory stage, and the
+// particle range of brick k+2 is being fetched into registers.
 template <int WHAT, bool HAS_PHI>
 __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
 {
 	constexpr int NACC = dep_nacc(WHAT), NCOMP = dep_ncomp(WHAT);
 	extern __shared__ double smem[];
-	double * tile = smem;                                   // [NCOMP][729]
-	double * tphi = smem + NCOMP * DT_SITES;                // [729]
-	__shared__ uint32_t heavy_first[GEVB_BRICK_CELLS], heavy_last[GEVB_BRICK_CELLS];
+	double * tile = smem;                                   // [NCOMP][DT_SITES] accumulators
+	double * stages = smem + NCOMP * DT_SITES;              // [2][DEP_STAGE_DOUBLES]
 	__shared__ uint16_t heavy_cell[GEVB_BRICK_CELLS];
 	__shared__ int nheavy;
 
 	const BrickGeom & G = D.G;
-	const uint32_t brick = blockIdx.x;
-	const uint32_t key0 = brick * GEVB_BRICK_CELLS;
-	if (D.cell_start[key0] == D.cell_start[key0 + GEVB_BRICK_CELLS]) return;   // empty brick
-	int x0, y0, zl0;
-	brick_origin(G, brick, x0, y0, zl0);
-
-	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES; idx += DEP_THREADS) tile[idx] = 0.;
+	const int tcol = threadIdx.x, ttx = tcol % DX, tty = tcol / DX;      // this thread's column of the tile (flush)
+	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES + 2 * DEP_STAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
 	if (threadIdx.x == 0) nheavy = 0;
-	for (int s = threadIdx.x; s < DT_SITES; s += DEP_THREADS)
-	{
-		double v = 0.;
-		if (HAS_PHI)
-		{
-			const int tz = s / (DT_EDGE * DT_EDGE), ty = (s / DT_EDGE) % DT_EDGE, tx = s % DT_EDGE;
-			const int plane = zl0 + tz + 1;
-			if (plane <= G.nzl + 1) v = __ldg(D.phi + ((size_t) plane * G.N + (y0 + ty) % G.N) * G.N + (x0 + tx) % G.N);
-		}
-		tphi[s] = v;
-	}
 	__syncthreads();
-
-	// ---- light pass: one thread per cell, DEP_LIGHT particles at most -------------------------
-	for (int c = threadIdx.x; c < GEVB_BRICK_CELLS; c += DEP_THREADS)
+	uint32_t brick = blockIdx.x;
+	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
+	brick_range(D, brick, first, last);
+	brick_range(D, brick + gridDim.x, nfirst, nlast);
+	stage_brick<HAS_PHI>(D, brick, first, last, stages);
+	cp_async_commit();
+	int cur = 0;
+	while (brick < G.nbricks)
 	{
-		const int sx = c & 7, sy = (c >> 3) & 7, sz = c >> 6;
-		const int site = (sz * DT_EDGE + sy) * DT_EDGE + sx;
-		const uint32_t first = D.cell_start[key0 + c], last = D.cell_start[key0 + c + 1];
-		const uint32_t n = last - first;
-		double acc[NACC];
-		#pragma unroll
-		for (int a = 0; a < NACC; a++) acc[a] = 0.;
-		double cphi[8];
-		#pragma unroll
-		for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];       // :967-974
-		if (n > 0)
+		const uint32_t nbrick = brick + gridDim.x;
+		brick_range(D, nbrick + gridDim.x, nnfirst, nnlast);                 // consumed at the end of this iteration
+		if (nbrick < G.nbricks) stage_brick<HAS_PHI>(D, nbrick, nfirst, nlast, stages + (cur ^ 1) * DEP_STAGE_DOUBLES);
+		cp_async_commit();
+		if (first != last)
 		{
-			const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;   // referPos, :963
-			const uint32_t nl = n < DEP_LIGHT ? n : DEP_LIGHT;
-			for (uint32_t j = 0; j < nl; j++) accumulate<WHAT, HAS_PHI>(acc, D, first + j, refx, refy, refz, cphi);
-			finalize<WHAT>(acc, D, cphi);
-			if (n > DEP_LIGHT)
+			int x0, y0, zl0;
+			brick_origin(G, brick, x0, y0, zl0);
+			cp_async_wait<1>();                             // everything but the newest group: this brick's stage has landed
+			__syncthreads();
+			const double * tphi = stages + cur * DEP_STAGE_DOUBLES;
+			const double * part = tphi + DT_SITES;
+			const uint32_t * ctab = (const uint32_t *) (part + 6 * DEP_PCAP);
+
+			// ---- light pass: one thread per cell, DEP_LIGHT particles at most -------------------------
+			#pragma unroll 1
+			for (int cc = 0; cc < GEVB_BRICK_CELLS / DEP_THREADS; cc++)
 			{
-				const int h = atomicAdd(&nheavy, 1);
-				heavy_cell[h] = (uint16_t) c; heavy_first[h] = first + DEP_LIGHT; heavy_last[h] = last;
+				const int c = cc * DEP_THREADS + threadIdx.x;
+				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
+				const int site = (sz * DY + sy) * DX + sx;
+				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
+				const uint32_t n = clast - cfirst;
+				double acc[NACC];
+				#pragma unroll
+				for (int a = 0; a < NACC; a++) acc[a] = 0.;
+				if (n > 0)
+				{
+					double cphi[8];
+					#pragma unroll
+					for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];   // :967-974
+					const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;   // referPos, :963
+					const uint32_t nl = n < DEP_LIGHT ? n : DEP_LIGHT;
+					for (uint32_t j = 0; j < nl; j++)
+					{
+						double pv[6];
+						load_particle(D, part, first, cfirst + j, pv);
+						accumulate<WHAT, HAS_PHI>(acc, D, pv, refx, refy, refz, cphi);
+					}
+					finalize<WHAT>(acc, D, cphi);
+					if (n > DEP_LIGHT)
+					{
+						const int h = atomicAdd(&nheavy, 1);
+						heavy_cell[h] = (uint16_t) c;
+					}
+				}
+				// eight corner phases: within a phase every thread updates a different site
+				#pragma unroll
+				for (int k = 0; k < 8; k++)
+				{
+					if (n > 0)
+					{
+						#pragma unroll
+						for (int a = 0; a < NACC; a++)
+							if (acc_corner(WHAT, a) == k) tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(k)] += acc[a];
+					}
+					__syncthreads();
+				}
 			}
-		}
-		// eight corner phases: within a phase every thread updates a different site
-		#pragma unroll
-		for (int k = 0; k < 8; k++)
-		{
-			if (n > 0)
+
+			// ---- heavy pass: one warp per crowded cell -------------------------------------------------
+			const int nh = nheavy;
+			for (int h = threadIdx.x >> 5; h < nh; h += DEP_THREADS / 32)
 			{
+				const int c = heavy_cell[h];
+				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
+				const int site = (sz * DY + sy) * DX + sx;
+				double acc[NACC];
+				#pragma unroll
+				for (int a = 0; a < NACC; a++) acc[a] = 0.;
+				double cphi[8];
+				#pragma unroll
+				for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];
+				const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;
+				const uint32_t hlast = ctab[c + 1];
+				for (uint32_t i = ctab[c] + DEP_LIGHT + (threadIdx.x & 31); i < hlast; i += 32)
+				{
+					double pv[6];
+					load_particle(D, part, first, i, pv);
+					accumulate<WHAT, HAS_PHI>(acc, D, pv, refx, refy, refz, cphi);
+				}
 				#pragma unroll
 				for (int a = 0; a < NACC; a++)
-					if (acc_corner(WHAT, a) == k) tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(k)] += acc[a];
+					for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+				finalize<WHAT>(acc, D, cphi);
+				if ((threadIdx.x & 31) == 0)
+				{
+					#pragma unroll
+					for (int a = 0; a < NACC; a++) atomicAdd(&tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(acc_corner(WHAT, a))], acc[a]);
+				}
 			}
-			__syncthreads();
-		}
-	}
+			__syncthreads();                                // stage `cur` is free from here on
+			if (threadIdx.x == 0) nheavy = 0;
 
-	// ---- heavy pass: one warp per crowded cell -------------------------------------------------
-	const int nh = nheavy;
-	for (int h = threadIdx.x >> 5; h < nh; h += DEP_THREADS / 32)
-	{
-		const int c = heavy_cell[h];
-		const int sx = c & 7, sy = (c >> 3) & 7, sz = c >> 6;
-		const int site = (sz * DT_EDGE + sy) * DT_EDGE + sx;
-		double acc[NACC];
-		#pragma unroll
-		for (int a = 0; a < NACC; a++) acc[a] = 0.;
-		double cphi[8];
-		#pragma unroll
-		for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];
-		const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;
-		for (uint32_t i = heavy_first[h] + (threadIdx.x & 31); i < heavy_last[h]; i += 32) accumulate<WHAT, HAS_PHI>(acc, D, i, refx, refy, refz, cphi);
-		#pragma unroll
-		for (int a = 0; a < NACC; a++)
-			for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-		finalize<WHAT>(acc, D, cphi);
-		if ((threadIdx.x & 31) == 0)
-		{
-			#pragma unroll
-			for (int a = 0; a < NACC; a++) atomicAdd(&tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(acc_corner(WHAT, a))], acc[a]);
+			// ---- flush the tile: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row;
+			//      the tile is left zeroed for the next brick
+			if (tcol < DX * DY)
+			{
+				const size_t gcol = (size_t) ((y0 + tty) % G.N) * G.N + (x0 + ttx) % G.N;
+				#pragma unroll
+				for (int tz = 0; tz < DZ; tz++)
+				{
+					const int s = (tz * DY + tty) * DX + ttx;
+					const size_t off = (size_t) (zl0 + tz + 1) * G.N * G.N + gcol;
+					#pragma unroll
+					for (int k = 0; k < NCOMP; k++)
+					{
+						const double v = tile[k * DT_SITES + s];
+						if (v != 0.) { atomicAdd(D.out[k] + off, v); tile[k * DT_SITES + s] = 0.; }
+					}
+				}
+			}
 		}
-	}
-	__syncthreads();
-
-	// ---- flush the tile: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row
-	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES; idx += DEP_THREADS)
-	{
-		const double v = tile[idx];
-		if (v == 0.) continue;
-		const int comp = idx / DT_SITES, s = idx - comp * DT_SITES;
-		const int tz = s / (DT_EDGE * DT_EDGE), ty = (s / DT_EDGE) % DT_EDGE, tx = s % DT_EDGE;
-		const size_t off = ((size_t) (zl0 + tz + 1) * G.N + (y0 + ty) % G.N) * G.N + (x0 + tx) % G.N;
-		atomicAdd(D.out[comp] + off, v);
+		brick = nbrick; cur ^= 1;
+		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
 	}
 }
 
@@ -287,16 +392,18 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 	D.x = p->x[b]; D.y = p->y[b]; D.z = p->z[b]; D.qx = p->qx[b]; D.qy = p->qy[b]; D.qz = p->qz[b];
 	D.phi = phi ? phi->data : NULL;
 	for (int k = 0; k < 7; k++) D.out[k] = k < dep_ncomp(WHAT) ? out[k] : NULL;
-	const size_t smem = (size_t) (dep_ncomp(WHAT) + 1) * DT_SITES * sizeof(double);
+	const size_t smem = ((size_t) dep_ncomp(WHAT) * DT_SITES + 2 * DEP_STAGE_DOUBLES) * sizeof(double);
+	const uint32_t persistent = (uint32_t) c->num_sms * 2;
+	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;
 	if (phi)
 	{
 		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, true><<<D.G.nbricks, DEP_THREADS, smem, c->stream>>>(D);
+		k_deposit<WHAT, true><<<grid, DEP_THREADS, smem, c->stream>>>(D);
 	}
 	else
 	{
 		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, false><<<D.G.nbricks, DEP_THREADS, smem, c->stream>>>(D);
+		k_deposit<WHAT, false><<<grid, DEP_THREADS, smem, c->stream>>>(D);
 	}
 	KERNEL_CHECK(c);
 	return 0;

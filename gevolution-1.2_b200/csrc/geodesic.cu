@@ -3,12 +3,12 @@
 //   Particles::updateVel + update_q / update_q_Newton        main.cpp:775; gevolution.hpp:570-678, 709-776
 //   Particles::moveParticles + update_pos / update_pos_Newton main.cpp:798; gevolution.hpp:810-871, 900-903
 //
-// One thread block per brick of 8^3 cells (particles are stored brick by brick,
-// gevb_internal.cuh): the block stages the 10^3-site tile (one ghost layer below
-// and above) of phi, chi and B_i in shared memory with periodic wrap applied
-// once per tile, then every thread takes particles of the brick from the
-// coalesced SoA stream (48 B in, 24 or 48 B out) and gathers its ~90 stencil
-// values from shared memory at compile-time offsets.
+// One thread block per brick of 16 x 8 x 4 cells (particles are stored brick by
+// brick, gevb_internal.cuh): the block stages the 18 x 10 x 6-site tile (one
+// ghost layer below and above) of phi, chi and B_i in shared memory with the
+// periodic wrap applied once per tile, then every thread takes particles of
+// the brick from the coalesced SoA stream (48 B in, 24 or 48 B out) and gathers
+// its ~90 stencil values from shared memory at compile-time offsets.
 // The fused kernel does kick and drift in one pass: between main.cpp:775 and
 // :798 only `a` changes (rungekutta4bg, :792), positions and fields do not.
 // After a drift the new sort key is written and histogrammed (first half of the
@@ -19,8 +19,10 @@
 
 namespace {
 
-#define TILE_EDGE 10
-#define TILE_SITES 1000
+#define TX (GEVB_BX + 2)
+#define TY (GEVB_BY + 2)
+#define TZ (GEVB_BZ + 2)
+#define TILE_SITES (TX * TY * TZ)
 
 struct GParams
 {
@@ -28,6 +30,7 @@ struct GParams
 	int nranks, pow2;
 	size_t plane, csB;
 	double dx, rN;             // rN = (double) N: pos/dx == pos*rN exactly when N is a power of two
+	double binv_kick, binv_drift;   // 1 / params[1] (the a^2 N that un-scales the stored B, main.cpp:772)
 	const double * phi, * chi, * B;
 	int nfmax;                 // how many of {phi, chi, B} the tile needs
 	// kick
@@ -46,6 +49,7 @@ struct GParams
 
 // scaled coordinate pos/dx (LATfield2 drivers use pos/dx; the product is bit-identical for power-of-two N)
 __device__ __forceinline__ double scaled(const GParams & P, double p) { return P.pow2 ? p * P.rN : p / P.dx; }
+__device__ __forceinline__ double by_dx(const GParams & P, double v) { return P.pow2 ? v * P.rN : v / P.dx; }
 __device__ __forceinline__ int cell_scaled(double s, int N)
 {
 	int c = (int) floor(s);
@@ -54,7 +58,7 @@ __device__ __forceinline__ int cell_scaled(double s, int N)
 }
 
 // T(f, i, j, k): value of tile component f at the particle's cell + (i, j, k), i, j, k in {-1, 0, 1}
-#define T(f, i, j, k) t[(f) * TILE_SITES + (k) * (TILE_EDGE * TILE_EDGE) + (j) * TILE_EDGE + (i)]
+#define T(f, i, j, k) t[(f) * TILE_SITES + (k) * (TX * TY) + (j) * TX + (i)]
 
 // one-sided CIC gradient, gevolution.hpp:585-596 (GRADIENT_ORDER == 1)
 __device__ __forceinline__ void grad_cic(const double * t, int f, const double * r, double * g)
@@ -89,7 +93,7 @@ __device__ __forceinline__ double tri_cic(const double * t, int f, const double 
 	return v;
 }
 
-// update_q (gevolution.hpp:570-678) / update_q_Newton (:709-776); returns v^2/a^2
+// update_q (gevolution.hpp:570-678) / update_q_Newton (:709-776); returns q^2 after the kick
 __device__ __forceinline__ double kick(const GParams & P, const double * t, const double * r, double * q)
 {
 	double g[3], v2;
@@ -130,13 +134,14 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 			pg2 += r[0] * (1. - r[1]) * ((r[2] - 1.) * T(4, 1, 0, -1) + (1. - 2. * r[2]) * T(4, 1, 0, 0) + r[2] * T(4, 1, 0, 1)) * q[2];
 			pg2 += (1. - r[0]) * r[1] * ((r[2] - 1.) * T(4, 0, 1, -1) + (1. - 2. * r[2]) * T(4, 0, 1, 0) + r[2] * T(4, 0, 1, 1)) * q[2];
 			pg2 += r[0] * r[1] * ((r[2] - 1.) * T(4, 1, 1, -1) + (1. - 2. * r[2]) * T(4, 1, 1, 0) + r[2] * T(4, 1, 1, 1)) * q[2];
-			g[0] += pg0 / P.bscale_kick / e2;                                      // :658-660
-			g[1] += pg1 / P.bscale_kick / e2;
-			g[2] += pg2 / P.bscale_kick / e2;
+			const double s = P.binv_kick / e2;                                     // :658-660 (pg / params[1] / e2)
+			g[0] += pg0 * s;
+			g[1] += pg1 * s;
+			g[2] += pg2 * s;
 		}
 		v2 = 0.;
 		#pragma unroll
-		for (int i = 0; i < 3; i++) { q[i] -= P.dtau_kick * e2 * g[i] / P.dx; v2 += q[i] * q[i]; }   // :664-668
+		for (int i = 0; i < 3; i++) { q[i] -= by_dx(P, P.dtau_kick * e2 * g[i]); v2 += q[i] * q[i]; }   // :664-668
 	}
 	else
 	{
@@ -148,9 +153,9 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 		}
 		v2 = 0.;
 		#pragma unroll
-		for (int i = 0; i < 3; i++) { q[i] -= P.dtau_kick * P.a_kick * g[i] / P.dx; v2 += q[i] * q[i]; }   // :764-768
+		for (int i = 0; i < 3; i++) { q[i] -= by_dx(P, P.dtau_kick * P.a_kick * g[i]); v2 += q[i] * q[i]; }   // :764-768
 	}
-	return v2 / P.a_kick / P.a_kick;                                               // :670 / :770
+	return v2;                                                                     // :670 / :770 return v2/a/a: the monotonic division is applied to the maximum on the host
 }
 
 // update_pos (gevolution.hpp:810-871) / update_pos_Newton (:900-903)
@@ -185,7 +190,7 @@ __device__ __forceinline__ void drift(const GParams & P, const double * t, const
 		b[0] += T(2, 0, 1, 1) * r[1] * r[2];                                       // :862
 		b[2] += T(4, 1, 1, 0) * r[0] * r[1];                                       // :863
 		#pragma unroll
-		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * (v[l] + b[l] / P.bscale_drift);   // :865
+		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * (v[l] + b[l] * P.binv_drift);     // :865 (b / params[1])
 	}
 	else
 	{
@@ -208,86 +213,137 @@ __device__ __forceinline__ int wrap_index(int v, int N)
 	return v < 0 ? v + N : v;
 }
 
-// MODE 0: kick only, 1: drift only, 2: fused kick + drift.  One block per brick.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_geodesic(GParams P)
+__device__ __forceinline__ void cp_async8(double * smem_dst, const double * gmem_src)
 {
-	extern __shared__ double tile[];
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// asynchronous copy (LDGSTS) of one brick's field tile into shared memory: site (lx, ly, lz) of the tile is
+// lattice site (x0 - 1 + lx, y0 - 1 + ly, local z = zl0 - 1 + lz); a thread keeps its (lx, ly) column and
+// walks z, so the periodic wrap is resolved once per thread and all copies of a thread are in flight together
+__device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, double * tile)
+{
+	if (threadIdx.x >= TX * TY) return;
 	const BrickGeom & G = P.G;
-	const uint32_t brick = blockIdx.x;
-	const uint32_t first = P.cell_start[brick * GEVB_BRICK_CELLS], last = P.cell_start[(brick + 1) * GEVB_BRICK_CELLS];
-	if (first == last) return;
 	int x0, y0, zl0;
 	brick_origin(G, brick, x0, y0, zl0);
-	// stage the field tiles: site (lx, ly, lz) of the tile is lattice site (x0 - 1 + lx, y0 - 1 + ly, local z = zl0 - 1 + lz)
+	const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+	const size_t col = (size_t) wrap_index(y0 - 1 + ly, G.N) * G.N + wrap_index(x0 - 1 + lx, G.N);
+	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
+	#pragma unroll
+	for (int lz = 0; lz < TZ; lz++)
 	{
-		const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
-		for (int idx = threadIdx.x; idx < ncomp * TILE_SITES; idx += blockDim.x)
+		const int plane = zl0 + lz;                              // ghost-offset plane index of local z = zl0 - 1 + lz
+		if (plane > G.nzl + 1) break;                            // partial brick at the top of the slab: never read
+		const size_t off = (size_t) plane * P.plane + col;
+		double * d = tile + (lz * TY + ly) * TX + lx;
+		if (ncomp >= 1) cp_async8(d, P.phi + off);
+		if (ncomp >= 2) cp_async8(d + TILE_SITES, P.chi + off);
+		if (ncomp >= 5)
 		{
-			const int f = idx / TILE_SITES, s = idx - f * TILE_SITES;
-			const int lz = s / (TILE_EDGE * TILE_EDGE), ly = (s / TILE_EDGE) % TILE_EDGE, lx = s % TILE_EDGE;
-			const int plane = zl0 + lz;                              // ghost-offset plane index of local z = zl0 - 1 + lz
-			double v = 0.;
-			if (plane <= G.nzl + 1)
-			{
-				const size_t off = ((size_t) plane * G.N + wrap_index(y0 - 1 + ly, G.N)) * G.N + wrap_index(x0 - 1 + lx, G.N);
-				const double * src = f == 0 ? P.phi : (f == 1 ? P.chi : P.B + (size_t) (f - 2) * P.csB);
-				v = __ldg(src + off);
-			}
-			tile[idx] = v;
+			cp_async8(d + 2 * TILE_SITES, P.B + off);
+			cp_async8(d + 3 * TILE_SITES, P.B + P.csB + off);
+			cp_async8(d + 4 * TILE_SITES, P.B + 2 * P.csB + off);
 		}
 	}
-	__syncthreads();
-	double vmax = 0.;
-	for (uint32_t i = first + threadIdx.x; i < last; i += blockDim.x)
+}
+
+// first non-empty brick at or after b in this block's stride; returns its particle range
+__device__ __forceinline__ uint32_t next_brick(const GParams & P, uint32_t b, uint32_t & first, uint32_t & last)
+{
+	while (b < P.G.nbricks)
 	{
-		double pos[3] = {P.x[i], P.y[i], P.z[i]};
-		double q[3] = {P.qx[i], P.qy[i], P.qz[i]};
-		// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
-		double r[3], ip;
-		const double * t;
+		first = __ldg(P.cell_start + (size_t) b * GEVB_BRICK_CELLS); last = __ldg(P.cell_start + (size_t) (b + 1) * GEVB_BRICK_CELLS);
+		if (first != last) break;
+		b += gridDim.x;
+	}
+	return b;
+}
+
+// MODE 0: kick only, 1: drift only, 2: fused kick + drift.
+// Persistent blocks walk the bricks with stride gridDim.x; the field tile of the next brick is copied
+// asynchronously into the second shared-memory buffer while the particles of the current one are processed.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_geodesic(GParams P)
+{
+	extern __shared__ double smem[];
+	const BrickGeom & G = P.G;
+	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
+	const int tile_doubles = ncomp * TILE_SITES;
+	uint32_t first = 0, last = 0, nfirst = 0, nlast = 0;
+	uint32_t brick = next_brick(P, blockIdx.x, first, last);
+	if (brick < G.nbricks) stage_tile(P, brick, smem);
+	cp_async_commit();
+	int cur = 0;
+	double vmax = 0.;
+	while (brick < G.nbricks)
+	{
+		const uint32_t nbrick = next_brick(P, brick + gridDim.x, nfirst, nlast);
+		if (nbrick < G.nbricks) stage_tile(P, nbrick, smem + (cur ^ 1) * tile_doubles);
+		cp_async_commit();
+		int x0, y0, zl0;
+		brick_origin(G, brick, x0, y0, zl0);
+		// the first particle of every thread is requested before waiting for the tile
+		uint32_t i = first + threadIdx.x;
+		double pos[3] = {0., 0., 0.}, q[3] = {0., 0., 0.};
+		if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+		cp_async_wait<1>();                                      // everything but the newest group: this brick's tile has landed
+		__syncthreads();
+		const double * tile = smem + cur * tile_doubles;
+		while (i < last)
 		{
-			const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
-			const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
-			r[0] = modf(sx, &ip); r[1] = modf(sy, &ip); r[2] = modf(sz, &ip);
-			t = tile + ((cz - G.z0 - zl0 + 1) * TILE_EDGE + (cy - y0 + 1)) * TILE_EDGE + (cx - x0 + 1);
-		}
-		if (MODE == 0 || MODE == 2)
-		{
-			const double v2 = kick(P, t, r, q);
-			vmax = fmax(vmax, v2);
-			P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
-		}
-		if (MODE == 1 || MODE == 2)
-		{
-			drift(P, t, r, q, pos);
-			pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
-			const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
-			const int zl = cz - G.z0;
-			uint32_t key;
-			if (P.nranks > 1 && (zl < 0 || zl >= G.nzl))
+			// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
+			double r[3];
+			const double * t;
 			{
-				// at most one slab per move (main.cpp:281-286): periodic distance decides the neighbour
-				const int d = (zl + G.N) % G.N;
-				const int dir = d < G.N / 2 ? 1 : 0;
-				const unsigned long long slot = atomicAdd(P.nsend + dir, 1ull);
-				if ((int64_t) slot < P.sendcap)
+				const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
+				const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
+				r[0] = sx - floor(sx); r[1] = sy - floor(sy); r[2] = sz - floor(sz);      // modf(pos/dx) for pos >= 0
+				t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + 1);
+			}
+			if (MODE == 0 || MODE == 2)
+			{
+				const double v2 = kick(P, t, r, q);
+				vmax = fmax(vmax, v2);
+				P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
+			}
+			if (MODE == 1 || MODE == 2)
+			{
+				drift(P, t, r, q, pos);
+				pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
+				const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
+				const int zl = cz - G.z0;
+				uint32_t key;
+				if (P.nranks > 1 && (zl < 0 || zl >= G.nzl))
 				{
-					double * sb = P.sendbuf[dir];
-					sb[slot] = pos[0]; sb[P.sendcap + slot] = pos[1]; sb[2 * P.sendcap + slot] = pos[2];
-					sb[3 * P.sendcap + slot] = q[0]; sb[4 * P.sendcap + slot] = q[1]; sb[5 * P.sendcap + slot] = q[2];
-					sb[6 * P.sendcap + slot] = __longlong_as_double((long long) P.id[i]);
+					// at most one slab per move (main.cpp:281-286): periodic distance decides the neighbour
+					const int d = (zl + G.N) % G.N;
+					const int dir = d < G.N / 2 ? 1 : 0;
+					const unsigned long long slot = atomicAdd(P.nsend + dir, 1ull);
+					if ((int64_t) slot < P.sendcap)
+					{
+						double * sb = P.sendbuf[dir];
+						sb[slot] = pos[0]; sb[P.sendcap + slot] = pos[1]; sb[2 * P.sendcap + slot] = pos[2];
+						sb[3 * P.sendcap + slot] = q[0]; sb[4 * P.sendcap + slot] = q[1]; sb[5 * P.sendcap + slot] = q[2];
+						sb[6 * P.sendcap + slot] = __longlong_as_double((long long) P.id[i]);
+					}
+					key = GEVB_INVALID_KEY;
 				}
-				key = GEVB_INVALID_KEY;
+				else
+				{
+					key = brick_key(G, cx, cy, zl);
+					atomicAdd(P.cell_count + key, 1u);              // histogram of the counting sort (particles.cu)
+				}
+				P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
+				P.key[i] = key;
 			}
-			else
-			{
-				key = brick_key(G, cx, cy, zl);
-				atomicAdd(P.cell_count + key, 1u);                  // histogram of the counting sort (particles.cu)
-			}
-			P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
-			P.key[i] = key;
+			i += blockDim.x;
+			if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
 		}
+		__syncthreads();                                         // tile[cur] is free for the brick after next
+		brick = nbrick; first = nfirst; last = nlast; cur ^= 1;
 	}
 	if (MODE == 0 || MODE == 2)
 	{
@@ -353,9 +409,11 @@ template <int MODE>
 int launch_geodesic(gevb_pcls * p, const GParams & P)
 {
 	gevb_ctx * c = p->ctx;
-	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
-	const size_t smem = (size_t) (ncomp > 0 ? ncomp : 1) * TILE_SITES * sizeof(double);
-	k_geodesic<MODE><<<P.G.nbricks, 256, smem, c->stream>>>(P);
+	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
+	const size_t smem = (size_t) 2 * ncomp * TILE_SITES * sizeof(double);     // two tile buffers
+	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	const uint32_t persistent = (uint32_t) c->num_sms * 2;
+	k_geodesic<MODE><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, 256, smem, c->stream>>>(P);
 	KERNEL_CHECK(c);
 	return 0;
 }
@@ -443,7 +501,7 @@ extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * c
 	CUDA_TRY(cudaSetDevice(c->device));
 	GParams P;
 	base_params(P, p, fields, nfields);
-	P.fn = fn; P.nf_kick = nfields; P.dtau_kick = dtau; P.a_kick = params[0]; P.bscale_kick = params[1];
+	P.fn = fn; P.nf_kick = nfields; P.dtau_kick = dtau; P.a_kick = params[0]; P.bscale_kick = params[1]; P.binv_kick = 1.0 / params[1];
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
@@ -454,7 +512,7 @@ extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * c
 	{
 		CUDA_TRY(cudaMemcpyAsync(c->h_red, P.maxv2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		*maxvel = sqrt(c->h_red[0]);           // LATfield2 updateVel returns sqrt(max v^2), cf. main.cpp:816-822
+		*maxvel = sqrt(c->h_red[0] / params[0] / params[0]);   // callback returns v2/a/a (gevolution.hpp:670); LATfield2 updateVel returns sqrt(max), cf. main.cpp:816-822
 	}
 	return 0;
 }
@@ -469,7 +527,7 @@ extern "C" int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field
 	CUDA_TRY(cudaSetDevice(c->device));
 	GParams P;
 	base_params(P, p, fields, nfields);
-	P.fn = fn; P.nf_drift = nfields; P.dtau_drift = dtau; P.a_drift = params[0]; P.bscale_drift = params[1];
+	P.fn = fn; P.nf_drift = nfields; P.dtau_drift = dtau; P.a_drift = params[0]; P.bscale_drift = params[1]; P.binv_drift = 1.0 / params[1];
 	GEVB_TRY(setup_migration(p, P));
 	if (p->n > 0)
 	{
@@ -494,8 +552,8 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 	GParams P;
 	base_params(P, p, fields, nf);
 	P.fn = fn;
-	P.nf_kick = nfields_kick; P.dtau_kick = dtau_kick; P.a_kick = params_kick[0]; P.bscale_kick = params_kick[1];
-	P.nf_drift = nfields_drift; P.dtau_drift = dtau_drift; P.a_drift = params_drift[0]; P.bscale_drift = params_drift[1];
+	P.nf_kick = nfields_kick; P.dtau_kick = dtau_kick; P.a_kick = params_kick[0]; P.bscale_kick = params_kick[1]; P.binv_kick = 1.0 / params_kick[1];
+	P.nf_drift = nfields_drift; P.dtau_drift = dtau_drift; P.a_drift = params_drift[0]; P.bscale_drift = params_drift[1]; P.binv_drift = 1.0 / params_drift[1];
 	GEVB_TRY(setup_migration(p, P));
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
@@ -509,7 +567,7 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 	{
 		CUDA_TRY(cudaMemcpyAsync(c->h_red, P.maxv2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		*maxvel = sqrt(c->h_red[0]);
+		*maxvel = sqrt(c->h_red[0] / params_kick[0] / params_kick[0]);
 	}
 	return 0;
 }

@@ -121,13 +121,21 @@ struct gevb_plan
 };
 
 // ---------------------------------------------------------------- particles --
-// Particle order: "brick-major cell order".  The local slab is cut into bricks of 8 x 8 x 8 cells; the sort
-// key of a particle is (brick index << 9) | (cell inside the brick), so that the particles of one brick are
-// contiguous (one thread block stages the brick's field tile in shared memory) and, inside the brick, the
-// particles of one cell are contiguous (deposits accumulate per cell).  cell_start[key] is the exclusive
-// prefix sum of the per-cell counts in key order (the counting sort's offsets), kept valid at all times.
-#define GEVB_BRICK 8
+// Particle order: "brick-major cell order".  The local slab is cut into bricks of 16 x 8 x 4 cells (x, y, z);
+// the sort key of a particle is (brick index << 9) | (cell inside the brick), so that the particles of one
+// brick are contiguous (one thread block stages the brick's field tile in shared memory) and, inside the
+// brick, the particles of one cell are contiguous (deposits accumulate per cell).  16 cells along x: the 16
+// lanes of a half-warp that hold consecutive cells touch 16 consecutive doubles of a tile row, which is
+// free of shared-memory bank conflicts for 8-byte accesses.  cell_start[key] is the exclusive prefix sum of
+// the per-cell counts in key order (the counting sort's offsets), kept valid at all times.
+#define GEVB_BX 16
+#define GEVB_BY 8
+#define GEVB_BZ 4
+#define GEVB_BX_BITS 4
+#define GEVB_BY_BITS 3
+#define GEVB_BZ_BITS 2
 #define GEVB_BRICK_CELLS 512
+#define GEVB_BRICK_BITS 9
 #define GEVB_INVALID_KEY 0xffffffffu
 struct BrickGeom
 {
@@ -137,18 +145,13 @@ struct BrickGeom
 };
 __host__ __device__ __forceinline__ uint32_t brick_key(const BrickGeom & G, int cx, int cy, int czl)
 {
-	const uint32_t b = ((uint32_t) (czl >> 3) * G.nby + (uint32_t) (cy >> 3)) * G.nbx + (uint32_t) (cx >> 3);
-	return (b << 9) | (uint32_t) (((czl & 7) << 6) | ((cy & 7) << 3) | (cx & 7));
+	const uint32_t b = ((uint32_t) (czl >> GEVB_BZ_BITS) * G.nby + (uint32_t) (cy >> GEVB_BY_BITS)) * G.nbx + (uint32_t) (cx >> GEVB_BX_BITS);
+	return (b << GEVB_BRICK_BITS) | (uint32_t) (((czl & (GEVB_BZ - 1)) << (GEVB_BX_BITS + GEVB_BY_BITS)) | ((cy & (GEVB_BY - 1)) << GEVB_BX_BITS) | (cx & (GEVB_BX - 1)));
 }
 __host__ __device__ __forceinline__ void brick_origin(const BrickGeom & G, uint32_t brick, int & x0, int & y0, int & zl0)
 {
-	x0 = (int) (brick % G.nbx) * GEVB_BRICK; const uint32_t r = brick / G.nbx;
-	y0 = (int) (r % G.nby) * GEVB_BRICK; zl0 = (int) (r / G.nby) * GEVB_BRICK;
-}
-__host__ __device__ __forceinline__ void key_to_cell(const BrickGeom & G, uint32_t key, int & cx, int & cy, int & czl)
-{
-	brick_origin(G, key >> 9, cx, cy, czl);
-	cx += key & 7; cy += (key >> 3) & 7; czl += (key >> 6) & 7;
+	x0 = (int) (brick % G.nbx) * GEVB_BX; const uint32_t r = brick / G.nbx;
+	y0 = (int) (r % G.nby) * GEVB_BY; zl0 = (int) (r / G.nby) * GEVB_BZ;
 }
 // cell = floor(pos/dx) clamped into the lattice (LATfield2 filing rule, reference uses at gevolution.hpp:979-983)
 __device__ __forceinline__ int cell_of(double p, double dx, int N)

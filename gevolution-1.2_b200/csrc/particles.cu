@@ -121,8 +121,8 @@ extern "C" int gevb_pcls_create(gevb_ctx * c, gevb_pcls ** out, double mass)
 	GEVB_CHECK_ARG(c != NULL && out != NULL, "gevb_pcls_create: NULL argument");
 	BrickGeom G;
 	G.N = c->N; G.nzl = c->nzl; G.z0 = c->z0;
-	G.nbx = G.nby = (c->N + GEVB_BRICK - 1) / GEVB_BRICK;
-	G.nbz = (c->nzl + GEVB_BRICK - 1) / GEVB_BRICK;
+	G.nbx = (c->N + GEVB_BX - 1) / GEVB_BX; G.nby = (c->N + GEVB_BY - 1) / GEVB_BY;
+	G.nbz = (c->nzl + GEVB_BZ - 1) / GEVB_BZ;
 	const uint64_t ncells = (uint64_t) G.nbx * G.nby * G.nbz * GEVB_BRICK_CELLS;
 	GEVB_CHECK_ARG(ncells < (1ull << 31), "gevb_pcls_create: local slab has more than 2^31 cells");
 	G.nbricks = (uint32_t) (ncells / GEVB_BRICK_CELLS); G.ncells = (uint32_t) ncells;
@@ -155,6 +155,13 @@ extern "C" int gevb_pcls_destroy(gevb_pcls * p)
 }
 
 extern "C" double gevb_pcls_mass(gevb_pcls * p) { return p ? p->mass : 0.; }
+
+extern "C" void gevb_brick_dims(int * bx, int * by, int * bz)
+{
+	if (bx) *bx = GEVB_BX;
+	if (by) *by = GEVB_BY;
+	if (bz) *bz = GEVB_BZ;
+}
 
 // grow capacity, keeping the live particles (and their keys)
 int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)

@@ -32,7 +32,7 @@ SYMBOLS = [
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
     "gevb_field_device_ptr", "gevb_projection_init", "gevb_field_updateHalo", "gevb_projection_comm", "gevb_field_sum",
     "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_pcls_create",
-    "gevb_pcls_destroy", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass",
+    "gevb_pcls_destroy", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
@@ -78,6 +78,8 @@ def _declare(L):
     L.gevb_sim_pcls.argtypes = [vp, i]
     L.gevb_pcls_mass.restype = d
     L.gevb_pcls_mass.argtypes = [vp]
+    L.gevb_brick_dims.restype = None
+    L.gevb_brick_dims.argtypes = [C.POINTER(i)] * 3
     L.gevb_timing_class_name.restype = C.c_char_p
     L.gevb_timing_class_name.argtypes = [i]
     L.gevb_timing_num_classes.restype = i
@@ -129,6 +131,21 @@ def _ptr(a):
 def _darr(v):
     a = np.ascontiguousarray(v, dtype=np.float64)
     return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def brick_dims():
+    b = [C.c_int(), C.c_int(), C.c_int()]
+    lib().gevb_brick_dims(*[C.byref(v) for v in b])
+    return tuple(v.value for v in b)
+
+
+def storage_key(N, nzl, cx, cy, czl):
+    """Sort key of the device particle order (include/gevb.h, gevb_brick_dims): brick-major, then cell in brick."""
+    bx, by, bz = brick_dims()
+    nbx, nby = -(-N // bx), -(-N // by)
+    cx, cy, czl = (np.asarray(v, dtype=np.int64) for v in (cx, cy, czl))
+    brick = ((czl // bz) * nby + cy // by) * nbx + cx // bx
+    return brick * (bx * by * bz) + ((czl % bz) * by + cy % by) * bx + cx % bx
 
 
 def nccl_unique_id():

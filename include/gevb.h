@@ -112,7 +112,7 @@ int gevb_plan_execute(gevb_plan * plan, int direction);
 /* ---- particles ---------------------------------------------------------------
  * Particles::initialize + addParticle_global (ic_basic.hpp:1990,1429): particles
  * whose cell lies in this rank's slab are kept, the rest ignored.  Storage is
- * cell-sorted FP64 structure-of-arrays (bricks of 8^3 cells, then cells inside the
+ * cell-sorted FP64 structure-of-arrays (bricks of cells, then cells inside the
  * brick); cell = floor(pos/dx) per axis.                                      */
 int gevb_pcls_create(gevb_ctx * ctx, gevb_pcls ** out, double mass);
 int gevb_pcls_destroy(gevb_pcls * p);
@@ -122,6 +122,9 @@ int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);
 /* bit-exact contract: particles per cell of the local slab, uint32[nz_local][N][N] */
 int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts);
 double gevb_pcls_mass(gevb_pcls * p);
+/* storage order of the particle arrays: bricks of bx * by * bz cells (z-major brick index), then the cell
+ * inside the brick (z-major), i.e. key = (brick << 9) | (sz * by + sy) * bx + sx                        */
+void gevb_brick_dims(int * bx, int * by, int * bz);
 
 /* ---- particle -> mesh projections (gevolution.hpp:927,1046,1173; main.cpp:385,402,427,439)
  * phi may be NULL (no geometric correction, gevolution.hpp:949,965).  Target

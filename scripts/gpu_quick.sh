@@ -1,0 +1,14 @@
+#!/bin/bash
+# quick GPU visit: parity tests + one bench line (no CPU baseline, no ncu).  usage: bash scripts/gpu_quick.sh <tag> [bench args]
+TAG=${1:-q}; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_gpu.log
+timeout 900 python bench.py --no-cpu-baseline "$@" > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; tail -c 400 $OUT/bench.err
+python - <<PY
+import json
+d=json.load(open("$OUT/bench.json"))
+print("ms_per_step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"])
+for k,v in sorted(d["kernels"].items(), key=lambda kv:-kv[1]["ms_per_step"]):
+    print(f"{k:32s} {v['ms_per_step']:8.3f} ms/step calls {v['calls_per_step']:.0f} frac {v.get('frac',float('nan')):.3f}")
+PY

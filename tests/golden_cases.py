@@ -138,8 +138,7 @@ def run_gpu(g, ctx, inp):
     dx = 1.0 / N
     c = np.minimum(np.floor(dpos / dx).astype(np.int64), N - 1)
     keys = (c[:, 2] * N + c[:, 1]) * N + c[:, 0]
-    nb = (N + 7) // 8        # storage order: bricks of 8^3 cells, then cells inside the brick
-    bkey = ((((c[:, 2] >> 3) * nb + (c[:, 1] >> 3)) * nb + (c[:, 0] >> 3)) << 9) | ((c[:, 2] & 7) << 6) | ((c[:, 1] & 7) << 3) | (c[:, 0] & 7)
+    bkey = g.storage_key(N, N, c[:, 0], c[:, 1], c[:, 2])      # storage order: bricks, then cells inside the brick
     assert np.all(np.diff(bkey) >= 0), "device particle order is not brick-major cell-sorted"
     out["cell"] = keys[order].astype(np.int32)
     assert np.array_equal(dpos[order], pos) and np.array_equal(dvel[order], vel)

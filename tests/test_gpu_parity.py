@@ -213,8 +213,6 @@ def test_full_size_properties(gevb, ctx, N):
     o0, ob = np.argsort(i0), np.argsort(before[0])
     assert np.array_equal(i0[o0], before[0][ob]) and np.array_equal(x0[o0], before[1][ob])
     k0 = np.minimum(np.floor(x0 * N).astype(np.int64), N - 1)
-    nb = (N + 7) // 8        # storage order: bricks of 8^3 cells, cells inside the brick, both z-major
-    brick = ((k0[:, 2] >> 3) * nb + (k0[:, 1] >> 3)) * nb + (k0[:, 0] >> 3)
-    key = (brick << 9) | ((k0[:, 2] & 7) << 6) | ((k0[:, 1] & 7) << 3) | (k0[:, 0] & 7)
+    key = gevb.storage_key(N, N, k0[:, 0], k0[:, 1], k0[:, 2])      # storage order: bricks, then cells inside the brick
     assert np.all(np.diff(key) >= 0), "brick-major cell order lost"
     assert np.array_equal(p0.cell_counts(), counts)
