@@ -5,21 +5,25 @@
 //   projection_Tij_project       gevolution.hpp:1173-1297
 //   scalarProjectionCIC_project  LATfield2 (main.cpp:402), plain CIC
 //
-// One thread block per brick of 16 x 8 x 4 cells (particles are stored brick by
-// brick and, inside a brick, cell by cell -- gevb_internal.cuh).  The block owns a
-// 17 x 9 x 5-site shared-memory tile per target component (the brick's sites plus
-// the upper apron the CIC cloud reaches) and a tile of phi of the same shape.
+// Persistent thread blocks walk the bricks of 16 x 8 x 4 cells (particles are
+// stored brick by brick and, inside a brick, cell by cell -- gevb_internal.cuh).
+// A block owns a 17 x 9 x 5-site shared-memory tile per target component (the
+// brick's sites plus the upper apron the CIC cloud reaches); the brick's slice of
+// cell_start[] and its phi tile arrive by asynchronous copies (LDGSTS) one brick
+// ahead, the particles by register prefetch one batch ahead.
 //
-//   1. every thread owns cells of the brick and accumulates the contributions of
-//      the cell's particles in registers -- exactly the reference's per-cell
-//      "localCube" accumulators (gevolution.hpp:953,1199-1200); particle loads are
-//      coalesced because consecutive threads own consecutive cells = consecutive
-//      particles.  Cells holding more than DEP_LIGHT particles hand the excess to
-//      a warp-cooperative pass (strided loads, shuffle reduction), so clustered
-//      states do not serialise on one thread.
-//   2. the per-cell sums go into the tile in eight corner phases: in one phase
-//      all threads write the same corner of their own cell, i.e. distinct sites,
-//      so the shared-memory update is a plain read-add-write, no atomics.
+//   1. one thread per particle (coalesced 48-byte SoA loads); the per-particle
+//      factors (weights, e, f, m q_i q_j / e) stay in registers.
+//   2. the tile is updated in eight corner phases: in one phase every particle adds
+//      to the same corner of its own cell, so particles of different cells touch
+//      different sites and the shared-memory update is a plain read-add-write.
+//      Particles that share a cell are neighbours in the sorted order: their
+//      contributions are combined by a segmented warp reduction (shuffles, only in
+//      warps that hold such particles) and the first lane of the segment writes --
+//      the GPU form of the reference's per-cell "localCube" accumulators
+//      (gevolution.hpp:953,1199-1200).  Only a cell whose particles straddle two
+//      warps needs a shared-memory atomic.  Work per thread does not depend on
+//      the clustering state.
 //   3. the tile is flushed to the field in HBM with FP64 reductions (RED.ADD.F64),
 //      one per non-zero tile site and component -- about 5 k per brick instead of
 //      38 per particle; consecutive lanes flush consecutive sites of a row.
@@ -34,32 +38,13 @@ namespace {
 #define DY (GEVB_BY + 1)
 #define DZ (GEVB_BZ + 1)
 #define DT_SITES (DX * DY * DZ)
-#define DEP_LIGHT 4
 #define DEP_THREADS 256
 
 enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
 
-// accumulators per cell and tile components per projection
-__host__ __device__ constexpr int dep_nacc(int what) { return what == DEP_T00 ? 8 : what == DEP_TIJ ? 30 : what == DEP_T00_TIJ ? 38 : 12; }
+// tile components per projection; Tij components follow the field order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
 __host__ __device__ constexpr int dep_ncomp(int what) { return what == DEP_T00 ? 1 : what == DEP_TIJ ? 6 : what == DEP_T00_TIJ ? 7 : 3; }
-
-// symmetric-tensor accumulators: 24 diagonal (tii[k + 8 d], gevolution.hpp:1199) then 6 off-diagonal (tij[0..5], :1198)
-__host__ __device__ constexpr int tij_comp(int a) { return a < 24 ? (a / 8 == 0 ? 0 : a / 8 == 1 ? 3 : 5) : (a - 24 < 2 ? 1 : a - 24 < 4 ? 2 : 4); }
-__host__ __device__ constexpr int tij_corner(int a) { return a < 24 ? a % 8 : (a == 24 || a == 26 || a == 28 ? 0 : a == 25 ? 1 : a == 27 ? 2 : 4); }   // :1277-1294
-// T0i accumulators qi[0..11] (gevolution.hpp:1107-1126): component a / 4, corner from the write-back at :1129-1144
-__host__ __device__ constexpr int t0i_corner(int a)
-{
-	return a == 0 || a == 4 || a == 8 ? 0 : a == 1 ? 2 : a == 2 ? 1 : a == 3 ? 3 : a == 5 ? 4 : a == 6 ? 1 : a == 7 ? 5 : a == 9 ? 4 : a == 10 ? 2 : 6;
-}
-// tile component and corner (4X + 2Y + Z, gevolution.hpp:953) of accumulator a
-__host__ __device__ constexpr int acc_comp(int what, int a)
-{
-	return what == DEP_T00 ? 0 : what == DEP_TIJ ? tij_comp(a) : what == DEP_T00_TIJ ? (a < 8 ? 0 : 1 + tij_comp(a - 8)) : a / 4;
-}
-__host__ __device__ constexpr int acc_corner(int what, int a)
-{
-	return what == DEP_T00 ? a : what == DEP_TIJ ? tij_corner(a) : what == DEP_T00_TIJ ? (a < 8 ? a : tij_corner(a - 8)) : t0i_corner(a);
-}
+// corner index 4X + 2Y + Z (gevolution.hpp:953) -> offset inside the tile
 __host__ __device__ constexpr int corner_offset(int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * DX + (k & 1) * DX * DY; }
 
 struct DParams
@@ -73,90 +58,6 @@ struct DParams
 	double * out[7];           // target component pointers in tile-component order
 };
 
-// contributions of one particle to the cell's accumulators
-template <int WHAT, bool HAS_PHI>
-__device__ __forceinline__ void accumulate(double * acc, const DParams & D, const double * pv, double refx, double refy, double refz, const double * cphi)
-{
-	double up[3], dn[3];
-	if (D.pow2)
-	{
-		up[0] = (pv[0] - refx) * D.rN; up[1] = (pv[1] - refy) * D.rN; up[2] = (pv[2] - refz) * D.rN;      // == / dx exactly (dx = 2^-k)
-	}
-	else
-	{
-		up[0] = (pv[0] - refx) / D.dx; up[1] = (pv[1] - refy) / D.dx; up[2] = (pv[2] - refz) / D.dx;      // gevolution.hpp:981 / :1101 / :1231
-	}
-	dn[0] = 1.0 - up[0]; dn[1] = 1.0 - up[1]; dn[2] = 1.0 - up[2];                                          // :982
-	const double q0 = pv[3], q1 = pv[4], q2 = pv[5];
-	if (WHAT == DEP_T0I)
-	{
-		double w = D.mass * q0;                                                    // :1107
-		acc[0] += w * dn[1] * dn[2]; acc[1] += w * up[1] * dn[2]; acc[2] += w * dn[1] * up[2]; acc[3] += w * up[1] * up[2];       // :1109-1112
-		w = D.mass * q1;                                                           // :1114
-		acc[4] += w * dn[0] * dn[2]; acc[5] += w * up[0] * dn[2]; acc[6] += w * dn[0] * up[2]; acc[7] += w * up[0] * up[2];       // :1116-1119
-		w = D.mass * q2;                                                           // :1121
-		acc[8] += w * dn[0] * dn[1]; acc[9] += w * up[0] * dn[1]; acc[10] += w * dn[0] * up[1]; acc[11] += w * up[0] * up[1];     // :1123-1126
-		return;
-	}
-	const double qsq = q0 * q0 + q1 * q1 + q2 * q2;
-	double w[8];
-	#pragma unroll
-	for (int k = 0; k < 8; k++) w[k] = ((k & 4) ? up[0] : dn[0]) * ((k & 2) ? up[1] : dn[1]) * ((k & 1) ? up[2] : dn[2]);
-	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
-	{
-		double e = D.a, f = 0.;
-		if (HAS_PHI) { e = sqrt(qsq + D.a * D.a); f = 3. * e + qsq / e; }          // :989-991
-		#pragma unroll
-		for (int k = 0; k < 8; k++) acc[k] += w[k] * (e + f * cphi[k]);            // :995-1009 (mass applied at write-back, :1012)
-	}
-	if (WHAT == DEP_TIJ || WHAT == DEP_T00_TIJ)
-	{
-		double * t = acc + (WHAT == DEP_T00_TIJ ? 8 : 0);
-		const double e = sqrt(qsq + D.a * D.a);                                    // :1237
-		const double f = 4. + D.a * D.a / (qsq + D.a * D.a);                       // :1238
-		const double qq[3] = {q0, q1, q2};
-		double g[8];
-		#pragma unroll
-		for (int k = 0; k < 8; k++) g[k] = w[k] * (1. + f * cphi[k]);
-		#pragma unroll
-		for (int d = 0; d < 3; d++)
-		{
-			const double wd = D.mass * qq[d] * qq[d] / e;                          // :1243
-			#pragma unroll
-			for (int k = 0; k < 8; k++) t[d * 8 + k] += wd * g[k];                 // :1245-1259
-		}
-		double wo = D.mass * q0 * q1 / e;                                          // :1262
-		t[24] += wo * dn[2] * (1. + f * 0.25 * (cphi[0] + cphi[2] + cphi[4] + cphi[6]));
-		t[25] += wo * up[2] * (1. + f * 0.25 * (cphi[1] + cphi[3] + cphi[5] + cphi[7]));
-		wo = D.mass * q0 * q2 / e;                                                 // :1266
-		t[26] += wo * dn[1] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[4] + cphi[5]));
-		t[27] += wo * up[1] * (1. + f * 0.25 * (cphi[2] + cphi[3] + cphi[6] + cphi[7]));
-		wo = D.mass * q1 * q2 / e;                                                 // :1270
-		t[28] += wo * dn[0] * (1. + f * 0.25 * (cphi[0] + cphi[1] + cphi[2] + cphi[3]));
-		t[29] += wo * up[0] * (1. + f * 0.25 * (cphi[4] + cphi[5] + cphi[6] + cphi[7]));
-	}
-}
-
-// per-cell factors the reference applies at write-back
-template <int WHAT>
-__device__ __forceinline__ void finalize(double * acc, const DParams & D, const double * cphi)
-{
-	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
-	{
-		#pragma unroll
-		for (int k = 0; k < 8; k++) acc[k] *= D.mass;                              // :1012-1019
-	}
-	if (WHAT == DEP_T0I)
-	{
-		#pragma unroll
-		for (int a = 0; a < 12; a++)
-		{
-			const int k = t0i_corner(a), own = a / 4 == 0 ? 4 : a / 4 == 1 ? 2 : 1;   // the component's own axis bit
-			acc[a] *= 1. + cphi[k] + cphi[k + own];                                // :1129-1144
-		}
-	}
-}
-
 __device__ __forceinline__ void cp_async8(void * smem_dst, const void * gmem_src)
 {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -168,27 +69,20 @@ __device__ __forceinline__ void cp_async4(void * smem_dst, const void * gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-#define DEP_CELLTAB (GEVB_BRICK_CELLS + 4)      // 513 prefix sums of a brick, padded
-#define DEP_PCAP 512                            // particles of a brick staged in shared memory (the rest is read from HBM directly)
-#define DEP_STAGE_DOUBLES (DT_SITES + 6 * DEP_PCAP + DEP_CELLTAB / 2)   // one pipeline stage: phi tile, 6 particle arrays, cell table
+#define DEP_CELLTAB (GEVB_BRICK_CELLS + 4)                      // 513 prefix sums of a brick, padded
+#define DEP_STAGE_DOUBLES (DT_SITES + DEP_CELLTAB / 2)          // one pipeline stage: phi tile, cell table
 
-// asynchronous copy (LDGSTS) of everything a brick's deposit reads: its slice of cell_start[], the phi tile and the
-// first DEP_PCAP particles.  For the tile a thread keeps its (tx, ty) column and walks z.
+// asynchronous copy (LDGSTS) of a brick's slice of cell_start[] and its phi tile.  For the tile a thread keeps its
+// (tx, ty) column and walks z.
 template <bool HAS_PHI>
 __device__ __forceinline__ void stage_brick(const DParams & D, uint32_t brick, uint32_t first, uint32_t last, double * stage)
 {
 	const BrickGeom & G = D.G;
-	double * tphi = stage, * part = stage + DT_SITES;
-	uint32_t * ctab = (uint32_t *) (stage + DT_SITES + 6 * DEP_PCAP);
+	double * tphi = stage;
+	uint32_t * ctab = (uint32_t *) (stage + DT_SITES);
 	if (first == last) return;
 	const uint32_t * src = D.cell_start + (size_t) brick * GEVB_BRICK_CELLS;
 	for (int k = threadIdx.x; k <= GEVB_BRICK_CELLS; k += DEP_THREADS) cp_async4(ctab + k, src + k);
-	const uint32_t n = last - first < DEP_PCAP ? last - first : DEP_PCAP;
-	for (uint32_t k = threadIdx.x; k < n; k += DEP_THREADS)
-	{
-		cp_async8(part + k, D.x + first + k); cp_async8(part + DEP_PCAP + k, D.y + first + k); cp_async8(part + 2 * DEP_PCAP + k, D.z + first + k);
-		cp_async8(part + 3 * DEP_PCAP + k, D.qx + first + k); cp_async8(part + 4 * DEP_PCAP + k, D.qy + first + k); cp_async8(part + 5 * DEP_PCAP + k, D.qz + first + k);
-	}
 	if (HAS_PHI && threadIdx.x < DX * DY)
 	{
 		int x0, y0, zl0;
@@ -205,44 +99,200 @@ __device__ __forceinline__ void stage_brick(const DParams & D, uint32_t brick, u
 	}
 }
 
-// particle i of the current brick: from the staged copy if it is there, else from HBM
-__device__ __forceinline__ void load_particle(const DParams & D, const double * part, uint32_t bfirst, uint32_t i, double * pv)
-{
-	const uint32_t k = i - bfirst;
-	if (k < DEP_PCAP)
-	{
-		#pragma unroll
-		for (int a = 0; a < 6; a++) pv[a] = part[a * DEP_PCAP + k];
-	}
-	else
-	{
-		pv[0] = D.x[i]; pv[1] = D.y[i]; pv[2] = D.z[i]; pv[3] = D.qx[i]; pv[4] = D.qy[i]; pv[5] = D.qz[i];
-	}
-}
-
 __device__ __forceinline__ void brick_range(const DParams & D, uint32_t b, uint32_t & first, uint32_t & last)
 {
 	first = last = 0;
 	if (b < D.G.nbricks) { first = __ldg(D.cell_start + (size_t) b * GEVB_BRICK_CELLS); last = __ldg(D.cell_start + (size_t) (b + 1) * GEVB_BRICK_CELLS); }
 }
 
-// Persistent blocks walk the bricks with stride gridDim.x in a two-stage software pipeline: while brick k is
-// accumulated and flushed, everything brick k+1 needs is in flight into the other shared-memory stage, and the
-// particle range of brick k+2 is being fetched into registers.
-template <int WHAT, bool HAS_PHI>
-__global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
+// per-particle factors, computed once and kept in registers through the eight phases
+struct PInv
 {
-	constexpr int NACC = dep_nacc(WHAT), NCOMP = dep_ncomp(WHAT);
+	double wx[2], wy[2], wz[2];    // CIC weights: [0] = 1 - up ("down"), [1] = up     gevolution.hpp:979-983
+	double eT, fT;                 // T00: mass * (e + f phi)                           :989-1009
+	double f;                      // Tij: 4 + a^2 / (q^2 + a^2)                        :1238
+	double wd[3], wo[3];           // Tij: mass q_d^2 / e ; mass q_i q_j / e (01, 02, 12)  :1243,:1262-1270
+	double m[3];                   // T0i: mass q_i                                     :1107-1121
+};
+
+template <int WHAT, bool HAS_PHI>
+__device__ __forceinline__ void particle_factors(PInv & I, const DParams & D, const double * pv, int cx, int cy, int cz)
+{
+	double up[3];
+	const double refx = cx * D.dx, refy = cy * D.dx, refz = cz * D.dx;                                     // referPos, :963
+	if (D.pow2) { up[0] = (pv[0] - refx) * D.rN; up[1] = (pv[1] - refy) * D.rN; up[2] = (pv[2] - refz) * D.rN; }   // == / dx exactly (dx = 2^-k)
+	else { up[0] = (pv[0] - refx) / D.dx; up[1] = (pv[1] - refy) / D.dx; up[2] = (pv[2] - refz) / D.dx; }          // :981 / :1101 / :1231
+	I.wx[1] = up[0]; I.wy[1] = up[1]; I.wz[1] = up[2];
+	I.wx[0] = 1.0 - up[0]; I.wy[0] = 1.0 - up[1]; I.wz[0] = 1.0 - up[2];                                     // :982
+	const double q0 = pv[3], q1 = pv[4], q2 = pv[5];
+	if (WHAT == DEP_T0I) { I.m[0] = D.mass * q0; I.m[1] = D.mass * q1; I.m[2] = D.mass * q2; return; }      // :1107,:1114,:1121
+	const double qsq = q0 * q0 + q1 * q1 + q2 * q2;
+	// one square root and one division per particle: e = sqrt(q^2 + a^2) and 1/e; the reference's quotients
+	// x / e become x * (1/e) (one extra rounding, 1e-16 relative, against a 1e-10 tolerance)
+	const double e = sqrt(qsq + D.a * D.a);                                        // :990 / :1237
+	const double inv_e = 1.0 / e;
+	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
+	{
+		I.eT = D.a * D.mass; I.fT = 0.;
+		if (HAS_PHI) { I.eT = e * D.mass; I.fT = (3. * e + qsq * inv_e) * D.mass; }   // :989-991; mass applied at write-back in the reference (:1012)
+	}
+	if (WHAT == DEP_TIJ || WHAT == DEP_T00_TIJ)
+	{
+		I.f = 4. + D.a * D.a * inv_e * inv_e;                                      // :1238
+		const double me = D.mass * inv_e;
+		I.wd[0] = me * q0 * q0; I.wd[1] = me * q1 * q1; I.wd[2] = me * q2 * q2;    // :1243
+		I.wo[0] = me * q0 * q1; I.wo[1] = me * q0 * q2; I.wo[2] = me * q1 * q2;    // :1262,:1266,:1270
+	}
+}
+
+// how a lane writes its contributions
+struct Writer
+{
+	double * tile;                 // tile + site of the particle's cell
+	int after, steps;              // lanes after this one in the same cell (within the warp); shuffle steps of the segmented sum
+	bool write;                    // this lane writes: alone in its cell, or first lane of its cell's segment in this warp
+	bool plain;                    // no other warp holds particles of this cell: plain read-add-write is safe
+};
+
+// tile component of the j-th contribution of corner K (j = -1: how many contributions corner K has)
+__host__ __device__ constexpr int phase_comp(int what, int K, int j)
+{
+	const int X = (K >> 2) & 1, Y = (K >> 1) & 1, Z = K & 1;
+	int comps[7] = {0, 0, 0, 0, 0, 0, 0};
+	int n = 0;
+	if (what == DEP_T0I)
+	{
+		if (X == 0) comps[n++] = 0;
+		if (Y == 0) comps[n++] = 1;
+		if (Z == 0) comps[n++] = 2;
+	}
+	else
+	{
+		const int o = what == DEP_T00_TIJ ? 1 : 0;
+		if (what != DEP_TIJ) comps[n++] = 0;
+		if (what != DEP_T00)
+		{
+			comps[n++] = o; comps[n++] = o + 3; comps[n++] = o + 5;
+			if (X == 0 && Y == 0) comps[n++] = o + 1;
+			if (X == 0 && Z == 0) comps[n++] = o + 2;
+			if (Y == 0 && Z == 0) comps[n++] = o + 4;
+		}
+	}
+	return j < 0 ? n : comps[j];
+}
+
+// contributions of one particle to corner K of its cell, in the order of phase_comp()
+template <int WHAT, bool HAS_PHI, int K>
+__device__ __forceinline__ void phase_values(const PInv & I, const double * ph, double * v)
+{
+	constexpr int X = (K >> 2) & 1, Y = (K >> 1) & 1, Z = K & 1;
+	#define PHI(k) (HAS_PHI ? ph[corner_offset(k)] : 0.)
+	int n = 0;
+	if (WHAT == DEP_T0I)
+	{
+		// component i is NGP along i and CIC across (:1109-1126); edge factor 1 + phi(x) + phi(x + e_i) (:1129-1144)
+		if (X == 0) v[n++] = I.m[0] * I.wy[Y] * I.wz[Z] * (1. + PHI(K) + PHI(K + 4));
+		if (Y == 0) v[n++] = I.m[1] * I.wx[X] * I.wz[Z] * (1. + PHI(K) + PHI(K + 2));
+		if (Z == 0) v[n++] = I.m[2] * I.wx[X] * I.wy[Y] * (1. + PHI(K) + PHI(K + 1));
+		return;
+	}
+	const double w = I.wx[X] * I.wy[Y] * I.wz[Z];
+	const double p = PHI(K);
+	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ) v[n++] = w * (I.eT + I.fT * p);                             // :995-1019
+	if (WHAT == DEP_TIJ || WHAT == DEP_T00_TIJ)
+	{
+		const double g = w * (1. + I.f * p);
+		v[n++] = I.wd[0] * g; v[n++] = I.wd[1] * g; v[n++] = I.wd[2] * g;                                   // :1245-1259
+		// off-diagonal (i,j) lives on the plaquette centre: CIC along the third axis only, phi averaged over the plaquette
+		if (X == 0 && Y == 0) v[n++] = I.wo[0] * I.wz[Z] * (1. + I.f * 0.25 * (PHI(Z) + PHI(2 + Z) + PHI(4 + Z) + PHI(6 + Z)));                       // :1263-1264, at x (Z=0) and x+e2 (Z=1) :1279,:1290
+		if (X == 0 && Z == 0) v[n++] = I.wo[1] * I.wy[Y] * (1. + I.f * 0.25 * (PHI(2 * Y) + PHI(2 * Y + 1) + PHI(2 * Y + 4) + PHI(2 * Y + 5)));       // :1267-1268, x and x+e1
+		if (Y == 0 && Z == 0) v[n++] = I.wo[2] * I.wx[X] * (1. + I.f * 0.25 * (PHI(4 * X) + PHI(4 * X + 1) + PHI(4 * X + 2) + PHI(4 * X + 3)));       // :1271-1272, x and x+e0
+	}
+	#undef PHI
+}
+
+// one corner phase of a batch.  Particles of different cells update different sites, so the update is a plain
+// read-add-write.  Particles of one cell are contiguous lanes: their contributions are summed by a segmented
+// shuffle reduction and the first lane of the segment writes -- with a shared-memory atomic if the cell's
+// particles straddle warps (the only case in which two warps can meet on a site within a phase).
+template <int WHAT, bool HAS_PHI, int K, int STEPS>
+__device__ __forceinline__ void phase(const PInv & I, const Writer & W, const double * ph)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	double v[NV > 0 ? NV : 1];
+	phase_values<WHAT, HAS_PHI, K>(I, ph, v);
+	#pragma unroll
+	for (int s = 0; s < STEPS; s++)
+	{
+		#pragma unroll
+		for (int j = 0; j < NV; j++)
+		{
+			const double t = __shfl_down_sync(0xffffffffu, v[j], 1 << s);
+			if ((1 << s) <= W.after) v[j] += t;
+		}
+	}
+	if (W.write)
+	{
+		double * p = W.tile + corner_offset(K);
+		#pragma unroll
+		for (int j = 0; j < NV; j++)
+		{
+			if (W.plain) p[phase_comp(WHAT, K, j) * DT_SITES] += v[j];
+			else atomicAdd(p + phase_comp(WHAT, K, j) * DT_SITES, v[j]);
+		}
+	}
+	__syncthreads();
+}
+
+// cell = floor(pos/dx) clamped into the lattice; pos * N is bit-identical to pos / dx for power-of-two N
+__device__ __forceinline__ int cell_scaled(const DParams & D, double p)
+{
+	int c = (int) floor(D.pow2 ? p * D.rN : p / D.dx);
+	c = c >= D.G.N ? D.G.N - 1 : c;
+	return c < 0 ? 0 : c;
+}
+
+__device__ __forceinline__ void load_particle(const DParams & D, uint32_t i, double * pv)
+{
+	pv[0] = D.x[i]; pv[1] = D.y[i]; pv[2] = D.z[i]; pv[3] = D.qx[i]; pv[4] = D.qy[i]; pv[5] = D.qz[i];
+}
+
+// the eight corner phases of one batch
+template <int WHAT, bool HAS_PHI, int STEPS>
+__device__ __forceinline__ void phases(const PInv & I, const Writer & W, const double * ph)
+{
+	phase<WHAT, HAS_PHI, 0, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 1, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 2, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 3, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 4, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 5, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 6, STEPS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 7, STEPS>(I, W, ph);
+}
+
+// barrier pattern of phases() for a warp that holds no particle of the batch
+__device__ __forceinline__ void idle_phases()
+{
+	#pragma unroll
+	for (int k = 0; k < 8; k++) __syncthreads();
+}
+
+// Persistent blocks walk the bricks with stride gridDim.x in a software pipeline: while brick k is accumulated and
+// flushed, the cell table and phi tile of brick k+1 are in flight into the other shared-memory stage, the particle
+// range of brick k+2 is being fetched, and the next batch of particles is already requested.
+template <int WHAT, bool HAS_PHI>
+__global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
+{
+	constexpr int NCOMP = dep_ncomp(WHAT);
 	extern __shared__ double smem[];
 	double * tile = smem;                                   // [NCOMP][DT_SITES] accumulators
 	double * stages = smem + NCOMP * DT_SITES;              // [2][DEP_STAGE_DOUBLES]
-	__shared__ uint16_t heavy_cell[GEVB_BRICK_CELLS];
-	__shared__ int nheavy;
 
 	const BrickGeom & G = D.G;
 	const int tcol = threadIdx.x, ttx = tcol % DX, tty = tcol / DX;      // this thread's column of the tile (flush)
+	const int lane = threadIdx.x & 31;
 	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES + 2 * DEP_STAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
-	if (threadIdx.x == 0) nheavy = 0;
 	__syncthreads();
 	uint32_t brick = blockIdx.x;
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
@@ -250,6 +300,8 @@ __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
 	brick_range(D, brick + gridDim.x, nfirst, nlast);
 	stage_brick<HAS_PHI>(D, brick, first, last, stages);
 	cp_async_commit();
+	double pv[6] = {0., 0., 0., 0., 0., 0.};
+	if (first + threadIdx.x < last) load_particle(D, first + threadIdx.x, pv);
 	int cur = 0;
 	while (brick < G.nbricks)
 	{
@@ -264,91 +316,54 @@ __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
 			cp_async_wait<1>();                             // everything but the newest group: this brick's stage has landed
 			__syncthreads();
 			const double * tphi = stages + cur * DEP_STAGE_DOUBLES;
-			const double * part = tphi + DT_SITES;
-			const uint32_t * ctab = (const uint32_t *) (part + 6 * DEP_PCAP);
+			const uint32_t * ctab = (const uint32_t *) (tphi + DT_SITES);
 
-			// ---- light pass: one thread per cell, DEP_LIGHT particles at most -------------------------
-			#pragma unroll 1
-			for (int cc = 0; cc < GEVB_BRICK_CELLS / DEP_THREADS; cc++)
+			for (uint32_t base = first; base < last; base += DEP_THREADS)
 			{
-				const int c = cc * DEP_THREADS + threadIdx.x;
-				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
-				const int site = (sz * DY + sy) * DX + sx;
-				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
-				const uint32_t n = clast - cfirst;
-				double acc[NACC];
-				#pragma unroll
-				for (int a = 0; a < NACC; a++) acc[a] = 0.;
-				if (n > 0)
+				const uint32_t i = base + threadIdx.x;
+				const bool valid = i < last;
+				PInv I;
+				Writer W;
+				const double * ph;
 				{
-					double cphi[8];
-					#pragma unroll
-					for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];   // :967-974
-					const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;   // referPos, :963
-					const uint32_t nl = n < DEP_LIGHT ? n : DEP_LIGHT;
-					for (uint32_t j = 0; j < nl; j++)
+					// the particle's cell (it lies in this brick: the storage order is maintained by the re-bin)
+					int cx = 0, cy = 0, cz = 0, site = 0;
+					uint32_t cfirst = i, clast = i + 1;
+					if (valid)
 					{
-						double pv[6];
-						load_particle(D, part, first, cfirst + j, pv);
-						accumulate<WHAT, HAS_PHI>(acc, D, pv, refx, refy, refz, cphi);
+						cx = cell_scaled(D, pv[0]); cy = cell_scaled(D, pv[1]); cz = cell_scaled(D, pv[2]);
+						const int sx = cx - x0, sy = cy - y0, sz = cz - G.z0 - zl0;
+						site = (sz * DY + sy) * DX + sx;
+						const int c = (sz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (sy << GEVB_BX_BITS) | sx;
+						cfirst = ctab[c]; clast = ctab[c + 1];
 					}
-					finalize<WHAT>(acc, D, cphi);
-					if (n > DEP_LIGHT)
-					{
-						const int h = atomicAdd(&nheavy, 1);
-						heavy_cell[h] = (uint16_t) c;
-					}
+					particle_factors<WHAT, HAS_PHI>(I, D, pv, cx, cy, cz);
+					// lanes of this warp that share the cell form a contiguous segment [seg_lo, seg_hi)
+					const uint32_t warp_lo = i - lane, warp_hi = warp_lo + 32;
+					const uint32_t seg_lo = cfirst > warp_lo ? cfirst : warp_lo, seg_hi = clast < warp_hi ? clast : warp_hi;
+					const int maxlen = __reduce_max_sync(0xffffffffu, (int) (seg_hi - seg_lo));
+					W.tile = tile + site; ph = tphi + site;
+					W.after = (int) (seg_hi - 1 - i);
+					W.steps = maxlen > 1 ? 32 - __clz(maxlen - 1) : 0;
+					W.write = valid && i == seg_lo;
+					W.plain = cfirst >= warp_lo && clast <= warp_hi;
 				}
-				// eight corner phases: within a phase every thread updates a different site
-				#pragma unroll
-				for (int k = 0; k < 8; k++)
+				// request the next batch (of this brick, else the first batch of the next brick) while the phases run
 				{
-					if (n > 0)
-					{
-						#pragma unroll
-						for (int a = 0; a < NACC; a++)
-							if (acc_corner(WHAT, a) == k) tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(k)] += acc[a];
-					}
-					__syncthreads();
+					const uint32_t nb = base + DEP_THREADS;
+					const uint32_t j = nb < last ? nb + threadIdx.x : nfirst + threadIdx.x;
+					if (j < (nb < last ? last : nlast)) load_particle(D, j, pv);
 				}
+				// shuffle steps of the segmented sum are a warp-uniform property of the batch: 0 when no two lanes share a cell;
+				// a warp without particles (tail of the brick) only keeps the barriers company
+				if (W.steps == 0) phases<WHAT, HAS_PHI, 0>(I, W, ph);
+				else if (W.steps == 1) phases<WHAT, HAS_PHI, 1>(I, W, ph);
+				else if (W.steps == 2) phases<WHAT, HAS_PHI, 2>(I, W, ph);
+				else phases<WHAT, HAS_PHI, 5>(I, W, ph);
 			}
-
-			// ---- heavy pass: one warp per crowded cell -------------------------------------------------
-			const int nh = nheavy;
-			for (int h = threadIdx.x >> 5; h < nh; h += DEP_THREADS / 32)
-			{
-				const int c = heavy_cell[h];
-				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
-				const int site = (sz * DY + sy) * DX + sx;
-				double acc[NACC];
-				#pragma unroll
-				for (int a = 0; a < NACC; a++) acc[a] = 0.;
-				double cphi[8];
-				#pragma unroll
-				for (int k = 0; k < 8; k++) cphi[k] = tphi[site + corner_offset(k)];
-				const double refx = (x0 + sx) * D.dx, refy = (y0 + sy) * D.dx, refz = (G.z0 + zl0 + sz) * D.dx;
-				const uint32_t hlast = ctab[c + 1];
-				for (uint32_t i = ctab[c] + DEP_LIGHT + (threadIdx.x & 31); i < hlast; i += 32)
-				{
-					double pv[6];
-					load_particle(D, part, first, i, pv);
-					accumulate<WHAT, HAS_PHI>(acc, D, pv, refx, refy, refz, cphi);
-				}
-				#pragma unroll
-				for (int a = 0; a < NACC; a++)
-					for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-				finalize<WHAT>(acc, D, cphi);
-				if ((threadIdx.x & 31) == 0)
-				{
-					#pragma unroll
-					for (int a = 0; a < NACC; a++) atomicAdd(&tile[acc_comp(WHAT, a) * DT_SITES + site + corner_offset(acc_corner(WHAT, a))], acc[a]);
-				}
-			}
-			__syncthreads();                                // stage `cur` is free from here on
-			if (threadIdx.x == 0) nheavy = 0;
 
 			// ---- flush the tile: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row;
-			//      the tile is left zeroed for the next brick
+			//      the tile is left zeroed for the next brick (stage `cur` is free from here on)
 			if (tcol < DX * DY)
 			{
 				const size_t gcol = (size_t) ((y0 + tty) % G.N) * G.N + (x0 + ttx) % G.N;
@@ -366,6 +381,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit(DParams D)
 				}
 			}
 		}
+		else if (nbrick < G.nbricks && nfirst + threadIdx.x < nlast) load_particle(D, nfirst + threadIdx.x, pv);   // empty brick: nothing was prefetched
 		brick = nbrick; cur ^= 1;
 		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
 	}
@@ -393,7 +409,7 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 	D.phi = phi ? phi->data : NULL;
 	for (int k = 0; k < 7; k++) D.out[k] = k < dep_ncomp(WHAT) ? out[k] : NULL;
 	const size_t smem = ((size_t) dep_ncomp(WHAT) * DT_SITES + 2 * DEP_STAGE_DOUBLES) * sizeof(double);
-	const uint32_t persistent = (uint32_t) c->num_sms * 2;
+	const uint32_t persistent = (uint32_t) c->num_sms * 3;
 	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;
 	if (phi)
 	{

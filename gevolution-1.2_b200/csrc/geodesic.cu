@@ -102,7 +102,8 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 		v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                             // :581
 		double e2 = v2 + P.a_kick * P.a_kick;                                      // :582
 		grad_cic(t, 0, r, g);                                                      // :585-596
-		const double boost = (v2 + e2) / e2;
+		const double inv_e2 = 1. / e2;                                             // the only division of the kick: x / e2 -> x * (1/e2), 1/e -> e * (1/e2)
+		const double boost = (v2 + e2) * inv_e2;
 		g[0] *= boost; g[1] *= boost; g[2] *= boost;                               // :613-615
 		if (P.nf_kick >= 2)
 		{
@@ -134,7 +135,7 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 			pg2 += r[0] * (1. - r[1]) * ((r[2] - 1.) * T(4, 1, 0, -1) + (1. - 2. * r[2]) * T(4, 1, 0, 0) + r[2] * T(4, 1, 0, 1)) * q[2];
 			pg2 += (1. - r[0]) * r[1] * ((r[2] - 1.) * T(4, 0, 1, -1) + (1. - 2. * r[2]) * T(4, 0, 1, 0) + r[2] * T(4, 0, 1, 1)) * q[2];
 			pg2 += r[0] * r[1] * ((r[2] - 1.) * T(4, 1, 1, -1) + (1. - 2. * r[2]) * T(4, 1, 1, 0) + r[2] * T(4, 1, 1, 1)) * q[2];
-			const double s = P.binv_kick / e2;                                     // :658-660 (pg / params[1] / e2)
+			const double s = P.binv_kick * e2 * inv_e2;                            // :658-660 (pg / params[1] / e2, e2 now holds e)
 			g[0] += pg0 * s;
 			g[1] += pg1 * s;
 			g[2] += pg2 * s;
@@ -172,7 +173,8 @@ __device__ __forceinline__ void drift(const GParams & P, const double * t, const
 	double ph = 0., ch = 0.;
 	if (P.nf_drift >= 1) ph = tri_cic(t, 0, r);                                    // :820-827
 	if (P.nf_drift >= 2) ch = tri_cic(t, 1, r);                                    // :832-839
-	v2 = (1. + (3. - v2 / e2) * ph - ch) / sqrt(e2);                               // :842
+	const double inv_e2 = 1. / e2;                                                 // the only division of the drift
+	v2 = (1. + (3. - v2 * inv_e2) * ph - ch) * (sqrt(e2) * inv_e2);                // :842
 	double v[3] = {q[0] * v2, q[1] * v2, q[2] * v2};                               // :844-846
 	if (P.nf_drift >= 3)
 	{

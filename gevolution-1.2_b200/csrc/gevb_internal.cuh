@@ -136,22 +136,36 @@ struct gevb_plan
 #define GEVB_BZ_BITS 2
 #define GEVB_BRICK_CELLS 512
 #define GEVB_BRICK_BITS 9
+// Bricks are numbered super-brick by super-brick (4 x 4 x 8 bricks = 64 x 32 x 32 cells): the persistent kernels
+// walk the bricks in index order, so the few hundred bricks in flight at any time form a compact region of the
+// lattice and the tile aprons they share (deposit flushes, field tiles) meet in L2 instead of HBM.
+#define GEVB_SX_BITS 2
+#define GEVB_SY_BITS 2
+#define GEVB_SZ_BITS 3
+#define GEVB_SUPER_BITS (GEVB_SX_BITS + GEVB_SY_BITS + GEVB_SZ_BITS)
 #define GEVB_INVALID_KEY 0xffffffffu
 struct BrickGeom
 {
 	int N, nzl, z0;
-	int nbx, nby, nbz;         // bricks per dimension (last ones may be partial)
-	uint32_t nbricks, ncells;  // ncells = nbricks * 512 (cells of partial bricks that lie outside the slab stay empty)
+	int nsx, nsy, nsz;         // super-bricks per dimension (the last ones may be partial: their missing bricks stay empty)
+	uint32_t nbricks, ncells;  // nbricks = nsx nsy nsz 128, ncells = nbricks * 512
 };
 __host__ __device__ __forceinline__ uint32_t brick_key(const BrickGeom & G, int cx, int cy, int czl)
 {
-	const uint32_t b = ((uint32_t) (czl >> GEVB_BZ_BITS) * G.nby + (uint32_t) (cy >> GEVB_BY_BITS)) * G.nbx + (uint32_t) (cx >> GEVB_BX_BITS);
+	const uint32_t bx = (uint32_t) cx >> GEVB_BX_BITS, by = (uint32_t) cy >> GEVB_BY_BITS, bz = (uint32_t) czl >> GEVB_BZ_BITS;
+	const uint32_t super = ((bz >> GEVB_SZ_BITS) * G.nsy + (by >> GEVB_SY_BITS)) * G.nsx + (bx >> GEVB_SX_BITS);
+	const uint32_t local = (((bz & ((1u << GEVB_SZ_BITS) - 1)) << GEVB_SY_BITS | (by & ((1u << GEVB_SY_BITS) - 1))) << GEVB_SX_BITS) | (bx & ((1u << GEVB_SX_BITS) - 1));
+	const uint32_t b = (super << GEVB_SUPER_BITS) | local;
 	return (b << GEVB_BRICK_BITS) | (uint32_t) (((czl & (GEVB_BZ - 1)) << (GEVB_BX_BITS + GEVB_BY_BITS)) | ((cy & (GEVB_BY - 1)) << GEVB_BX_BITS) | (cx & (GEVB_BX - 1)));
 }
 __host__ __device__ __forceinline__ void brick_origin(const BrickGeom & G, uint32_t brick, int & x0, int & y0, int & zl0)
 {
-	x0 = (int) (brick % G.nbx) * GEVB_BX; const uint32_t r = brick / G.nbx;
-	y0 = (int) (r % G.nby) * GEVB_BY; zl0 = (int) (r / G.nby) * GEVB_BZ;
+	const uint32_t local = brick & ((1u << GEVB_SUPER_BITS) - 1), super = brick >> GEVB_SUPER_BITS;
+	const uint32_t sx = super % G.nsx, r = super / G.nsx, sy = r % G.nsy, sz = r / G.nsy;
+	const uint32_t lx = local & ((1u << GEVB_SX_BITS) - 1), ly = (local >> GEVB_SX_BITS) & ((1u << GEVB_SY_BITS) - 1), lz = local >> (GEVB_SX_BITS + GEVB_SY_BITS);
+	x0 = (int) (((sx << GEVB_SX_BITS) | lx) << GEVB_BX_BITS);
+	y0 = (int) (((sy << GEVB_SY_BITS) | ly) << GEVB_BY_BITS);
+	zl0 = (int) (((sz << GEVB_SZ_BITS) | lz) << GEVB_BZ_BITS);
 }
 // cell = floor(pos/dx) clamped into the lattice (LATfield2 filing rule, reference uses at gevolution.hpp:979-983)
 __device__ __forceinline__ int cell_of(double p, double dx, int N)

@@ -121,9 +121,9 @@ extern "C" int gevb_pcls_create(gevb_ctx * c, gevb_pcls ** out, double mass)
 	GEVB_CHECK_ARG(c != NULL && out != NULL, "gevb_pcls_create: NULL argument");
 	BrickGeom G;
 	G.N = c->N; G.nzl = c->nzl; G.z0 = c->z0;
-	G.nbx = (c->N + GEVB_BX - 1) / GEVB_BX; G.nby = (c->N + GEVB_BY - 1) / GEVB_BY;
-	G.nbz = (c->nzl + GEVB_BZ - 1) / GEVB_BZ;
-	const uint64_t ncells = (uint64_t) G.nbx * G.nby * G.nbz * GEVB_BRICK_CELLS;
+	const int spanx = GEVB_BX << GEVB_SX_BITS, spany = GEVB_BY << GEVB_SY_BITS, spanz = GEVB_BZ << GEVB_SZ_BITS;   // cells per super-brick edge
+	G.nsx = (c->N + spanx - 1) / spanx; G.nsy = (c->N + spany - 1) / spany; G.nsz = (c->nzl + spanz - 1) / spanz;
+	const uint64_t ncells = ((uint64_t) G.nsx * G.nsy * G.nsz << GEVB_SUPER_BITS) * GEVB_BRICK_CELLS;
 	GEVB_CHECK_ARG(ncells < (1ull << 31), "gevb_pcls_create: local slab has more than 2^31 cells");
 	G.nbricks = (uint32_t) (ncells / GEVB_BRICK_CELLS); G.ncells = (uint32_t) ncells;
 	CUDA_TRY(cudaSetDevice(c->device));
@@ -156,11 +156,10 @@ extern "C" int gevb_pcls_destroy(gevb_pcls * p)
 
 extern "C" double gevb_pcls_mass(gevb_pcls * p) { return p ? p->mass : 0.; }
 
-extern "C" void gevb_brick_dims(int * bx, int * by, int * bz)
+extern "C" void gevb_brick_dims(int * brick3, int * super3)
 {
-	if (bx) *bx = GEVB_BX;
-	if (by) *by = GEVB_BY;
-	if (bz) *bz = GEVB_BZ;
+	if (brick3) { brick3[0] = GEVB_BX; brick3[1] = GEVB_BY; brick3[2] = GEVB_BZ; }
+	if (super3) { super3[0] = 1 << GEVB_SX_BITS; super3[1] = 1 << GEVB_SY_BITS; super3[2] = 1 << GEVB_SZ_BITS; }
 }
 
 // grow capacity, keeping the live particles (and their keys)

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgevb.so")
+LIB_PATH = os.environ.get("GEVB_LIB") or os.path.join(os.path.dirname(_HERE), "libgevb.so")   # GEVB_LIB: experiment builds (scripts/ablate.sh)
 
 REAL, CPLX = 0, 1
 FFT_FORWARD, FFT_BACKWARD = 1, -1
@@ -79,7 +79,7 @@ def _declare(L):
     L.gevb_pcls_mass.restype = d
     L.gevb_pcls_mass.argtypes = [vp]
     L.gevb_brick_dims.restype = None
-    L.gevb_brick_dims.argtypes = [C.POINTER(i)] * 3
+    L.gevb_brick_dims.argtypes = [C.POINTER(i)] * 2
     L.gevb_timing_class_name.restype = C.c_char_p
     L.gevb_timing_class_name.argtypes = [i]
     L.gevb_timing_num_classes.restype = i
@@ -134,18 +134,21 @@ def _darr(v):
 
 
 def brick_dims():
-    b = [C.c_int(), C.c_int(), C.c_int()]
-    lib().gevb_brick_dims(*[C.byref(v) for v in b])
-    return tuple(v.value for v in b)
+    b, sp = (C.c_int * 3)(), (C.c_int * 3)()
+    lib().gevb_brick_dims(b, sp)
+    return tuple(b), tuple(sp)
 
 
 def storage_key(N, nzl, cx, cy, czl):
-    """Sort key of the device particle order (include/gevb.h, gevb_brick_dims): brick-major, then cell in brick."""
-    bx, by, bz = brick_dims()
-    nbx, nby = -(-N // bx), -(-N // by)
+    """Sort key of the device particle order (include/gevb.h, gevb_brick_dims): super-brick, brick, cell -- all z-major."""
+    (bx, by, bz), (sx, sy, sz) = brick_dims()
+    nsx, nsy = -(-N // (bx * sx)), -(-N // (by * sy))
     cx, cy, czl = (np.asarray(v, dtype=np.int64) for v in (cx, cy, czl))
-    brick = ((czl // bz) * nby + cy // by) * nbx + cx // bx
-    return brick * (bx * by * bz) + ((czl % bz) * by + cy % by) * bx + cx % bx
+    kx, ky, kz = cx // bx, cy // by, czl // bz                        # brick coordinates
+    sup = ((kz // sz) * nsy + ky // sy) * nsx + kx // sx
+    loc = ((kz % sz) * sy + ky % sy) * sx + kx % sx
+    cell = ((czl % bz) * by + cy % by) * bx + cx % bx
+    return (sup * (sx * sy * sz) + loc) * (bx * by * bz) + cell
 
 
 def nccl_unique_id():

@@ -122,9 +122,10 @@ int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);
 /* bit-exact contract: particles per cell of the local slab, uint32[nz_local][N][N] */
 int gevb_pcls_cell_counts(gevb_pcls * p, uint32_t * counts);
 double gevb_pcls_mass(gevb_pcls * p);
-/* storage order of the particle arrays: bricks of bx * by * bz cells (z-major brick index), then the cell
- * inside the brick (z-major), i.e. key = (brick << 9) | (sz * by + sy) * bx + sx                        */
-void gevb_brick_dims(int * bx, int * by, int * bz);
+/* storage order of the particle arrays (all indices z-major): super-bricks of super3[] bricks, then the brick
+ * inside the super-brick, then the cell inside the brick of brick3[] cells:
+ * key = ((super * bricks_per_super + brick) * cells_per_brick) + cell                                       */
+void gevb_brick_dims(int * brick3, int * super3);
 
 /* ---- particle -> mesh projections (gevolution.hpp:927,1046,1173; main.cpp:385,402,427,439)
  * phi may be NULL (no geometric correction, gevolution.hpp:949,965).  Target
