@@ -219,6 +219,57 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def clustered_particles_local(N, a, seed):
+    """z ~ 0 like occupancy at full size: 70 % of the particles in Gaussian blobs (sigma 4..40 cells), 30 % Poisson floor"""
+    rng = np.random.default_rng(seed)
+    n = N ** 3
+    nblob = 4096
+    centres = rng.random((nblob, 3))
+    widths = 10 ** rng.uniform(np.log10(4.0 / N), np.log10(40.0 / N), nblob)
+    which = rng.integers(0, nblob, n)
+    pos = rng.standard_normal((n, 3))
+    pos *= widths[which, None]
+    pos += centres[which]
+    floor = rng.random(n) < 0.3
+    pos[floor] = rng.random((int(floor.sum()), 3))
+    pos -= np.floor(pos)
+    pos[pos >= 1.0] = 0.0
+    vel = rng.standard_normal((n, 3))
+    vel *= 1e-3 * a
+    return np.arange(n, dtype=np.int64), pos, vel
+
+
+def particle_regime(gevb, ctx, common, N, label, ds, cosmo, mass, phi, chi):
+    """deposit / kick+drift / re-bin times of 2 cycles on a fresh particle state (single rank)"""
+    a0 = 1.0 / (1.0 + ds[3])
+    if label == "lattice":
+        ids, pos, vel = local_particles(N, 0, N, a0, 43)
+        vel *= 0.03                                           # cold (30 km/s): positions stay at one particle per cell
+        what = "one particle per cell (sigma 0.05 cell), q ~ N(0,(3e-5 a)^2): occupancy stays exactly 1"
+    else:
+        ids, pos, vel = clustered_particles_local(N, a0, 44)
+        what = "70 % of the particles in 4096 Gaussian blobs (sigma 4..40 cells) + 30 % Poisson floor"
+    sim = gevb.Sim(ctx, 1, 0, ds, cosmo)
+    sim.set_particles(0, ids, pos, vel, mass)
+    sim.set_field("phi", phi); sim.set_field("chi", chi)
+    counts = sim.pcls(0).cell_counts()
+    occ = {"max_per_cell": int(counts.max()), "empty_cells_frac": float((counts == 0).mean()), "particles_in_shared_cells_frac": float(counts[counts > 1].sum() / counts.sum())}
+    del counts
+    sim.step()
+    ctx.sync(); ctx.timing(True); ctx.timing_read()
+    nst = 2
+    for _ in range(nst):
+        sim.step()
+    per = ctx.timing_read()
+    ctx.timing(False)
+    sim.close()
+    out = {"what": what, "occupancy": occ}
+    for k in ("projection_T00_Tij_project", "kick_drift", "rebin_sort"):
+        if k in per:
+            out[k + "_ms"] = per[k][0] / nst
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import torch                      # first: its bundled NCCL must be the one mapped into the process
@@ -351,7 +402,8 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     bytes_per = algorithmic_bytes(N, ctx.nzl, np_local, world)
     kernels = {}
-    total_ms = sum(v[0] for v in per_class.values()) or 1.0
+    NESTED = ("fft_alltoall", "fft_transpose")                 # timed inside fft_forward / fft_backward
+    total_ms = sum(v[0] for k, v in per_class.items() if k not in NESTED) or 1.0
     for name, (kms, cnt) in per_class.items():
         b = bytes_per.get(name)
         ncomp_calls = cnt
@@ -368,6 +420,13 @@ def run_ours(args, rank, world, local_rank):
         if name in kernels and per_class[name][0] > 0:
             gbs = 16 * ctx.nzl * N * N * ncomp_per_step * args.steps / (per_class[name][0] * 1e-3) / 1e9
             kernels[name].update({"bytes_per_launch": 16 * ctx.nzl * N * N, "achieved_gbs": gbs, "frac": gbs / peak, "note": "cuFFT; ideal 16 B per site and component"})
+    nvlink = None
+    if world > 1 and "fft_alltoall" in per_class and per_class["fft_alltoall"][0] > 0:
+        # bytes one rank puts on NVLink per step: 12 component transforms x 16 B x local k-sites x (P-1)/P
+        sent = 12 * 16 * (N // 2 + 1) * N * (N // world) * (world - 1) / world
+        a2a_ms = per_class["fft_alltoall"][0] / args.steps
+        nvlink = {"bound": "nvlink", "kernel": "fft_alltoall (NCCL grouped send/recv)", "achieved": sent / (a2a_ms * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s per direction per GPU",
+                  "frac": sent / (a2a_ms * 1e-3) / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md (900 nominal)", "bytes_sent_per_rank_per_step": int(sent), "ms_per_step": a2a_ms}
     own = {k: v for k, v in kernels.items() if not k.startswith("fft_") and "frac" in v}
     top = max(own, key=lambda k: own[k]["ms_per_step"]) if own else None
     traffic = ncu_traffic().get(top) if top else None
@@ -376,6 +435,13 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"kernel": top, "bound": "hbm", "achieved": own[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": own[top]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": own[top]["ms_per_step"] / max(own[top]["calls_per_step"], 1e-9), "share_of_step": own[top]["share"]}
+
+    # ---- the particle kernels in the other occupancy regimes (report lattice-like and clustered) ---
+    regimes = None
+    if world == 1 and not args.no_regimes:
+        regimes = {"timed_run": "quasi-uniform ICs evolved by warmup+steps cycles (hot synthetic velocities: cell occupancy drifts from exactly 1 towards Poisson)"}
+        for label in ("lattice", "clustered"):
+            regimes[label] = particle_regime(gevb, ctx, common, N, label, ds, cosmo, mass, phi, chi)
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------------
     cpu = None
@@ -400,6 +466,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "nvlink": nvlink,
+            "regimes": regimes,
             "cpu_baseline": cpu,
             "kernels": kernels,
         }
@@ -417,6 +485,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 512))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the extra lattice / clustered measurements of the particle kernels")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

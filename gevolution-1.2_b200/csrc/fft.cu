@@ -5,10 +5,16 @@
 // one rank the global transpose is one NCCL all-to-all per execute:
 //
 //   nranks == 1 : one batched 3-D D2Z / Z2D plan over all components.
-//   nranks  > 1 : forward  = 2-D D2Z on every local z-plane  -> pack -> all-to-all
-//                            -> unpack/transposed to [ky][kx][kz] -> 1-D Z2Z along kz
-//                 backward = 1-D Z2Z^-1 along kz (out of place) -> pack -> all-to-all
-//                            -> unpack to [z][ky][kx] -> 2-D Z2D per plane.
+//   nranks  > 1 : forward  = 2-D D2Z on every local z-plane, written by cuFFT's
+//                            strided output directly in send order [ky][zl][kx]
+//                            (the ky-slab of every destination rank is contiguous)
+//                            -> all-to-all -> tile transpose to [ky][kx][kz]
+//                            -> 1-D Z2Z along kz
+//                 backward = 1-D Z2Z^-1 along kz (out of place) -> tile transpose
+//                            into send order -> all-to-all, which lands as
+//                            [ky][zl][kx] -> 2-D Z2D per plane reading that layout.
+//                 One pass over the data less per direction than pack / exchange /
+//                 unpack: the exchange buffers are cuFFT's own output / input.
 //
 // The Fourier input of a backward transform is preserved (the reference keeps
 // BiFT as persistent state across steps, main.cpp:586-593): cuFFT's multi-dim
@@ -17,22 +23,7 @@
 
 namespace {
 
-// [c][zl][ky][kx] (2-D transformed planes)  ->  send buffer [dst rank][c][zl][ky in dst slab][kx]
-__global__ void k_pack_fwd(const double2 * __restrict__ w, double2 * __restrict__ send, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
-{
-	const size_t total = (size_t) ncomp * nzl * N * nh;
-	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
-	{
-		int kx = (int) (i % nh); size_t r = i / nh;
-		int ky = (int) (r % N); r /= N;
-		int zl = (int) (r % nzl); int c = (int) (r / nzl);
-		int dst = ky / nkyl, kyl = ky % nkyl;
-		size_t o = ((((size_t) dst * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx;
-		send[o] = w[i];
-	}
-}
-
-// recv buffer [src rank][c][zl of src][kyl][kx]  ->  slab layout [c][kyl][kx][kz = src*nzl + zl]
+// recv buffer [src rank][c][kyl][zl of src][kx]  ->  slab layout [c][kyl][kx][kz = src*nzl + zl]
 // tile transpose (kz <-> kx) through shared memory so that reads and writes are both coalesced
 __global__ void k_unpack_fwd(const double2 * __restrict__ recv, double2 * __restrict__ out, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
 {
@@ -46,7 +37,7 @@ __global__ void k_unpack_fwd(const double2 * __restrict__ recv, double2 * __rest
 		if (kz < N && kx < nh)
 		{
 			int src = kz / nzl, zl = kz % nzl;
-			tile[j][threadIdx.x] = recv[((((size_t) src * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx];
+			tile[j][threadIdx.x] = recv[((((size_t) src * ncomp + c) * nkyl + kyl) * nzl + zl) * nh + kx];
 		}
 	}
 	__syncthreads();
@@ -57,7 +48,7 @@ __global__ void k_unpack_fwd(const double2 * __restrict__ recv, double2 * __rest
 	}
 }
 
-// slab layout [c][kyl][kx][z]  ->  send buffer [dst rank][c][zl in dst slab][kyl][kx]   (transpose back)
+// slab layout [c][kyl][kx][z]  ->  send buffer [dst rank][c][kyl][zl in dst slab][kx]   (transpose back)
 __global__ void k_pack_bwd(const double2 * __restrict__ in, double2 * __restrict__ send, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
 {
 	__shared__ double2 tile[32][33];
@@ -75,33 +66,24 @@ __global__ void k_pack_bwd(const double2 * __restrict__ in, double2 * __restrict
 		if (z < N && kx < nh)
 		{
 			int dst = z / nzl, zl = z % nzl;
-			send[((((size_t) dst * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx] = tile[threadIdx.x][j];
+			send[((((size_t) dst * ncomp + c) * nkyl + kyl) * nzl + zl) * nh + kx] = tile[threadIdx.x][j];
 		}
 	}
 }
 
-// recv buffer [src rank][c][zl][kyl of src][kx]  ->  [c][zl][ky = src*nkyl + kyl][kx]
-__global__ void k_unpack_bwd(const double2 * __restrict__ recv, double2 * __restrict__ w, int N, int nh, int nzl, int nkyl, int ncomp, int nranks)
-{
-	const size_t total = (size_t) ncomp * nzl * N * nh;
-	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
-	{
-		int kx = (int) (i % nh); size_t r = i / nh;
-		int ky = (int) (r % N); r /= N;
-		int zl = (int) (r % nzl); int c = (int) (r / nzl);
-		int src = ky / nkyl, kyl = ky % nkyl;
-		w[i] = recv[((((size_t) src * ncomp + c) * nzl + zl) * nkyl + kyl) * nh + kx];
-	}
-}
-
-int alltoall(gevb_ctx * c, const double2 * send, double2 * recv, size_t per_pair)
+// one chunk of `chunk` complex numbers per (peer rank, component).  Send side: [peer][c] when send_peer_major, else
+// [c][peer]; same for the receive side.
+int alltoall(gevb_ctx * c, const double2 * send, double2 * recv, size_t chunk, int ncomp, bool send_peer_major, bool recv_peer_major)
 {
 	NCCL_TRY(ncclGroupStart());
 	for (int r = 0; r < c->nranks; r++)
-	{
-		NCCL_TRY(ncclSend(send + (size_t) r * per_pair, per_pair * 2, ncclDouble, r, c->comm, c->stream));
-		NCCL_TRY(ncclRecv(recv + (size_t) r * per_pair, per_pair * 2, ncclDouble, r, c->comm, c->stream));
-	}
+		for (int k = 0; k < ncomp; k++)
+		{
+			const size_t so = send_peer_major ? (size_t) r * ncomp + k : (size_t) k * c->nranks + r;
+			const size_t ro = recv_peer_major ? (size_t) r * ncomp + k : (size_t) k * c->nranks + r;
+			NCCL_TRY(ncclSend(send + so * chunk, chunk * 2, ncclDouble, r, c->comm, c->stream));
+			NCCL_TRY(ncclRecv(recv + ro * chunk, chunk * 2, ncclDouble, r, c->comm, c->stream));
+		}
 	NCCL_TRY(ncclGroupEnd());
 	return 0;
 }
@@ -132,10 +114,10 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 	else
 	{
 		int n2[2] = {N, N};
-		int rembed[2] = {N, N}, kembed[2] = {N, nh};
-		// one call per component: nzl planes, contiguous in both the real bulk and the staging buffer
-		CUFFT_TRY(cufftPlanMany(&p->fwd2d, 2, n2, rembed, 1, N * N, kembed, 1, N * nh, CUFFT_D2Z, c->nzl));
-		CUFFT_TRY(cufftPlanMany(&p->bwd2d, 2, n2, kembed, 1, N * nh, rembed, 1, N * N, CUFFT_Z2D, c->nzl));
+		// real side: plane after plane; Fourier side: [ky][zl][kx], i.e. row pitch nzl*nh and plane distance nh
+		int rembed[2] = {N, N}, kembed[2] = {N, c->nzl * nh};
+		CUFFT_TRY(cufftPlanMany(&p->fwd2d, 2, n2, rembed, 1, N * N, kembed, 1, nh, CUFFT_D2Z, c->nzl));
+		CUFFT_TRY(cufftPlanMany(&p->bwd2d, 2, n2, kembed, 1, nh, rembed, 1, N * N, CUFFT_Z2D, c->nzl));
 		int n1[1] = {N};
 		CUFFT_TRY(cufftPlanMany(&p->z1d, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, rf->ncomp * c->nkyl * nh));
 		CUFFT_TRY(cufftSetStream(p->fwd2d, c->stream));
@@ -185,8 +167,9 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		return 0;
 	}
 	// ---- slab-decomposed transform ------------------------------------------------
-	const size_t wsites = (size_t) nc * c->nzl * N * nh;             // == nc * nkyl * nh * N
-	const size_t per_pair = (size_t) nc * c->nzl * c->nkyl * nh;
+	const size_t comp_sites = (size_t) c->nzl * N * nh;                 // == nkyl * nh * N: complex sites of one component on this rank
+	const size_t wsites = (size_t) nc * comp_sites;
+	const size_t chunk = (size_t) c->nkyl * c->nzl * nh;               // what one rank sends to one peer per component
 	void * s1, * s2;
 	GEVB_TRY(gevb_ctx_scratch(c, wsites * sizeof(double2), &s1));
 	GEVB_TRY(gevb_ctx_scratch2(c, wsites * sizeof(double2), &s2));
@@ -194,14 +177,16 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 	dim3 tb(32, 8), tg((nh + 31) / 32, (N + 31) / 32, nc * c->nkyl);
 	if (direction == GEVB_FFT_FORWARD)
 	{
+		// A: [c][ky][zl][kx] -- the ky-slab of peer r is the contiguous chunk r of component c
 		for (int k = 0; k < nc; k++)
-			CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * c->nzl * N * nh)));
+			CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * comp_sites)));
 		c->launches += nc;
-		k_pack_fwd<<<gevb_grid(c, wsites, 256), 256, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
-		KERNEL_CHECK(c);
-		GEVB_TRY(alltoall(c, B, A, per_pair));
-		k_unpack_fwd<<<tg, tb, 0, c->stream>>>(A, (double2 *) cf->data, N, nh, c->nzl, c->nkyl, nc, c->nranks);
-		KERNEL_CHECK(c);
+		{ Timed t_(c, CLS_FFT_A2A); GEVB_TRY(alltoall(c, A, B, chunk, nc, false, true)); }   // B: [src][c][kyl][zl of src][kx]
+		{
+			Timed t_(c, CLS_FFT_TRANSPOSE);
+			k_unpack_fwd<<<tg, tb, 0, c->stream>>>(B, (double2 *) cf->data, N, nh, c->nzl, c->nkyl, nc, c->nranks);
+			KERNEL_CHECK(c);
+		}
 		CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) cf->data, CUFFT_FORWARD));
 		c->launches++;
 	}
@@ -209,13 +194,14 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 	{
 		CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
 		c->launches++;
-		k_pack_bwd<<<tg, tb, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
-		KERNEL_CHECK(c);
-		GEVB_TRY(alltoall(c, B, A, per_pair));
-		k_unpack_bwd<<<gevb_grid(c, wsites, 256), 256, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);
-		KERNEL_CHECK(c);
+		{
+			Timed t_(c, CLS_FFT_TRANSPOSE);
+			k_pack_bwd<<<tg, tb, 0, c->stream>>>(A, B, N, nh, c->nzl, c->nkyl, nc, c->nranks);  // B: [dst][c][kyl][zl of dst][kx]
+			KERNEL_CHECK(c);
+		}
+		{ Timed t_(c, CLS_FFT_A2A); GEVB_TRY(alltoall(c, B, A, chunk, nc, true, false)); }   // A: [c][src][kyl][zl][kx] == [c][ky][zl][kx]
 		for (int k = 0; k < nc; k++)
-			CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (B + (size_t) k * c->nzl * N * nh), rbulk + k * rf->comp_stride));
+			CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (A + (size_t) k * comp_sites), rbulk + k * rf->comp_stride));
 		c->launches += nc;
 	}
 	return 0;

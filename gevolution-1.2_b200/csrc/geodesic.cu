@@ -252,16 +252,10 @@ __device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, do
 	}
 }
 
-// first non-empty brick at or after b in this block's stride; returns its particle range
-__device__ __forceinline__ uint32_t next_brick(const GParams & P, uint32_t b, uint32_t & first, uint32_t & last)
+__device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint32_t & first, uint32_t & last)
 {
-	while (b < P.G.nbricks)
-	{
-		first = __ldg(P.cell_start + (size_t) b * GEVB_BRICK_CELLS); last = __ldg(P.cell_start + (size_t) (b + 1) * GEVB_BRICK_CELLS);
-		if (first != last) break;
-		b += gridDim.x;
-	}
-	return b;
+	first = last = 0;
+	if (b < P.G.nbricks) { first = __ldg(P.cell_start + (size_t) b * GEVB_BRICK_CELLS); last = __ldg(P.cell_start + (size_t) (b + 1) * GEVB_BRICK_CELLS); }
 }
 
 // MODE 0: kick only, 1: drift only, 2: fused kick + drift.
@@ -274,17 +268,23 @@ __global__ void __launch_bounds__(256, 2) k_geodesic(GParams P)
 	const BrickGeom & G = P.G;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
 	const int tile_doubles = ncomp * TILE_SITES;
-	uint32_t first = 0, last = 0, nfirst = 0, nlast = 0;
-	uint32_t brick = next_brick(P, blockIdx.x, first, last);
-	if (brick < G.nbricks) stage_tile(P, brick, smem);
+	// software pipeline over the bricks of this block (stride gridDim.x): tile of brick k+1 in flight, particle range
+	// of brick k+2 being fetched, while brick k is processed
+	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
+	uint32_t brick = blockIdx.x;
+	brick_range(P, brick, first, last);
+	brick_range(P, brick + gridDim.x, nfirst, nlast);
+	if (first != last) stage_tile(P, brick, smem);
 	cp_async_commit();
 	int cur = 0;
 	double vmax = 0.;
 	while (brick < G.nbricks)
 	{
-		const uint32_t nbrick = next_brick(P, brick + gridDim.x, nfirst, nlast);
-		if (nbrick < G.nbricks) stage_tile(P, nbrick, smem + (cur ^ 1) * tile_doubles);
+		const uint32_t nbrick = brick + gridDim.x;
+		brick_range(P, nbrick + gridDim.x, nnfirst, nnlast);             // consumed at the end of this iteration
+		if (nfirst != nlast) stage_tile(P, nbrick, smem + (cur ^ 1) * tile_doubles);
 		cp_async_commit();
+		if (first == last) { brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1; continue; }   // empty brick (block-uniform)
 		int x0, y0, zl0;
 		brick_origin(G, brick, x0, y0, zl0);
 		// the first particle of every thread is requested before waiting for the tile
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256, 2) k_geodesic(GParams P)
 			if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
 		}
 		__syncthreads();                                         // tile[cur] is free for the brick after next
-		brick = nbrick; first = nfirst; last = nlast; cur ^= 1;
+		brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1;
 	}
 	if (MODE == 0 || MODE == 2)
 	{

@@ -50,13 +50,14 @@ enum
 {
 	CLS_INIT = 0, CLS_T00, CLS_TIJ, CLS_T00_TIJ, CLS_T0I, CLS_COMM, CLS_SUM, CLS_PREP_SCALAR, CLS_PREP_TENSOR, CLS_FFT_FWD, CLS_FFT_BWD,
 	CLS_POISSON, CLS_FTSCALAR, CLS_EVOLVE, CLS_FTVECTOR, CLS_FTTENSOR, CLS_HALO, CLS_KICK, CLS_DRIFT, CLS_KICK_DRIFT, CLS_SORT, CLS_SPECTRUM,
-	CLS_MIGRATE, GEVB_NCLS
+	CLS_MIGRATE, CLS_FFT_A2A, CLS_FFT_TRANSPOSE, GEVB_NCLS
 };
 struct GevbTimer
 {
 	bool on = false;
 	std::vector<cudaEvent_t> ev;
 	std::vector<int> cls;
+	std::vector<size_t> open;  // indices of the begun, not yet ended pairs (scopes nest: the FFT times its exchange inside itself)
 	size_t used = 0;
 };
 struct gevb_ctx;

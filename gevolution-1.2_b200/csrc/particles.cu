@@ -62,23 +62,40 @@ __global__ void k_make_keys(BrickGeom G, int64_t first, int64_t n, const double 
 }
 
 // the move of the counting sort: slot = cell_start[key] + (number of particles of this cell not yet placed) - 1.
-// Counting down leaves cell_count all zero again, ready for the next histogram.
+// Counting down leaves cell_count all zero again, ready for the next histogram.  Four particles per thread and
+// iteration, all loads and atomics of the four issued before the first dependent store (the chain key -> atomic ->
+// slot -> stores is latency bound otherwise).
+#define SCATTER_ILP 4
 __global__ void __launch_bounds__(256) k_scatter(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ cell_start, uint32_t * count,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
                           double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
                           double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
 {
-	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t i0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i0 < n; i0 += SCATTER_ILP * stride)
 	{
-		const uint32_t k = key[i];
-		if (k == GEVB_INVALID_KEY) continue;                  // left the slab (sent to a neighbour rank)
-		const double vx = x[i], vy = y[i], vz = z[i], wx = qx[i], wy = qy[i], wz = qz[i];
-		const int64_t vid = id[i];
-		const uint32_t d = __ldg(cell_start + k) + atomicSub(count + k, 1u) - 1u;
-		ox[d] = vx; oy[d] = vy; oz[d] = vz;
-		oqx[d] = wx; oqy[d] = wy; oqz[d] = wz;
-		oid[d] = vid;
+		uint32_t k[SCATTER_ILP], d[SCATTER_ILP];
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+		{
+			const int64_t i = i0 + u * stride;
+			k[u] = i < n ? __ldcs(key + i) : GEVB_INVALID_KEY;    // GEVB_INVALID_KEY: left the slab (sent to a neighbour rank)
+		}
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+			if (k[u] != GEVB_INVALID_KEY) d[u] = __ldg(cell_start + k[u]) + atomicSub(count + k[u], 1u) - 1u;
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+		{
+			const int64_t i = i0 + u * stride;
+			if (k[u] == GEVB_INVALID_KEY) continue;
+			const double vx = __ldcs(x + i), vy = __ldcs(y + i), vz = __ldcs(z + i), wx = __ldcs(qx + i), wy = __ldcs(qy + i), wz = __ldcs(qz + i);
+			const int64_t vid = __ldcs(id + i);
+			ox[d[u]] = vx; oy[d[u]] = vy; oz[d[u]] = vz;
+			oqx[d[u]] = wx; oqy[d[u]] = wy; oqz[d[u]] = wz;
+			oid[d[u]] = vid;
+		}
 	}
 }
 
@@ -273,6 +290,8 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		p->n += (int64_t) nloc;
 	}
 	if (p->n == n_before) return 0;
+	// slabs exchange particles every step: head-room so that the arrays are not regrown in the time loop
+	if (c->nranks > 1 && p->cap < p->n + p->n / 8) GEVB_TRY(gevb_pcls_reserve(p, p->n + p->n / 8 + 65536));
 	// keys + histogram of everything (old particles included: their keys are not kept between calls)
 	return gevb_pcls_rebin(p, p->n, p->n, false);
 }

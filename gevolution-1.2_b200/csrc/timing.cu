@@ -10,7 +10,7 @@ static const char * k_names[GEVB_NCLS] = {
 	"projection_init", "projection_T00_project", "projection_Tij_project", "projection_T00_Tij_project", "projection_T0i_project",
 	"projection_comm", "field_sum", "prepareFTsource_scalar", "prepareFTsource_tensor", "fft_forward", "fft_backward",
 	"solveModifiedPoissonFT", "projectFTscalar", "evolveFTvector", "projectFTvector", "projectFTtensor", "updateHalo",
-	"updateVel", "moveParticles", "kick_drift", "rebin_sort", "extractPowerSpectrum", "migrate"
+	"updateVel", "moveParticles", "kick_drift", "rebin_sort", "extractPowerSpectrum", "migrate", "fft_alltoall", "fft_transpose"
 };
 
 extern "C" const char * gevb_timing_class_name(int cls) { return (cls >= 0 && cls < GEVB_NCLS) ? k_names[cls] : NULL; }
@@ -36,14 +36,16 @@ void gevb_timer_begin(gevb_ctx * c, int cls)
 	}
 	t->cls.push_back(cls);
 	cudaEventRecord(t->ev[t->used], c->stream);
+	t->open.push_back(t->used);
 	t->used += 2;
 }
 
 void gevb_timer_end(gevb_ctx * c)
 {
 	GevbTimer * t = c->timer;
-	if (t == NULL || !t->on || t->used == 0) return;
-	cudaEventRecord(t->ev[t->used - 1], c->stream);
+	if (t == NULL || !t->on || t->open.empty()) return;
+	cudaEventRecord(t->ev[t->open.back() + 1], c->stream);
+	t->open.pop_back();
 }
 
 // totals since the last read: milliseconds and call counts per class (arrays of gevb_timing_num_classes())
@@ -60,6 +62,6 @@ extern "C" int gevb_ctx_timing_read(gevb_ctx * c, double * ms, int64_t * counts)
 		CUDA_TRY(cudaEventElapsedTime(&e, t->ev[2 * k], t->ev[2 * k + 1]));
 		ms[t->cls[k]] += e; counts[t->cls[k]]++;
 	}
-	t->cls.clear(); t->used = 0;
+	t->cls.clear(); t->open.clear(); t->used = 0;
 	return 0;
 }
