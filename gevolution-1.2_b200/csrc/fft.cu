@@ -100,7 +100,7 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 	CUDA_TRY(cudaSetDevice(c->device));
 	gevb_plan * p = new gevb_plan();
 	memset(p, 0, sizeof(*p));
-	p->ctx = c; p->real_field = rf; p->cplx_field = cf; p->multi = c->nranks > 1;
+	p->ctx = c; p->real_field = rf; p->cplx_field = cf; p->multi = c->nranks > 1; p->preserve = true;
 	const int N = c->N, nh = c->nh;
 	if (!p->multi)
 	{
@@ -139,6 +139,13 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	return 0;
 }
 
+extern "C" int gevb_plan_set_preserve_input(gevb_plan * p, int preserve)
+{
+	GEVB_CHECK_ARG(p != NULL, "gevb_plan_set_preserve_input: NULL plan");
+	p->preserve = preserve != 0;
+	return 0;
+}
+
 extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 {
 	GEVB_CHECK_ARG(p != NULL, "gevb_plan_execute: NULL plan");
@@ -158,9 +165,12 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		}
 		else
 		{
-			void * stage;
-			GEVB_TRY(gevb_ctx_scratch2(c, cf->bytes, &stage));
-			CUDA_TRY(cudaMemcpyAsync(stage, cf->data, cf->bytes, cudaMemcpyDeviceToDevice, c->stream));
+			void * stage = cf->data;
+			if (p->preserve)
+			{
+				GEVB_TRY(gevb_ctx_scratch2(c, cf->bytes, &stage));
+				CUDA_TRY(cudaMemcpyAsync(stage, cf->data, cf->bytes, cudaMemcpyDeviceToDevice, c->stream));
+			}
 			CUFFT_TRY(cufftExecZ2D(p->bwd, (cufftDoubleComplex *) stage, rbulk));
 			c->launches++;
 		}

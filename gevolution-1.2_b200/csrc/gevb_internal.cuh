@@ -119,6 +119,7 @@ struct gevb_plan
 	cufftHandle fwd, bwd;      // nranks == 1: 3-D D2Z / Z2D batched over components
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
 	bool multi;
+	bool preserve;             // backward execute keeps the Fourier field intact (default)
 };
 
 // ---------------------------------------------------------------- particles --

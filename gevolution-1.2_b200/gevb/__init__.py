@@ -31,7 +31,7 @@ SYMBOLS = [
     "gevb_ctx_timing", "gevb_ctx_timing_read", "gevb_timing_num_classes", "gevb_timing_class_name", "gevb_parallel_sum", "gevb_parallel_max",
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
     "gevb_field_device_ptr", "gevb_projection_init", "gevb_field_updateHalo", "gevb_projection_comm", "gevb_field_sum",
-    "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_pcls_create",
+    "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_plan_set_preserve_input", "gevb_pcls_create",
     "gevb_pcls_destroy", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
@@ -95,7 +95,7 @@ def _declare(L):
         "gevb_field_destroy": [vp], "gevb_field_upload": [vp, vp], "gevb_field_download": [vp, vp],
         "gevb_field_components": [vp], "gevb_projection_init": [vp], "gevb_field_updateHalo": [vp],
         "gevb_projection_comm": [vp], "gevb_field_sum": [vp, i, pd], "gevb_field_add_constant": [vp, i, d],
-        "gevb_plan_create": [C.POINTER(vp), vp, vp], "gevb_plan_destroy": [vp], "gevb_plan_execute": [vp, i],
+        "gevb_plan_create": [C.POINTER(vp), vp, vp], "gevb_plan_destroy": [vp], "gevb_plan_execute": [vp, i], "gevb_plan_set_preserve_input": [vp, i],
         "gevb_pcls_create": [vp, C.POINTER(vp), d], "gevb_pcls_destroy": [vp],
         "gevb_pcls_add": [vp, i64, vp, vp, vp], "gevb_pcls_count": [vp, C.POINTER(i64)],
         "gevb_pcls_download": [vp, vp, vp, vp], "gevb_pcls_cell_counts": [vp, vp],
@@ -277,6 +277,9 @@ class PlanFFT:
 
     def execute(self, direction):
         _ck(lib().gevb_plan_execute(self.h, direction), "PlanFFT.execute")
+
+    def preserve_input(self, keep):
+        _ck(lib().gevb_plan_set_preserve_input(self.h, int(bool(keep))), "PlanFFT.preserve_input")
 
     def close(self):
         if self.h:

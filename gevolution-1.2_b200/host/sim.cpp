@@ -51,6 +51,9 @@ extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int
 	s->plan_source.initialize(&s->source, &s->scalarFT);
 	s->plan_phi.initialize(&s->phi, &s->scalarFT);
 	s->plan_chi.initialize(&s->chi, &s->scalarFT);
+	// scalarFT is scratch: every backward transform of it is followed by a forward one that overwrites it
+	s->plan_phi.preserveInput(false);
+	s->plan_chi.preserveInput(false);
 	s->Sij.initialize(lat, 3, 3, symmetric);
 	s->SijFT.initialize(lat, 3, 3, symmetric);
 	s->plan_Sij.initialize(&s->Sij, &s->SijFT);
@@ -126,7 +129,14 @@ extern "C" int gevb_sim_set_state(gevb_sim * s, const double * in)
 	return 0;
 }
 
-extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused) { s->fused = fused; return 0; }
+extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
+{
+	s->fused = fused;
+	// fused mode treats scalarFT as scratch (its backward transforms may clobber it); unfused keeps LATfield2's semantics
+	s->plan_phi.preserveInput(!fused);
+	s->plan_chi.preserveInput(!fused);
+	return 0;
+}
 
 static int sim_step(gevb_sim * s);
 

@@ -108,6 +108,10 @@ int gevb_field_add_constant(gevb_field * f, int comp, double value);
 int gevb_plan_create(gevb_plan ** out, gevb_field * real_field, gevb_field * cplx_field);
 int gevb_plan_destroy(gevb_plan * plan);
 int gevb_plan_execute(gevb_plan * plan, int direction);
+/* preserve = 0: a backward execute may clobber the plan's Fourier field (saves one copy of it per execute).
+ * The main loop does this for plan_phi / plan_chi, whose scalarFT is scratch that the next forward
+ * transform overwrites (main.cpp:477-488,558-563).  Default 1 (LATfield2 semantics).               */
+int gevb_plan_set_preserve_input(gevb_plan * plan, int preserve);
 
 /* ---- particles ---------------------------------------------------------------
  * Particles::initialize + addParticle_global (ic_basic.hpp:1990,1429): particles
@@ -182,7 +186,7 @@ gevb_field * gevb_sim_field(gevb_sim * sim, int which);
 gevb_pcls * gevb_sim_pcls(gevb_sim * sim, int species);
 int gevb_sim_get_state(gevb_sim * sim, double * out9);     /* a,tau,dtau,dtau_old,cycle,maxvel0,maxvel1,T00hom,fourpiG */
 int gevb_sim_set_state(gevb_sim * sim, const double * in7);
-int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fused deposit + fused kick/drift; 0: one call per reference call */
+int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fused deposit + fused kick/drift, scalarFT is scratch after a cycle; 0: one call per reference call */
 int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
 
 #ifdef __cplusplus

@@ -121,6 +121,8 @@ public:
 	~PlanFFT() { if (p_) gevb_plan_destroy(p_); }
 	void initialize(Field<Real> * r, Field<T> * k) { check(gevb_plan_create(&p_, r->handle(), k->handle()), "PlanFFT"); }
 	void execute(int direction) { check(gevb_plan_execute(p_, direction), "PlanFFT::execute"); }
+	// extension: a backward execute may clobber the Fourier field (it is scratch for the caller)
+	void preserveInput(bool keep) { check(gevb_plan_set_preserve_input(p_, keep ? 1 : 0), "PlanFFT::preserveInput"); }
 };
 
 struct part_simple { long ID; Real pos[3]; Real vel[3]; };
