@@ -336,6 +336,20 @@ def run_ours(args, rank, world, local_rank):
     value = np_total * args.steps / (ms * 1e-3)
     state = sim.state()
 
+    # ---- optional ablation of kernel variants (stderr; not part of the bench line) ------------------------------
+    if args.ablate and world == 1:
+        for spec in args.ablate.split(","):
+            knob, vals = spec.split("=")
+            for v in vals.split(":"):
+                gevb.tuning(knob, int(v))
+                sim.step()
+                ctx.sync(); ctx.timing(True); ctx.timing_read()
+                for _ in range(2):
+                    sim.step()
+                per = ctx.timing_read(); ctx.timing(False)
+                print(json.dumps({"ablate": knob, "value": int(v), "ms": {k: round(t / 2, 3) for k, (t, n) in per.items() if t / 2 > 0.3}}), file=sys.stderr, flush=True)
+            gevb.tuning(knob, int(vals.split(":")[0]))
+
     # ---- end to end through the C ABI with host buffers ---------------------------------------
     e2e_steps = max(1, min(args.steps, env_int("GEVB_E2E_STEPS", 2)))
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
@@ -485,6 +499,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 512))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ablate", default="", help="e.g. geodesic_variant=1:0:2,deposit_variant=0:1 -- times 2 cycles per setting (stderr), first value is restored")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra lattice / clustered measurements of the particle kernels")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

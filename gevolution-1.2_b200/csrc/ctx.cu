@@ -32,6 +32,33 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 	return 0;
 }
 
+// ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
+//      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "deposit_variant"};
+static int tune_values[GEVB_NTUNE] = {1, 0};
+static bool tune_env_read = false;
+static void tune_read_env()
+{
+	if (tune_env_read) return;
+	tune_env_read = true;
+	for (int k = 0; k < GEVB_NTUNE; k++)
+	{
+		std::string name = "GEVB_";
+		for (const char * q = tune_names[k]; *q; q++) name += (char) toupper(*q);
+		const char * e = getenv(name.c_str());
+		if (e) tune_values[k] = atoi(e);
+	}
+}
+int gevb_tune(int knob) { tune_read_env(); return tune_values[knob]; }
+extern "C" int gevb_tuning(const char * knob, int value)
+{
+	GEVB_CHECK_ARG(knob != NULL, "gevb_tuning: NULL knob");
+	tune_read_env();
+	for (int k = 0; k < GEVB_NTUNE; k++)
+		if (strcmp(knob, tune_names[k]) == 0) { tune_values[k] = value; return 0; }
+	GEVB_FAIL("gevb_tuning: unknown knob '%s'", knob);
+}
+
 extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank, int nranks, const void * nccl_id)
 {
 	GEVB_CHECK_ARG(out != NULL, "gevb_ctx_create: NULL output");

@@ -64,7 +64,11 @@ __global__ void __launch_bounds__(256) k_evolve_vector(KLayout L, const double *
 	K_SITE_LOOP(L)
 	{
 		int kx, ky, kz; k_decode(L, i, kx, ky, kz);
-		if ((kx | ky | kz) == 0) { stc(B + i, cmk(0., 0.)); stc(B + cb + i, cmk(0., 0.)); stc(B + 2 * cb + i, cmk(0., 0.)); continue; }   // :304-310
+		if ((kx | ky | kz) == 0)                                                                               // :304-310
+		{
+			stc(B + i, cmk(0., 0.)); stc(B + cb + i, cmk(0., 0.)); stc(B + 2 * cb + i, cmk(0., 0.));
+			continue;
+		}
 		const double g0 = __ldg(gridk2 + kx), g1 = __ldg(gridk2 + ky), g2 = __ldg(gridk2 + kz);
 		const double2 k0 = __ldg(kshift + kx), k1 = __ldg(kshift + ky), k2 = __ldg(kshift + kz);
 		double k4 = g0 + g1 + g2; k4 *= k4;                                                                  // :314-315
@@ -75,15 +79,18 @@ __global__ void __launch_bounds__(256) k_evolve_vector(KLayout L, const double *
 		// :317-319
 		t1 = csub(csub(csub(cscale(S00, g1 + g2), cscale(S11, g1)), cscale(S22, g2)), cmul(cmul(cscale(k1, 2.), k2), S12));
 		t2 = cscale(cadd(cmul(k1, S01), cmul(k2, S02)), g1 + g2 - g0);
-		stc(B + i, cadd(ldc(B + i), cmul(pref, cadd(cmul(cconj(k0), t1), t2))));
+		const double2 b0 = cadd(ldc(B + i), cmul(pref, cadd(cmul(cconj(k0), t1), t2)));
+		stc(B + i, b0);
 		// :320-322
 		t1 = csub(csub(csub(cscale(S11, g0 + g2), cscale(S00, g0)), cscale(S22, g2)), cmul(cmul(cscale(k0, 2.), k2), S02));
 		t2 = cscale(cadd(cmul(k0, S01), cmul(k2, S12)), g0 + g2 - g1);
-		stc(B + cb + i, cadd(ldc(B + cb + i), cmul(pref, cadd(cmul(cconj(k1), t1), t2))));
+		const double2 b1 = cadd(ldc(B + cb + i), cmul(pref, cadd(cmul(cconj(k1), t1), t2)));
+		stc(B + cb + i, b1);
 		// :323-325
 		t1 = csub(csub(csub(cscale(S22, g0 + g1), cscale(S00, g0)), cscale(S11, g1)), cmul(cmul(cscale(k0, 2.), k1), S01));
 		t2 = cscale(cadd(cmul(k0, S02), cmul(k1, S12)), g0 + g1 - g2);
-		stc(B + 2 * cb + i, cadd(ldc(B + 2 * cb + i), cmul(pref, cadd(cmul(cconj(k2), t1), t2))));
+		const double2 b2 = cadd(ldc(B + 2 * cb + i), cmul(pref, cadd(cmul(cconj(k2), t1), t2)));
+		stc(B + 2 * cb + i, b2);
 	}
 }
 

@@ -15,6 +15,7 @@
 // counting sort that re-files the particles); particles that leave the z-slab
 // are compacted into send buffers for the two ring neighbours (NCCL P2P).
 #include <math.h>
+#include <stdlib.h>
 #include "gevb_internal.cuh"
 
 namespace {
@@ -225,13 +226,15 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // asynchronous copy (LDGSTS) of one brick's field tile into shared memory: site (lx, ly, lz) of the tile is
 // lattice site (x0 - 1 + lx, y0 - 1 + ly, local z = zl0 - 1 + lz); a thread keeps its (lx, ly) column and
 // walks z, so the periodic wrap is resolved once per thread and all copies of a thread are in flight together
+template <int THREADS>
 __device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, double * tile)
 {
-	if (threadIdx.x >= TX * TY) return;
 	const BrickGeom & G = P.G;
 	int x0, y0, zl0;
 	brick_origin(G, brick, x0, y0, zl0);
-	const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+	for (int col_id = threadIdx.x; col_id < TX * TY; col_id += THREADS)
+	{
+	const int lx = col_id % TX, ly = col_id / TX;
 	const size_t col = (size_t) wrap_index(y0 - 1 + ly, G.N) * G.N + wrap_index(x0 - 1 + lx, G.N);
 	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
 	#pragma unroll
@@ -250,6 +253,7 @@ __device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, do
 			cp_async8(d + 4 * TILE_SITES, P.B + 2 * P.csB + off);
 		}
 	}
+	}
 }
 
 __device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint32_t & first, uint32_t & last)
@@ -259,92 +263,105 @@ __device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint3
 }
 
 // MODE 0: kick only, 1: drift only, 2: fused kick + drift.
-// Persistent blocks walk the bricks with stride gridDim.x; the field tile of the next brick is copied
-// asynchronously into the second shared-memory buffer while the particles of the current one are processed.
-template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_geodesic(GParams P)
+// Persistent blocks walk the bricks with stride gridDim.x.  NBUF == 2: the field tile of the next brick is copied
+// asynchronously into the second shared-memory buffer while the particles of the current one are processed
+// (2 blocks of 256 threads per SM).  NBUF == 1: one tile buffer per block and twice as many, smaller blocks per SM --
+// a block that waits for its tile leaves the SM to the others.  In both forms the first particle of the next brick is
+// requested before the current brick's closing barrier, so no DRAM latency is exposed at a brick boundary.
+template <int MODE, int THREADS, int NBUF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 {
 	extern __shared__ double smem[];
 	const BrickGeom & G = P.G;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
 	const int tile_doubles = ncomp * TILE_SITES;
-	// software pipeline over the bricks of this block (stride gridDim.x): tile of brick k+1 in flight, particle range
-	// of brick k+2 being fetched, while brick k is processed
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
 	uint32_t brick = blockIdx.x;
 	brick_range(P, brick, first, last);
 	brick_range(P, brick + gridDim.x, nfirst, nlast);
-	if (first != last) stage_tile(P, brick, smem);
+	if (first != last) stage_tile<THREADS>(P, brick, smem);
 	cp_async_commit();
 	int cur = 0;
 	double vmax = 0.;
+	uint32_t i = first + threadIdx.x;
+	double pos[3] = {0., 0., 0.}, q[3] = {0., 0., 0.};
+	if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
 	while (brick < G.nbricks)
 	{
 		const uint32_t nbrick = brick + gridDim.x;
 		brick_range(P, nbrick + gridDim.x, nnfirst, nnlast);             // consumed at the end of this iteration
-		if (nfirst != nlast) stage_tile(P, nbrick, smem + (cur ^ 1) * tile_doubles);
-		cp_async_commit();
-		if (first == last) { brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1; continue; }   // empty brick (block-uniform)
-		int x0, y0, zl0;
-		brick_origin(G, brick, x0, y0, zl0);
-		// the first particle of every thread is requested before waiting for the tile
-		uint32_t i = first + threadIdx.x;
-		double pos[3] = {0., 0., 0.}, q[3] = {0., 0., 0.};
-		if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
-		cp_async_wait<1>();                                      // everything but the newest group: this brick's tile has landed
-		__syncthreads();
-		const double * tile = smem + cur * tile_doubles;
-		while (i < last)
+		if (NBUF == 2)
 		{
-			// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
-			double r[3];
-			const double * t;
-			{
-				const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
-				const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
-				r[0] = sx - floor(sx); r[1] = sy - floor(sy); r[2] = sz - floor(sz);      // modf(pos/dx) for pos >= 0
-				t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + 1);
-			}
-			if (MODE == 0 || MODE == 2)
-			{
-				const double v2 = kick(P, t, r, q);
-				vmax = fmax(vmax, v2);
-				P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
-			}
-			if (MODE == 1 || MODE == 2)
-			{
-				drift(P, t, r, q, pos);
-				pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
-				const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
-				const int zl = cz - G.z0;
-				uint32_t key;
-				if (P.nranks > 1 && (zl < 0 || zl >= G.nzl))
-				{
-					// at most one slab per move (main.cpp:281-286): periodic distance decides the neighbour
-					const int d = (zl + G.N) % G.N;
-					const int dir = d < G.N / 2 ? 1 : 0;
-					const unsigned long long slot = atomicAdd(P.nsend + dir, 1ull);
-					if ((int64_t) slot < P.sendcap)
-					{
-						double * sb = P.sendbuf[dir];
-						sb[slot] = pos[0]; sb[P.sendcap + slot] = pos[1]; sb[2 * P.sendcap + slot] = pos[2];
-						sb[3 * P.sendcap + slot] = q[0]; sb[4 * P.sendcap + slot] = q[1]; sb[5 * P.sendcap + slot] = q[2];
-						sb[6 * P.sendcap + slot] = __longlong_as_double((long long) P.id[i]);
-					}
-					key = GEVB_INVALID_KEY;
-				}
-				else
-				{
-					key = brick_key(G, cx, cy, zl);
-					atomicAdd(P.cell_count + key, 1u);              // histogram of the counting sort (particles.cu)
-				}
-				P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
-				P.key[i] = key;
-			}
-			i += blockDim.x;
-			if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+			if (nfirst != nlast) stage_tile<THREADS>(P, nbrick, smem + (cur ^ 1) * tile_doubles);
+			cp_async_commit();
 		}
-		__syncthreads();                                         // tile[cur] is free for the brick after next
+		if (first != last)                                               // block-uniform
+		{
+			int x0, y0, zl0;
+			brick_origin(G, brick, x0, y0, zl0);
+			if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();  // this brick's tile has landed
+			__syncthreads();
+			const double * tile = smem + (NBUF == 2 ? cur * tile_doubles : 0);
+			while (i < last)
+			{
+				// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
+				double r[3];
+				const double * t;
+				{
+					const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
+					const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
+					r[0] = sx - floor(sx); r[1] = sy - floor(sy); r[2] = sz - floor(sz);      // modf(pos/dx) for pos >= 0
+					t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + 1);
+				}
+				if (MODE == 0 || MODE == 2)
+				{
+					const double v2 = kick(P, t, r, q);
+					vmax = fmax(vmax, v2);
+					P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
+				}
+				if (MODE == 1 || MODE == 2)
+				{
+					drift(P, t, r, q, pos);
+					pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
+					const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
+					const int zl = cz - G.z0;
+					uint32_t key;
+					if (P.nranks > 1 && (zl < 0 || zl >= G.nzl))
+					{
+						// at most one slab per move (main.cpp:281-286): periodic distance decides the neighbour
+						const int d = (zl + G.N) % G.N;
+						const int dir = d < G.N / 2 ? 1 : 0;
+						const unsigned long long slot = atomicAdd(P.nsend + dir, 1ull);
+						if ((int64_t) slot < P.sendcap)
+						{
+							double * sb = P.sendbuf[dir];
+							sb[slot] = pos[0]; sb[P.sendcap + slot] = pos[1]; sb[2 * P.sendcap + slot] = pos[2];
+							sb[3 * P.sendcap + slot] = q[0]; sb[4 * P.sendcap + slot] = q[1]; sb[5 * P.sendcap + slot] = q[2];
+							sb[6 * P.sendcap + slot] = __longlong_as_double((long long) P.id[i]);
+						}
+						key = GEVB_INVALID_KEY;
+					}
+					else
+					{
+						key = brick_key(G, cx, cy, zl);
+						atomicAdd(P.cell_count + key, 1u);              // histogram of the counting sort (particles.cu)
+					}
+					P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
+					P.key[i] = key;
+				}
+				i += THREADS;
+				if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+			}
+		}
+		// request the first particle of the next brick, then close this one
+		i = nfirst + threadIdx.x;
+		if (i < nlast) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+		if (first != last) __syncthreads();                      // the tile is free again
+		if (NBUF == 1)
+		{
+			if (nfirst != nlast) stage_tile<THREADS>(P, nbrick, smem);
+			cp_async_commit();
+		}
 		brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1;
 	}
 	if (MODE == 0 || MODE == 2)
@@ -407,17 +424,30 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
 }
 
-template <int MODE>
-int launch_geodesic(gevb_pcls * p, const GParams & P)
+template <int MODE, int THREADS, int NBUF, int MINB>
+int launch_variant(gevb_pcls * p, const GParams & P)
 {
 	gevb_ctx * c = p->ctx;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
-	const size_t smem = (size_t) 2 * ncomp * TILE_SITES * sizeof(double);     // two tile buffers
-	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	const uint32_t persistent = (uint32_t) c->num_sms * 2;
-	k_geodesic<MODE><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, 256, smem, c->stream>>>(P);
+	const size_t smem = (size_t) NBUF * ncomp * TILE_SITES * sizeof(double);
+	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE, THREADS, NBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	const uint32_t persistent = (uint32_t) c->num_sms * MINB;
+	k_geodesic<MODE, THREADS, NBUF, MINB><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P);
 	KERNEL_CHECK(c);
 	return 0;
+}
+
+// tuning knob geodesic_variant: 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 (default) = 128 threads, single
+// tile buffer, 4 blocks per SM; 2 = 256 threads, single buffer, 2 blocks per SM
+template <int MODE>
+int launch_geodesic(gevb_pcls * p, const GParams & P)
+{
+	switch (gevb_tune(TUNE_GEODESIC_VARIANT))
+	{
+		case 0: return launch_variant<MODE, 256, 2, 2>(p, P);
+		case 2: return launch_variant<MODE, 256, 1, 2>(p, P);
+		default: return launch_variant<MODE, 128, 1, 4>(p, P);
+	}
 }
 
 // after a drift: exchange slab-crossing particles with the ring neighbours, then re-file (counting sort)

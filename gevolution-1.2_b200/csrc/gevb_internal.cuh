@@ -12,6 +12,10 @@
 // ---------------------------------------------------------------- errors -----
 void gevb_set_error(const char * fmt, ...);
 
+// ---------------------------------------------------------------- tuning knobs (ctx.cu)
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, GEVB_NTUNE };
+int gevb_tune(int knob);
+
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
 struct GevbNccl
 {
@@ -61,6 +65,7 @@ struct GevbTimer
 	size_t used = 0;
 };
 struct gevb_ctx;
+struct gevb_plan;
 void gevb_timer_begin(gevb_ctx * c, int cls);
 void gevb_timer_end(gevb_ctx * c);
 struct Timed

@@ -26,10 +26,15 @@ __global__ void k_append(int64_t n, const int64_t * __restrict__ id, const doubl
 	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
 	{
 		const double pz = pos[3 * i + 2];
-		const int cz = cell_of(pz, dx, N);
-		if (cz < z0 || cz >= z0 + nzl) continue;
-		const unsigned long long slot = atomicAdd(counter, 1ull);
-		if ((int64_t) slot >= cap) continue;
+		unsigned long long slot;
+		if (counter == NULL) slot = (unsigned long long) (cap + i);     // single rank: everything is local, cap = first free slot
+		else
+		{
+			const int cz = cell_of(pz, dx, N);
+			if (cz < z0 || cz >= z0 + nzl) continue;
+			slot = atomicAdd(counter, 1ull);
+			if ((int64_t) slot >= cap) continue;
+		}
 		x[slot] = pos[3 * i]; y[slot] = pos[3 * i + 1]; z[slot] = pz;
 		qx[slot] = vel[3 * i]; qy[slot] = vel[3 * i + 1]; qz[slot] = vel[3 * i + 2];
 		oid[slot] = id[i];
@@ -252,9 +257,12 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 	gevb_ctx * c = p->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	const double dx = 1.0 / (double) c->N;
-	const int64_t chunk = 1 << 24;
+	// the host arrays are staged in chunks of at most 2^26 particles (3.5 GB) and transposed into the SoA arrays;
+	// no host synchronisation inside the loop on a single rank, so the copies run back to back at PCIe speed
+	const int64_t chunk = (int64_t) 1 << 26;
 	const int64_t n_before = p->n;
 	unsigned long long * counter = (unsigned long long *) (c->d_red + 4000);
+	if (c->nranks == 1) GEVB_TRY(gevb_pcls_reserve(p, p->n + n));
 	for (int64_t off = 0; off < n; off += chunk)
 	{
 		const int64_t m = (n - off < chunk) ? n - off : chunk;
@@ -265,7 +273,16 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		CUDA_TRY(cudaMemcpyAsync(did, id + off, sizeof(int64_t) * m, cudaMemcpyHostToDevice, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(dpos, pos + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(dvel, vel + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
-		// how many of this chunk are local?
+		if (c->nranks == 1)
+		{
+			const int b = p->cur;
+			k_append<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, did, dpos, dvel, c->N, c->z0, c->nzl, dx,
+				p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], NULL, p->n);
+			KERNEL_CHECK(c);
+			p->n += m;
+			continue;
+		}
+		// several ranks: how many of this chunk are filed in this rank's slab?
 		CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
 		k_count_local<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, dpos, c->N, c->z0, c->nzl, dx, counter);
 		KERNEL_CHECK(c);
@@ -278,7 +295,7 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 			int64_t want = p->n + (int64_t) nloc;
 			if (off + m < n) want += want / 4;      // more chunks to come
 			// scratch holds the staged chunk; reserve() syncs but does not touch scratch
-			GEVB_TRY(gevb_pcls_reserve(p, want));
+			GEVB_TRY(gevb_pcls_reserve(p, want + want / 8 + 65536));
 		}
 		const int b = p->cur;
 		unsigned long long start = (unsigned long long) p->n;
@@ -286,14 +303,23 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		k_append<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, did, dpos, dvel, c->N, c->z0, c->nzl, dx,
 			p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], counter, p->cap);
 		KERNEL_CHECK(c);
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));     // `start` lives on this stack frame
 		p->n += (int64_t) nloc;
 	}
 	if (p->n == n_before) return 0;
-	// slabs exchange particles every step: head-room so that the arrays are not regrown in the time loop
-	if (c->nranks > 1 && p->cap < p->n + p->n / 8) GEVB_TRY(gevb_pcls_reserve(p, p->n + p->n / 8 + 65536));
 	// keys + histogram of everything (old particles included: their keys are not kept between calls)
 	return gevb_pcls_rebin(p, p->n, p->n, false);
+}
+
+// Particles::initialize on an existing container: drops the particles, keeps the device arrays
+extern "C" int gevb_pcls_reset(gevb_pcls * p, double mass)
+{
+	GEVB_CHECK_ARG(p != NULL, "gevb_pcls_reset: NULL handle");
+	gevb_ctx * c = p->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	p->n = 0; p->mass = mass;
+	CUDA_TRY(cudaMemsetAsync(p->cell_start, 0, ((size_t) p->geom.ncells + 1) * sizeof(uint32_t), c->stream));
+	return 0;
 }
 
 extern "C" int gevb_pcls_count(gevb_pcls * p, int64_t * n_local)
@@ -311,21 +337,15 @@ extern "C" int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, dou
 	CUDA_TRY(cudaSetDevice(c->device));
 	const int b = p->cur;
 	void * stage;
-	GEVB_TRY(gevb_ctx_scratch(c, (size_t) p->n * 24, &stage));
+	GEVB_TRY(gevb_ctx_scratch(c, (size_t) p->n * 48, &stage));
+	double * spos = (double *) stage, * svel = spos + 3 * p->n;
 	const int grid = gevb_grid(c, (size_t) p->n, 256);
+	// all device work is queued before the first copy so that the three copies run back to back
+	if (pos) { k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->x[b], p->y[b], p->z[b], spos); KERNEL_CHECK(c); }
+	if (vel) { k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->qx[b], p->qy[b], p->qz[b], svel); KERNEL_CHECK(c); }
 	if (id) CUDA_TRY(cudaMemcpyAsync(id, p->id[b], sizeof(int64_t) * p->n, cudaMemcpyDeviceToHost, c->stream));
-	if (pos)
-	{
-		k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->x[b], p->y[b], p->z[b], (double *) stage);
-		KERNEL_CHECK(c);
-		CUDA_TRY(cudaMemcpyAsync(pos, stage, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
-	}
-	if (vel)
-	{
-		k_interleave3<<<grid, 256, 0, c->stream>>>(p->n, p->qx[b], p->qy[b], p->qz[b], (double *) stage);
-		KERNEL_CHECK(c);
-		CUDA_TRY(cudaMemcpyAsync(vel, stage, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
-	}
+	if (pos) CUDA_TRY(cudaMemcpyAsync(pos, spos, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
+	if (vel) CUDA_TRY(cudaMemcpyAsync(vel, svel, sizeof(double) * 3 * p->n, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return 0;
 }

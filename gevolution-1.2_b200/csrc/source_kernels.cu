@@ -4,7 +4,7 @@
 //   prepareFTsource (tensor)  gevolution.hpp:57-147   104 B / site (phi, 6 Tij in; 6 Sij out)
 //
 // PHINONLINEAR on, ORIGINALMETRIC off (reference makefile:21).  One thread per
-// site, x fastest so every load is a coalesced row segment; the phi stencil
+// pair of x-adjacent sites, x fastest so every load is a coalesced row segment; the phi stencil
 // neighbours (x+-1 in the row, y+-1 rows, z+-1 planes incl. ghost planes) are
 // served from L1/L2, so DRAM sees each phi value once.  x and y wrap by index
 // arithmetic; z uses the ghost planes filled by updateHalo.
@@ -14,66 +14,126 @@ namespace {
 
 struct RGeom { int N, nzl; size_t plane; };
 
-__global__ void __launch_bounds__(256) k_prepare_scalar(RGeom G, const double * __restrict__ phi, const double * __restrict__ chi, const double * source, double bgmodel, double * result, double coeff, double coeff2, double coeff3)
+// Two x-adjacent sites per thread: every stream (phi rows, the six T / S components, source, chi) moves as 16-byte
+// accesses, which halves the number of memory requests in flight per byte; the arithmetic per site is unchanged.
+// N is even (checked at context creation), so a pair never straddles a row and every double2 is aligned.
+__device__ __forceinline__ double2 ld2(const double * p) { return *(const double2 *) p; }
+__device__ __forceinline__ double2 ld2s(const double * p) { return __ldcs((const double2 *) p); }
+__device__ __forceinline__ void st2s(double * p, double a, double b) { __stcs((double2 *) p, make_double2(a, b)); }
+
+// gevolution.hpp:176-190 for one site
+__device__ __forceinline__ double scalar_site(double src, double p, double chi, double pxm, double pxp, double pym, double pyp, double pzm, double pzp,
+                                              double bgmodel, double coeff, double coeff2, double coeff3)
 {
-	const int N = G.N;
-	const size_t total = (size_t) G.nzl * G.plane;
-	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
+	double res = coeff2 * (src - bgmodel);                                          // :176
+	res *= 1. - 2. * p;                                                             // :184
+	const double d0 = pxm - pxp, d1 = pym - pyp, d2 = pzm - pzp;
+	res += 0.125 * d0 * d0;                                                         // :185
+	res += 0.125 * d1 * d1;                                                         // :186
+	res += 0.125 * d2 * d2;                                                         // :187
+	res += (coeff3 - coeff) * p - coeff3 * chi;                                     // :190
+	return res;
+}
+
+// partial: per-block sums of the incoming source (main.cpp:459-462 fused into this pass), or NULL
+__global__ void __launch_bounds__(256) k_prepare_scalar(RGeom G, const double * __restrict__ phi, const double * __restrict__ chi, const double * source, double bgmodel, double * result,
+                                                        double coeff, double coeff2, double coeff3, double * partial)
+{
+	const int N = G.N, half = N >> 1;
+	const size_t pairs = (size_t) G.nzl * G.plane / 2;
+	double acc = 0.;
+	for (size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x; j < pairs; j += (size_t) gridDim.x * blockDim.x)
 	{
-		const int x = (int) (i % N); const size_t r = i / N;
+		const int x = 2 * (int) (j % half); const size_t r = j / half;
 		const int y = (int) (r % N); const int zl = (int) (r / N);
 		const size_t row = ((size_t) (zl + 1) * N + y) * N;
-		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 2 ? 0 : x + 2;
 		const size_t rowm = ((size_t) (zl + 1) * N + (y == 0 ? N - 1 : y - 1)) * N;
 		const size_t rowp = ((size_t) (zl + 1) * N + (y == N - 1 ? 0 : y + 1)) * N;
-		const double p = phi[row + x];
-		double res = coeff2 * (__ldcs(source + row + x) - bgmodel);                     // :176
-		res *= 1. - 2. * p;                                                             // :184
-		const double d0 = phi[row + xm] - phi[row + xp];
-		const double d1 = phi[rowm + x] - phi[rowp + x];
-		const double d2 = phi[row + x - G.plane] - phi[row + x + G.plane];
-		res += 0.125 * d0 * d0;                                                         // :185
-		res += 0.125 * d1 * d1;                                                         // :186
-		res += 0.125 * d2 * d2;                                                         // :187
-		res += (coeff3 - coeff) * p - coeff3 * __ldcs(chi + row + x);                   // :190
-		__stcs(result + row + x, res);
+		const size_t s = row + x;
+		const double2 p = ld2(phi + s), ym = ld2(phi + rowm + x), yp = ld2(phi + rowp + x), zm = ld2(phi + s - G.plane), zp = ld2(phi + s + G.plane);
+		const double pm = phi[row + xm], pp = phi[row + xp];
+		const double2 src = ld2s(source + s), ch = ld2s(chi + s);
+		acc += src.x; acc += src.y;
+		const double ra = scalar_site(src.x, p.x, ch.x, pm, p.y, ym.x, yp.x, zm.x, zp.x, bgmodel, coeff, coeff2, coeff3);
+		const double rb = scalar_site(src.y, p.y, ch.y, p.x, pp, ym.y, yp.y, zm.y, zp.y, bgmodel, coeff, coeff2, coeff3);
+		st2s(result + s, ra, rb);
 	}
+	if (partial != NULL)
+	{
+		__shared__ double wsum[8];
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+		if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			double t = 0.;
+			for (int w = 0; w < 8; w++) t += wsum[w];
+			partial[blockIdx.x] = t;
+		}
+	}
+}
+
+__global__ void k_sum_partials(const double * __restrict__ partial, int n, double * out)
+{
+	__shared__ double sh[256];
+	double t = 0.;
+	for (int i = threadIdx.x; i < n; i += 256) t += partial[i];
+	sh[threadIdx.x] = t;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+	if (threadIdx.x == 0) *out = sh[0];
+}
+
+// gevolution.hpp:64-143 for one site: the six S components in field order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
+struct PhiStencil { double p0, px, mx, py, my, pz, mz, pxy, pxz, pyz; };
+__device__ __forceinline__ void tensor_site(const PhiStencil & f, const double * t, double coeff, double * o)
+{
+	double v;
+	v = coeff * t[0]; v += 0.5 * (f.px - f.mx) * (f.px - f.mx); o[0] = v;                                      // :64,70
+	v = coeff * t[3]; v += 0.5 * (f.py - f.my) * (f.py - f.my); o[3] = v;                                      // :75,81
+	v = coeff * t[5]; v += 0.5 * (f.pz - f.mz) * (f.pz - f.mz); o[5] = v;                                      // :86,92
+	v = coeff * t[1];                                                                                         // :97
+	v += f.px * f.py - f.p0 * f.pxy;                                                                          // :99
+	v += 0.5 * f.p0 * f.p0; v -= 0.5 * f.px * f.px; v -= 0.5 * f.py * f.py; v += 0.5 * f.pxy * f.pxy;          // :106-109
+	o[1] = v;
+	v = coeff * t[2];                                                                                         // :114
+	v += f.px * f.pz - f.p0 * f.pxz;                                                                          // :116
+	v += 0.5 * f.p0 * f.p0; v -= 0.5 * f.px * f.px; v -= 0.5 * f.pz * f.pz; v += 0.5 * f.pxz * f.pxz;          // :123-126
+	o[2] = v;
+	v = coeff * t[4];                                                                                         // :131
+	v += f.py * f.pz - f.p0 * f.pyz;                                                                          // :133
+	v += 0.5 * f.p0 * f.p0; v -= 0.5 * f.py * f.py; v -= 0.5 * f.pz * f.pz; v += 0.5 * f.pyz * f.pyz;          // :140-143
+	o[4] = v;
 }
 
 __global__ void __launch_bounds__(256) k_prepare_tensor(RGeom G, const double * __restrict__ phi, const double * T, double * S, size_t cs, double coeff)
 {
-	const int N = G.N;
-	const size_t total = (size_t) G.nzl * G.plane;
-	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
+	const int N = G.N, half = N >> 1;
+	const size_t pairs = (size_t) G.nzl * G.plane / 2;
+	const size_t pl = G.plane;
+	for (size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x; j < pairs; j += (size_t) gridDim.x * blockDim.x)
 	{
-		const int x = (int) (i % N); const size_t r = i / N;
+		const int x = 2 * (int) (j % half); const size_t r = j / half;
 		const int y = (int) (r % N); const int zl = (int) (r / N);
-		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 2 ? 0 : x + 2;
 		const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
-		const size_t pl = G.plane;
 		const size_t row = ((size_t) (zl + 1) * N + y) * N, rowm = ((size_t) (zl + 1) * N + ym) * N, rowp = ((size_t) (zl + 1) * N + yp) * N;
 		const size_t s = row + x;
-		const double p0 = phi[s];
-		const double px = phi[row + xp], mx = phi[row + xm];
-		const double py = phi[rowp + x], my = phi[rowm + x];
-		const double pz = phi[s + pl], mz = phi[s - pl];
-		const double pxy = phi[rowp + xp], pxz = phi[row + xp + pl], pyz = phi[rowp + x + pl];
-		double v;
-		v = coeff * __ldcs(T + 0 * cs + s); v += 0.5 * (px - mx) * (px - mx); __stcs(S + 0 * cs + s, v);          // :64,70
-		v = coeff * __ldcs(T + 3 * cs + s); v += 0.5 * (py - my) * (py - my); __stcs(S + 3 * cs + s, v);          // :75,81
-		v = coeff * __ldcs(T + 5 * cs + s); v += 0.5 * (pz - mz) * (pz - mz); __stcs(S + 5 * cs + s, v);          // :86,92
-		v = coeff * __ldcs(T + 1 * cs + s);                                                                     // :97
-		v += px * py - p0 * pxy;                                                                               // :99
-		v += 0.5 * p0 * p0; v -= 0.5 * px * px; v -= 0.5 * py * py; v += 0.5 * pxy * pxy;                      // :106-109
-		__stcs(S + 1 * cs + s, v);
-		v = coeff * __ldcs(T + 2 * cs + s);                                                                     // :114
-		v += px * pz - p0 * pxz;                                                                               // :116
-		v += 0.5 * p0 * p0; v -= 0.5 * px * px; v -= 0.5 * pz * pz; v += 0.5 * pxz * pxz;                      // :123-126
-		__stcs(S + 2 * cs + s, v);
-		v = coeff * __ldcs(T + 4 * cs + s);                                                                     // :131
-		v += py * pz - p0 * pyz;                                                                               // :133
-		v += 0.5 * p0 * p0; v -= 0.5 * py * py; v -= 0.5 * pz * pz; v += 0.5 * pyz * pyz;                      // :140-143
-		__stcs(S + 4 * cs + s, v);
+		double2 t[6];
+		#pragma unroll
+		for (int c = 0; c < 6; c++) t[c] = ld2s(T + c * cs + s);
+		const double2 p = ld2(phi + s), vyp = ld2(phi + rowp + x), vym = ld2(phi + rowm + x), vzp = ld2(phi + s + pl), vzm = ld2(phi + s - pl), vyz = ld2(phi + rowp + x + pl);
+		const double pm = phi[row + xm], pp = phi[row + xp], pyp = phi[rowp + xp], pzp = phi[row + xp + pl];
+		const PhiStencil fa = {p.x, p.y, pm, vyp.x, vym.x, vzp.x, vzm.x, vyp.y, vzp.y, vyz.x};
+		const PhiStencil fb = {p.y, pp, p.x, vyp.y, vym.y, vzp.y, vzm.y, pyp, pzp, vyz.y};
+		double ta[6], tb[6], oa[6], ob[6];
+		#pragma unroll
+		for (int c = 0; c < 6; c++) { ta[c] = t[c].x; tb[c] = t[c].y; }
+		tensor_site(fa, ta, coeff, oa);
+		tensor_site(fb, tb, coeff, ob);
+		#pragma unroll
+		for (int c = 0; c < 6; c++) st2s(S + c * cs + s, oa[c], ob[c]);
 	}
 }
 
@@ -87,7 +147,7 @@ int check_real(const gevb_field * f, int ncomp, const char * who, const char * n
 
 } // namespace
 
-extern "C" int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3)
+static int prepare_scalar(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3, double * sum_source)
 {
 	GEVB_TRY(check_real(phi, 1, "prepareFTsource", "phi"));
 	GEVB_TRY(check_real(chi, 1, "prepareFTsource", "chi"));
@@ -98,9 +158,31 @@ extern "C" int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, g
 	CUDA_TRY(cudaSetDevice(c->device));
 	Timed timed_(c, CLS_PREP_SCALAR);
 	RGeom G = {c->N, c->nzl, c->plane()};
-	k_prepare_scalar<<<gevb_grid(c, (size_t) c->nzl * c->plane(), 256), 256, 0, c->stream>>>(G, phi->data, chi->data, source->data, bgmodel, result->data, coeff, coeff2, coeff3);
+	const int grid = gevb_grid(c, (size_t) c->nzl * c->plane() / 2, 256);      // <= 8 blocks per SM: the partials fit d_red[0..2048)
+	GEVB_CHECK_ARG(sum_source == NULL || grid <= 2048, "prepareFTsource: reduction buffer too small for %d blocks", grid);
+	k_prepare_scalar<<<grid, 256, 0, c->stream>>>(G, phi->data, chi->data, source->data, bgmodel, result->data, coeff, coeff2, coeff3, sum_source ? c->d_red : NULL);
 	KERNEL_CHECK(c);
+	if (sum_source)
+	{
+		k_sum_partials<<<1, 256, 0, c->stream>>>(c->d_red, grid, c->d_red + 2048);
+		KERNEL_CHECK(c);
+		if (c->nranks > 1) NCCL_TRY(ncclAllReduce(c->d_red + 2048, c->d_red + 2048, 1, ncclDouble, ncclSum, c->comm, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->h_red, c->d_red + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		*sum_source = c->h_red[0];
+	}
 	return 0;
+}
+
+extern "C" int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3)
+{
+	return prepare_scalar(phi, chi, source, bgmodel, result, coeff, coeff2, coeff3, NULL);
+}
+
+extern "C" int gevb_prepareFTsource_scalar_sum(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3, double * sum_source)
+{
+	GEVB_CHECK_ARG(sum_source != NULL, "prepareFTsource: sum_source is NULL");
+	return prepare_scalar(phi, chi, source, bgmodel, result, coeff, coeff2, coeff3, sum_source);
 }
 
 extern "C" int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, gevb_field * Sij, double coeff)
@@ -112,7 +194,7 @@ extern "C" int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, g
 	CUDA_TRY(cudaSetDevice(c->device));
 	Timed timed_(c, CLS_PREP_TENSOR);
 	RGeom G = {c->N, c->nzl, c->plane()};
-	k_prepare_tensor<<<gevb_grid(c, (size_t) c->nzl * c->plane(), 256), 256, 0, c->stream>>>(G, phi->data, Tij->data, Sij->data, Sij->comp_stride, coeff);
+	k_prepare_tensor<<<gevb_grid(c, (size_t) c->nzl * c->plane() / 2, 256), 256, 0, c->stream>>>(G, phi->data, Tij->data, Sij->data, Sij->comp_stride, coeff);
 	KERNEL_CHECK(c);
 	return 0;
 }

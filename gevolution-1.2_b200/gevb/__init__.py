@@ -26,16 +26,16 @@ FIELD_COMPS = {"phi": 1, "chi": 1, "Bi": 3, "source": 1, "Sij": 6, "scalarFT": 1
 
 # every symbol include/gevb.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "gevb_last_error", "gevb_version", "gevb_nccl_unique_id", "gevb_ctx_create", "gevb_ctx_destroy", "gevb_ctx_sync",
+    "gevb_last_error", "gevb_version", "gevb_tuning", "gevb_nccl_unique_id", "gevb_ctx_create", "gevb_ctx_destroy", "gevb_ctx_sync",
     "gevb_ctx_geometry", "gevb_ctx_stream", "gevb_ctx_launch_count",
     "gevb_ctx_timing", "gevb_ctx_timing_read", "gevb_timing_num_classes", "gevb_timing_class_name", "gevb_parallel_sum", "gevb_parallel_max",
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
     "gevb_field_device_ptr", "gevb_projection_init", "gevb_field_updateHalo", "gevb_projection_comm", "gevb_field_sum",
     "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_plan_set_preserve_input", "gevb_pcls_create",
-    "gevb_pcls_destroy", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
+    "gevb_pcls_destroy", "gevb_pcls_reset", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
-    "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
+    "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
@@ -85,7 +85,7 @@ def _declare(L):
     L.gevb_timing_num_classes.restype = i
     L.gevb_timing_num_classes.argtypes = []
     sig = {
-        "gevb_nccl_unique_id": [vp],
+        "gevb_nccl_unique_id": [vp], "gevb_tuning": [C.c_char_p, i],
         "gevb_ctx_create": [C.POINTER(vp), i, i, i, i, vp],
         "gevb_ctx_destroy": [vp], "gevb_ctx_sync": [vp],
         "gevb_ctx_geometry": [vp] + [C.POINTER(i)] * 5,
@@ -96,13 +96,13 @@ def _declare(L):
         "gevb_field_components": [vp], "gevb_projection_init": [vp], "gevb_field_updateHalo": [vp],
         "gevb_projection_comm": [vp], "gevb_field_sum": [vp, i, pd], "gevb_field_add_constant": [vp, i, d],
         "gevb_plan_create": [C.POINTER(vp), vp, vp], "gevb_plan_destroy": [vp], "gevb_plan_execute": [vp, i], "gevb_plan_set_preserve_input": [vp, i],
-        "gevb_pcls_create": [vp, C.POINTER(vp), d], "gevb_pcls_destroy": [vp],
+        "gevb_pcls_create": [vp, C.POINTER(vp), d], "gevb_pcls_destroy": [vp], "gevb_pcls_reset": [vp, d],
         "gevb_pcls_add": [vp, i64, vp, vp, vp], "gevb_pcls_count": [vp, C.POINTER(i64)],
         "gevb_pcls_download": [vp, vp, vp, vp], "gevb_pcls_cell_counts": [vp, vp],
         "gevb_projection_T00_project": [vp, vp, d, vp, d], "gevb_projection_T0i_project": [vp, vp, vp, d],
         "gevb_projection_Tij_project": [vp, vp, d, vp, d], "gevb_scalarProjectionCIC_project": [vp, vp],
         "gevb_projection_T00_Tij_project": [vp, vp, vp, d, vp, d],
-        "gevb_prepareFTsource_scalar": [vp, vp, vp, d, vp, d, d, d], "gevb_prepareFTsource_tensor": [vp, vp, vp, d],
+        "gevb_prepareFTsource_scalar": [vp, vp, vp, d, vp, d, d, d], "gevb_prepareFTsource_scalar_sum": [vp, vp, vp, d, vp, d, d, d, C.POINTER(C.c_double)], "gevb_prepareFTsource_tensor": [vp, vp, vp, d],
         "gevb_solveModifiedPoissonFT": [vp, vp, d, d], "gevb_projectFTscalar": [vp, vp, i],
         "gevb_evolveFTvector": [vp, vp, d], "gevb_projectFTvector": [vp, vp, d, d], "gevb_projectFTtensor": [vp, vp],
         "gevb_updateVel": [vp, i, d, C.POINTER(vp), i, pd, pd],
@@ -117,6 +117,11 @@ def _declare(L):
     for name, args in sig.items():
         f = getattr(L, name)
         f.restype, f.argtypes = C.c_int, args
+
+
+def tuning(knob, value):
+    """kernel-variant knob for ablation runs (gevb_tuning)"""
+    _ck(lib().gevb_tuning(knob.encode(), int(value)), "gevb_tuning")
 
 
 def _ck(status, what):

@@ -199,17 +199,21 @@ static int sim_step(gevb_sim * s)
 	if (s->gr_flag > 0)
 	{
 		double T00hom = 0.;
-		check(gevb_field_sum(source.handle(), 0, &T00hom), "T00hom");                         // :459-462 (sum + parallel.sum)
-		T00hom /= (double) ((long) s->numpts * (long) s->numpts * (long) s->numpts);          // :463
-		s->T00hom = T00hom;
+		const bool fuse_sum = fuse && dtau_old > 0.;                                          // the sum rides on prepareFTsource's pass
+		if (!fuse_sum) check(gevb_field_sum(source.handle(), 0, &T00hom), "T00hom");          // :459-462 (sum + parallel.sum)
 
 		if (dtau_old > 0.)
 		{
+			if (fuse_sum)
+				prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx, T00hom);
+			else
 			prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx);   // :472
 			s->plan_source.execute(FFT_FORWARD);                                              // :477
 			solveModifiedPoissonFT(scalarFT, scalarFT, 1. / (dx * dx), 3. * Hconf(a, fourpiG, cosmo) / dtau_old);   // :483
 			s->plan_phi.execute(FFT_BACKWARD);                                                // :488
 		}
+		T00hom /= (double) ((long) s->numpts * (long) s->numpts * (long) s->numpts);          // :463
+		s->T00hom = T00hom;
 	}
 	else
 	{

@@ -57,6 +57,9 @@ typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>
 const char * gevb_last_error(void);
 const char * gevb_version(void);
 
+/* kernel-variant knobs for ablation runs ("geodesic_variant", "deposit_variant"); results do not depend on them */
+int gevb_tuning(const char * knob, int value);
+
 /* ---- context: lattice geometry + device + communicator --------------------
  * replaces parallel.initialize(n,m) (main.cpp:152), Lattice lat(3,box,halo)
  * (main.cpp:213) and latFT.initializeRealFFT (main.cpp:215).
@@ -120,6 +123,8 @@ int gevb_plan_set_preserve_input(gevb_plan * plan, int preserve);
  * brick); cell = floor(pos/dx) per axis.                                      */
 int gevb_pcls_create(gevb_ctx * ctx, gevb_pcls ** out, double mass);
 int gevb_pcls_destroy(gevb_pcls * p);
+/* Particles::initialize on a container that already exists: drops its particles, keeps the device arrays */
+int gevb_pcls_reset(gevb_pcls * p, double mass);
 int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const double * pos, const double * vel);
 int gevb_pcls_count(gevb_pcls * p, int64_t * n_local);
 int gevb_pcls_download(gevb_pcls * p, int64_t * id, double * pos, double * vel);   /* storage (brick-major cell) order */
@@ -145,6 +150,9 @@ int gevb_projection_T00_Tij_project(gevb_pcls * p, gevb_field * T00, gevb_field 
 /* ---- real-space source preparation (gevolution.hpp:57,170; main.cpp:472,539);
  * result may alias source / Sij may alias Tij                                    */
 int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3);
+/* same, and also returns sum(source) over the lattice before it is modified -- the T00hom sum of main.cpp:459-462
+ * (local sum + parallel.sum) without its own pass over the field                     */
+int gevb_prepareFTsource_scalar_sum(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3, double * sum_source);
 int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, gevb_field * Sij, double coeff);
 
 /* ---- Fourier-space kernels (gevolution.hpp:211,284,350,411,501); outputs may alias inputs */

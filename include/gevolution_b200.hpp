@@ -122,6 +122,7 @@ public:
 	void initialize(Field<Real> * r, Field<T> * k) { check(gevb_plan_create(&p_, r->handle(), k->handle()), "PlanFFT"); }
 	void execute(int direction) { check(gevb_plan_execute(p_, direction), "PlanFFT::execute"); }
 	// extension: a backward execute may clobber the Fourier field (it is scratch for the caller)
+	gevb_plan * handle() const { return p_; }
 	void preserveInput(bool keep) { check(gevb_plan_set_preserve_input(p_, keep ? 1 : 0), "PlanFFT::preserveInput"); }
 };
 
@@ -147,6 +148,7 @@ public:
 	~Particles_gevolution() { if (p_) gevb_pcls_destroy(p_); }
 	void initialize(part_simple_info info, Lattice * lat)
 	{
+		if (p_ && lat_ == lat) { check(gevb_pcls_reset(p_, info.mass), "Particles::initialize"); return; }   // same lattice: keep the device arrays
 		if (p_) { gevb_pcls_destroy(p_); p_ = NULL; }
 		lat_ = lat;
 		check(gevb_pcls_create(lat->ctx(), &p_, info.mass), "Particles::initialize");
@@ -213,6 +215,10 @@ inline void prepareFTsource(Field<FieldType> & phi, Field<FieldType> & chi, Fiel
 { check(gevb_prepareFTsource_scalar(phi.handle(), chi.handle(), source.handle(), bgmodel, result.handle(), coeff, coeff2, coeff3), "prepareFTsource"); }
 inline void projectFTscalar(Field<Cplx> & SijFT, Field<Cplx> & chiFT, const int add = 0) { check(gevb_projectFTscalar(SijFT.handle(), chiFT.handle(), add), "projectFTscalar"); }
 inline void evolveFTvector(Field<Cplx> & SijFT, Field<Cplx> & BiFT, const Real a2dtau) { check(gevb_evolveFTvector(SijFT.handle(), BiFT.handle(), a2dtau), "evolveFTvector"); }
+// fused forms used by the time loop (same results, fewer passes over HBM)
+template <class FieldType>
+inline void prepareFTsource(Field<FieldType> & phi, Field<FieldType> & chi, Field<FieldType> & source, const FieldType bgmodel, Field<FieldType> & result, const double coeff, const double coeff2, const double coeff3, double & sum_source)
+{ check(gevb_prepareFTsource_scalar_sum(phi.handle(), chi.handle(), source.handle(), bgmodel, result.handle(), coeff, coeff2, coeff3, &sum_source), "prepareFTsource"); }
 inline void projectFTvector(Field<Cplx> & SiFT, Field<Cplx> & BiFT, const Real coeff = 1., const Real modif = 0.) { check(gevb_projectFTvector(SiFT.handle(), BiFT.handle(), coeff, modif), "projectFTvector"); }
 inline void projectFTtensor(Field<Cplx> & SijFT, Field<Cplx> & hijFT) { check(gevb_projectFTtensor(SijFT.handle(), hijFT.handle()), "projectFTtensor"); }
 inline void solveModifiedPoissonFT(Field<Cplx> & sourceFT, Field<Cplx> & potFT, Real coeff, const Real modif = 0.) { check(gevb_solveModifiedPoissonFT(sourceFT.handle(), potFT.handle(), coeff, modif), "solveModifiedPoissonFT"); }
