@@ -37,7 +37,7 @@ SYMBOLS = [
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_kick_drift",
-    "gevb_extractPowerSpectrum", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_particles", "gevb_sim_set_field",
+    "gevb_extractPowerSpectrum", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
     "gevb_sim_set_fused", "gevb_sim_step",
 ]
@@ -109,7 +109,7 @@ def _declare(L):
         "gevb_moveParticles": [vp, i, d, C.POINTER(vp), i, pd],
         "gevb_kick_drift": [vp, i, d, i, pd, d, i, pd, C.POINTER(vp), pd],
         "gevb_extractPowerSpectrum": [vp, vp, vp, vp, vp, vp, i, i, i],
-        "gevb_sim_create": [C.POINTER(vp), vp, i, i, pd, pd], "gevb_sim_destroy": [vp],
+        "gevb_sim_create": [C.POINTER(vp), vp, i, i, pd, pd], "gevb_sim_destroy": [vp], "gevb_background_eval": [pd, i, pd, pd, pd, d, d, d, pd], "gevb_sim_set_ncdm": [vp, i, pd, pd, pd, pd, pd, d, d], "gevb_sim_set_ncdm_maxvel": [vp, pd], "gevb_sim_get_ncdm_state": [vp, pd, C.POINTER(i)],
         "gevb_sim_set_particles": [vp, i, i64, vp, vp, vp, d], "gevb_sim_set_field": [vp, i, vp],
         "gevb_sim_get_field": [vp, i, vp], "gevb_sim_get_state": [vp, pd], "gevb_sim_set_state": [vp, pd],
         "gevb_sim_set_fused": [vp, i], "gevb_sim_step": [vp],
@@ -412,6 +412,14 @@ def extractPowerSpectrum(fldFT, numbins, deconvolve=True, ktype=1):
     return kbin, power, ksc, psc, occ
 
 
+def background_eval(cosmo, a, fourpiG, dtau=0.0, m_ncdm=(), T_ncdm=(), Omega_ncdm=()):
+    """host-side background (no device): dict(Hconf, bg_ncdm, particleHorizon, a_next)"""
+    keep = [_darr(v) for v in (cosmo, m_ncdm, T_ncdm, Omega_ncdm)]
+    out = np.zeros(4)
+    _ck(lib().gevb_background_eval(keep[0][1], len(m_ncdm), keep[1][1], keep[2][1], keep[3][1], a, fourpiG, dtau, out.ctypes.data_as(C.POINTER(C.c_double))), "gevb_background_eval")
+    return dict(Hconf=out[0], bg_ncdm=out[1], particleHorizon=out[2], a_next=out[3])
+
+
 class Sim:
     """State of main.cpp:217-246 on the device + one-cycle stepping (host loop is C++)."""
 
@@ -456,6 +464,19 @@ class Sim:
     def set_state(self, a, tau, dtau, dtau_old, cycle, maxvel=(0.0, 0.0)):
         s = np.array([a, tau, dtau, dtau_old, cycle, maxvel[0], maxvel[1]], dtype=np.float64)
         _ck(lib().gevb_sim_set_state(self.h, s.ctypes.data_as(C.POINTER(C.c_double))), "gevb_sim_set_state")
+
+    def set_ncdm(self, m_ncdm, T_ncdm, Omega_ncdm, z_switch_deltancdm, z_switch_Bncdm, z_switch_linearchi, movelimit):
+        keep = [_darr(v) for v in (m_ncdm, T_ncdm, Omega_ncdm, z_switch_deltancdm, z_switch_Bncdm)]
+        _ck(lib().gevb_sim_set_ncdm(self.h, len(m_ncdm), *[k[1] for k in keep], z_switch_linearchi, movelimit), "gevb_sim_set_ncdm")
+
+    def set_ncdm_maxvel(self, maxvel):
+        v = np.zeros(4); v[:len(maxvel)] = maxvel
+        _ck(lib().gevb_sim_set_ncdm_maxvel(self.h, v.ctypes.data_as(C.POINTER(C.c_double))), "gevb_sim_set_ncdm_maxvel")
+
+    def ncdm_state(self):
+        v, n = np.zeros(4), np.zeros(4, dtype=np.int32)
+        _ck(lib().gevb_sim_get_ncdm_state(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), n.ctypes.data_as(C.POINTER(C.c_int))), "gevb_sim_get_ncdm_state")
+        return v, n
 
     def set_fused(self, fused):
         lib().gevb_sim_set_fused(self.h, int(bool(fused)))

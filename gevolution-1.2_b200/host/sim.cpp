@@ -24,8 +24,11 @@ struct gevb_sim
 	double boxsize, Cf, steplimit, z_in, z_relax;
 	double fourpiG, a, tau, dtau, dtau_old, dx, T00hom;
 	int cycle;
-	double maxvel[2];
+	double maxvel[2 + GEVB_MAX_NCDM];                 // by species slot: cdm, baryons, ncdm 0..3 (main.cpp indexes [i+1+baryon_flag])
 	Particles_gevolution pcls_cdm, pcls_b;
+	Particles_gevolution pcls_ncdm[GEVB_MAX_NCDM];    // main.cpp:219
+	double z_switch_deltancdm[GEVB_MAX_NCDM], z_switch_Bncdm[GEVB_MAX_NCDM], z_switch_linearchi, movelimit;   // metadata.hpp:224-238
+	int numsteps_ncdm[GEVB_MAX_NCDM];
 	Field<Real> phi, source, chi, Sij, Bi;
 	Field<Cplx> scalarFT, SijFT, BiFT;
 	PlanFFT<Cplx> plan_source, plan_phi, plan_chi, plan_Sij, plan_Bi;
@@ -40,8 +43,13 @@ extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int
 	s->numpts = s->lat.size(0);
 	s->gr_flag = gr_flag; s->vector_flag = vector_flag; s->baryon_flag = 0; s->fused = 1;
 	s->boxsize = ds[0]; s->Cf = ds[1]; s->steplimit = ds[2]; s->z_in = ds[3]; s->z_relax = ds[4];
-	cosmology co = {c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10]};
+	cosmology co;
+	std::memset(&co, 0, sizeof(co));
+	co.Omega_cdm = c[0]; co.Omega_b = c[1]; co.Omega_m = c[2]; co.Omega_Lambda = c[3]; co.Omega_fld = c[4]; co.w0_fld = c[5]; co.wa_fld = c[6];
+	co.Omega_g = c[7]; co.Omega_ur = c[8]; co.Omega_rad = c[9]; co.h = c[10]; co.num_ncdm = 0;
 	s->cosmo = co;
+	s->z_switch_linearchi = 0.; s->movelimit = 1.e10;
+	for (int i = 0; i < GEVB_MAX_NCDM; i++) { s->z_switch_deltancdm[i] = s->z_switch_Bncdm[i] = 0.; s->numsteps_ncdm[i] = 1; }
 	Lattice & lat = s->lat;
 	// main.cpp:234-246
 	s->source.initialize(lat, 1);
@@ -69,19 +77,73 @@ extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int
 	else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
 	s->dtau_old = 0.;
 	s->cycle = 0; s->T00hom = 0.;
-	s->maxvel[0] = s->maxvel[1] = 0.;
+	for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) s->maxvel[i] = 0.;
 	*out = s;
+	return 0;
+}
+
+// non-cold dark matter species (cosmo.*_ncdm, metadata.hpp:284-288; switches metadata.hpp:224-238, parser.hpp:1755-1793)
+extern "C" int gevb_sim_set_ncdm(gevb_sim * s, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,
+                                 const double * z_switch_deltancdm, const double * z_switch_Bncdm, double z_switch_linearchi, double movelimit)
+{
+	if (s == NULL || num_ncdm < 0 || num_ncdm > GEVB_MAX_NCDM) return 1;
+	if (num_ncdm > 0 && (m_ncdm == NULL || T_ncdm == NULL || Omega_ncdm == NULL || z_switch_deltancdm == NULL || z_switch_Bncdm == NULL)) return 1;
+	s->cosmo.num_ncdm = num_ncdm;
+	for (int i = 0; i < num_ncdm; i++)
+	{
+		s->cosmo.m_ncdm[i] = m_ncdm[i]; s->cosmo.T_ncdm[i] = T_ncdm[i]; s->cosmo.Omega_ncdm[i] = Omega_ncdm[i];
+		s->z_switch_deltancdm[i] = z_switch_deltancdm[i]; s->z_switch_Bncdm[i] = z_switch_Bncdm[i];
+	}
+	s->z_switch_linearchi = z_switch_linearchi; s->movelimit = movelimit;
+	if (s->cycle == 0)
+	{
+		// the background changed: redo main.cpp:289-295 at the initial redshift
+		s->tau = particleHorizon(s->a, s->fourpiG, s->cosmo);
+		if (s->Cf * s->dx < s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo)) s->dtau = s->Cf * s->dx;
+		else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
+	}
+	return 0;
+}
+
+extern "C" int gevb_sim_get_ncdm_state(gevb_sim * s, double * maxvel, int * numsteps)
+{
+	if (s == NULL) return 1;
+	for (int i = 0; i < GEVB_MAX_NCDM; i++)
+	{
+		if (maxvel) maxvel[i] = s->maxvel[2 + i];
+		if (numsteps) numsteps[i] = s->numsteps_ncdm[i];
+	}
 	return 0;
 }
 
 extern "C" int gevb_sim_destroy(gevb_sim * s) { delete s; return 0; }
 
+// the host-side Friedmann background by itself (no device needed): out = {Hconf(a), bg_ncdm(a), particleHorizon(a),
+// a after rungekutta4bg(a, dtau)} -- background.hpp:103,137,167,200
+extern "C" int gevb_background_eval(const double * c, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,
+                                    double a, double fourpiG, double dtau, double * out4)
+{
+	if (c == NULL || out4 == NULL || num_ncdm < 0 || num_ncdm > GEVB_MAX_NCDM) return 1;
+	cosmology co;
+	std::memset(&co, 0, sizeof(co));
+	co.Omega_cdm = c[0]; co.Omega_b = c[1]; co.Omega_m = c[2]; co.Omega_Lambda = c[3]; co.Omega_fld = c[4]; co.w0_fld = c[5]; co.wa_fld = c[6];
+	co.Omega_g = c[7]; co.Omega_ur = c[8]; co.Omega_rad = c[9]; co.h = c[10]; co.num_ncdm = num_ncdm;
+	for (int i = 0; i < num_ncdm; i++) { co.m_ncdm[i] = m_ncdm[i]; co.T_ncdm[i] = T_ncdm[i]; co.Omega_ncdm[i] = Omega_ncdm[i]; }
+	out4[0] = Hconf(a, fourpiG, co);
+	out4[1] = bg_ncdm(a, co);
+	out4[2] = particleHorizon(a, fourpiG, co);
+	double a2 = a;
+	rungekutta4bg(a2, fourpiG, co, dtau);
+	out4[3] = a2;
+	return 0;
+}
+
 extern "C" int gevb_sim_set_particles(gevb_sim * s, int species, int64_t n, const int64_t * id, const double * pos, const double * vel, double mass)
 {
-	if (s == NULL || species < 0 || species > 1) return 1;
+	if (s == NULL || species < 0 || species >= 2 + GEVB_MAX_NCDM) return 1;
 	part_simple_info info;
-	info.mass = mass; info.relativistic = 0; std::strcpy(info.type_name, "part_simple");
-	Particles_gevolution & p = species == 0 ? s->pcls_cdm : s->pcls_b;
+	info.mass = mass; info.relativistic = species >= 2; std::strcpy(info.type_name, "part_simple");
+	Particles_gevolution & p = species == 0 ? s->pcls_cdm : (species == 1 ? s->pcls_b : s->pcls_ncdm[species - 2]);
 	p.initialize(info, &s->lat);
 	if (species == 1) s->baryon_flag = 1;
 	return gevb_pcls_add(p.handle(), n, id, pos, vel);
@@ -98,7 +160,11 @@ extern "C" gevb_field * gevb_sim_field(gevb_sim * s, int which)
 	return NULL;
 }
 
-extern "C" gevb_pcls * gevb_sim_pcls(gevb_sim * s, int species) { return species == 0 ? s->pcls_cdm.handle() : s->pcls_b.handle(); }
+extern "C" gevb_pcls * gevb_sim_pcls(gevb_sim * s, int species)
+{
+	if (s == NULL || species < 0 || species >= 2 + GEVB_MAX_NCDM) return NULL;
+	return species == 0 ? s->pcls_cdm.handle() : (species == 1 ? s->pcls_b.handle() : s->pcls_ncdm[species - 2].handle());
+}
 
 extern "C" int gevb_sim_set_field(gevb_sim * s, int which, const double * host)
 {
@@ -129,6 +195,14 @@ extern "C" int gevb_sim_set_state(gevb_sim * s, const double * in)
 	return 0;
 }
 
+// maxvel of the ncdm species as the IC generator returns it (main.cpp:330-340 feeds the first cycle's sub-stepping)
+extern "C" int gevb_sim_set_ncdm_maxvel(gevb_sim * s, const double * maxvel)
+{
+	if (s == NULL || maxvel == NULL) return 1;
+	for (int i = 0; i < GEVB_MAX_NCDM; i++) s->maxvel[2 + i] = maxvel[i];
+	return 0;
+}
+
 extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
 {
 	s->fused = fused;
@@ -156,7 +230,16 @@ static int sim_step(gevb_sim * s)
 	Field<Real> & phi = s->phi, & chi = s->chi, & source = s->source, & Sij = s->Sij, & Bi = s->Bi;
 	Field<Cplx> & scalarFT = s->scalarFT, & SijFT = s->SijFT, & BiFT = s->BiFT;
 	Particles_gevolution & pcls_cdm = s->pcls_cdm, & pcls_b = s->pcls_b;
+	Particles_gevolution * pcls_ncdm = s->pcls_ncdm;
 	Field<Real> * update_cdm_fields[3] = {&phi, &chi, &Bi};
+	Field<Real> ** update_ncdm_fields = update_cdm_fields;                                    // main.cpp:255-261: the same three fields
+	bool ncdm_T00[GEVB_MAX_NCDM], ncdm_Tij[GEVB_MAX_NCDM];                                    // which ncdm species deposit this cycle
+	for (int i = 0; i < GEVB_MAX_NCDM; i++)
+	{
+		const bool have = i < cosmo.num_ncdm && pcls_ncdm[i].initialized();                   // sim.numpcl[1+sim.baryon_flag+i] > 0
+		ncdm_T00[i] = have && a >= 1. / (s->z_switch_deltancdm[i] + 1.);                      // :390
+		ncdm_Tij[i] = have && a >= 1. / (s->z_switch_linearchi + 1.);                         // :442-447
+	}
 	double f_params[5];
 	const bool fuse = s->fused && s->gr_flag > 0;
 
@@ -168,17 +251,31 @@ static int sim_step(gevb_sim * s)
 		// one pass over the particles deposits T00 and Tij (same sums as :385 and :439)
 		projection_T00_Tij_project(&pcls_cdm, &source, &Sij, a, &phi);
 		if (s->baryon_flag) projection_T00_Tij_project(&pcls_b, &source, &Sij, a, &phi);
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+		{
+			if (ncdm_T00[i] && ncdm_Tij[i]) projection_T00_Tij_project(pcls_ncdm + i, &source, &Sij, a, &phi);
+			else if (ncdm_T00[i]) projection_T00_project(pcls_ncdm + i, &source, a, &phi);
+			else if (ncdm_Tij[i]) projection_Tij_project(pcls_ncdm + i, &Sij, a, &phi);
+		}
 	}
 	else if (s->gr_flag > 0)
 	{
 		projection_T00_project(&pcls_cdm, &source, a, &phi);                                  // :385
 		if (s->baryon_flag) projection_T00_project(&pcls_b, &source, a, &phi);                // :387
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (ncdm_T00[i]) projection_T00_project(pcls_ncdm + i, &source, a, &phi);         // :391
 	}
 	else
 	{
 		scalarProjectionCIC_project(&pcls_cdm, &source);                                      // :402
 		if (s->baryon_flag) scalarProjectionCIC_project(&pcls_b, &source);                    // :404
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (ncdm_T00[i]) scalarProjectionCIC_project(pcls_ncdm + i, &source);             // :408
 	}
+	if (s->gr_flag > 0)
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (!ncdm_T00[i])                                                                 // :392-397 (radiation_flag == 0): homogeneous stand-in
+				check(gevb_field_add_constant(source.handle(), 0, bg_ncdm(a, cosmo, i)), "bg_ncdm");
 	projection_T00_comm(&source);                                                             // :411
 
 	if (s->vector_flag == VECTOR_ELLIPTIC)
@@ -186,6 +283,8 @@ static int sim_step(gevb_sim * s)
 		projection_init(&Bi);                                                                 // :426
 		projection_T0i_project(&pcls_cdm, &Bi, &phi);                                         // :427
 		if (s->baryon_flag) projection_T0i_project(&pcls_b, &Bi, &phi);                       // :429
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (pcls_ncdm[i].initialized() && a >= 1. / (s->z_switch_Bncdm[i] + 1.)) projection_T0i_project(pcls_ncdm + i, &Bi, &phi);   // :432-433
 		projection_T0i_comm(&Bi);                                                             // :435
 	}
 
@@ -193,6 +292,8 @@ static int sim_step(gevb_sim * s)
 	{
 		projection_Tij_project(&pcls_cdm, &Sij, a, &phi);                                     // :439
 		if (s->baryon_flag) projection_Tij_project(&pcls_b, &Sij, a, &phi);                   // :441
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (ncdm_Tij[i]) projection_Tij_project(pcls_ncdm + i, &Sij, a, &phi);            // :442-448
 	}
 	projection_Tij_comm(&Sij);                                                                // :450
 
@@ -244,6 +345,51 @@ static int sim_step(gevb_sim * s)
 		Bi.updateHalo();                                                                      // :598
 	}
 
+	// number of step subdivisions for the ncdm particle updates (main.cpp:696-701)
+	for (int i = 0; i < cosmo.num_ncdm; i++)
+	{
+		if (dtau * s->maxvel[2 + i] > dx * s->movelimit)
+			s->numsteps_ncdm[i] = (int) ceil(dtau * s->maxvel[2 + i] / dx / s->movelimit);
+		else s->numsteps_ncdm[i] = 1;
+	}
+
+	// non-cold DM particle update (main.cpp:729-765)
+	for (int i = 0; i < cosmo.num_ncdm; i++)
+	{
+		if (!pcls_ncdm[i].initialized()) continue;
+		double tmp = a;
+		const int numsteps = s->numsteps_ncdm[i];
+		for (int j = 0; j < numsteps; j++)
+		{
+			f_params[0] = tmp;
+			f_params[1] = tmp * tmp * s->numpts;
+			if (fuse)
+			{
+				double tmp_half = tmp;
+				rungekutta4bg(tmp_half, fourpiG, cosmo, 0.5 * dtau / numsteps);               // :748
+				double d_params[2] = {tmp_half, tmp_half * tmp_half * s->numpts};
+				const int nf = (1. / a < s->z_relax + 1. ? 3 : 2);
+				s->maxvel[2 + i] = pcls_ncdm[i].kickDrift(update_q, (dtau + dtau_old) / 2. / numsteps, nf, f_params, dtau / numsteps, nf, d_params, update_ncdm_fields);
+				tmp = tmp_half;
+			}
+			else
+			{
+				if (s->gr_flag > 0)
+					s->maxvel[2 + i] = pcls_ncdm[i].updateVel(update_q, (dtau + dtau_old) / 2. / numsteps, update_ncdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);   // :738
+				else
+					s->maxvel[2 + i] = pcls_ncdm[i].updateVel(update_q_Newton, (dtau + dtau_old) / 2. / numsteps, update_ncdm_fields, 1, f_params);   // :740 (no radiation / fluid)
+				rungekutta4bg(tmp, fourpiG, cosmo, 0.5 * dtau / numsteps);                    // :748
+				f_params[0] = tmp;
+				f_params[1] = tmp * tmp * s->numpts;
+				if (s->gr_flag > 0)
+					pcls_ncdm[i].moveParticles(update_pos, dtau / numsteps, update_ncdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);   // :753
+				else
+					pcls_ncdm[i].moveParticles(update_pos_Newton, dtau / numsteps, NULL, 0, f_params);   // :755
+			}
+			rungekutta4bg(tmp, fourpiG, cosmo, 0.5 * dtau / numsteps);                        // :761
+		}
+	}
+
 	// cdm and baryon particle update (main.cpp:771-807)
 	f_params[0] = a;
 	f_params[1] = a * a * s->numpts;
@@ -289,9 +435,9 @@ static int sim_step(gevb_sim * s)
 
 	rungekutta4bg(a, fourpiG, cosmo, 0.5 * dtau);                                             // :814
 
-	s->lat.max(s->maxvel, 1 + s->baryon_flag);                                                // :816
+	s->lat.max(s->maxvel, 2 + cosmo.num_ncdm);                                                // :816 (numspecies entries; an absent baryon slot stays 0)
 	if (s->gr_flag > 0)
-		for (int i = 0; i < 1 + s->baryon_flag; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);   // :818-822
+		for (int i = 0; i < 2 + cosmo.num_ncdm; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);   // :818-822
 
 	s->tau += dtau;                                                                           // :825
 	dtau_old = dtau;                                                                          // :867

@@ -185,8 +185,21 @@ int gevb_extractPowerSpectrum(gevb_field * fldFT, double * kbin, double * power,
  * dsettings: boxsize, Cf, steplimit, z_in, z_relax
  * cosmo    : Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h */
 typedef struct gevb_sim gevb_sim;
+/* host-side background model by itself, no device needed (background.hpp:103,137,167,200):
+ * out4 = Hconf(a), bg_ncdm(a), particleHorizon(a), a after rungekutta4bg(a, dtau) */
+int gevb_background_eval(const double * cosmo, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,
+                         double a, double fourpiG, double dtau, double * out4);
 int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int vector_flag, const double * dsettings, const double * cosmo);
 int gevb_sim_destroy(gevb_sim * sim);
+/* non-cold dark matter species (at most 4 = MAX_PCL_SPECIES-2, metadata.hpp:48): masses [eV], temperatures
+ * [T_cmb], density parameters (metadata.hpp:284-288), the redshifts at which their T00 / T0i deposits switch
+ * on ("switch delta_ncdm", "switch B ncdm", parser.hpp:1755-1793), "switch linear chi" (Tij) and the move limit
+ * that sets the sub-cycling of their updates (main.cpp:696-701).  Their particles are species 2..5.          */
+int gevb_sim_set_ncdm(gevb_sim * sim, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,
+                      const double * z_switch_deltancdm, const double * z_switch_Bncdm, double z_switch_linearchi, double movelimit);
+int gevb_sim_set_ncdm_maxvel(gevb_sim * sim, const double * maxvel4);          /* max |v| per ncdm species as the IC generator returns it */
+int gevb_sim_get_ncdm_state(gevb_sim * sim, double * maxvel4, int * numsteps4); /* after a cycle: max |v| and step subdivisions used  */
+/* species: 0 cdm, 1 baryons, 2..5 ncdm */
 int gevb_sim_set_particles(gevb_sim * sim, int species, int64_t n, const int64_t * id, const double * pos, const double * vel, double mass);
 int gevb_sim_set_field(gevb_sim * sim, int which, const double * host);   /* 0 phi,1 chi,2 Bi,3 source,4 Sij,10 scalarFT,11 BiFT,12 SijFT */
 int gevb_sim_get_field(gevb_sim * sim, int which, double * host);

@@ -66,6 +66,10 @@ _SIGS = {
     "sim_set_state": (None, [_vp, _dp]),
     "sim_get_timers": (None, [_vp, _dp]),
     "sim_step": (None, [_vp]),
+    "sim_set_ncdm": (None, [_vp, _i, _dp, _dp, _dp, _dp, _dp, _d, _d]),
+    "sim_set_ncdm_maxvel": (None, [_vp, _dp]),
+    "sim_get_ncdm_state": (None, [_vp, _dp, _i32p]),
+    "bg_ncdm": (_d, [_d, _dp, _i, _dp, _dp, _dp]),
 }
 
 FIELD_IDS = {"phi": 0, "chi": 1, "Bi": 2, "source": 3, "Sij": 4, "scalarFT": 10, "BiFT": 11, "SijFT": 12}
@@ -220,6 +224,10 @@ class Oracle:
     def rungekutta4bg(self, a, fourpiG, cosmo, dtau):
         return self.fn["rungekutta4bg"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64), dtau)
 
+    def bg_ncdm(self, a, cosmo, m_ncdm, T_ncdm, Omega_ncdm):
+        arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (m_ncdm, T_ncdm, Omega_ncdm)]
+        return self.fn["bg_ncdm"](a, np.ascontiguousarray(cosmo, dtype=np.float64), len(arr[0]), *arr)
+
     def particleHorizon(self, a, fourpiG, cosmo):
         return self.fn["particleHorizon"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64))
 
@@ -269,6 +277,19 @@ class Sim:
 
     def set_state(self, a, tau, dtau, dtau_old, cycle, maxvel=(0.0, 0.0)):
         self.o.fn["sim_set_state"](self.h, np.array([a, tau, dtau, dtau_old, cycle, maxvel[0], maxvel[1]], dtype=np.float64))
+
+    def set_ncdm(self, m_ncdm, T_ncdm, Omega_ncdm, z_switch_deltancdm, z_switch_Bncdm, z_switch_linearchi, movelimit):
+        arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (m_ncdm, T_ncdm, Omega_ncdm, z_switch_deltancdm, z_switch_Bncdm)]
+        self.o.fn["sim_set_ncdm"](self.h, len(arr[0]), *arr, z_switch_linearchi, movelimit)
+
+    def set_ncdm_maxvel(self, maxvel):
+        v = np.zeros(4); v[:len(maxvel)] = maxvel
+        self.o.fn["sim_set_ncdm_maxvel"](self.h, v)
+
+    def ncdm_state(self):
+        v, n = np.zeros(4), np.zeros(4, dtype=np.int32)
+        self.o.fn["sim_get_ncdm_state"](self.h, v, n)
+        return v, n
 
     def timers(self):
         t = np.zeros(6)

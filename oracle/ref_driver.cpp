@@ -392,8 +392,12 @@ struct RefSim
 	int gr_flag, vector_flag, baryon_flag;
 	double fourpiG, a, tau, dtau, dtau_old, dx, T00hom;
 	int cycle;
-	double maxvel[2];
+	double maxvel[2 + MAX_PCL_SPECIES - 2];    // by species slot: cdm, baryons, ncdm i (main.cpp indexes [i+1+baryon_flag])
 	Pcls pcls_cdm, pcls_b;
+	Pcls pcls_ncdm[MAX_PCL_SPECIES - 2];       // main.cpp:219
+	bool have_ncdm[MAX_PCL_SPECIES - 2];
+	double z_switch_deltancdm[MAX_PCL_SPECIES - 2], z_switch_Bncdm[MAX_PCL_SPECIES - 2], z_switch_linearchi, movelimit;
+	int numsteps_ncdm[MAX_PCL_SPECIES - 2];
 	bool have_b;
 	Field<Real> phi, source, chi, Sij, Bi;
 	Field<Cplx> scalarFT, SijFT, BiFT;
@@ -410,6 +414,7 @@ void * ref_sim_create(int N, int gr_flag, int vector_flag, const double * dsetti
 	RefSim * s = new RefSim();
 	s->N = N; s->L = &get_lat(N);
 	s->cosmo = make_cosmo(cosmo);
+	bg_ncdm(-1., s->cosmo);   // flush background.hpp's per-process cache of the last bg_ncdm value (an earlier model may have had ncdm)
 	s->boxsize = dsettings[0]; s->Cf = dsettings[1]; s->steplimit = dsettings[2]; s->z_in = dsettings[3]; s->z_relax = dsettings[4];
 	s->gr_flag = gr_flag; s->vector_flag = vector_flag; s->baryon_flag = 0; s->have_b = false;
 	Lattice & lat = s->L->lat; Lattice & latFT = s->L->latFT;
@@ -432,18 +437,57 @@ void * ref_sim_create(int N, int gr_flag, int vector_flag, const double * dsetti
 	else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
 	s->dtau_old = 0.;
 	s->cycle = 0; s->T00hom = 0.;
-	s->maxvel[0] = s->maxvel[1] = 0.;
+	for (int i = 0; i < MAX_PCL_SPECIES; i++) s->maxvel[i] = 0.;
+	for (int i = 0; i < MAX_PCL_SPECIES - 2; i++) { s->have_ncdm[i] = false; s->z_switch_deltancdm[i] = s->z_switch_Bncdm[i] = 0.; s->numsteps_ncdm[i] = 1; }
+	s->z_switch_linearchi = 0.; s->movelimit = 1.e10;
 	s->projection_time = s->gravity_solver_time = s->fft_time = s->update_q_time = s->moveParts_time = s->cycle_time = 0.;
 	return s;
 }
 
 void ref_sim_destroy(void * h) { delete (RefSim *) h; }
 
+// ncdm species: cosmo.*_ncdm (metadata.hpp:284-288) and the switches (metadata.hpp:224-238)
+void ref_sim_set_ncdm(void * h, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,
+                      const double * zsw_delta, const double * zsw_B, double z_switch_linearchi, double movelimit)
+{
+	RefSim * s = (RefSim *) h;
+	s->cosmo.num_ncdm = num_ncdm;
+	for (int i = 0; i < num_ncdm; i++)
+	{
+		s->cosmo.m_ncdm[i] = m_ncdm[i]; s->cosmo.T_ncdm[i] = T_ncdm[i]; s->cosmo.Omega_ncdm[i] = Omega_ncdm[i]; s->cosmo.deg_ncdm[i] = 1.;
+		s->z_switch_deltancdm[i] = zsw_delta[i]; s->z_switch_Bncdm[i] = zsw_B[i];
+	}
+	s->z_switch_linearchi = z_switch_linearchi; s->movelimit = movelimit;
+	bg_ncdm(-1., s->cosmo);   // background.hpp:105-117 caches the last value by scale factor alone: flush it, the model changed
+	if (s->cycle == 0)
+	{
+		s->tau = particleHorizon(s->a, s->fourpiG, s->cosmo);
+		if (s->Cf * s->dx < s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo)) s->dtau = s->Cf * s->dx;
+		else s->dtau = s->steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
+	}
+}
+void ref_sim_set_ncdm_maxvel(void * h, const double * maxvel) { RefSim * s = (RefSim *) h; for (int i = 0; i < MAX_PCL_SPECIES - 2; i++) s->maxvel[2 + i] = maxvel[i]; }
+void ref_sim_get_ncdm_state(void * h, double * maxvel, int * numsteps)
+{
+	RefSim * s = (RefSim *) h;
+	for (int i = 0; i < MAX_PCL_SPECIES - 2; i++) { maxvel[i] = s->maxvel[2 + i]; numsteps[i] = s->numsteps_ncdm[i]; }
+}
+double ref_bg_ncdm(double a, const double * cosmo, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm)
+{
+	cosmology co = make_cosmo(cosmo);
+	co.num_ncdm = num_ncdm;
+	for (int i = 0; i < num_ncdm; i++) { co.m_ncdm[i] = m_ncdm[i]; co.T_ncdm[i] = T_ncdm[i]; co.Omega_ncdm[i] = Omega_ncdm[i]; }
+	double r = 0.;
+	for (int i = 0; i < num_ncdm; i++) r += bg_ncdm(a, co, i);
+	return r;
+}
+
 void ref_sim_set_particles(void * h, int species, long np, const int64_t * ids, const double * pos, const double * vel, double mass)
 {
 	RefSim * s = (RefSim *) h;
 	if (species == 0) make_pcls(s->pcls_cdm, *s->L, np, pos, vel, mass, ids);
-	else { make_pcls(s->pcls_b, *s->L, np, pos, vel, mass, ids); s->have_b = true; s->baryon_flag = 1; }
+	else if (species == 1) { make_pcls(s->pcls_b, *s->L, np, pos, vel, mass, ids); s->have_b = true; s->baryon_flag = 1; }
+	else { make_pcls(s->pcls_ncdm[species - 2], *s->L, np, pos, vel, mass, ids); s->have_ncdm[species - 2] = true; }
 }
 
 // which: 0 phi, 1 chi, 2 Bi(3), 3 source, 4 Sij(6)  [real];  10 scalarFT, 11 BiFT(3), 12 SijFT(6) [Fourier]
@@ -467,13 +511,14 @@ void ref_sim_get_field(void * h, int which, double * data)
 	RefSim * s = (RefSim *) h;
 	if (which < 10) store_real(*real_field(s, which), data); else store_cplx(*cplx_field(s, which), data);
 }
-long ref_sim_num_particles(void * h, int species) { RefSim * s = (RefSim *) h; return species == 0 ? s->pcls_cdm.numParticles() : s->pcls_b.numParticles(); }
+static Pcls & species_pcls(RefSim * s, int species) { return species == 0 ? s->pcls_cdm : (species == 1 ? s->pcls_b : s->pcls_ncdm[species - 2]); }
+long ref_sim_num_particles(void * h, int species) { RefSim * s = (RefSim *) h; return species_pcls(s, species).numParticles(); }
 
 // particles out in lattice iteration order (cell-sorted, x fastest)
 void ref_sim_get_particles(void * h, int species, int64_t * ids, double * pos, double * vel)
 {
 	RefSim * s = (RefSim *) h;
-	Pcls & p = species == 0 ? s->pcls_cdm : s->pcls_b;
+	Pcls & p = species_pcls(s, species);
 	Site x(p.lattice());
 	long n = 0;
 	for (x.first(); x.test(); x.next())
@@ -526,11 +571,23 @@ void ref_sim_step(void * h)
 	{
 		projection_T00_project(&s->pcls_cdm, &s->source, a, &s->phi);
 		if (s->baryon_flag) projection_T00_project(&s->pcls_b, &s->source, a, &s->phi);
+		for (int i = 0; i < cosmo.num_ncdm; i++)     // main.cpp:388-399 (radiation_flag == 0)
+		{
+			if (a >= 1. / (s->z_switch_deltancdm[i] + 1.) && s->have_ncdm[i])
+				projection_T00_project(s->pcls_ncdm + i, &s->source, a, &s->phi);
+			else
+			{
+				double tmp = bg_ncdm(a, cosmo, i);
+				for (x.first(); x.test(); x.next()) s->source(x) += tmp;
+			}
+		}
 	}
 	else
 	{
 		scalarProjectionCIC_project(&s->pcls_cdm, &s->source);
 		if (s->baryon_flag) scalarProjectionCIC_project(&s->pcls_b, &s->source);
+		for (int i = 0; i < cosmo.num_ncdm; i++)     // main.cpp:405-409
+			if (a >= 1. / (s->z_switch_deltancdm[i] + 1.) && s->have_ncdm[i]) scalarProjectionCIC_project(s->pcls_ncdm + i, &s->source);
 	}
 	projection_T00_comm(&s->source);
 
@@ -540,6 +597,8 @@ void ref_sim_step(void * h)
 		projection_init(&s->Bi);
 		projection_T0i_project(&s->pcls_cdm, &s->Bi, &s->phi);
 		if (s->baryon_flag) projection_T0i_project(&s->pcls_b, &s->Bi, &s->phi);
+		for (int i = 0; i < cosmo.num_ncdm; i++)     // main.cpp:430-434
+			if (a >= 1. / (s->z_switch_Bncdm[i] + 1.) && s->have_ncdm[i]) projection_T0i_project(s->pcls_ncdm + i, &s->Bi, &s->phi);
 		projection_T0i_comm(&s->Bi);
 	}
 
@@ -547,6 +606,9 @@ void ref_sim_step(void * h)
 	projection_init(&s->Sij);
 	projection_Tij_project(&s->pcls_cdm, &s->Sij, a, &s->phi);
 	if (s->baryon_flag) projection_Tij_project(&s->pcls_b, &s->Sij, a, &s->phi);
+	if (a >= 1. / (s->z_switch_linearchi + 1.))      // main.cpp:442-449
+		for (int i = 0; i < cosmo.num_ncdm; i++)
+			if (s->have_ncdm[i]) projection_Tij_project(s->pcls_ncdm + i, &s->Sij, a, &s->phi);
 	projection_Tij_comm(&s->Sij);
 
 	t1 = now_s(); s->projection_time += t1 - t0;
@@ -602,6 +664,37 @@ void ref_sim_step(void * h)
 
 	t2 = now_s(); s->gravity_solver_time += t2 - t1;
 
+	// main.cpp:696-701  step subdivisions for the ncdm updates
+	for (int i = 0; i < cosmo.num_ncdm; i++)
+	{
+		if (dtau * s->maxvel[2 + i] > dx * s->movelimit)
+			s->numsteps_ncdm[i] = (int) ceil(dtau * s->maxvel[2 + i] / dx / s->movelimit);
+		else s->numsteps_ncdm[i] = 1;
+	}
+	// main.cpp:729-765  non-cold DM particle update
+	for (int i = 0; i < cosmo.num_ncdm; i++)
+	{
+		if (!s->have_ncdm[i]) continue;
+		double tmp = a;
+		for (int j = 0; j < s->numsteps_ncdm[i]; j++)
+		{
+			f_params[0] = tmp;
+			f_params[1] = tmp * tmp * s->N;
+			if (s->gr_flag > 0)
+				s->maxvel[2 + i] = s->pcls_ncdm[i].updateVel(update_q, (dtau + dtau_old) / 2. / s->numsteps_ncdm[i], update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);
+			else
+				s->maxvel[2 + i] = s->pcls_ncdm[i].updateVel(update_q_Newton, (dtau + dtau_old) / 2. / s->numsteps_ncdm[i], update_cdm_fields, 1, f_params);
+			rungekutta4bg(tmp, fourpiG, cosmo, 0.5 * dtau / s->numsteps_ncdm[i]);
+			f_params[0] = tmp;
+			f_params[1] = tmp * tmp * s->N;
+			if (s->gr_flag > 0)
+				s->pcls_ncdm[i].moveParticles(update_pos, dtau / s->numsteps_ncdm[i], update_cdm_fields, (1. / a < s->z_relax + 1. ? 3 : 2), f_params);
+			else
+				s->pcls_ncdm[i].moveParticles(update_pos_Newton, dtau / s->numsteps_ncdm[i], NULL, 0, f_params);
+			rungekutta4bg(tmp, fourpiG, cosmo, 0.5 * dtau / s->numsteps_ncdm[i]);
+		}
+	}
+
 	// main.cpp:771-784  kick
 	f_params[0] = a;
 	f_params[1] = a * a * s->N;
@@ -638,7 +731,7 @@ void ref_sim_step(void * h)
 
 	// main.cpp:816-822
 	if (s->gr_flag > 0)
-		for (int i = 0; i < 1 + s->baryon_flag; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);
+		for (int i = 0; i < 2 + cosmo.num_ncdm; i++) s->maxvel[i] /= sqrt(s->maxvel[i] * s->maxvel[i] + 1.0);
 
 	s->tau += dtau;         // main.cpp:825
 	dtau_old = dtau;        // main.cpp:867

@@ -87,3 +87,26 @@ def rel_linf(a, b):
 
 def to_cplx(F):
     return F[..., 0] + 1j * F[..., 1]
+
+
+def ncdm_model(cosmo, masses=(0.1, 0.2)):
+    """Two massive-neutrino species (BASELINE config 4): m [eV], T_ncdm [T_cmb] and Omega_ncdm = m / (93.14 eV h^2);
+    returns (cosmo with Omega_m, Omega_Lambda adjusted as parser.hpp:1700-1748 does, m, T, Omega)."""
+    m = np.array(masses, dtype=np.float64)
+    T = np.full(len(m), 0.71611)
+    Om = m / 93.14 / H / H
+    c = np.array(cosmo, dtype=np.float64)
+    c[2] = c[0] + c[1] + Om.sum()
+    c[3] = 1.0 - c[2] - c[9] - c[4]
+    return c, m, T, Om
+
+
+def thermal_particles(rng, N, per_dim, a, qrms):
+    """hot species: coarser lattice (per_dim^3) with large Gaussian displacements and momenta q ~ N(0, qrms^2)"""
+    g = (np.arange(per_dim) + 0.5) / per_dim
+    z, y, x = np.meshgrid(g, g, g, indexing="ij")
+    pos = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1) + rng.standard_normal((per_dim ** 3, 3)) * (0.4 / N)
+    pos -= np.floor(pos)
+    pos[pos >= 1.0] = 0.0
+    vel = rng.standard_normal(pos.shape) * qrms
+    return np.arange(len(pos), dtype=np.int64), np.ascontiguousarray(pos), np.ascontiguousarray(vel)

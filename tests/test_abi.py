@@ -57,3 +57,25 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".py", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_host_background_matches_reference(gevb, ref):
+    """product host scalars (gevolution-1.2_b200/host/background.hpp) against the reference's background.hpp,
+    with and without ncdm species; the horizon only to the reference's own quadrature request (1e-7)"""
+    import numpy as np
+    import common
+    cosmo = common.shipped_cosmology()
+    fourpiG = 1.5 * 320.0 ** 2 / 2997.92458 ** 2
+    for a in (0.0099, 0.05, 0.3, 1.0):
+        g = gevb.background_eval(cosmo, a, fourpiG, 0.01)
+        assert abs(g["Hconf"] - ref.Hconf(a, fourpiG, cosmo)) <= 1e-14 * g["Hconf"]
+        assert abs(g["a_next"] - ref.rungekutta4bg(a, fourpiG, cosmo, 0.01)) <= 1e-14 * a
+        assert abs(g["particleHorizon"] - ref.particleHorizon(a, fourpiG, cosmo)) <= 1e-6 * g["particleHorizon"]
+    c2, m, T, Om = common.ncdm_model(cosmo)
+    for a in (0.0099, 0.05, 0.3, 1.0):
+        g = gevb.background_eval(c2, a, fourpiG, 0.01, m, T, Om)
+        r = ref.bg_ncdm(a, c2, m, T, Om)
+        assert r > 0 and abs(g["bg_ncdm"] - r) <= 1e-12 * r
+    # non-relativistic limit: bg_ncdm -> Omega_ncdm (background.hpp:78 with w >> 1)
+    g = gevb.background_eval(c2, 1.0, fourpiG, 0.0, m, T, Om)
+    assert abs(g["bg_ncdm"] - Om.sum()) < 2e-4 * Om.sum()

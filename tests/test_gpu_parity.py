@@ -177,6 +177,103 @@ def test_time_loop_newton_and_baryons(gevb, ctx, ref):
         rs.close(); gs.close()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_time_loop_ncdm_subcycling(gevb, ctx, ref, fused):
+    """BASELINE config 4 in small: cdm + baryons + 2 massive-neutrino species whose updates are sub-cycled
+    (main.cpp:696-765); neutrino T00 switches on after the first cycle (z_switch_deltancdm), before that the
+    homogeneous bg_ncdm stand-in is added (main.cpp:392-397)"""
+    N = 16
+    rng = np.random.default_rng(77)
+    cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
+    cosmo, m, T, Om = common.ncdm_model(cosmo)
+    a0 = 1.0 / (1.0 + ds[3])
+    rs, gs = ref.sim(N, 1, 0, ds, cosmo), gevb.Sim(ctx(N), 1, 0, ds, cosmo)
+    gs.set_fused(fused)
+    z1 = 1.0 / rs.state()["a"] - 1.0
+    for s in (rs, gs):
+        # species 0 switches its T00 on only after the first cycle; species 1 from the start
+        s.set_ncdm(m, T, Om, [z1 - 0.5, 1e4], [1e4, 1e4], 1e4, 0.05)
+        s.set_ncdm_maxvel([0.07, 0.05])
+    ids, pos, vel = common.quasi_uniform_particles(rng, N, sigma=0.2, a=a0, qscale=3e-3)
+    half = len(ids) // 2
+    parts = [(ids[:half], pos[:half], vel[:half], cosmo[0] / half), (ids[half:], pos[half:], vel[half:], cosmo[1] / (len(ids) - half))]
+    for k in range(2):
+        i2, p2, v2 = common.thermal_particles(rng, N, N // 2, a0, 0.06 * a0 * (1 + k))
+        parts.append((i2, p2, v2, Om[k] / len(i2)))
+    phi, chi, Bi = common.metric_fields(rng, N, a0)
+    for s in (rs, gs):
+        for sp, (i_, p_, v_, mass) in enumerate(parts):
+            s.set_particles(sp, i_, p_, v_, mass)
+        s.set_field("phi", phi); s.set_field("chi", chi); s.set_field("Bi", Bi)
+    BiFT = ref.fft_forward(Bi)
+    rs.set_field("BiFT", BiFT); gs.set_field("BiFT", BiFT)
+    assert abs(rs.state()["dtau"] - gs.state()["dtau"]) <= 1e-13 * rs.state()["dtau"]
+    saw_subcycling = False
+    for step in range(3):
+        rs.step(); gs.step()
+        e = _compare_sims(rs, gs, N, nspecies=4)
+        (rv, rn), (gv, gn) = rs.ncdm_state(), gs.ncdm_state()
+        assert np.array_equal(rn, gn), (rn, gn)
+        assert np.abs(rv - gv).max() <= 1e-12
+        saw_subcycling |= bool(rn.max() > 1)
+        skip = ("state_tau",) + (("scalarFT",) if fused else ())
+        tol = FIELD_TOL * (1 + step)
+        bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= tol))}
+        assert bad == {}, (step, e)
+    assert saw_subcycling
+    rs.close(); gs.close()
+
+
+def test_run_to_z0_power_spectra_and_snapshot_statistics(gevb, ctx, ref):
+    """north_star: phi, chi and B power spectra and the particle snapshot statistics at z = 0 within 1e-5 of the
+    reference CPU run from identical initial conditions (N = 32, z = 100 -> 0: 117 cycles, structure forms --
+    at the end 70 % of the cells are empty and the densest holds ~50 particles)"""
+    N, numbins = 32, 16
+    rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=5)
+    ids0, pos0, _ = rs.get_particles(0)
+    pos0 = pos0[np.argsort(ids0)]
+    ncycles = 0
+    while rs.state()["a"] < 1.0 and ncycles < 400:
+        rs.step(); gs.step(); ncycles += 1
+    r, g = rs.state(), gs.state()
+    assert ncycles > 50 and g["cycle"] == r["cycle"] and abs(g["a"] - r["a"]) <= 1e-12 * r["a"]
+    assert abs(g["T00hom"] - r["T00hom"]) <= 1e-9 * r["T00hom"]
+    # spectra the way writeSpectra takes them (main.cpp:639-679, tools.hpp:53-212): forward FFT of the field, binned |.|^2
+    c = gs.ctx
+    worst = {}
+    for name, ncomp in (("phi", 1), ("chi", 1), ("Bi", 3)):
+        fr = rs.get_field(name)
+        kb, pw, ks, ps, occ = ref.extractPowerSpectrum(ref.fft_forward(fr), numbins)
+        F, K = gevb.Field(c, gevb.REAL, ncomp, data=gs.get_field(name)), gevb.Field(c, gevb.CPLX, ncomp)
+        plan = gevb.PlanFFT(F, K)
+        plan.execute(gevb.FFT_FORWARD)
+        gkb, gpw, gks, gps, gocc = gevb.extractPowerSpectrum(K, numbins)
+        assert np.array_equal(occ, gocc)
+        m = occ > 0
+        worst[name] = float(np.max(np.abs(gpw[m] - pw[m]) / np.abs(pw[m])))
+        assert np.max(np.abs(gkb[m] - kb[m]) / kb[m]) <= 1e-12
+        plan.close(); F.close(); K.close()
+    assert all(v <= 1e-5 for v in worst.values()), worst
+    # snapshot statistics: displacement and momentum moments, extremes, and the occupancy histogram
+    rid, rpos, rvel = rs.get_particles(0)
+    gid, gpos, gvel = gs.pcls(0).download()
+    ro, go = np.argsort(rid), np.argsort(gid)
+    assert np.array_equal(rid[ro], gid[go])
+    rpos, rvel, gpos, gvel = rpos[ro], rvel[ro], gpos[go], gvel[go]
+    def stats(pos, vel):
+        d = pos - pos0
+        d -= np.round(d)
+        cells = np.minimum(np.floor(pos * N).astype(np.int64), N - 1)
+        occ = np.bincount((cells[:, 2] * N + cells[:, 1]) * N + cells[:, 0], minlength=N ** 3)
+        return np.array([np.sqrt((d ** 2).mean()), np.abs(d).max(), np.sqrt((vel ** 2).mean()), np.abs(vel).max(),
+                         (vel ** 2).sum(axis=1).max(), float((occ == 0).mean()), float(occ.max()), float((occ.astype(np.float64) ** 2).mean())])
+    sr, sg = stats(rpos, rvel), stats(gpos, gvel)
+    assert np.max(np.abs(sg - sr) / np.abs(sr)) <= 1e-5, (sr, sg)
+    assert np.abs(gpos - rpos).max() <= 1e-7 and common.rel_linf(gvel, rvel) <= 1e-5, (np.abs(gpos - rpos).max(), common.rel_linf(gvel, rvel))
+    print("z=0 parity: cycles", ncycles, "spectra rel err", worst, "max |dx|", np.abs(gpos - rpos).max())
+    rs.close(); gs.close()
+
+
 # ---- size-independent properties at the benchmark size (SURVEY 8c/8d) --------------------
 @pytest.mark.parametrize("N", [128])
 def test_full_size_properties(gevb, ctx, N):
