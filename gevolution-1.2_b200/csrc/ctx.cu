@@ -34,8 +34,8 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
-static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "deposit_variant"};
-static int tune_values[GEVB_NTUNE] = {1, 0};
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "deposit_variant", "fft_exchange"};
+static int tune_values[GEVB_NTUNE] = {1, 0, 1};
 static bool tune_env_read = false;
 static void tune_read_env()
 {
@@ -66,6 +66,7 @@ extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank,
 	GEVB_CHECK_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "gevb_ctx_create: bad rank %d of %d", rank, nranks);
 	GEVB_CHECK_ARG(ngrid % nranks == 0, "gevb_ctx_create: Ngrid %d not divisible by %d ranks", ngrid, nranks);
 	GEVB_CHECK_ARG(nranks == 1 || ngrid / nranks >= 2, "gevb_ctx_create: slabs must be at least 2 planes thick");
+	GEVB_CHECK_ARG(nranks <= GEVB_MAX_RANKS, "gevb_ctx_create: at most %d ranks", GEVB_MAX_RANKS);
 	GEVB_CHECK_ARG(nranks == 1 || nccl_id != NULL, "gevb_ctx_create: nccl_id required when nranks > 1");
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -115,6 +116,7 @@ extern "C" int gevb_ctx_destroy(gevb_ctx * c)
 	if (c == NULL) return 0;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	gevb_xchg_release(c);
 	if (c->have_comm) ncclCommDestroy(c->comm);
 	cudaFree(c->d_gridk2); cudaFree(c->d_kshift); cudaFree(c->d_red); cudaFreeHost(c->h_red);
 	if (c->scratch) cudaFree(c->scratch);

@@ -69,6 +69,9 @@ __device__ __forceinline__ void cp_async4(void * smem_dst, const void * gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// periodic wrap of an index in [0, 2N) (a tile reaches one site past the brick; bricks of a partial super-brick lie past N)
+__device__ __forceinline__ int wrap_up(int v, int N) { v = v >= N ? v - N : v; return v >= N ? v % N : v; }
+
 #define DEP_CELLTAB (GEVB_BRICK_CELLS + 4)                      // 513 prefix sums of a brick, padded
 #define DEP_STAGE_DOUBLES (DT_SITES + DEP_CELLTAB / 2)          // one pipeline stage: phi tile, cell table
 
@@ -88,7 +91,7 @@ __device__ __forceinline__ void stage_brick(const DParams & D, uint32_t brick, u
 		int x0, y0, zl0;
 		brick_origin(G, brick, x0, y0, zl0);
 		const int tx = threadIdx.x % DX, ty = threadIdx.x / DX;
-		const size_t gcol = (size_t) ((y0 + ty) % G.N) * G.N + (x0 + tx) % G.N;
+		const size_t gcol = (size_t) wrap_up(y0 + ty, G.N) * G.N + wrap_up(x0 + tx, G.N);
 		#pragma unroll
 		for (int tz = 0; tz < DZ; tz++)
 		{
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 			//      the tile is left zeroed for the next brick (stage `cur` is free from here on)
 			if (tcol < DX * DY)
 			{
-				const size_t gcol = (size_t) ((y0 + tty) % G.N) * G.N + (x0 + ttx) % G.N;
+				const size_t gcol = (size_t) wrap_up(y0 + tty, G.N) * G.N + wrap_up(x0 + ttx, G.N);
 				#pragma unroll
 				for (int tz = 0; tz < DZ; tz++)
 				{

@@ -16,6 +16,21 @@
 //                 One pass over the data less per direction than pack / exchange /
 //                 unpack: the exchange buffers are cuFFT's own output / input.
 //
+// Exchange over peer memory (default when the ranks can map each other's memory, cudaIpc over NVLink / NVSwitch):
+// the transpose kernel itself performs the exchange -- it reads local tiles and stores the transposed tiles
+// straight into the destination rank's buffer, already in the layout the next local transform reads, so the
+// exchange and the layout change are one pass and the NVLink traffic of all peers overlaps tile by tile:
+//
+//                 forward  = 2-D D2Z (local)  ->  k_push_fwd: [ky][zl][kx] tiles -> peer [kyl][kx][kz]  -> barrier
+//                            -> 1-D Z2Z out of place from the exchange buffer into the Fourier field
+//                 backward = 1-D Z2Z^-1 (local, out of place) -> k_push_bwd: [kx][z] tiles -> peer [ky][zl][kx]
+//                            -> barrier -> 2-D Z2D from the exchange buffer
+//
+// Two exchange buffers alternate, so one barrier per transform (a 4-byte NCCL all-reduce on the same stream) is
+// enough: nobody can start overwriting a buffer before every rank has passed the barrier of the transform in
+// between, which each rank enters only after it has consumed the buffer.  tuning knob fft_exchange = 0 selects
+// the NCCL path above (also the fallback where peer mapping is unavailable).
+//
 // The Fourier input of a backward transform is preserved (the reference keeps
 // BiFT as persistent state across steps, main.cpp:586-593): cuFFT's multi-dim
 // Z2D may overwrite its input, so it runs on a staged copy.
@@ -71,6 +86,117 @@ __global__ void k_pack_bwd(const double2 * __restrict__ in, double2 * __restrict
 	}
 }
 
+struct PeerPtrs { double2 * p[GEVB_MAX_RANKS]; };
+
+// forward exchange: local A [c][ky][zl][kx]  ->  rank d = ky / nkyl : X_d [c][kyl][kx][kz = rank * nzl + zl]
+__global__ void __launch_bounds__(256) k_push_fwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank)
+{
+	__shared__ double2 tile[32][33];
+	const int c = blockIdx.z / N, ky = blockIdx.z % N;
+	const int d = ky / nkyl, kyl = ky % nkyl;
+	const int kx0 = blockIdx.x * 32, zl0 = blockIdx.y * 32;
+	const double2 * src = A + ((size_t) c * N + ky) * nzl * nh;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		const int zl = zl0 + j, kx = kx0 + threadIdx.x;
+		if (zl < nzl && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) zl * nh + kx);
+	}
+	__syncthreads();
+	double2 * dst = X.p[d] + ((size_t) c * nkyl + kyl) * nh * N + (size_t) rank * nzl;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		const int kx = kx0 + j, zl = zl0 + threadIdx.x;
+		if (zl < nzl && kx < nh) dst[(size_t) kx * N + zl] = tile[threadIdx.x][j];
+	}
+}
+
+// backward exchange: local A [c][kyl][kx][z]  ->  rank d = z / nzl : X_d [c][ky = rank * nkyl + kyl][zl][kx]
+__global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank)
+{
+	__shared__ double2 tile[32][33];
+	const int c = blockIdx.z / nkyl, kyl = blockIdx.z % nkyl;
+	const int kx0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+	const double2 * src = A + ((size_t) c * nkyl + kyl) * nh * N;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		const int kx = kx0 + j, z = z0 + threadIdx.x;
+		if (z < N && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) kx * N + z);
+	}
+	__syncthreads();
+	const size_t row = ((size_t) c * N + (size_t) rank * nkyl + kyl) * nzl;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	{
+		const int z = z0 + j, kx = kx0 + threadIdx.x;
+		if (z < N && kx < nh)
+		{
+			const int d = z / nzl, zl = z % nzl;
+			X.p[d][(row + zl) * nh + kx] = tile[threadIdx.x][j];
+		}
+	}
+}
+
+// stream-ordered barrier across the ranks: every rank's earlier work on its stream (the pushes into peer memory) has
+// completed before any rank's later work starts
+int rank_barrier(gevb_ctx * c)
+{
+	NCCL_TRY(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream));
+	return 0;
+}
+
+// (re)allocate the two exchange buffers and map every peer's pair (collective: all ranks create the same plans in the
+// same order).  Any failure to map leaves xchg_state = -1 on every rank and the NCCL exchange in use.
+int xchg_ensure(gevb_ctx * c, size_t bytes)
+{
+	if (c->xchg_state < 0 || (c->xchg_state == 1 && c->xchg_bytes >= bytes)) return 0;
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	gevb_xchg_release(c);
+	if (c->d_barrier == NULL) { CUDA_TRY(cudaMalloc(&c->d_barrier, 64)); CUDA_TRY(cudaMemset(c->d_barrier, 0, 64)); }
+	int ok = 1;
+	cudaIpcMemHandle_t mine[2], all[GEVB_MAX_RANKS][2];
+	memset(mine, 0, sizeof(mine));
+	for (int b = 0; b < 2 && ok; b++)
+	{
+		if (cudaMalloc(&c->xchg[b][c->rank], bytes) != cudaSuccess) { c->xchg[b][c->rank] = NULL; ok = 0; break; }
+		if (cudaIpcGetMemHandle(&mine[b], c->xchg[b][c->rank]) != cudaSuccess) ok = 0;
+	}
+	cudaGetLastError();
+	// all handles to all ranks through the communicator (device staging in the reduction buffer)
+	char * stage = (char *) (c->d_red + 5000);                                   // (nranks + 1) * 128 bytes
+	const size_t hb = sizeof(mine);
+	CUDA_TRY(cudaMemcpyAsync(stage + (size_t) c->nranks * hb, mine, hb, cudaMemcpyHostToDevice, c->stream));
+	NCCL_TRY(ncclGroupStart());
+	for (int r = 0; r < c->nranks; r++)
+	{
+		NCCL_TRY(ncclSend(stage + (size_t) c->nranks * hb, hb, ncclChar, r, c->comm, c->stream));
+		NCCL_TRY(ncclRecv(stage + (size_t) r * hb, hb, ncclChar, r, c->comm, c->stream));
+	}
+	NCCL_TRY(ncclGroupEnd());
+	CUDA_TRY(cudaMemcpyAsync(all, stage, (size_t) c->nranks * hb, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for (int r = 0; r < c->nranks && ok; r++)
+	{
+		if (r == c->rank) continue;
+		for (int b = 0; b < 2; b++)
+			if (cudaIpcOpenMemHandle(&c->xchg[b][r], all[r][b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { c->xchg[b][r] = NULL; ok = 0; }
+	}
+	cudaGetLastError();
+	// agree: one rank without mappings sends everyone to the NCCL exchange
+	int * flag = c->d_barrier + 1;
+	CUDA_TRY(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	NCCL_TRY(ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, c->comm, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if (!ok)
+	{
+		gevb_xchg_release(c);
+		c->xchg_state = -1;
+		fprintf(stderr, "gevb: rank %d: peer memory mapping unavailable, slab FFT exchanges through NCCL\n", c->rank);
+		return 0;
+	}
+	c->xchg_state = 1; c->xchg_bytes = bytes;
+	return 0;
+}
+
 // one chunk of `chunk` complex numbers per (peer rank, component).  Send side: [peer][c] when send_peer_major, else
 // [c][peer]; same for the receive side.
 int alltoall(gevb_ctx * c, const double2 * send, double2 * recv, size_t chunk, int ncomp, bool send_peer_major, bool recv_peer_major)
@@ -89,6 +215,19 @@ int alltoall(gevb_ctx * c, const double2 * send, double2 * recv, size_t chunk, i
 }
 
 } // namespace
+
+void gevb_xchg_release(gevb_ctx * c)
+{
+	for (int b = 0; b < 2; b++)
+		for (int r = 0; r < GEVB_MAX_RANKS; r++)
+		{
+			if (c->xchg[b][r] == NULL) continue;
+			if (r == c->rank) cudaFree(c->xchg[b][r]); else cudaIpcCloseMemHandle(c->xchg[b][r]);
+			c->xchg[b][r] = NULL;
+		}
+	c->xchg_bytes = 0;
+	if (c->xchg_state == 1) c->xchg_state = 0;
+}
 
 extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * cf)
 {
@@ -123,6 +262,9 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 		CUFFT_TRY(cufftSetStream(p->fwd2d, c->stream));
 		CUFFT_TRY(cufftSetStream(p->bwd2d, c->stream));
 		CUFFT_TRY(cufftSetStream(p->z1d, c->stream));
+		// exchange buffers large enough for this field (collective; grow-only)
+		// (sized for six components from the start -- the largest field of the time loop -- so that they are mapped once)
+		GEVB_TRY(xchg_ensure(c, (size_t) (rf->ncomp > 6 ? rf->ncomp : 6) * c->nzl * N * nh * sizeof(double2)));
 	}
 	*out = p;
 	return 0;
@@ -185,6 +327,44 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 	GEVB_TRY(gevb_ctx_scratch2(c, wsites * sizeof(double2), &s2));
 	double2 * A = (double2 *) s1, * B = (double2 *) s2;
 	dim3 tb(32, 8), tg((nh + 31) / 32, (N + 31) / 32, nc * c->nkyl);
+	if (c->xchg_state == 1 && gevb_tune(TUNE_FFT_EXCHANGE) != 0)
+	{
+		// ---- exchange fused into the transpose, over peer memory ----------------------------------
+		const int buf = (int) (c->xchg_epoch++ & 1);
+		PeerPtrs X;
+		for (int r = 0; r < GEVB_MAX_RANKS; r++) X.p[r] = (double2 *) c->xchg[buf][r];
+		double2 * Xl = (double2 *) c->xchg[buf][c->rank];
+		if (direction == GEVB_FFT_FORWARD)
+		{
+			for (int k = 0; k < nc; k++)
+				CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * comp_sites)));
+			c->launches += nc;
+			{
+				Timed t_(c, CLS_FFT_A2A);
+				dim3 pg((nh + 31) / 32, (c->nzl + 31) / 32, nc * N);
+				k_push_fwd<<<pg, tb, 0, c->stream>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank);
+				KERNEL_CHECK(c);
+				GEVB_TRY(rank_barrier(c));
+			}
+			CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) Xl, (cufftDoubleComplex *) cf->data, CUFFT_FORWARD));
+			c->launches++;
+		}
+		else
+		{
+			CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
+			c->launches++;
+			{
+				Timed t_(c, CLS_FFT_A2A);
+				k_push_bwd<<<tg, tb, 0, c->stream>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank);
+				KERNEL_CHECK(c);
+				GEVB_TRY(rank_barrier(c));
+			}
+			for (int k = 0; k < nc; k++)
+				CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (Xl + (size_t) k * comp_sites), rbulk + k * rf->comp_stride));
+			c->launches += nc;
+		}
+		return 0;
+	}
 	if (direction == GEVB_FFT_FORWARD)
 	{
 		// A: [c][ky][zl][kx] -- the ky-slab of peer r is the contiguous chunk r of component c

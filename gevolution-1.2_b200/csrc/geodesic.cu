@@ -212,8 +212,9 @@ __device__ __forceinline__ double wrap_pos(double p)
 
 __device__ __forceinline__ int wrap_index(int v, int N)
 {
-	v %= N;
-	return v < 0 ? v + N : v;
+	// v is within one lattice length of [0, N) except for bricks of a partial super-brick (never staged with particles)
+	if (v < 0) v += N; else if (v >= N) v -= N;
+	return (unsigned) v >= (unsigned) N ? ((v % N) + N) % N : v;
 }
 
 __device__ __forceinline__ void cp_async8(double * smem_dst, const double * gmem_src)

@@ -13,7 +13,7 @@
 void gevb_set_error(const char * fmt, ...);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, TUNE_FFT_EXCHANGE, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -64,6 +64,7 @@ struct GevbTimer
 	std::vector<size_t> open;  // indices of the begun, not yet ended pairs (scopes nest: the FFT times its exchange inside itself)
 	size_t used = 0;
 };
+#define GEVB_MAX_RANKS 16
 struct gevb_ctx;
 struct gevb_plan;
 void gevb_timer_begin(gevb_ctx * c, int cls);
@@ -96,12 +97,20 @@ struct gevb_ctx
 	double * d_red;            // small device reduction buffer (4096 doubles)
 	double * h_red;            // pinned mirror
 	int64_t launches;
+	// slab FFT exchange over peer memory (fft.cu): xchg[b][r] is buffer b of rank r as mapped into this process
+	// (cudaIpc; r == rank is the local allocation).  Two buffers alternate so that one barrier per transform suffices.
+	void * xchg[2][GEVB_MAX_RANKS];
+	size_t xchg_bytes;
+	uint64_t xchg_epoch;
+	int xchg_state;            // 0 not tried, 1 mapped, -1 unavailable (NCCL exchange is used)
+	int * d_barrier;
 	size_t plane() const { return (size_t) N * N; }
 	size_t real_comp_stride() const { return (size_t) (nzl + 2) * N * N; }
 	size_t cplx_comp_stride() const { return nranks == 1 ? (size_t) N * N * nh : (size_t) nkyl * nh * N; }
 };
 
 int gevb_ctx_scratch(gevb_ctx * ctx, size_t bytes, void ** out);
+void gevb_xchg_release(gevb_ctx * ctx);      // fft.cu: unmap / free the peer exchange buffers
 int gevb_ctx_scratch2(gevb_ctx * ctx, size_t bytes, void ** out);
 
 // ---------------------------------------------------------------- fields -----
@@ -155,6 +164,7 @@ struct BrickGeom
 {
 	int N, nzl, z0;
 	int nsx, nsy, nsz;         // super-bricks per dimension (the last ones may be partial: their missing bricks stay empty)
+	int sx_shift, sy_shift;    // log2(nsx), log2(nsy) when both are powers of two (the usual lattice sizes), else -1: no integer division per brick
 	uint32_t nbricks, ncells;  // nbricks = nsx nsy nsz 128, ncells = nbricks * 512
 };
 __host__ __device__ __forceinline__ uint32_t brick_key(const BrickGeom & G, int cx, int cy, int czl)
@@ -168,7 +178,9 @@ __host__ __device__ __forceinline__ uint32_t brick_key(const BrickGeom & G, int 
 __host__ __device__ __forceinline__ void brick_origin(const BrickGeom & G, uint32_t brick, int & x0, int & y0, int & zl0)
 {
 	const uint32_t local = brick & ((1u << GEVB_SUPER_BITS) - 1), super = brick >> GEVB_SUPER_BITS;
-	const uint32_t sx = super % G.nsx, r = super / G.nsx, sy = r % G.nsy, sz = r / G.nsy;
+	uint32_t sx, sy, sz;
+	if (G.sx_shift >= 0) { sx = super & ((1u << G.sx_shift) - 1); sy = (super >> G.sx_shift) & ((1u << G.sy_shift) - 1); sz = super >> (G.sx_shift + G.sy_shift); }
+	else { const uint32_t r = super / G.nsx; sx = super % G.nsx; sy = r % G.nsy; sz = r / G.nsy; }
 	const uint32_t lx = local & ((1u << GEVB_SX_BITS) - 1), ly = (local >> GEVB_SX_BITS) & ((1u << GEVB_SY_BITS) - 1), lz = local >> (GEVB_SX_BITS + GEVB_SY_BITS);
 	x0 = (int) (((sx << GEVB_SX_BITS) | lx) << GEVB_BX_BITS);
 	y0 = (int) (((sy << GEVB_SY_BITS) | ly) << GEVB_BY_BITS);

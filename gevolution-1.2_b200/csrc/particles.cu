@@ -145,6 +145,12 @@ extern "C" int gevb_pcls_create(gevb_ctx * c, gevb_pcls ** out, double mass)
 	G.N = c->N; G.nzl = c->nzl; G.z0 = c->z0;
 	const int spanx = GEVB_BX << GEVB_SX_BITS, spany = GEVB_BY << GEVB_SY_BITS, spanz = GEVB_BZ << GEVB_SZ_BITS;   // cells per super-brick edge
 	G.nsx = (c->N + spanx - 1) / spanx; G.nsy = (c->N + spany - 1) / spany; G.nsz = (c->nzl + spanz - 1) / spanz;
+	G.sx_shift = G.sy_shift = -1;
+	if ((G.nsx & (G.nsx - 1)) == 0 && (G.nsy & (G.nsy - 1)) == 0)
+	{
+		G.sx_shift = 0; while ((1 << G.sx_shift) < G.nsx) G.sx_shift++;
+		G.sy_shift = 0; while ((1 << G.sy_shift) < G.nsy) G.sy_shift++;
+	}
 	const uint64_t ncells = ((uint64_t) G.nsx * G.nsy * G.nsz << GEVB_SUPER_BITS) * GEVB_BRICK_CELLS;
 	GEVB_CHECK_ARG(ncells < (1ull << 31), "gevb_pcls_create: local slab has more than 2^31 cells");
 	G.nbricks = (uint32_t) (ncells / GEVB_BRICK_CELLS); G.ncells = (uint32_t) ncells;

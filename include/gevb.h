@@ -57,7 +57,8 @@ typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>
 const char * gevb_last_error(void);
 const char * gevb_version(void);
 
-/* kernel-variant knobs for ablation runs ("geodesic_variant", "deposit_variant"); results do not depend on them */
+/* kernel-variant knobs for ablation runs ("geodesic_variant", "deposit_variant", "fft_exchange": 1 = transposes pushed
+ * over peer memory, 0 = NCCL all-to-all + local transpose); results do not depend on them */
 int gevb_tuning(const char * knob, int value);
 
 /* ---- context: lattice geometry + device + communicator --------------------

@@ -7,7 +7,7 @@ nvidia-smi -L > $OUT/gpus.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_worker.py > $OUT/multigpu_parity_$NG.log 2>&1; echo "parity exit $?"; grep -E "BAD|MULTIGPU|Error|error" $OUT/multigpu_parity_$NG.log | head -20
 for n in ${@:-$NG}; do
   if [ "$n" = "1" ]; then timeout 900 python bench.py --no-cpu-baseline > $OUT/bench_$n.json 2> $OUT/bench_$n.err
-  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --no-cpu-baseline > $OUT/bench_$n.json 2> $OUT/bench_$n.err; fi
+  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --no-cpu-baseline $GEVB_BENCH_EXTRA > $OUT/bench_$n.json 2> $OUT/bench_$n.err; fi
   echo "bench $n exit $?"; tail -c 300 $OUT/bench_$n.err
   python - <<PY
 import json

@@ -3,7 +3,7 @@ against the single-lattice CPU checker.  Driven by tests/test_multigpu.py and sc
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_worker.py
 
-Covers: distributed FFT (2-D local, NCCL all-to-all, 1-D local) both ways, ghost-plane exchange (updateHalo), deposit
+Covers: distributed FFT (2-D local, exchange by NCCL all-to-all and by transposes pushed over peer memory, 1-D local) both ways, ghost-plane exchange (updateHalo), deposit
 fold (projection_comm), slab migration of particles (moveParticles), parallel.sum / max, and whole cycles of the time loop
 -- decomposition independence: P slabs must reproduce the undecomposed result to round-off.
 """
@@ -186,7 +186,11 @@ def main():
         box = [gevb.nccl_unique_id() if rank == 0 else None]          # one NCCL communicator (and id) per context
         dist.broadcast_object_list(box, src=0)
         ctx = gevb.Context(N, device=local, rank=rank, nranks=world, nccl_id=box[0])
-        case_fft(ctx, N, failures)
+        for xch in (0, 1):                                            # NCCL all-to-all + local transpose, then the peer-memory push (default)
+            gevb.tuning("fft_exchange", xch)
+            if rank == 0:
+                print(f" fft_exchange = {xch}", flush=True)
+            case_fft(ctx, N, failures)
         case_particles(ctx, chk, N, failures)
         if N == sizes[0]:
             for vector_flag, fused in ((0, 1), (1, 0)):
