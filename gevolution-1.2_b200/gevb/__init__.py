@@ -37,7 +37,8 @@ SYMBOLS = [
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_kick_drift",
-    "gevb_extractPowerSpectrum", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
+    "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
+    "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
     "gevb_sim_set_fused", "gevb_sim_step",
 ]
@@ -113,10 +114,22 @@ def _declare(L):
         "gevb_sim_set_particles": [vp, i, i64, vp, vp, vp, d], "gevb_sim_set_field": [vp, i, vp],
         "gevb_sim_get_field": [vp, i, vp], "gevb_sim_get_state": [vp, pd], "gevb_sim_set_state": [vp, pd],
         "gevb_sim_set_fused": [vp, i], "gevb_sim_step": [vp],
+        "gevb_writePowerSpectrum": [vp, vp, vp, vp, vp, i, d, d, C.c_char_p, C.c_char_p, d, d],
+        "gevb_pcls_saveGadget2": [vp, C.c_char_p, vp, i, d, d, vp],
+        "gevb_pcls_gadget2_arrays": [vp, d, d, i, d, d, vp, vp, vp, vp, C.POINTER(i64)],
+        "gevb_ctx_ranks": [vp, C.POINTER(i), C.POINTER(i)],
+        "gevb_sim_write_spectra": [vp, C.c_char_p, i, i, i, d],
+        "gevb_sim_save_gadget2": [vp, i, C.c_char_p, i, d, d],
     }
     for name, args in sig.items():
         f = getattr(L, name)
         f.restype, f.argtypes = C.c_int, args
+
+
+def writePowerSpectrum(kbin, power, kscatter, pscatter, occupation, rescalek, rescalep, filename, description, a, z_target=-1.0):
+    occ = np.ascontiguousarray(occupation, dtype=np.int32)
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (kbin, power, kscatter, pscatter)]
+    _ck(lib().gevb_writePowerSpectrum(*[_ptr(v) for v in arrs], _ptr(occ), len(occ), rescalek, rescalep, filename.encode(), description.encode(), a, z_target), "gevb_writePowerSpectrum")
 
 
 def tuning(knob, value):
@@ -477,6 +490,12 @@ class Sim:
         v, n = np.zeros(4), np.zeros(4, dtype=np.int32)
         _ck(lib().gevb_sim_get_ncdm_state(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), n.ctypes.data_as(C.POINTER(C.c_int))), "gevb_sim_get_ncdm_state")
         return v, n
+
+    def write_spectra(self, prefix, pkcount, numbins, mask, z_target=-1.0):
+        _ck(lib().gevb_sim_write_spectra(self.h, prefix.encode(), pkcount, numbins, mask, z_target), "gevb_sim_write_spectra")
+
+    def save_gadget2(self, species, filename, tracer_factor=1, dtau_pos=0.0, dtau_vel=0.0):
+        _ck(lib().gevb_sim_save_gadget2(self.h, species, filename.encode(), tracer_factor, dtau_pos, dtau_vel), "gevb_sim_save_gadget2")
 
     def set_fused(self, fused):
         lib().gevb_sim_set_fused(self.h, int(bool(fused)))

@@ -5,8 +5,10 @@
 // against include/gevolution_b200.hpp so that it reads like the reference's own
 // loop.  Exposed through the C ABI as gevb_sim_* (include/gevb.h).
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 #define GEVB_THROW_ON_ERROR
 #include "../../include/gevolution_b200.hpp"
 #include "background.hpp"
@@ -213,6 +215,85 @@ extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
 }
 
 static int sim_step(gevb_sim * s);
+
+// the phi / chi / hij / B part of writeSpectra (output.hpp:1945-1981,2151-2155; call main.cpp:639-679): forward
+// transforms, TT projection for hij, binning on the device, one text file per spectrum named <prefix><pkcount>_<name>.dat
+static int write_spectra(gevb_sim * s, const char * prefix, int pkcount, int numbins, int mask, double z_target)
+{
+	const double a = s->a, fourpiG = s->fourpiG;
+	const double numpts3d = (double) s->numpts * (double) s->numpts * (double) s->numpts;
+	std::vector<double> kbin(numbins), power(numbins), kscatter(numbins), pscatter(numbins);
+	std::vector<int> occupation(numbins);
+	char filename[1024];
+	int rank = 0;
+	gevb_ctx_ranks(s->lat.ctx(), &rank, NULL);
+	auto emit = [&](Field<Cplx> & fld, const char * tag, double rescalep, const char * description)
+	{
+		extractPowerSpectrum(fld, kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, false, 1 /* KTYPE_LINEAR */);
+		std::snprintf(filename, sizeof(filename), "%s%03d_%s.dat", prefix, pkcount, tag);
+		if (rank == 0)                                                                       // parallel.isRoot(), tools.hpp:270
+			check(gevb_writePowerSpectrum(kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, s->boxsize, rescalep, filename, description, a, z_target), "writePowerSpectrum");
+	};
+	if (mask & 1)                                                                            // MASK_PHI, output.hpp:1945-1951
+	{
+		s->plan_phi.execute(FFT_FORWARD);
+		emit(s->scalarFT, "phi", numpts3d * numpts3d * 2. * M_PI * M_PI, "power spectrum of phi");
+	}
+	if (mask & 2)                                                                            // MASK_CHI, :1953-1959
+	{
+		s->plan_chi.execute(FFT_FORWARD);
+		emit(s->scalarFT, "chi", numpts3d * numpts3d * 2. * M_PI * M_PI, "power spectrum of chi");
+	}
+	if (mask & 128)                                                                          // MASK_HIJ, :1961-1981
+	{
+		projection_init(&s->Sij);
+		projection_Tij_project(&s->pcls_cdm, &s->Sij, a, &s->phi);
+		if (s->baryon_flag) projection_Tij_project(&s->pcls_b, &s->Sij, a, &s->phi);
+		for (int i = 0; i < s->cosmo.num_ncdm; i++)
+			if (s->pcls_ncdm[i].initialized()) projection_Tij_project(s->pcls_ncdm + i, &s->Sij, a, &s->phi);
+		projection_Tij_comm(&s->Sij);
+		prepareFTsource<Real>(s->phi, s->Sij, s->Sij, 2. * fourpiG / (double) s->numpts / (double) s->numpts / a);
+		s->plan_Sij.execute(FFT_FORWARD);
+		projectFTtensor(s->SijFT, s->SijFT);
+		emit(s->SijFT, "hij", 2. * M_PI * M_PI, "power spectrum of hij");
+	}
+	if (mask & 8)                                                                            // MASK_B, :2151-2155
+		emit(s->BiFT, "B", a * a * a * a * s->numpts * s->numpts * 2. * M_PI * M_PI, "power spectrum of B");
+	return 0;
+}
+
+extern "C" int gevb_sim_write_spectra(gevb_sim * s, const char * prefix, int pkcount, int numbins, int mask, double z_target)
+{
+	if (s == NULL || prefix == NULL || numbins < 1) return 1;
+	try { return write_spectra(s, prefix, pkcount, numbins, mask, z_target); }
+	catch (const gevb_error &) { return 1; }
+}
+
+// snapshot of one species in Gadget-2 format (writeSnapshots, output.hpp:62-470 -> saveGadget2): the header is filled
+// as output.hpp:360-402 does (mass in 1e10 M_sun/h from the critical density, box in kpc/h)
+extern "C" int gevb_sim_save_gadget2(gevb_sim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel)
+{
+	if (s == NULL || filename == NULL) return 1;
+	gevb_pcls * p = gevb_sim_pcls(s, species);
+	if (p == NULL) return 1;
+	struct { uint32_t npart[6]; double mass[6]; double time, redshift; int32_t flag_sfr, flag_feedback; uint32_t npartTotal[6]; int32_t flag_cooling, num_files;
+	         double BoxSize, Omega0, OmegaLambda, HubbleParam; int32_t flag_age, flag_metals; uint32_t npartTotalHW[6]; char fill[64]; } hdr;   // metadata.hpp:152-171
+	static_assert(sizeof(hdr) == 256, "gadget2 header must be 256 bytes");
+	std::memset(&hdr, 0, sizeof(hdr));
+	hdr.num_files = 1;
+	hdr.Omega0 = s->cosmo.Omega_m; hdr.OmegaLambda = s->cosmo.Omega_Lambda; hdr.HubbleParam = s->cosmo.h;
+	hdr.BoxSize = s->boxsize / 0.001;                                                        // GADGET_LENGTH_CONVERSION, output.hpp:369
+	hdr.time = s->a; hdr.redshift = (1. / s->a) - 1.;
+	int64_t n_local = 0;
+	gevb_pcls_count(p, &n_local);
+	double ntot = (double) n_local;
+	if (gevb_parallel_sum(s->lat.ctx(), &ntot, 1) != 0) return 1;
+	const int64_t nsel = ((int64_t) ntot + tracer_factor - 1) / tracer_factor;               // output.hpp:396 (saveGadget2 overwrites npart[1] with the count it finds)
+	hdr.npart[1] = (uint32_t) (nsel % (1ll << 32)); hdr.npartTotal[1] = hdr.npart[1]; hdr.npartTotalHW[1] = (uint32_t) (nsel / (1ll << 32));
+	// C_RHO_CRIT = 2.77459457e11 (M_sun/h) / (Mpc/h)^3, metadata.hpp:99; species mass fraction times the box mass
+	hdr.mass[1] = (double) tracer_factor * 2.77459457e11 * gevb_pcls_mass(p) * s->boxsize * s->boxsize * s->boxsize / 1.0e10;   // output.hpp:400-402,417,433
+	return gevb_pcls_saveGadget2(p, filename, &hdr, tracer_factor, dtau_pos, dtau_vel, s->phi.handle());
+}
 
 // one cycle of the main loop (main.cpp:372-879 without outputs); errors come back as a status
 extern "C" int gevb_sim_step(gevb_sim * s)

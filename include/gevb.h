@@ -182,6 +182,23 @@ int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfields_kick, c
  * normalisation of tools.hpp:186-193 (all ranks receive the result)             */
 int gevb_extractPowerSpectrum(gevb_field * fldFT, double * kbin, double * power, double * kscatter, double * pscatter, int * occupation, int numbins, int deconvolve, int ktype);
 
+/* tools.hpp:268-346: the reference's power-spectrum text file (rank 0 calls it), including the interpolation to the
+ * exact output redshift when the file of the previous cycle exists (EXACT_OUTPUT_REDSHIFTS); z_target < 0 disables it */
+int gevb_writePowerSpectrum(const double * kbin, const double * power, const double * kscatter, const double * pscatter, const int * occupation, int numbins,
+                            double rescalek, double rescalep, const char * filename, const char * description, double a, double z_target);
+
+/* ---- snapshots (Particles_gevolution.hpp:30-251) ---------------------------------
+ * saveGadget2: Gadget-2 binary file of one species, float32 positions [kpc/h] / velocities [km/s / sqrt(a)], int64
+ * IDs, tracers ID % tracer_factor == 0, with the half-step corrections of EXACT_OUTPUT_REDSHIFTS (dtau_pos, dtau_vel,
+ * phi may be NULL).  header256 is the caller's 256-byte gadget2_header (metadata.hpp:152-171); its npart[1] is set
+ * to the number written.  Collective: every rank writes its share of the one file.
+ * gevb_pcls_gadget2_arrays is the device half (selection, corrections, units) returning host arrays.            */
+int gevb_pcls_saveGadget2(gevb_pcls * p, const char * filename, void * header256, int tracer_factor, double dtau_pos, double dtau_vel, gevb_field * phi);
+int gevb_pcls_gadget2_arrays(gevb_pcls * p, double a, double boxsize, int tracer_factor, double dtau_pos, double dtau_vel, gevb_field * phi,
+                             float * pos, float * vel, int64_t * ids, int64_t * n_out);
+gevb_ctx * gevb_pcls_ctx(gevb_pcls * p);
+int gevb_ctx_ranks(gevb_ctx * ctx, int * rank, int * nranks);
+
 /* ---- time loop (main.cpp:372-879, outputs stripped), host side in C++ ---------
  * dsettings: boxsize, Cf, steplimit, z_in, z_relax
  * cosmo    : Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h */
@@ -209,6 +226,11 @@ gevb_pcls * gevb_sim_pcls(gevb_sim * sim, int species);
 int gevb_sim_get_state(gevb_sim * sim, double * out9);     /* a,tau,dtau,dtau_old,cycle,maxvel0,maxvel1,T00hom,fourpiG */
 int gevb_sim_set_state(gevb_sim * sim, const double * in7);
 int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fused deposit + fused kick/drift, scalarFT is scratch after a cycle; 0: one call per reference call */
+/* writeSpectra for phi, chi, hij, B (output.hpp:1945-1981,2151-2155): mask = MASK_PHI 1 | MASK_CHI 2 | MASK_B 8 |
+ * MASK_HIJ 128 (metadata.hpp:56-63); files <prefix><pkcount %03d>_<phi|chi|hij|B>.dat                         */
+int gevb_sim_write_spectra(gevb_sim * sim, const char * prefix, int pkcount, int numbins, int mask, double z_target);
+/* writeSnapshots' Gadget-2 branch for one species (output.hpp:95-131 header, then saveGadget2) */
+int gevb_sim_save_gadget2(gevb_sim * sim, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel);
 int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
 
 #ifdef __cplusplus

@@ -314,3 +314,104 @@ def test_full_size_properties(gevb, ctx, N):
     key = gevb.storage_key(N, N, k0[:, 0], k0[:, 1], k0[:, 2])      # storage order: bricks, then cells inside the brick
     assert np.all(np.diff(key) >= 0), "brick-major cell order lost"
     assert np.array_equal(p0.cell_counts(), counts)
+
+
+# ---- outputs the parity metrics are defined on (f1 spectra files, f3 Gadget-2 snapshot) --------------------
+def _read_gadget2(path):
+    """minimal Gadget-2 reader (format 1, int64 IDs): header dict, pos[n][3] float32, vel[n][3] float32, ids[n]"""
+    import struct
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<I", raw, 0)[0] == 256 and struct.unpack_from("<I", raw, 260)[0] == 256
+    npart = struct.unpack_from("<6I", raw, 4)
+    mass = struct.unpack_from("<6d", raw, 4 + 24)
+    time, redshift = struct.unpack_from("<2d", raw, 4 + 24 + 48)
+    box = struct.unpack_from("<d", raw, 4 + 24 + 48 + 16 + 8 + 24 + 8)[0]
+    n = npart[1]
+    o = 264
+    assert struct.unpack_from("<I", raw, o)[0] == 12 * n
+    pos = np.frombuffer(raw, dtype="<f4", count=3 * n, offset=o + 4).reshape(n, 3)
+    o += 4 + 12 * n
+    assert struct.unpack_from("<2I", raw, o) == (12 * n, 12 * n)
+    vel = np.frombuffer(raw, dtype="<f4", count=3 * n, offset=o + 8).reshape(n, 3)
+    o += 8 + 12 * n
+    assert struct.unpack_from("<2I", raw, o) == (12 * n, 8 * n)
+    ids = np.frombuffer(raw, dtype="<i8", count=n, offset=o + 8)
+    o += 8 + 8 * n
+    assert struct.unpack_from("<I", raw, o)[0] == 8 * n and len(raw) == o + 4
+    return dict(npart=npart, mass=mass, time=time, redshift=redshift, BoxSize=box), pos, vel, ids
+
+
+def test_spectra_files_and_gadget2_snapshot(gevb, ctx, ref, tmp_path):
+    N, numbins = 16, 8
+    rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=41)
+    for _ in range(2):
+        rs.step(); gs.step()
+    st = gs.state()
+    a = st["a"]
+    # ---- f1: spectra files, phi / chi / hij / B (output.hpp:1945-1981,2151-2155; file format tools.hpp:268-346)
+    prefix = str(tmp_path / "pk")
+    gs.write_spectra(prefix, 3, numbins, 1 | 2 | 8 | 128)
+    cosmo = common.shipped_cosmology()
+    fourpiG, box = st["fourpiG"], 320.0
+    phi, chi = rs.get_field("phi"), rs.get_field("chi")
+    # the reference side of the hij branch: Tij of the particles, source with the snapshot coefficient, TT projection
+    rid, rpos, rvel = rs.get_particles(0)
+    mass = (cosmo[0] + cosmo[1]) / len(rid)
+    Tij = ref.projection_Tij(N, rpos, rvel, mass, a, phi[0])
+    hijFT = ref.projectFTtensor(ref.fft_forward(ref.prepareFTsource_tensor(phi[0], Tij, 2. * fourpiG / N / N / a)))
+    n3 = float(N) ** 3
+    expect = {
+        "phi": (ref.extractPowerSpectrum(ref.fft_forward(phi), numbins, deconvolve=False), n3 * n3 * 2 * np.pi ** 2),
+        "chi": (ref.extractPowerSpectrum(ref.fft_forward(chi), numbins, deconvolve=False), n3 * n3 * 2 * np.pi ** 2),
+        "hij": (ref.extractPowerSpectrum(hijFT, numbins, symmetric=True, deconvolve=False), 2 * np.pi ** 2),
+        "B": (ref.extractPowerSpectrum(rs.get_field("BiFT"), numbins, deconvolve=False), a ** 4 * N * N * 2 * np.pi ** 2),
+    }
+    for tag, ((kb, pw, ks, ps, occ), rescalep) in expect.items():
+        lines = open(f"{prefix}003_{tag}.dat").read().splitlines()
+        assert lines[0] == f"# power spectrum of {tag}" and lines[1] == "# redshift z=%f" % (1. / a - 1.) and lines[2].startswith("# k ")
+        rows = np.array([[float(v) for v in ln.split()] for ln in lines[3:]])
+        m = occ > 0
+        assert len(rows) == m.sum() and np.array_equal(rows[:, 4].astype(int), occ[m])
+        assert np.allclose(rows[:, 0], kb[m] / box, rtol=2e-6) and np.allclose(rows[:, 1], pw[m] / rescalep, rtol=2e-6), tag   # %e keeps 7 digits
+        assert np.allclose(rows[:, 3], ps[m] / rescalep / np.sqrt(occ[m]), rtol=1e-4, atol=1e-6 * np.abs(rows[:, 1]).max()), tag
+    # EXACT_OUTPUT_REDSHIFTS: a second write past the target redshift interpolates with the stored file (tools.hpp:277-315)
+    kb, pw, ks, ps, occ = expect["phi"][0]
+    fn = str(tmp_path / "interp.dat")
+    gevb.writePowerSpectrum(kb, pw, ks, ps, occ, box, 2.0, fn, "test", 1. / (1. + 10.0), 9.5)       # z = 10 > target: stored as is
+    gevb.writePowerSpectrum(kb, 3.0 * pw, ks, ps, occ, box, 2.0, fn, "test", 1. / (1. + 9.0), 9.5)  # z = 9 < target 9.5: half-way
+    lines = open(fn).read().splitlines()
+    assert lines[1] == "# redshift z=%f" % 9.5
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[3:]])
+    assert np.allclose(rows[:, 1], 2.0 * pw[occ > 0] / 2.0, rtol=3e-6)
+    # ---- f3: Gadget-2 snapshot with the half-step corrections (Particles_gevolution.hpp:153-199)
+    fn = str(tmp_path / "snap_cdm")
+    dtau_pos, dtau_vel, tracer = 0.013, 0.021, 3
+    gs.save_gadget2(0, fn, tracer, dtau_pos, dtau_vel)
+    hdr, gpos, gvel, gids = _read_gadget2(fn)
+    sel = rid % tracer == 0
+    assert hdr["npart"][1] == sel.sum() and abs(hdr["time"] - a) < 1e-15 and hdr["BoxSize"] == box / 0.001
+    assert abs(hdr["mass"][1] - tracer * 2.77459457e11 * mass * box ** 3 / 1e10) <= 1e-12 * hdr["mass"][1]
+    o, ro = np.argsort(gids), np.argsort(rid[sel])
+    assert np.array_equal(gids[o], rid[sel][ro])
+    p, v = rpos[sel][ro], rvel[sel][ro]
+    f = phi[0]                                                           # [z][y][x]
+    s = p * N
+    c = np.minimum(np.floor(s).astype(int), N - 1)
+    r = s - np.floor(s)
+    def at(dx, dy, dz):
+        return f[(c[:, 2] + dz) % N, (c[:, 1] + dy) % N, (c[:, 0] + dx) % N]
+    w = [(1 - r[:, i], r[:, i]) for i in range(3)]
+    phip = sum(at(i, j, k) * w[0][i] * w[1][j] * w[2][k] for i in (0, 1) for j in (0, 1) for k in (0, 1))
+    grad = np.stack([sum((at(1, j, k) - at(0, j, k)) * w[1][j] * w[2][k] for j in (0, 1) for k in (0, 1)),
+                     sum((at(i, 1, k) - at(i, 0, k)) * w[0][i] * w[2][k] for i in (0, 1) for k in (0, 1)),
+                     sum((at(i, j, 1) - at(i, j, 0)) * w[0][i] * w[1][j] for i in (0, 1) for j in (0, 1))], axis=1)
+    v2 = (v ** 2).sum(axis=1)
+    e2 = v2 + a * a
+    e = np.sqrt(e2)
+    ssum = v2 + e2
+    corr = 1. + (4. - ssum / e2) * phip
+    xpos = np.modf(1. + p + dtau_pos * v * (corr / e)[:, None])[0] * hdr["BoxSize"]
+    xvel = (v - dtau_vel * (ssum / e)[:, None] * grad * N) / np.sqrt(a) / 3.335640952e-6 / a
+    assert np.allclose(gpos[o], xpos.astype(np.float32), rtol=3e-7, atol=hdr["BoxSize"] * 1e-7)
+    assert np.allclose(gvel[o], xvel.astype(np.float32), rtol=3e-6, atol=np.abs(xvel).max() * 1e-6)
+    rs.close(); gs.close()
