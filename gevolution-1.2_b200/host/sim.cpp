@@ -216,6 +216,124 @@ extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
 
 static int sim_step(gevb_sim * s);
 
+// ---- hibernation / restart (hibernation.hpp:38-611 writes, ic_read.hpp:58-400 reads) -----------------------------
+// The state set is the reference's: the particles of every species, phi, chi, the vector potential, and the scalars
+// a, tau, dtau, dtau_old, cycle, maxvel[] (+ the ncdm sub-stepping inputs).  The reference stores the fields and
+// particles as HDF5 (absent here) and rebuilds BiFT from Bi by a forward FFT at restart; this writer keeps one
+// self-describing binary file per rank, <filebase>.<rank>.gevb, and stores BiFT itself so that a restart continues
+// from exactly the state that was left.
+namespace {
+const char HIB_MAGIC[8] = {'G', 'E', 'V', 'B', 'H', 'I', 'B', '1'};
+struct HibHeader
+{
+	char magic[8];
+	int32_t ngrid, nranks, rank, z0, nzl, nky, gr_flag, vector_flag, baryon_flag, num_ncdm, cycle, reserved;
+	double a, tau, dtau, dtau_old, T00hom;
+	double maxvel[2 + GEVB_MAX_NCDM];
+	int64_t npart[2 + GEVB_MAX_NCDM];
+	double mass[2 + GEVB_MAX_NCDM];
+};
+bool put(FILE * f, const void * p, size_t bytes) { return bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes; }
+bool get(FILE * f, void * p, size_t bytes) { return bytes == 0 || std::fread(p, 1, bytes, f) == bytes; }
+Particles_gevolution * species_of(gevb_sim * s, int sp) { return sp == 0 ? &s->pcls_cdm : (sp == 1 ? &s->pcls_b : &s->pcls_ncdm[sp - 2]); }
+}
+
+extern "C" int gevb_sim_hibernate(gevb_sim * s, const char * filebase)
+{
+	if (s == NULL || filebase == NULL) return 1;
+	gevb_ctx * ctx = s->lat.ctx();
+	int rank = 0, nranks = 1, n, z0, nzl, ky0, nky;
+	gevb_ctx_ranks(ctx, &rank, &nranks);
+	gevb_ctx_geometry(ctx, &n, &z0, &nzl, &ky0, &nky);
+	HibHeader h;
+	std::memset(&h, 0, sizeof(h));
+	std::memcpy(h.magic, HIB_MAGIC, 8);
+	h.ngrid = n; h.nranks = nranks; h.rank = rank; h.z0 = z0; h.nzl = nzl; h.nky = nky;
+	h.gr_flag = s->gr_flag; h.vector_flag = s->vector_flag; h.baryon_flag = s->baryon_flag; h.num_ncdm = s->cosmo.num_ncdm; h.cycle = s->cycle;
+	h.a = s->a; h.tau = s->tau; h.dtau = s->dtau; h.dtau_old = s->dtau_old; h.T00hom = s->T00hom;
+	for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++)
+	{
+		h.maxvel[i] = s->maxvel[i];
+		Particles_gevolution * p = species_of(s, i);
+		h.npart[i] = p->initialized() ? p->numParticlesLocal() : -1;
+		h.mass[i] = p->initialized() ? gevb_pcls_mass(p->handle()) : 0.;
+	}
+	char name[1024];
+	std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
+	FILE * f = std::fopen(name, "wb");
+	bool ok = f != NULL && put(f, &h, sizeof(h));
+	const size_t bulk = (size_t) nzl * n * n, ksites = nranks == 1 ? (size_t) n * n * (n / 2 + 1) : (size_t) nky * (n / 2 + 1) * n;
+	std::vector<double> buf;
+	struct { gevb_field * f; size_t doubles; } fields[3] = {{s->phi.handle(), bulk}, {s->chi.handle(), bulk}, {s->BiFT.handle(), 3 * 2 * ksites}};
+	for (int k = 0; k < 3 && ok; k++)
+	{
+		buf.resize(fields[k].doubles);
+		ok = gevb_field_download(fields[k].f, buf.data()) == 0 && put(f, buf.data(), buf.size() * sizeof(double));
+	}
+	for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
+	{
+		if (h.npart[i] <= 0) continue;
+		const size_t np = (size_t) h.npart[i];
+		std::vector<int64_t> id(np);
+		std::vector<double> pos(3 * np), vel(3 * np);
+		ok = gevb_pcls_download(species_of(s, i)->handle(), id.data(), pos.data(), vel.data()) == 0
+			&& put(f, id.data(), np * 8) && put(f, pos.data(), np * 24) && put(f, vel.data(), np * 24);
+	}
+	if (f) ok = std::fclose(f) == 0 && ok;
+	double bad = ok ? 0. : 1.;
+	if (gevb_parallel_sum(ctx, &bad, 1) != 0) return 1;
+	return bad == 0. ? 0 : 1;
+}
+
+extern "C" int gevb_sim_restore(gevb_sim * s, const char * filebase)
+{
+	if (s == NULL || filebase == NULL) return 1;
+	gevb_ctx * ctx = s->lat.ctx();
+	int rank = 0, nranks = 1, n, z0, nzl, ky0, nky;
+	gevb_ctx_ranks(ctx, &rank, &nranks);
+	gevb_ctx_geometry(ctx, &n, &z0, &nzl, &ky0, &nky);
+	char name[1024];
+	std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
+	FILE * f = std::fopen(name, "rb");
+	HibHeader h;
+	bool ok = f != NULL && get(f, &h, sizeof(h)) && std::memcmp(h.magic, HIB_MAGIC, 8) == 0;
+	// a restart must use the decomposition the state was written with (the reference has the same restriction per file set)
+	ok = ok && h.ngrid == n && h.nranks == nranks && h.rank == rank && h.z0 == z0 && h.nzl == nzl && h.gr_flag == s->gr_flag && h.vector_flag == s->vector_flag
+		&& h.num_ncdm == s->cosmo.num_ncdm;
+	if (ok)
+	{
+		const size_t bulk = (size_t) nzl * n * n, ksites = nranks == 1 ? (size_t) n * n * (n / 2 + 1) : (size_t) nky * (n / 2 + 1) * n;
+		std::vector<double> buf;
+		const int which[3] = {0, 1, 11};
+		const size_t doubles[3] = {bulk, bulk, 3 * 2 * ksites};
+		for (int k = 0; k < 3 && ok; k++)
+		{
+			buf.resize(doubles[k]);
+			ok = get(f, buf.data(), buf.size() * sizeof(double)) && gevb_sim_set_field(s, which[k], buf.data()) == 0;     // fills the ghost planes too
+		}
+		for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
+		{
+			if (h.npart[i] < 0) continue;
+			const size_t np = (size_t) h.npart[i];
+			std::vector<int64_t> id(np);
+			std::vector<double> pos(3 * np), vel(3 * np);
+			ok = get(f, id.data(), np * 8) && get(f, pos.data(), np * 24) && get(f, vel.data(), np * 24)
+				&& gevb_sim_set_particles(s, i, (int64_t) np, id.data(), pos.data(), vel.data(), h.mass[i]) == 0;
+		}
+		if (ok)
+		{
+			s->a = h.a; s->tau = h.tau; s->dtau = h.dtau; s->dtau_old = h.dtau_old; s->cycle = h.cycle; s->T00hom = h.T00hom;
+			for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) s->maxvel[i] = h.maxvel[i];
+			// Bi in real space is derived state (main.cpp:593-598)
+			if (s->gr_flag > 0) { try { s->plan_Bi.execute(FFT_BACKWARD); s->Bi.updateHalo(); } catch (const gevb_error &) { ok = false; } }
+		}
+	}
+	if (f) std::fclose(f);
+	double bad = ok ? 0. : 1.;
+	if (gevb_parallel_sum(ctx, &bad, 1) != 0) return 1;
+	return bad == 0. ? 0 : 1;
+}
+
 // the phi / chi / hij / B part of writeSpectra (output.hpp:1945-1981,2151-2155; call main.cpp:639-679): forward
 // transforms, TT projection for hij, binning on the device, one text file per spectrum named <prefix><pkcount>_<name>.dat
 static int write_spectra(gevb_sim * s, const char * prefix, int pkcount, int numbins, int mask, double z_target)

@@ -231,6 +231,11 @@ int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fuse
 int gevb_sim_write_spectra(gevb_sim * sim, const char * prefix, int pkcount, int numbins, int mask, double z_target);
 /* writeSnapshots' Gadget-2 branch for one species (output.hpp:95-131 header, then saveGadget2) */
 int gevb_sim_save_gadget2(gevb_sim * sim, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel);
+/* hibernation / restart (hibernation.hpp:38-611, ic_read.hpp:58-400): particles of every species, phi, chi, BiFT and the
+ * loop scalars, one binary file <filebase>.<rank>.gevb per rank (the reference's HDF5 container is not available);
+ * restore needs a sim created with the same lattice, decomposition and flags.  Both are collective.            */
+int gevb_sim_hibernate(gevb_sim * sim, const char * filebase);
+int gevb_sim_restore(gevb_sim * sim, const char * filebase);
 int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
 
 #ifdef __cplusplus

@@ -415,3 +415,38 @@ def test_spectra_files_and_gadget2_snapshot(gevb, ctx, ref, tmp_path):
     assert np.allclose(gpos[o], xpos.astype(np.float32), rtol=3e-7, atol=hdr["BoxSize"] * 1e-7)
     assert np.allclose(gvel[o], xvel.astype(np.float32), rtol=3e-6, atol=np.abs(xvel).max() * 1e-6)
     rs.close(); gs.close()
+
+
+def test_hibernate_and_restart(gevb, ctx, ref, tmp_path):
+    """a run continued from a hibernation file reproduces the uninterrupted run (hibernation.hpp, ic_read.hpp)"""
+    N = 16
+    rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=61, baryons=True)
+    rs.close()
+    for _ in range(2):
+        gs.step()
+    base = str(tmp_path / "hib")
+    gs.hibernate(base)
+    for _ in range(2):
+        gs.step()
+    cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
+    g2 = gevb.Sim(gs.ctx, 1, 0, ds, cosmo)
+    g2.restore(base)
+    assert g2.state()["cycle"] == 2
+    for _ in range(2):
+        g2.step()
+    a, b = gs.state(), g2.state()
+    for k in ("a", "tau", "dtau", "dtau_old"):
+        assert a[k] == b[k], k
+    assert a["cycle"] == b["cycle"] == 4 and abs(a["T00hom"] - b["T00hom"]) <= 1e-13 * abs(a["T00hom"])
+    for name in ("phi", "chi", "Bi", "BiFT"):
+        assert common.rel_linf(g2.get_field(name), gs.get_field(name)) <= 1e-12, name
+    for sp in (0, 1):
+        i1, p1, v1 = gs.pcls(sp).download()
+        i2, p2, v2 = g2.pcls(sp).download()
+        o1, o2 = np.argsort(i1), np.argsort(i2)
+        assert np.array_equal(i1[o1], i2[o2]) and np.abs(p1[o1] - p2[o2]).max() <= 1e-14 and common.rel_linf(v2[o2], v1[o1]) <= 1e-12
+    # a file written for another lattice is refused
+    g3 = gevb.Sim(ctx(8), 1, 0, ds, cosmo)
+    with pytest.raises(gevb.GevbError):
+        g3.restore(base)
+    gs.close(); g2.close(); g3.close()
