@@ -336,6 +336,20 @@ def run_ours(args, rank, world, local_rank):
     value = np_total * args.steps / (ms * 1e-3)
     state = sim.state()
 
+    # ---- the FFT exchange by itself: two more cycles with the component pipeline off, so that the time of the pushes is
+    #      not hidden behind the local transforms (the timed run above keeps the overlap on)
+    exchange_ms = None
+    if world > 1:
+        gevb.tuning("fft_overlap", 0)
+        sim.step()
+        ctx.sync(); ctx.timing(True); ctx.timing_read()
+        for _ in range(2):
+            sim.step()
+        per_x = ctx.timing_read(); ctx.timing(False)
+        gevb.tuning("fft_overlap", 1)
+        if "fft_alltoall" in per_x:
+            exchange_ms = per_x["fft_alltoall"][0] / 2
+
     # ---- optional ablation of kernel variants (stderr; not part of the bench line) ------------------------------
     if args.ablate:
         for spec in args.ablate.split(","):
@@ -439,9 +453,11 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and "fft_alltoall" in per_class and per_class["fft_alltoall"][0] > 0:
         # bytes one rank puts on NVLink per step: 12 component transforms x 16 B x local k-sites x (P-1)/P
         sent = 12 * 16 * (N // 2 + 1) * N * (N // world) * (world - 1) / world
-        a2a_ms = per_class["fft_alltoall"][0] / args.steps
+        exposed_ms = per_class["fft_alltoall"][0] / args.steps
+        a2a_ms = exchange_ms if exchange_ms else exposed_ms
         nvlink = {"bound": "nvlink", "kernel": "k_push_fwd / k_push_bwd (FFT transposes stored straight into peer memory over NVLink) + barrier", "achieved": sent / (a2a_ms * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s per direction per GPU",
-                  "frac": sent / (a2a_ms * 1e-3) / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md (900 nominal)", "bytes_sent_per_rank_per_step": int(sent), "ms_per_step": a2a_ms}
+                  "frac": sent / (a2a_ms * 1e-3) / 1e9 / 770.0, "peak_source": "measured peer copy, B200_PROFILING.md (900 nominal)", "bytes_sent_per_rank_per_step": int(sent), "ms_per_step": a2a_ms,
+                  "exposed_ms_per_step_in_timed_run": exposed_ms, "note": "ms_per_step: exchange measured with the component pipeline off; exposed: what the main stream still waited for in the timed run (pushes overlap the local transforms)"}
     own = {k: v for k, v in kernels.items() if not k.startswith("fft_") and "frac" in v}
     top = max(own, key=lambda k: own[k]["ms_per_step"]) if own else None
     traffic = ncu_traffic().get(top) if top else None

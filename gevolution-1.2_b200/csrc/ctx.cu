@@ -34,8 +34,8 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
-static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "deposit_variant", "fft_exchange"};
-static int tune_values[GEVB_NTUNE] = {1, 0, 1};
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "deposit_variant", "fft_exchange", "fft_overlap"};
+static int tune_values[GEVB_NTUNE] = {1, 0, 1, 1};
 static bool tune_env_read = false;
 static void tune_read_env()
 {
@@ -117,6 +117,12 @@ extern "C" int gevb_ctx_destroy(gevb_ctx * c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	gevb_xchg_release(c);
+	if (c->d_barrier)
+	{
+		cudaFree(c->d_barrier);
+		cudaStreamDestroy(c->xstream);
+		for (int k = 0; k < 8; k++) cudaEventDestroy(c->xev[k]);
+	}
 	if (c->have_comm) ncclCommDestroy(c->comm);
 	cudaFree(c->d_gridk2); cudaFree(c->d_kshift); cudaFree(c->d_red); cudaFreeHost(c->h_red);
 	if (c->scratch) cudaFree(c->scratch);

@@ -89,57 +89,73 @@ __global__ void k_pack_bwd(const double2 * __restrict__ in, double2 * __restrict
 struct PeerPtrs { double2 * p[GEVB_MAX_RANKS]; };
 
 // forward exchange: local A [c][ky][zl][kx]  ->  rank d = ky / nkyl : X_d [c][kyl][kx][kz = rank * nzl + zl]
-__global__ void __launch_bounds__(256) k_push_fwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank)
+// Blocks walk the 32 x 32 tiles with stride gridDim.x: the launch decides how much of the machine the exchange takes
+// (all of it when it runs alone, a few hundred resident blocks when it shares the SMs with the next local transform).
+__global__ void __launch_bounds__(256) k_push_fwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp)
 {
 	__shared__ double2 tile[32][33];
-	const int c = blockIdx.z / N, ky = blockIdx.z % N;
-	const int d = ky / nkyl, kyl = ky % nkyl;
-	const int kx0 = blockIdx.x * 32, zl0 = blockIdx.y * 32;
-	const double2 * src = A + ((size_t) c * N + ky) * nzl * nh;
-	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	const int tkx = (nh + 31) / 32, tz = (nzl + 31) / 32;
+	const long ntiles = (long) tkx * tz * ncomp * N;
+	for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
-		const int zl = zl0 + j, kx = kx0 + threadIdx.x;
-		if (zl < nzl && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) zl * nh + kx);
-	}
-	__syncthreads();
-	double2 * dst = X.p[d] + ((size_t) c * nkyl + kyl) * nh * N + (size_t) rank * nzl;
-	for (int j = threadIdx.y; j < 32; j += blockDim.y)
-	{
-		const int kx = kx0 + j, zl = zl0 + threadIdx.x;
-		if (zl < nzl && kx < nh) dst[(size_t) kx * N + zl] = tile[threadIdx.x][j];
+		const int kx0 = (int) (t % tkx) * 32; long r = t / tkx;
+		const int zl0 = (int) (r % tz) * 32; r /= tz;
+		const int c = c0 + (int) (r / N), ky = (int) (r % N);
+		const int d = ky / nkyl, kyl = ky % nkyl;
+		const double2 * src = A + ((size_t) c * N + ky) * nzl * nh;
+		for (int j = threadIdx.y; j < 32; j += blockDim.y)
+		{
+			const int zl = zl0 + j, kx = kx0 + threadIdx.x;
+			if (zl < nzl && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) zl * nh + kx);
+		}
+		__syncthreads();
+		double2 * dst = X.p[d] + ((size_t) c * nkyl + kyl) * nh * N + (size_t) rank * nzl;
+		for (int j = threadIdx.y; j < 32; j += blockDim.y)
+		{
+			const int kx = kx0 + j, zl = zl0 + threadIdx.x;
+			if (zl < nzl && kx < nh) dst[(size_t) kx * N + zl] = tile[threadIdx.x][j];
+		}
+		__syncthreads();
 	}
 }
 
 // backward exchange: local A [c][kyl][kx][z]  ->  rank d = z / nzl : X_d [c][ky = rank * nkyl + kyl][zl][kx]
-__global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank)
+__global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp)
 {
 	__shared__ double2 tile[32][33];
-	const int c = blockIdx.z / nkyl, kyl = blockIdx.z % nkyl;
-	const int kx0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
-	const double2 * src = A + ((size_t) c * nkyl + kyl) * nh * N;
-	for (int j = threadIdx.y; j < 32; j += blockDim.y)
+	const int tkx = (nh + 31) / 32, tz = (N + 31) / 32;
+	const long ntiles = (long) tkx * tz * ncomp * nkyl;
+	for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
-		const int kx = kx0 + j, z = z0 + threadIdx.x;
-		if (z < N && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) kx * N + z);
-	}
-	__syncthreads();
-	const size_t row = ((size_t) c * N + (size_t) rank * nkyl + kyl) * nzl;
-	for (int j = threadIdx.y; j < 32; j += blockDim.y)
-	{
-		const int z = z0 + j, kx = kx0 + threadIdx.x;
-		if (z < N && kx < nh)
+		const int kx0 = (int) (t % tkx) * 32; long r = t / tkx;
+		const int z0 = (int) (r % tz) * 32; r /= tz;
+		const int c = c0 + (int) (r / nkyl), kyl = (int) (r % nkyl);
+		const double2 * src = A + ((size_t) c * nkyl + kyl) * nh * N;
+		for (int j = threadIdx.y; j < 32; j += blockDim.y)
 		{
-			const int d = z / nzl, zl = z % nzl;
-			X.p[d][(row + zl) * nh + kx] = tile[threadIdx.x][j];
+			const int kx = kx0 + j, z = z0 + threadIdx.x;
+			if (z < N && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) kx * N + z);
 		}
+		__syncthreads();
+		const size_t row = ((size_t) c * N + (size_t) rank * nkyl + kyl) * nzl;
+		for (int j = threadIdx.y; j < 32; j += blockDim.y)
+		{
+			const int z = z0 + j, kx = kx0 + threadIdx.x;
+			if (z < N && kx < nh)
+			{
+				const int d = z / nzl, zl = z % nzl;
+				X.p[d][(row + zl) * nh + kx] = tile[threadIdx.x][j];
+			}
+		}
+		__syncthreads();
 	}
 }
 
 // stream-ordered barrier across the ranks: every rank's earlier work on its stream (the pushes into peer memory) has
 // completed before any rank's later work starts
-int rank_barrier(gevb_ctx * c)
+int rank_barrier(gevb_ctx * c, cudaStream_t stream)
 {
-	NCCL_TRY(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream));
+	NCCL_TRY(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, stream));
 	return 0;
 }
 
@@ -150,7 +166,14 @@ int xchg_ensure(gevb_ctx * c, size_t bytes)
 	if (c->xchg_state < 0 || (c->xchg_state == 1 && c->xchg_bytes >= bytes)) return 0;
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	gevb_xchg_release(c);
-	if (c->d_barrier == NULL) { CUDA_TRY(cudaMalloc(&c->d_barrier, 64)); CUDA_TRY(cudaMemset(c->d_barrier, 0, 64)); }
+	if (c->d_barrier == NULL)
+	{
+		CUDA_TRY(cudaMalloc(&c->d_barrier, 64)); CUDA_TRY(cudaMemset(c->d_barrier, 0, 64));
+		int prio_lo = 0, prio_hi = 0;
+		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CUDA_TRY(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, prio_hi));     // its blocks are placed before the local transform's
+		for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreateWithFlags(&c->xev[k], cudaEventDisableTiming));
+	}
 	int ok = 1;
 	cudaIpcMemHandle_t mine[2], all[GEVB_MAX_RANKS][2];
 	memset(mine, 0, sizeof(mine));
@@ -262,6 +285,8 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 		CUFFT_TRY(cufftSetStream(p->fwd2d, c->stream));
 		CUFFT_TRY(cufftSetStream(p->bwd2d, c->stream));
 		CUFFT_TRY(cufftSetStream(p->z1d, c->stream));
+		CUFFT_TRY(cufftPlanMany(&p->z1d_one, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, c->nkyl * nh));
+		CUFFT_TRY(cufftSetStream(p->z1d_one, c->stream));
 		// exchange buffers large enough for this field (collective; grow-only)
 		// (sized for six components from the start -- the largest field of the time loop -- so that they are mapped once)
 		GEVB_TRY(xchg_ensure(c, (size_t) (rf->ncomp > 6 ? rf->ncomp : 6) * c->nzl * N * nh * sizeof(double2)));
@@ -276,7 +301,7 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
 	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); }
-	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); }
+	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); }
 	delete p;
 	return 0;
 }
@@ -334,30 +359,61 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		PeerPtrs X;
 		for (int r = 0; r < GEVB_MAX_RANKS; r++) X.p[r] = (double2 *) c->xchg[buf][r];
 		double2 * Xl = (double2 *) c->xchg[buf][c->rank];
+		// component pipeline: the push of component k (xstream) overlaps the local transform of component k+1 (stream);
+		// the time the main stream then still waits for the exchange is what CLS_FFT_A2A measures
+		const bool overlap = gevb_tune(TUNE_FFT_OVERLAP) != 0 && nc > 1 && nc <= 7;
+		cudaStream_t xs = overlap ? c->xstream : c->stream;
+		// resident blocks of the exchange: two per SM when it shares the machine with a local transform, else eight
+		const long pcap = (long) c->num_sms * (overlap ? 2 : 8);
 		if (direction == GEVB_FFT_FORWARD)
 		{
+			const long ntiles = (long) ((nh + 31) / 32) * ((c->nzl + 31) / 32) * (overlap ? 1 : nc) * N;
+			const int pg = (int) (ntiles < pcap ? ntiles : pcap);
 			for (int k = 0; k < nc; k++)
+			{
 				CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * comp_sites)));
-			c->launches += nc;
+				c->launches++;
+				if (overlap)
+				{
+					CUDA_TRY(cudaEventRecord(c->xev[k], c->stream));
+					CUDA_TRY(cudaStreamWaitEvent(xs, c->xev[k], 0));
+					k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1);
+					KERNEL_CHECK(c);
+				}
+			}
 			{
 				Timed t_(c, CLS_FFT_A2A);
-				dim3 pg((nh + 31) / 32, (c->nzl + 31) / 32, nc * N);
-				k_push_fwd<<<pg, tb, 0, c->stream>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank);
-				KERNEL_CHECK(c);
-				GEVB_TRY(rank_barrier(c));
+				if (!overlap) { k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc); KERNEL_CHECK(c); }
+				GEVB_TRY(rank_barrier(c, xs));
+				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[7], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[7], 0)); }
 			}
 			CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) Xl, (cufftDoubleComplex *) cf->data, CUFFT_FORWARD));
 			c->launches++;
 		}
 		else
 		{
-			CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
-			c->launches++;
+			const long ntiles = (long) ((nh + 31) / 32) * ((N + 31) / 32) * (overlap ? 1 : nc) * c->nkyl;
+			const int pg = (int) (ntiles < pcap ? ntiles : pcap);
+			if (overlap)
+				for (int k = 0; k < nc; k++)
+				{
+					CUFFT_TRY(cufftExecZ2Z(p->z1d_one, (cufftDoubleComplex *) cf->data + (size_t) k * comp_sites, (cufftDoubleComplex *) (A + (size_t) k * comp_sites), CUFFT_INVERSE));
+					c->launches++;
+					CUDA_TRY(cudaEventRecord(c->xev[k], c->stream));
+					CUDA_TRY(cudaStreamWaitEvent(xs, c->xev[k], 0));
+					k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1);
+					KERNEL_CHECK(c);
+				}
+			else
+			{
+				CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
+				c->launches++;
+			}
 			{
 				Timed t_(c, CLS_FFT_A2A);
-				k_push_bwd<<<tg, tb, 0, c->stream>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank);
-				KERNEL_CHECK(c);
-				GEVB_TRY(rank_barrier(c));
+				if (!overlap) { k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc); KERNEL_CHECK(c); }
+				GEVB_TRY(rank_barrier(c, xs));
+				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[7], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[7], 0)); }
 			}
 			for (int k = 0; k < nc; k++)
 				CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (Xl + (size_t) k * comp_sites), rbulk + k * rf->comp_stride));

@@ -95,9 +95,19 @@ __device__ __forceinline__ double tri_cic(const double * t, int f, const double 
 }
 
 // update_q (gevolution.hpp:570-678) / update_q_Newton (:709-776); returns q^2 after the kick
-__device__ __forceinline__ double kick(const GParams & P, const double * t, const double * r, double * q)
+__device__ __forceinline__ double kick(const GParams & P, const double * t, const double * r, double * q, int64_t pid)
 {
 	double g[3], v2;
+	if (P.fn == GEVB_INITIALIZE_Q_IC_BASIC)
+	{
+		// initialize_q_ic_basic (ic_basic.hpp:118-152): q = -coeff grad(potential) / dx; with two potentials every eighth ID uses the second
+		const int f = (P.nf_kick > 1 && (pid & 7) == 0) ? 1 : 0;                   // :124-127
+		grad_cic(t, f, r, g);                                                      // :129-140
+		v2 = 0.;
+		#pragma unroll
+		for (int i = 0; i < 3; i++) { q[i] = -by_dx(P, g[i]) * P.dtau_kick; v2 += q[i] * q[i]; }   // :142-150
+		return v2;
+	}
 	if (P.fn == GEVB_UPDATE_Q)
 	{
 		v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                             // :581
@@ -161,13 +171,24 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 }
 
 // update_pos (gevolution.hpp:810-871) / update_pos_Newton (:900-903)
-__device__ __forceinline__ void drift(const GParams & P, const double * t, const double * r, const double * q, double * pos)
+// returns the squared displacement for displace_pcls_ic_basic (its reduction output, ic_basic.hpp:88-89), else 0
+__device__ __forceinline__ double drift(const GParams & P, const double * t, const double * r, const double * q, double * pos, int64_t pid)
 {
+	if (P.fn == GEVB_DISPLACE_PCLS_IC_BASIC)
+	{
+		// displace_pcls_ic_basic (ic_basic.hpp:60-92): pos += coeff grad(xi) / dx
+		double g[3], d2 = 0.;
+		const int f = (P.nf_drift > 1 && (pid & 7) == 0) ? 1 : 0;                  // :65-68
+		grad_cic(t, f, r, g);                                                      // :70-81
+		#pragma unroll
+		for (int l = 0; l < 3; l++) { g[l] = by_dx(P, g[l]); d2 += g[l] * g[l]; pos[l] += P.dtau_drift * g[l]; }   // :83-91
+		return P.dtau_drift * P.dtau_drift * d2;
+	}
 	if (P.fn != GEVB_UPDATE_Q)
 	{
 		#pragma unroll
 		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * q[l] / P.a_drift;     // :902
-		return;
+		return 0.;
 	}
 	double v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                           // :813
 	const double e2 = v2 + P.a_drift * P.a_drift;                                  // :814
@@ -200,6 +221,7 @@ __device__ __forceinline__ void drift(const GParams & P, const double * t, const
 		#pragma unroll
 		for (int l = 0; l < 3; l++) pos[l] += P.dtau_drift * v[l];                 // :869
 	}
+	return 0.;
 }
 #undef T
 
@@ -314,15 +336,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 					r[0] = sx - floor(sx); r[1] = sy - floor(sy); r[2] = sz - floor(sz);      // modf(pos/dx) for pos >= 0
 					t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + 1);
 				}
+				const int64_t pid = P.fn >= GEVB_DISPLACE_PCLS_IC_BASIC ? P.id[i] : 0;      // only the IC callbacks look at the ID
 				if (MODE == 0 || MODE == 2)
 				{
-					const double v2 = kick(P, t, r, q);
+					const double v2 = kick(P, t, r, q, pid);
 					vmax = fmax(vmax, v2);
 					P.qx[i] = q[0]; P.qy[i] = q[1]; P.qz[i] = q[2];
 				}
 				if (MODE == 1 || MODE == 2)
 				{
-					drift(P, t, r, q, pos);
+					const double d2 = drift(P, t, r, q, pos, pid);
+					if (MODE == 1) vmax = fmax(vmax, d2);
 					pos[0] = wrap_pos(pos[0]); pos[1] = wrap_pos(pos[1]); pos[2] = wrap_pos(pos[2]);
 					const int cx = cell_scaled(scaled(P, pos[0]), G.N), cy = cell_scaled(scaled(P, pos[1]), G.N), cz = cell_scaled(scaled(P, pos[2]), G.N);
 					const int zl = cz - G.z0;
@@ -365,7 +389,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 		}
 		brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1;
 	}
-	if (MODE == 0 || MODE == 2)
 	{
 		for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_down_sync(0xffffffffu, vmax, o));
 		if ((threadIdx.x & 31) == 0 && vmax > 0.) atomicMax(P.maxv2, (unsigned long long) __double_as_longlong(vmax));
@@ -526,8 +549,11 @@ int setup_migration(gevb_pcls * p, GParams & P)
 
 extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * maxvel)
 {
-	GEVB_CHECK_ARG(p != NULL && params != NULL, "updateVel: NULL argument");
-	GEVB_CHECK_ARG(fn == GEVB_UPDATE_Q || fn == GEVB_UPDATE_Q_NEWTON, "updateVel: unknown callback %d (only update_q and update_q_Newton can run on the device)", fn);
+	static const double no_params[2] = {1., 1.};
+	GEVB_CHECK_ARG(p != NULL, "updateVel: NULL argument");
+	GEVB_CHECK_ARG(fn == GEVB_UPDATE_Q || fn == GEVB_UPDATE_Q_NEWTON || fn == GEVB_INITIALIZE_Q_IC_BASIC, "updateVel: unknown callback %d (only update_q, update_q_Newton and initialize_q_ic_basic can run on the device)", fn);
+	if (fn == GEVB_INITIALIZE_Q_IC_BASIC) { params = no_params; GEVB_CHECK_ARG(nfields <= 2, "updateVel: initialize_q_ic_basic takes one or two potentials"); }
+	GEVB_CHECK_ARG(params != NULL, "updateVel: NULL params");
 	gevb_ctx * c = p->ctx;
 	GEVB_TRY(check_fields(c, fields, nfields, "updateVel"));
 	GEVB_CHECK_ARG(nfields >= 1, "updateVel: needs at least phi");
@@ -550,10 +576,27 @@ extern "C" int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * c
 	return 0;
 }
 
+static int move_particles(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * output_max);
+
 extern "C" int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params)
 {
-	GEVB_CHECK_ARG(p != NULL && params != NULL, "moveParticles: NULL argument");
-	GEVB_CHECK_ARG(fn == GEVB_UPDATE_Q || fn == GEVB_UPDATE_Q_NEWTON, "moveParticles: unknown callback %d (only update_pos and update_pos_Newton can run on the device)", fn);
+	return move_particles(p, fn, dtau, fields, nfields, params, NULL);
+}
+
+extern "C" int gevb_moveParticles_max(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * output_max)
+{
+	GEVB_CHECK_ARG(output_max != NULL, "moveParticles: NULL output");
+	return move_particles(p, fn, dtau, fields, nfields, params, output_max);
+}
+
+static int move_particles(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * output_max)
+{
+	static const double no_params[2] = {1., 1.};
+	GEVB_CHECK_ARG(p != NULL, "moveParticles: NULL argument");
+	GEVB_CHECK_ARG(fn == GEVB_UPDATE_Q || fn == GEVB_UPDATE_Q_NEWTON || fn == GEVB_DISPLACE_PCLS_IC_BASIC, "moveParticles: unknown callback %d (only update_pos, update_pos_Newton and displace_pcls_ic_basic can run on the device)", fn);
+	if (fn == GEVB_DISPLACE_PCLS_IC_BASIC) { params = no_params; GEVB_CHECK_ARG(nfields >= 1 && nfields <= 2, "moveParticles: displace_pcls_ic_basic takes one or two displacement fields"); }
+	GEVB_CHECK_ARG(params != NULL, "moveParticles: NULL params");
+	GEVB_CHECK_ARG(output_max == NULL || fn == GEVB_DISPLACE_PCLS_IC_BASIC, "moveParticles: only displace_pcls_ic_basic has a reduction output");
 	gevb_ctx * c = p->ctx;
 	if (fn == GEVB_UPDATE_Q_NEWTON) nfields = 0;
 	GEVB_TRY(check_fields(c, fields, nfields, "moveParticles"));
@@ -562,12 +605,21 @@ extern "C" int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field
 	base_params(P, p, fields, nfields);
 	P.fn = fn; P.nf_drift = nfields; P.dtau_drift = dtau; P.a_drift = params[0]; P.bscale_drift = params[1]; P.binv_drift = 1.0 / params[1];
 	GEVB_TRY(setup_migration(p, P));
+	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
 		Timed timed_(c, CLS_DRIFT);
 		GEVB_TRY(launch_geodesic<1>(p, P));
 	}
-	return finish_move(p, P);
+	GEVB_TRY(finish_move(p, P));
+	if (output_max)
+	{
+		// the callback's reduction output (largest displacement, ic_basic.hpp:88-89) of the LOCAL particles; the caller reduces over ranks
+		CUDA_TRY(cudaMemcpyAsync(c->h_red, P.maxv2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		*output_max = sqrt(c->h_red[0]);
+	}
+	return 0;
 }
 
 extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfields_kick, const double * params_kick,

@@ -13,7 +13,7 @@
 void gevb_set_error(const char * fmt, ...);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, TUNE_FFT_EXCHANGE, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -104,6 +104,8 @@ struct gevb_ctx
 	uint64_t xchg_epoch;
 	int xchg_state;            // 0 not tried, 1 mapped, -1 unavailable (NCCL exchange is used)
 	int * d_barrier;
+	cudaStream_t xstream;      // the pushes of component k run here while the local transform of component k+1 runs on `stream`
+	cudaEvent_t xev[8];        // [0..6] component k's local transform is done; [7] exchange + barrier are done
 	size_t plane() const { return (size_t) N * N; }
 	size_t real_comp_stride() const { return (size_t) (nzl + 2) * N * N; }
 	size_t cplx_comp_stride() const { return nranks == 1 ? (size_t) N * N * nh : (size_t) nkyl * nh * N; }
@@ -132,6 +134,7 @@ struct gevb_plan
 	gevb_field * real_field, * cplx_field;
 	cufftHandle fwd, bwd;      // nranks == 1: 3-D D2Z / Z2D batched over components
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
+	cufftHandle z1d_one;             // 1-D along z for one component (component-pipelined backward transform)
 	bool multi;
 	bool preserve;             // backward execute keeps the Fourier field intact (default)
 };

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("GEVB_LIB") or os.path.join(os.path.dirname(_HERE), "l
 
 REAL, CPLX = 0, 1
 FFT_FORWARD, FFT_BACKWARD = 1, -1
-UPDATE_Q, UPDATE_Q_NEWTON = 0, 1
+UPDATE_Q, UPDATE_Q_NEWTON, DISPLACE_PCLS_IC_BASIC, INITIALIZE_Q_IC_BASIC = 0, 1, 2, 3
 
 FIELD_IDS = {"phi": 0, "chi": 1, "Bi": 2, "source": 3, "Sij": 4, "scalarFT": 10, "BiFT": 11, "SijFT": 12}
 FIELD_COMPS = {"phi": 1, "chi": 1, "Bi": 3, "source": 1, "Sij": 6, "scalarFT": 1, "BiFT": 3, "SijFT": 6}
@@ -36,7 +36,7 @@ SYMBOLS = [
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
-    "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_kick_drift",
+    "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
     "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
@@ -108,6 +108,7 @@ def _declare(L):
         "gevb_evolveFTvector": [vp, vp, d], "gevb_projectFTvector": [vp, vp, d, d], "gevb_projectFTtensor": [vp, vp],
         "gevb_updateVel": [vp, i, d, C.POINTER(vp), i, pd, pd],
         "gevb_moveParticles": [vp, i, d, C.POINTER(vp), i, pd],
+        "gevb_moveParticles_max": [vp, i, d, C.POINTER(vp), i, pd, pd],
         "gevb_kick_drift": [vp, i, d, i, pd, d, i, pd, C.POINTER(vp), pd],
         "gevb_extractPowerSpectrum": [vp, vp, vp, vp, vp, vp, i, i, i],
         "gevb_sim_create": [C.POINTER(vp), vp, i, i, pd, pd], "gevb_sim_destroy": [vp], "gevb_background_eval": [pd, i, pd, pd, pd, d, d, d, pd], "gevb_sim_set_ncdm": [vp, i, pd, pd, pd, pd, pd, d, d], "gevb_sim_set_ncdm_maxvel": [vp, pd], "gevb_sim_get_ncdm_state": [vp, pd, C.POINTER(i)],
@@ -381,6 +382,13 @@ class Particles:
     def moveParticles(self, fn, dtau, fields, nfields, params):
         pa, pp = _darr(params)
         _ck(lib().gevb_moveParticles(self.h, fn, dtau, _handles(fields), nfields, pp), "moveParticles")
+
+    def moveParticles_max(self, fn, dtau, fields, nfields, params=(1.0, 1.0)):
+        """moveParticles with the callback's reduction output (largest displacement of displace_pcls_ic_basic)"""
+        pa, pp = _darr(params)
+        out = C.c_double()
+        _ck(lib().gevb_moveParticles_max(self.h, fn, dtau, _handles(fields), nfields, pp, C.byref(out)), "moveParticles")
+        return out.value
 
     def kick_drift(self, fn, dtau_kick, nf_kick, params_kick, dtau_drift, nf_drift, params_drift, fields):
         ka, kp = _darr(params_kick)

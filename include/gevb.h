@@ -52,13 +52,16 @@ typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>
  * function pointers cannot run on the device, so the known ones are an enum  */
 #define GEVB_UPDATE_Q 0                 /* update_q         gevolution.hpp:570 ; update_pos         :810 */
 #define GEVB_UPDATE_Q_NEWTON 1          /* update_q_Newton  gevolution.hpp:709 ; update_pos_Newton  :900 */
+#define GEVB_DISPLACE_PCLS_IC_BASIC 2   /* displace_pcls_ic_basic  ic_basic.hpp:60  (moveParticles only)  */
+#define GEVB_INITIALIZE_Q_IC_BASIC 3    /* initialize_q_ic_basic   ic_basic.hpp:118 (updateVel only)      */
 
 /* ---- errors / versioning -------------------------------------------------- */
 const char * gevb_last_error(void);
 const char * gevb_version(void);
 
 /* kernel-variant knobs for ablation runs ("geodesic_variant", "deposit_variant", "fft_exchange": 1 = transposes pushed
- * over peer memory, 0 = NCCL all-to-all + local transpose); results do not depend on them */
+ * over peer memory, 0 = NCCL all-to-all + local transpose; "fft_overlap": 1 = the push of component k overlaps the local transform of
+ * component k+1); results do not depend on them */
 int gevb_tuning(const char * knob, int value);
 
 /* ---- context: lattice geometry + device + communicator --------------------
@@ -171,6 +174,10 @@ int gevb_projectFTtensor(gevb_field * SijFT, gevb_field * hijFT);
  * fields = {phi, chi, Bi} with valid ghost planes; params = {a, a^2 N}.         */
 int gevb_updateVel(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * maxvel);
 int gevb_moveParticles(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params);
+/* moveParticles with the callback's reduction output (LATfield2's output / reduce_type / noutput arguments, used
+ * by the IC generator: moveParticles(displace_pcls_ic_basic, 1., fields, n, NULL, &max_displacement, &MAX, 1),
+ * ic_basic.hpp:1995): *output_max = largest displacement of the LOCAL particles (caller reduces)              */
+int gevb_moveParticles_max(gevb_pcls * p, int fn, double dtau, gevb_field * const * fields, int nfields, const double * params, double * output_max);
 /* fused kick (main.cpp:775) + drift (main.cpp:798) in one pass over the particles: positions
  * do not change between the two reference calls, only params (a advances by rungekutta4bg,
  * main.cpp:792), so the result equals updateVel followed by moveParticles.      */

@@ -137,6 +137,9 @@ inline Real update_q(double, double, part_simple *, double *, part_simple_info, 
 inline Real update_q_Newton(double, double, part_simple *, double *, part_simple_info, Field<Real> **, Site *, int, double *, double *, int) { return 0.; }   // gevolution.hpp:709
 inline void update_pos(double, double, part_simple *, double *, part_simple_info, Field<Real> **, Site *, int, double *, double *, int) {}                   // gevolution.hpp:810
 inline void update_pos_Newton(double, double, part_simple *, double *, part_simple_info, Field<Real> **, Site *, int, double *, double *, int) {}            // gevolution.hpp:900
+inline void displace_pcls_ic_basic(double, double, part_simple *, double *, part_simple_info, Field<Real> **, Site *, int, double *, double *, int) {}       // ic_basic.hpp:60
+inline Real initialize_q_ic_basic(double, double, part_simple *, double *, part_simple_info, Field<Real> **, Site *, int, double *, double *, int) { return 0.; }   // ic_basic.hpp:118
+#define MAX 1                              // LATfield2 reduction type of the callback outputs (only MAX is used, ic_basic.hpp:1994)
 
 class Particles_gevolution
 {
@@ -158,10 +161,10 @@ public:
 	// bulk form of addParticle_global (ic_basic.hpp:1429)
 	void addParticles_global(int64_t n, const int64_t * id, const double * pos, const double * vel) { check(gevb_pcls_add(p_, n, id, pos, vel), "Particles::addParticle_global"); }
 	int64_t numParticlesLocal() const { int64_t n = 0; gevb_pcls_count(p_, &n); return n; }
-	Real updateVel(updateVel_fn fn, double dtau, Field<Real> ** fields, int nfields, double * params)
+	Real updateVel(updateVel_fn fn, double dtau, Field<Real> ** fields, int nfields, double * params = NULL)
 	{
 		int kind = -1;
-		if (fn == &update_q) kind = GEVB_UPDATE_Q; else if (fn == &update_q_Newton) kind = GEVB_UPDATE_Q_NEWTON;
+		if (fn == &update_q) kind = GEVB_UPDATE_Q; else if (fn == &update_q_Newton) kind = GEVB_UPDATE_Q_NEWTON; else if (fn == &initialize_q_ic_basic) kind = GEVB_INITIALIZE_Q_IC_BASIC;
 		gevb_field * h[3] = {NULL, NULL, NULL};
 		handles(fields, nfields, h);
 		double maxvel = 0.;
@@ -171,10 +174,21 @@ public:
 	void moveParticles(moveParticles_fn fn, double dtau, Field<Real> ** fields, int nfields, double * params)
 	{
 		int kind = -1;
-		if (fn == &update_pos) kind = GEVB_UPDATE_Q; else if (fn == &update_pos_Newton) kind = GEVB_UPDATE_Q_NEWTON;
+		if (fn == &update_pos) kind = GEVB_UPDATE_Q; else if (fn == &update_pos_Newton) kind = GEVB_UPDATE_Q_NEWTON; else if (fn == &displace_pcls_ic_basic) kind = GEVB_DISPLACE_PCLS_IC_BASIC;
 		gevb_field * h[3] = {NULL, NULL, NULL};
 		if (fields) handles(fields, nfields, h);
 		check(gevb_moveParticles(p_, kind, dtau, h, fields ? nfields : 0, params), "Particles::moveParticles");
+	}
+	// with the callback's reduction output (ic_basic.hpp:1995: displace_pcls_ic_basic reports the largest displacement)
+	void moveParticles(moveParticles_fn fn, double dtau, Field<Real> ** fields, int nfields, double * params, double * output, int * reduce_type, int noutput)
+	{
+		if (noutput <= 0 || output == NULL) { moveParticles(fn, dtau, fields, nfields, params); return; }
+		int kind = (fn == &displace_pcls_ic_basic) ? GEVB_DISPLACE_PCLS_IC_BASIC : -1;
+		if (noutput != 1 || reduce_type == NULL || reduce_type[0] != MAX) kind = -1;       // nothing else is used by the reference
+		gevb_field * h[3] = {NULL, NULL, NULL};
+		handles(fields, nfields, h);
+		check(gevb_moveParticles_max(p_, kind, dtau, h, nfields, params, output), "Particles::moveParticles");
+		lat_->max(output, 1);                                                            // LATfield2 reduces the outputs over the ranks
 	}
 	// fused form of main.cpp:775 + :798 (same result, one pass over the particles)
 	Real kickDrift(updateVel_fn fn, double dtau_kick, int nf_kick, double * params_kick, double dtau_drift, int nf_drift, double * params_drift, Field<Real> ** fields)

@@ -450,3 +450,61 @@ def test_hibernate_and_restart(gevb, ctx, ref, tmp_path):
     with pytest.raises(gevb.GevbError):
         g3.restore(base)
     gs.close(); g2.close(); g3.close()
+
+
+def _cic_gradient(field, pos, N):
+    """CIC gradient of a scalar lattice field [z][y][x] at the particle positions, in the reference's operation order
+    (ic_basic.hpp:70-85 / 129-144), already divided by the lattice resolution"""
+    s = pos * N
+    c = np.minimum(np.floor(s).astype(int), N - 1)
+    r = s - np.floor(s)
+    def at(dx, dy, dz):
+        return field[(c[:, 2] + dz) % N, (c[:, 1] + dy) % N, (c[:, 0] + dx) % N]
+    g = np.empty_like(pos)
+    g[:, 0] = (1 - r[:, 1]) * (1 - r[:, 2]) * (at(1, 0, 0) - at(0, 0, 0)); g[:, 1] = (1 - r[:, 0]) * (1 - r[:, 2]) * (at(0, 1, 0) - at(0, 0, 0)); g[:, 2] = (1 - r[:, 0]) * (1 - r[:, 1]) * (at(0, 0, 1) - at(0, 0, 0))
+    g[:, 0] += r[:, 1] * (1 - r[:, 2]) * (at(1, 1, 0) - at(0, 1, 0)); g[:, 1] += r[:, 0] * (1 - r[:, 2]) * (at(1, 1, 0) - at(1, 0, 0)); g[:, 2] += r[:, 0] * (1 - r[:, 1]) * (at(1, 0, 1) - at(1, 0, 0))
+    g[:, 0] += (1 - r[:, 1]) * r[:, 2] * (at(1, 0, 1) - at(0, 0, 1)); g[:, 1] += (1 - r[:, 0]) * r[:, 2] * (at(0, 1, 1) - at(0, 0, 1)); g[:, 2] += (1 - r[:, 0]) * r[:, 1] * (at(0, 1, 1) - at(0, 1, 0))
+    g[:, 0] += r[:, 1] * r[:, 2] * (at(1, 1, 1) - at(0, 1, 1)); g[:, 1] += r[:, 0] * r[:, 2] * (at(1, 1, 1) - at(1, 0, 1)); g[:, 2] += r[:, 0] * r[:, 1] * (at(1, 1, 1) - at(1, 1, 0))
+    return g * N
+
+
+@pytest.mark.parametrize("nfields", [1, 2])
+def test_ic_callbacks(gevb, ctx, nfields):
+    """the two IC-generator callbacks of the drop-in boundary: displace_pcls_ic_basic under moveParticles with its
+    MAX reduction output, initialize_q_ic_basic under updateVel; with two fields every eighth ID uses the second
+    (baryon treatment = hybrid, ic_basic.hpp:65-68,124-127)"""
+    N = 16
+    rng = np.random.default_rng(90 + nfields)
+    c = ctx(N)
+    ids, pos, vel = common.quasi_uniform_particles(rng, N, sigma=0.25, a=0.01)
+    xi = common.gaussian_field(rng, N, 2, 3e-3 / N)                 # displacements of a fraction of a cell
+    F = [gevb.Field(c, gevb.REAL, 1, data=xi[k:k + 1]) for k in range(2)]
+    for f in F:
+        f.updateHalo()
+    which = ((ids % 8 == 0) & (nfields > 1)).astype(int)
+    g = np.where(which[:, None] == 1, _cic_gradient(xi[1], pos, N), _cic_gradient(xi[0], pos, N))
+    # velocities first (positions unchanged), then the displacement
+    p = gevb.Particles(c, 1.0).add(ids, pos, vel)
+    coeff_q = 0.7
+    vmax = p.updateVel(gevb.INITIALIZE_Q_IC_BASIC, coeff_q, F[:nfields], nfields, [1.0, 1.0])
+    gid, gpos, gvel = p.download()
+    o = np.argsort(gid)
+    assert common.rel_linf(gvel[o], -g * coeff_q) <= PCL_TOL and np.array_equal(gpos[o], pos)
+    assert abs(vmax - np.sqrt(((g * coeff_q) ** 2).sum(axis=1).max())) <= 1e-12 * vmax
+    dmax = p.moveParticles_max(gevb.DISPLACE_PCLS_IC_BASIC, 1.0, F[:nfields], nfields)
+    gid, gpos, gvel = p.download()
+    o = np.argsort(gid)
+    want = pos + g
+    want -= np.floor(want)
+    assert np.abs(gpos[o] - want).max() <= 1e-15 and abs(dmax - np.sqrt((g ** 2).sum(axis=1).max())) <= 1e-12 * dmax
+    # re-filed under the new cells, bit-exact
+    cell = np.minimum(np.floor(gpos[o] * N).astype(np.int64), N - 1)
+    assert np.array_equal(p.cell_counts(), np.bincount((cell[:, 2] * N + cell[:, 1]) * N + cell[:, 0], minlength=N ** 3).astype(np.uint32))
+    # a callback under the wrong driver is refused
+    with pytest.raises(gevb.GevbError):
+        p.moveParticles(gevb.INITIALIZE_Q_IC_BASIC, 1.0, F[:1], 1, [1.0, 1.0])
+    with pytest.raises(gevb.GevbError):
+        p.updateVel(gevb.DISPLACE_PCLS_IC_BASIC, 1.0, F[:1], 1, [1.0, 1.0])
+    p.close()
+    for f in F:
+        f.close()
