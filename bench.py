@@ -197,22 +197,43 @@ def cpu_reference_run(ngrid, steps, warmup):
     return dict(seconds=dt, particles=len(ids), kind=kind, timers=timers, description=ref.description)
 
 
+def reference_replicas(ngrid, steps, warmup, nproc):
+    """nproc independent single-threaded replicas of the reference cycle, one per host core, started together: the
+    throughput the reference's own MPI decomposition could reach at best on these cores (its MPI build cannot be
+    produced here: mpic++ / LATfield2 / FFTW are absent)"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--replica", "--steps", str(steps), "--warmup", str(warmup), "--ngrid-ref", str(ngrid)]
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(nproc)]
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.perf_counter() - t0
+    res = [json.loads(o.strip().splitlines()[-1]) for o, p in zip(outs, procs) if p.returncode == 0 and o.strip()]
+    if not res:
+        raise RuntimeError("no reference replica finished")
+    seconds = max(r["seconds"] for r in res)                 # all replicas run concurrently: the slowest one bounds the rate
+    return dict(seconds=seconds, particles=sum(r["particles"] for r in res), replicas=len(res), wall=wall, kind=res[0]["kind"])
+
+
 def run_reference(args, rank):
+    if args.replica:
+        r = cpu_reference_run(args.ngrid_ref, args.steps, args.warmup)
+        print(json.dumps({"seconds": r["seconds"], "particles": r["particles"], "kind": r["kind"]}), flush=True)
+        return
     if rank != 0:
         return
     ngrid = env_int("GEVB_REF_NGRID", 128)
-    cores = int(os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1)))
-    r = cpu_reference_run(ngrid, args.steps, args.warmup)
+    cores = env_int("GEVB_REF_PROCS", os.cpu_count() or 1)
+    r = reference_replicas(ngrid, args.steps, args.warmup, cores)
     value = r["particles"] * args.steps / r["seconds"]
     sample = (f"{args.steps} cycles of the reference main loop (gevolution.hpp compiled against the single-rank LATfield2 shim; "
-              f"MPI/LATfield2/FFTW absent) at {ngrid}^3 grid / {ngrid}^3 particles, same GR parabolic path; "
-              f"FFT lines on {cores} OpenMP threads, particle and field loops on 1 thread")
+              f"MPI/LATfield2/FFTW absent) at {ngrid}^3 grid / {ngrid}^3 particles, same GR parabolic path; {r['replicas']} independent "
+              f"single-threaded replicas run concurrently, one per host core (upper bound of what the MPI build could reach on these cores)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "GR 512^3 grid / 512^3 particles (parabolic B); CPU arm runs a bounded sample", "sample_ngrid": ngrid},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample},
+        "config": {"workload": "GR 512^3 grid / 512^3 particles (parabolic B); CPU arm runs a bounded sample", "sample_ngrid": ngrid, "replicas": r["replicas"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["replicas"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -477,12 +498,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ngrid_cpu = env_int("GEVB_REF_NGRID", 128)
-        cores = int(os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1)))
-        r = cpu_reference_run(ngrid_cpu, env_int("GEVB_REF_STEPS", 8), 1)
-        cpu = {"value": r["particles"] * env_int("GEVB_REF_STEPS", 8) / r["seconds"], "unit": UNIT, "cores": cores, "kind": r["kind"],
-               "sample": f"{env_int('GEVB_REF_STEPS', 8)} cycles of the reference main loop (gevolution.hpp over the single-rank LATfield2 shim) at "
-                         f"{ngrid_cpu}^3 grid / {ngrid_cpu}^3 particles; FFT on {cores} OpenMP threads, particle and field loops on 1 thread"}
+        ngrid_cpu, nst = env_int("GEVB_REF_NGRID", 128), env_int("GEVB_REF_STEPS", 6)
+        r = reference_replicas(ngrid_cpu, nst, 1, env_int("GEVB_REF_PROCS", os.cpu_count() or 1))
+        cpu = {"value": r["particles"] * nst / r["seconds"], "unit": UNIT, "cores": r["replicas"], "kind": r["kind"],
+               "sample": f"{nst} cycles of the reference main loop (gevolution.hpp over the single-rank LATfield2 shim) at {ngrid_cpu}^3 grid / {ngrid_cpu}^3 "
+                         f"particles in {r['replicas']} independent single-threaded replicas run concurrently, one per host core"}
 
     if rank == 0:
         line = {
@@ -516,6 +536,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 512))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replica", action="store_true", help="(internal) one replica of the CPU reference arm")
+    ap.add_argument("--ngrid-ref", type=int, default=128)
     ap.add_argument("--ablate", default="", help="e.g. geodesic_variant=1:0:2,deposit_variant=0:1 -- times 2 cycles per setting (stderr), first value is restored")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra lattice / clustered measurements of the particle kernels")
     args = ap.parse_args()
