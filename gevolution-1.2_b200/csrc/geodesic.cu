@@ -291,13 +291,17 @@ __device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint3
 // (2 blocks of 256 threads per SM).  NBUF == 1: one tile buffer per block and twice as many, smaller blocks per SM --
 // a block that waits for its tile leaves the SM to the others.  In both forms the first particle of the next brick is
 // requested before the current brick's closing barrier, so no DRAM latency is exposed at a brick boundary.
-template <int MODE, int THREADS, int NBUF, int MINB>
+// PREF: the next particle of every thread (the next of this brick, else the first of the next brick) is fetched by
+// asynchronous copies into a private shared-memory slot while the current one is processed -- a register prefetch at
+// the bottom of the loop is consumed immediately at its top and hides nothing within the warp.
+template <int MODE, int THREADS, int NBUF, int MINB, bool PREF>
 __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 {
 	extern __shared__ double smem[];
 	const BrickGeom & G = P.G;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
 	const int tile_doubles = ncomp * TILE_SITES;
+	double * slot = smem + NBUF * tile_doubles + threadIdx.x;           // [6][THREADS] staging of the prefetched particle (PREF)
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
 	uint32_t brick = blockIdx.x;
 	brick_range(P, brick, first, last);
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 	while (brick < G.nbricks)
 	{
 		const uint32_t nbrick = brick + gridDim.x;
+		bool have_next = false;                                          // registers already hold this thread's first particle of the next brick
 		brick_range(P, nbrick + gridDim.x, nnfirst, nnlast);             // consumed at the end of this iteration
 		if (NBUF == 2)
 		{
@@ -327,6 +332,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 			const double * tile = smem + (NBUF == 2 ? cur * tile_doubles : 0);
 			while (i < last)
 			{
+				uint32_t inext = i + THREADS;
+				bool fetched = false;
+				if (PREF)
+				{
+					// next particle of this brick, else this thread's first particle of the next brick
+					const uint32_t j = inext < last ? inext : nfirst + threadIdx.x;
+					fetched = inext < last || j < nlast;
+					if (fetched)
+					{
+						cp_async8(slot, P.x + j); cp_async8(slot + THREADS, P.y + j); cp_async8(slot + 2 * THREADS, P.z + j);
+						cp_async8(slot + 3 * THREADS, P.qx + j); cp_async8(slot + 4 * THREADS, P.qy + j); cp_async8(slot + 5 * THREADS, P.qz + j);
+					}
+					cp_async_commit();
+				}
 				// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
 				double r[3];
 				const double * t;
@@ -374,13 +393,29 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 					P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
 					P.key[i] = key;
 				}
-				i += THREADS;
-				if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+				if (PREF)
+				{
+					// the copies were issued at the top of this iteration; only this thread reads its slot, so no barrier
+					cp_async_wait<0>();
+					i = inext;
+					if (fetched) { pos[0] = slot[0]; pos[1] = slot[THREADS]; pos[2] = slot[2 * THREADS]; q[0] = slot[3 * THREADS]; q[1] = slot[4 * THREADS]; q[2] = slot[5 * THREADS]; }
+					have_next = fetched && i >= last;
+					if (have_next) i = nfirst + threadIdx.x;
+				}
+				else
+				{
+					i += THREADS;
+					if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+				}
+				if (have_next) break;
 			}
 		}
-		// request the first particle of the next brick, then close this one
-		i = nfirst + threadIdx.x;
-		if (i < nlast) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+		// request the first particle of the next brick (unless it is already in the registers), then close this one
+		if (!have_next)
+		{
+			i = nfirst + threadIdx.x;
+			if (i < nlast) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
+		}
 		if (first != last) __syncthreads();                      // the tile is free again
 		if (NBUF == 1)
 		{
@@ -448,29 +483,31 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
 }
 
-template <int MODE, int THREADS, int NBUF, int MINB>
+template <int MODE, int THREADS, int NBUF, int MINB, bool PREF>
 int launch_variant(gevb_pcls * p, const GParams & P)
 {
 	gevb_ctx * c = p->ctx;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
-	const size_t smem = (size_t) NBUF * ncomp * TILE_SITES * sizeof(double);
-	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE, THREADS, NBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	const size_t smem = ((size_t) NBUF * ncomp * TILE_SITES + (PREF ? 6 * THREADS : 0)) * sizeof(double);
+	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE, THREADS, NBUF, MINB, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	const uint32_t persistent = (uint32_t) c->num_sms * MINB;
-	k_geodesic<MODE, THREADS, NBUF, MINB><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P);
+	k_geodesic<MODE, THREADS, NBUF, MINB, PREF><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P);
 	KERNEL_CHECK(c);
 	return 0;
 }
 
 // tuning knob geodesic_variant: 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 (default) = 128 threads, single
-// tile buffer, 4 blocks per SM; 2 = 256 threads, single buffer, 2 blocks per SM
+// tile buffer, 4 blocks per SM; 4 = the same with the next particle fetched by cp.async into shared memory (measured slower:
+// 10.4 vs 7.7 ms at 512^3, profiles/r1q); 2 = 256 threads, single buffer, 2 blocks per SM
 template <int MODE>
 int launch_geodesic(gevb_pcls * p, const GParams & P)
 {
 	switch (gevb_tune(TUNE_GEODESIC_VARIANT))
 	{
-		case 0: return launch_variant<MODE, 256, 2, 2>(p, P);
-		case 2: return launch_variant<MODE, 256, 1, 2>(p, P);
-		default: return launch_variant<MODE, 128, 1, 4>(p, P);
+		case 0: return launch_variant<MODE, 256, 2, 2, false>(p, P);
+		case 2: return launch_variant<MODE, 256, 1, 2, false>(p, P);
+		case 4: return launch_variant<MODE, 128, 1, 4, true>(p, P);
+		default: return launch_variant<MODE, 128, 1, 4, false>(p, P);
 	}
 }
 
