@@ -356,6 +356,15 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value = np_total * args.steps / (ms * 1e-3)
     state = sim.state()
+    # size-independent invariants of the timed run (full benchmark size): no particle lost in re-binning / migration,
+    # mass conservation of the deposit (T00hom = Omega_cdm + Omega_b up to the O(phi) metric correction)
+    n_now = torch.tensor([float(sim.pcls(0).count())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(n_now)
+    invariants = {"particles_after": int(n_now.item()), "particles_conserved": int(n_now.item()) == np_total,
+                  "T00hom_over_Omega_m_minus_1": state["T00hom"] / (cosmo[0] + cosmo[1]) - 1.0}
+    if not invariants["particles_conserved"] or abs(invariants["T00hom_over_Omega_m_minus_1"]) > 1e-3:
+        raise RuntimeError(f"benchmark run violates an invariant: {invariants}")
 
     # ---- the FFT exchange by itself: two more cycles with the component pipeline off, so that the time of the pushes is
     #      not hidden behind the local transforms (the timed run above keeps the overlap on)
@@ -516,6 +525,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "invariants": invariants,
             "roofline": roofline,
             "nvlink": nvlink,
             "regimes": regimes,

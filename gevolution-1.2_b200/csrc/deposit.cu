@@ -130,10 +130,10 @@ __device__ __forceinline__ void particle_factors(PInv & I, const DParams & D, co
 	const double q0 = pv[3], q1 = pv[4], q2 = pv[5];
 	if (WHAT == DEP_T0I) { I.m[0] = D.mass * q0; I.m[1] = D.mass * q1; I.m[2] = D.mass * q2; return; }      // :1107,:1114,:1121
 	const double qsq = q0 * q0 + q1 * q1 + q2 * q2;
-	// one square root and one division per particle: e = sqrt(q^2 + a^2) and 1/e; the reference's quotients
-	// x / e become x * (1/e) (one extra rounding, 1e-16 relative, against a 1e-10 tolerance)
-	const double e = sqrt(qsq + D.a * D.a);                                        // :990 / :1237
-	const double inv_e = 1.0 / e;
+	// neither a square root nor a division per particle: r = (q^2 + a^2)^(-1/2) gives 1/e = r and e = (q^2 + a^2) r; the
+	// reference's quotients x / e become x * r (a few ulp, 1e-16 relative, against a 1e-10 tolerance)
+	const double inv_e = rsqrt(qsq + D.a * D.a);
+	const double e = (qsq + D.a * D.a) * inv_e;                                    // :990 / :1237
 	if (WHAT == DEP_T00 || WHAT == DEP_T00_TIJ)
 	{
 		I.eT = D.a * D.mass; I.fT = 0.;

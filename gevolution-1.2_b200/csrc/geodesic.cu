@@ -113,7 +113,9 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 		v2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];                             // :581
 		double e2 = v2 + P.a_kick * P.a_kick;                                      // :582
 		grad_cic(t, 0, r, g);                                                      // :585-596
-		const double inv_e2 = 1. / e2;                                             // the only division of the kick: x / e2 -> x * (1/e2), 1/e -> e * (1/e2)
+		// no division and no square root in the kick: r = e2^(-1/2) gives 1/e2 = r r and sqrt(e2) = e2 r (each within 2 ulp)
+		const double rs = rsqrt(e2);
+		const double inv_e2 = rs * rs;
 		const double boost = (v2 + e2) * inv_e2;
 		g[0] *= boost; g[1] *= boost; g[2] *= boost;                               // :613-615
 		if (P.nf_kick >= 2)
@@ -121,7 +123,7 @@ __device__ __forceinline__ double kick(const GParams & P, const double * t, cons
 			double gc[3]; grad_cic(t, 1, r, gc);                                   // :617-631
 			g[0] -= gc[0]; g[1] -= gc[1]; g[2] -= gc[2];
 		}
-		e2 = sqrt(e2);                                                             // :633
+		e2 = e2 * rs;                                                              // :633 sqrt(e2)
 		if (P.nf_kick >= 3)
 		{
 			double pg0, pg1, pg2;
@@ -195,8 +197,8 @@ __device__ __forceinline__ double drift(const GParams & P, const double * t, con
 	double ph = 0., ch = 0.;
 	if (P.nf_drift >= 1) ph = tri_cic(t, 0, r);                                    // :820-827
 	if (P.nf_drift >= 2) ch = tri_cic(t, 1, r);                                    // :832-839
-	const double inv_e2 = 1. / e2;                                                 // the only division of the drift
-	v2 = (1. + (3. - v2 * inv_e2) * ph - ch) * (sqrt(e2) * inv_e2);                // :842
+	const double rs = rsqrt(e2);                                                   // 1/e2 = rs rs, 1/sqrt(e2) = rs
+	v2 = (1. + (3. - v2 * (rs * rs)) * ph - ch) * rs;                              // :842 (... / sqrt(e2))
 	double v[3] = {q[0] * v2, q[1] * v2, q[2] * v2};                               // :844-846
 	if (P.nf_drift >= 3)
 	{

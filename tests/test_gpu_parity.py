@@ -275,7 +275,7 @@ def test_run_to_z0_power_spectra_and_snapshot_statistics(gevb, ctx, ref):
 
 
 # ---- size-independent properties at the benchmark size --------------------
-@pytest.mark.parametrize("N", [128])
+@pytest.mark.parametrize("N", [128, 256])          # 256^3 grid / 256^3 particles is BASELINE config 2
 def test_full_size_properties(gevb, ctx, N):
     rng = np.random.default_rng(9)
     c = ctx(N)
