@@ -13,7 +13,7 @@
 void gevb_set_error(const char * fmt, ...);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_DEPOSIT_VARIANT, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -133,6 +133,7 @@ struct gevb_plan
 	gevb_ctx * ctx;
 	gevb_field * real_field, * cplx_field;
 	cufftHandle fwd, bwd;      // nranks == 1: 3-D D2Z / Z2D batched over components
+	cufftHandle f2d, bz1d, b2d; // nranks == 1, one component: 2-D D2Z per plane, 1-D Z2Z along z (stride N*nh), 2-D Z2D per plane
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
 	cufftHandle z1d_one;             // 1-D along z for one component (component-pipelined backward transform)
 	bool multi;
