@@ -145,6 +145,7 @@ def algorithmic_bytes(N, nzl, np_local, P):
         "solveModifiedPoissonFT": 32 * Vk,
         "projectFTscalar": 112 * Vk,
         "evolveFTvector": 192 * Vk,
+        "projectFTscalar_evolveFTvector": 208 * Vk,                  # 6 S read once, chi written, B_i read + written
         "projectFTvector": 96 * Vk,
         "projectFTtensor": 192 * Vk,
         "fft_forward": 16 * V, "fft_backward": 16 * V,              # ideal: 8 r + 8 w per real site and component

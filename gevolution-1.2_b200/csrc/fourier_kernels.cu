@@ -94,6 +94,49 @@ __global__ void __launch_bounds__(256) k_evolve_vector(KLayout L, const double *
 	}
 }
 
+// projectFTscalar (gevolution.hpp:211-265) and evolveFTvector (:284-330) on the same read of the six S components:
+// main.cpp:558 and :586 both consume SijFT and write different fields (the backward transform of chi in between does
+// not touch it), so one pass over SijFT serves both -- 208 instead of 304 bytes per k-site
+__global__ void __launch_bounds__(256) k_ftscalar_evolve(KLayout L, const double * __restrict__ gridk2, const double2 * __restrict__ kshift, const double2 * S, size_t cs,
+                                                         double2 * chi, double2 * B, size_t cb, double a2dtau)
+{
+	K_SITE_LOOP(L)
+	{
+		int kx, ky, kz; k_decode(L, i, kx, ky, kz);
+		if ((kx | ky | kz) == 0)
+		{
+			stc(chi + i, cmk(0., 0.));                                                                           // :230-234
+			stc(B + i, cmk(0., 0.)); stc(B + cb + i, cmk(0., 0.)); stc(B + 2 * cb + i, cmk(0., 0.));             // :304-310
+			continue;
+		}
+		const double g0 = __ldg(gridk2 + kx), g1 = __ldg(gridk2 + ky), g2 = __ldg(gridk2 + kz);
+		const double2 k0 = __ldg(kshift + kx), k1 = __ldg(kshift + ky), k2 = __ldg(kshift + kz);
+		const double2 S00 = ldc(S + i), S01 = ldc(S + cs + i), S02 = ldc(S + 2 * cs + i);
+		const double2 S11 = ldc(S + 3 * cs + i), S12 = ldc(S + 4 * cs + i), S22 = ldc(S + 5 * cs + i);
+		// ---- chi, same operation order as k_ftscalar
+		double2 num = cscale(S00, g1 + g2 - 2. * g0);                                                            // :253
+		num = cadd(num, cscale(S11, g0 + g2 - 2. * g1));                                                         // :254
+		num = cadd(num, cscale(S22, g0 + g1 - 2. * g2));                                                         // :255
+		num = csub(num, cmul(cmul(cscale(k0, 6.), k1), S01));                                                    // :256
+		num = csub(num, cmul(cmul(cscale(k0, 6.), k2), S02));                                                    // :257
+		num = csub(num, cmul(cmul(cscale(k1, 6.), k2), S12));                                                    // :258
+		stc(chi + i, cdiv(num, 2. * (g0 + g1 + g2) * (g0 + g1 + g2) * L.N));                                     // :259
+		// ---- B, same operation order as k_evolve_vector
+		double k4 = g0 + g1 + g2; k4 *= k4;                                                                      // :314-315
+		const double2 pref = cmk(0., -2. * a2dtau / k4);
+		double2 t1, t2;
+		t1 = csub(csub(csub(cscale(S00, g1 + g2), cscale(S11, g1)), cscale(S22, g2)), cmul(cmul(cscale(k1, 2.), k2), S12));
+		t2 = cscale(cadd(cmul(k1, S01), cmul(k2, S02)), g1 + g2 - g0);
+		stc(B + i, cadd(ldc(B + i), cmul(pref, cadd(cmul(cconj(k0), t1), t2))));                                 // :317-319
+		t1 = csub(csub(csub(cscale(S11, g0 + g2), cscale(S00, g0)), cscale(S22, g2)), cmul(cmul(cscale(k0, 2.), k2), S02));
+		t2 = cscale(cadd(cmul(k0, S01), cmul(k2, S12)), g0 + g2 - g1);
+		stc(B + cb + i, cadd(ldc(B + cb + i), cmul(pref, cadd(cmul(cconj(k1), t1), t2))));                       // :320-322
+		t1 = csub(csub(csub(cscale(S22, g0 + g1), cscale(S00, g0)), cscale(S11, g1)), cmul(cmul(cscale(k0, 2.), k1), S01));
+		t2 = cscale(cadd(cmul(k0, S02), cmul(k1, S12)), g0 + g1 - g2);
+		stc(B + 2 * cb + i, cadd(ldc(B + 2 * cb + i), cmul(pref, cadd(cmul(cconj(k2), t1), t2))));               // :323-325
+	}
+}
+
 __global__ void __launch_bounds__(256) k_ftvector(KLayout L, const double * __restrict__ gridk2, const double2 * __restrict__ kshift, const double2 * Si, double2 * B, size_t cs, double coeff, double modif)
 {
 	K_SITE_LOOP(L)
@@ -201,6 +244,22 @@ extern "C" int gevb_evolveFTvector(gevb_field * SijFT, gevb_field * BiFT, double
 	Timed timed_(c, CLS_EVOLVE);
 	KLayout L = make_klayout(c);
 	k_evolve_vector<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SijFT->data, SijFT->comp_stride, (double2 *) BiFT->data, BiFT->comp_stride, a2dtau);
+	KERNEL_CHECK(c);
+	return 0;
+}
+
+extern "C" int gevb_projectFTscalar_evolveFTvector(gevb_field * SijFT, gevb_field * chiFT, gevb_field * BiFT, double a2dtau)
+{
+	GEVB_TRY(check_cplx(SijFT, 6, "projectFTscalar_evolveFTvector", "SijFT"));
+	GEVB_TRY(check_cplx(chiFT, 1, "projectFTscalar_evolveFTvector", "chiFT"));
+	GEVB_TRY(check_cplx(BiFT, 3, "projectFTscalar_evolveFTvector", "BiFT"));
+	GEVB_CHECK_ARG(chiFT != SijFT && BiFT != SijFT, "projectFTscalar_evolveFTvector: outputs must not alias SijFT");
+	gevb_ctx * c = BiFT->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FTSCALAR_EVOLVE);
+	KLayout L = make_klayout(c);
+	k_ftscalar_evolve<<<gevb_grid(c, L.sites, 256), 256, 0, c->stream>>>(L, c->d_gridk2, c->d_kshift, (const double2 *) SijFT->data, SijFT->comp_stride,
+		(double2 *) chiFT->data, (double2 *) BiFT->data, BiFT->comp_stride, a2dtau);
 	KERNEL_CHECK(c);
 	return 0;
 }

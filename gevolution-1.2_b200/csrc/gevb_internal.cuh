@@ -54,7 +54,7 @@ enum
 {
 	CLS_INIT = 0, CLS_T00, CLS_TIJ, CLS_T00_TIJ, CLS_T0I, CLS_COMM, CLS_SUM, CLS_PREP_SCALAR, CLS_PREP_TENSOR, CLS_FFT_FWD, CLS_FFT_BWD,
 	CLS_POISSON, CLS_FTSCALAR, CLS_EVOLVE, CLS_FTVECTOR, CLS_FTTENSOR, CLS_HALO, CLS_KICK, CLS_DRIFT, CLS_KICK_DRIFT, CLS_SORT, CLS_SPECTRUM,
-	CLS_MIGRATE, CLS_FFT_A2A, CLS_FFT_TRANSPOSE, GEVB_NCLS
+	CLS_MIGRATE, CLS_FFT_A2A, CLS_FFT_TRANSPOSE, CLS_FTSCALAR_EVOLVE, GEVB_NCLS
 };
 struct GevbTimer
 {

@@ -10,7 +10,8 @@ static const char * k_names[GEVB_NCLS] = {
 	"projection_init", "projection_T00_project", "projection_Tij_project", "projection_T00_Tij_project", "projection_T0i_project",
 	"projection_comm", "field_sum", "prepareFTsource_scalar", "prepareFTsource_tensor", "fft_forward", "fft_backward",
 	"solveModifiedPoissonFT", "projectFTscalar", "evolveFTvector", "projectFTvector", "projectFTtensor", "updateHalo",
-	"updateVel", "moveParticles", "kick_drift", "rebin_sort", "extractPowerSpectrum", "migrate", "fft_alltoall", "fft_transpose"
+	"updateVel", "moveParticles", "kick_drift", "rebin_sort", "extractPowerSpectrum", "migrate", "fft_alltoall", "fft_transpose",
+	"projectFTscalar_evolveFTvector"
 };
 
 extern "C" const char * gevb_timing_class_name(int cls) { return (cls >= 0 && cls < GEVB_NCLS) ? k_names[cls] : NULL; }

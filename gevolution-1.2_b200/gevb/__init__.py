@@ -36,7 +36,7 @@ SYMBOLS = [
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
-    "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
+    "gevb_projectFTscalar_evolveFTvector", "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
     "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
@@ -105,7 +105,7 @@ def _declare(L):
         "gevb_projection_T00_Tij_project": [vp, vp, vp, d, vp, d],
         "gevb_prepareFTsource_scalar": [vp, vp, vp, d, vp, d, d, d], "gevb_prepareFTsource_scalar_sum": [vp, vp, vp, d, vp, d, d, d, C.POINTER(C.c_double)], "gevb_prepareFTsource_tensor": [vp, vp, vp, d],
         "gevb_solveModifiedPoissonFT": [vp, vp, d, d], "gevb_projectFTscalar": [vp, vp, i],
-        "gevb_evolveFTvector": [vp, vp, d], "gevb_projectFTvector": [vp, vp, d, d], "gevb_projectFTtensor": [vp, vp],
+        "gevb_evolveFTvector": [vp, vp, d], "gevb_projectFTscalar_evolveFTvector": [vp, vp, vp, d], "gevb_projectFTvector": [vp, vp, d, d], "gevb_projectFTtensor": [vp, vp],
         "gevb_updateVel": [vp, i, d, C.POINTER(vp), i, pd, pd],
         "gevb_moveParticles": [vp, i, d, C.POINTER(vp), i, pd],
         "gevb_moveParticles_max": [vp, i, d, C.POINTER(vp), i, pd, pd],
@@ -417,6 +417,10 @@ def projectFTscalar(SijFT, chiFT, add=0):
 
 def evolveFTvector(SijFT, BiFT, a2dtau):
     _ck(lib().gevb_evolveFTvector(SijFT.h, BiFT.h, a2dtau), "evolveFTvector")
+
+
+def projectFTscalar_evolveFTvector(SijFT, chiFT, BiFT, a2dtau):
+    _ck(lib().gevb_projectFTscalar_evolveFTvector(SijFT.h, chiFT.h, BiFT.h, a2dtau), "projectFTscalar_evolveFTvector")
 
 
 def projectFTvector(SiFT, BiFT, coeff=1.0, modif=0.0):

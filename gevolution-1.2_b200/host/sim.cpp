@@ -526,7 +526,10 @@ static int sim_step(gevb_sim * s)
 
 	prepareFTsource<Real>(phi, Sij, Sij, 2. * fourpiG * dx * dx / a);                         // :539
 	s->plan_Sij.execute(FFT_FORWARD);                                                         // :544
-	projectFTscalar(SijFT, scalarFT);                                                         // :558
+	// parabolic B: :558 and :586 both read SijFT and nothing in between writes it, so one pass over it serves both
+	const bool fuse_chi_B = fuse && s->vector_flag != VECTOR_ELLIPTIC;
+	if (fuse_chi_B) projectFTscalar_evolveFTvector(SijFT, scalarFT, BiFT, a * a * dtau_old);  // :558 + :586
+	else projectFTscalar(SijFT, scalarFT);                                                    // :558
 	s->plan_chi.execute(FFT_BACKWARD);                                                        // :563
 	chi.updateHalo();                                                                         // :568
 
@@ -535,7 +538,7 @@ static int sim_step(gevb_sim * s)
 		s->plan_Bi.execute(FFT_FORWARD);                                                      // :575
 		projectFTvector(BiFT, BiFT, fourpiG * dx * dx);                                       // :580
 	}
-	else
+	else if (!fuse_chi_B)
 		evolveFTvector(SijFT, BiFT, a * a * dtau_old);                                        // :586
 
 	if (s->gr_flag > 0)

@@ -164,6 +164,8 @@ int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, gevb_field *
 int gevb_solveModifiedPoissonFT(gevb_field * sourceFT, gevb_field * potFT, double coeff, double modif);
 int gevb_projectFTscalar(gevb_field * SijFT, gevb_field * chiFT, int add);
 int gevb_evolveFTvector(gevb_field * SijFT, gevb_field * BiFT, double a2dtau);
+/* projectFTscalar (main.cpp:558) and evolveFTvector (:586) on one read of SijFT: same results as the two calls */
+int gevb_projectFTscalar_evolveFTvector(gevb_field * SijFT, gevb_field * chiFT, gevb_field * BiFT, double a2dtau);
 int gevb_projectFTvector(gevb_field * SiFT, gevb_field * BiFT, double coeff, double modif);
 int gevb_projectFTtensor(gevb_field * SijFT, gevb_field * hijFT);
 

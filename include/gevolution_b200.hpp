@@ -230,6 +230,8 @@ inline void prepareFTsource(Field<FieldType> & phi, Field<FieldType> & chi, Fiel
 inline void projectFTscalar(Field<Cplx> & SijFT, Field<Cplx> & chiFT, const int add = 0) { check(gevb_projectFTscalar(SijFT.handle(), chiFT.handle(), add), "projectFTscalar"); }
 inline void evolveFTvector(Field<Cplx> & SijFT, Field<Cplx> & BiFT, const Real a2dtau) { check(gevb_evolveFTvector(SijFT.handle(), BiFT.handle(), a2dtau), "evolveFTvector"); }
 // fused forms used by the time loop (same results, fewer passes over HBM)
+inline void projectFTscalar_evolveFTvector(Field<Cplx> & SijFT, Field<Cplx> & chiFT, Field<Cplx> & BiFT, const Real a2dtau)
+{ check(gevb_projectFTscalar_evolveFTvector(SijFT.handle(), chiFT.handle(), BiFT.handle(), a2dtau), "projectFTscalar_evolveFTvector"); }
 template <class FieldType>
 inline void prepareFTsource(Field<FieldType> & phi, Field<FieldType> & chi, Field<FieldType> & source, const FieldType bgmodel, Field<FieldType> & result, const double coeff, const double coeff2, const double coeff3, double & sum_source)
 { check(gevb_prepareFTsource_scalar_sum(phi.handle(), chi.handle(), source.handle(), bgmodel, result.handle(), coeff, coeff2, coeff3, &sum_source), "prepareFTsource"); }

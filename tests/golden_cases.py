@@ -117,6 +117,9 @@ def run_gpu(g, ctx, inp):
     pot.upload(srcFT); g.projectFTscalar(TFT, pot, 1); out["ftscalar_add"] = pot.download()
     B3 = g.Field(ctx, g.CPLX, 3, data=SiFT)
     g.evolveFTvector(TFT, B3, 0.37); out["evolve"] = B3.download()
+    # fused projectFTscalar + evolveFTvector: same two results from one pass over SijFT
+    B3.upload(SiFT); c1 = g.Field(ctx, g.CPLX, 1)
+    g.projectFTscalar_evolveFTvector(TFT, c1, B3, 0.37); out["ftscalar_fusedB"], out["evolve_fusedchi"] = c1.download(), B3.download()
     B3.upload(SiFT); g.projectFTvector(B3, B3, 1.3, 0.0); out["ftvector"] = B3.download()
     B3.upload(SiFT); g.projectFTvector(B3, B3, 1.3, 0.6); out["ftvector_mod"] = B3.download()
     g.projectFTtensor(TFT, TFT); out["fttensor"] = TFT.download()

@@ -53,6 +53,7 @@ def test_against_checker(gevb, ctx, checker, N, seed):
     ref_out = golden_cases.run_cpu(checker, inp)
     out = golden_cases.run_gpu(gevb, ctx(N), inp)
     assert _check(out, lambda k: ref_out[k], ref_out.keys()) == []
+    assert common.rel_linf(out["ftscalar_fusedB"], out["ftscalar"]) <= 1e-14 and common.rel_linf(out["evolve_fusedchi"], out["evolve"]) <= 1e-14
     # fused kick+drift == updateVel followed by moveParticles
     vel, vmax = checker.updateVel(N, inp["pos"], inp["vel"], 0, inp["dtau_kick"], inp["phi"], inp["chi"], inp["Bi"], 3, inp["params"])
     pos = checker.moveParticles(N, inp["pos"], vel, 0, inp["dtau"], inp["phi"], inp["chi"], inp["Bi"], 3, inp["params"])
