@@ -204,6 +204,8 @@ extern "C" int gevb_field_create(gevb_ctx * c, gevb_field ** out, int kind, int 
 	GEVB_CHECK_ARG(kind == GEVB_REAL || kind == GEVB_CPLX, "gevb_field_create: bad kind %d", kind);
 	GEVB_CHECK_ARG(ncomp >= 1 && ncomp <= 16, "gevb_field_create: bad component count %d", ncomp);
 	GEVB_CHECK_ARG(!symmetric || ncomp == 6, "gevb_field_create: symmetric fields are 3x3 (6 components)");
+	GEVB_CHECK_ARG(kind == GEVB_REAL || (c->cplx_comp_stride() < (1ull << 31) && c->cplx_comp_stride() * (size_t) c->N < (1ull << 40)),
+		"gevb_field_create: too many Fourier sites per rank for the 32-bit index decode (use more ranks)");
 	CUDA_TRY(cudaSetDevice(c->device));
 	gevb_field * f = new gevb_field();
 	f->ctx = c; f->kind = kind; f->ncomp = ncomp; f->symmetric = symmetric;

@@ -223,25 +223,32 @@ struct KLayout
 {
 	int N, nh, slab, ky0, nkyl;
 	size_t sites;              // complex sites per component on this rank
+	uint64_t mN, mnh;          // ceil(2^40 / N), ceil(2^40 / nh): i / d == (i * m) >> 40 exactly for i * d < 2^40 (no integer division per site)
 };
 static inline KLayout make_klayout(const gevb_ctx * c)
 {
 	KLayout L;
 	L.N = c->N; L.nh = c->nh; L.slab = c->nranks > 1; L.ky0 = c->ky0; L.nkyl = c->nkyl;
 	L.sites = c->cplx_comp_stride();
+	L.mN = ((1ull << 40) + (uint64_t) L.N - 1) / (uint64_t) L.N;
+	L.mnh = ((1ull << 40) + (uint64_t) L.nh - 1) / (uint64_t) L.nh;
 	return L;
 }
 __device__ __forceinline__ void k_decode(const KLayout & L, size_t i, int & kx, int & ky, int & kz)
 {
+	// i < 2^31 (checked where the fields are created): quotients by multiply-shift, see KLayout
+	const uint32_t ii = (uint32_t) i;
 	if (L.slab)
 	{
-		kz = (int) (i % L.N); size_t r = i / L.N;
-		kx = (int) (r % L.nh); ky = (int) (r / L.nh) + L.ky0;
+		const uint32_t r = (uint32_t) (((uint64_t) ii * L.mN) >> 40), q = (uint32_t) (((uint64_t) r * L.mnh) >> 40);
+		kz = (int) (ii - r * (uint32_t) L.N);
+		kx = (int) (r - q * (uint32_t) L.nh); ky = (int) q + L.ky0;
 	}
 	else
 	{
-		kx = (int) (i % L.nh); size_t r = i / L.nh;
-		ky = (int) (r % L.N); kz = (int) (r / L.N);
+		const uint32_t r = (uint32_t) (((uint64_t) ii * L.mnh) >> 40), q = (uint32_t) (((uint64_t) r * L.mN) >> 40);
+		kx = (int) (ii - r * (uint32_t) L.nh);
+		ky = (int) (r - q * (uint32_t) L.N); kz = (int) q;
 	}
 }
 

@@ -509,3 +509,44 @@ def test_ic_callbacks(gevb, ctx, nfields):
     p.close()
     for f in F:
         f.close()
+
+
+def test_extreme_occupancy(gevb, ctx, checker):
+    """collisions as the domain has them: thousands of particles in one cell (segmented reduction over whole warps, cells
+    that span many warps and batches), next to empty bricks and a cell at the periodic corner"""
+    N = 16
+    rng = np.random.default_rng(123)
+    a = 0.05
+    blob = (np.array([5.0, 3.0, 9.0]) + rng.random((3000, 3))) / N                  # one cell
+    corner = (np.array([15.0, 15.0, 15.0]) + rng.random((700, 3))) / N              # the cell whose CIC cloud wraps in all directions
+    few = rng.random((50, 3))
+    pos = np.ascontiguousarray(np.concatenate([blob, corner, few]))
+    vel = rng.standard_normal(pos.shape) * 0.02 * a
+    ids = np.arange(len(pos), dtype=np.int64)
+    phi, chi, Bi = common.metric_fields(rng, N, a)
+    c = ctx(N)
+    P = gevb.Field(c, gevb.REAL, 1, data=phi); P.updateHalo()
+    X = gevb.Field(c, gevb.REAL, 1, data=chi); X.updateHalo()
+    B = gevb.Field(c, gevb.REAL, 3, data=Bi); B.updateHalo()
+    p = gevb.Particles(c, 1e-4).add(ids, pos, vel)
+    counts = p.cell_counts()
+    assert counts.max() >= 3000 and counts.sum() == len(ids)
+    t00, T = gevb.Field(c, gevb.REAL, 1), gevb.Field(c, gevb.REAL, 6)
+    p.projection_T00_Tij_project(t00, T, a, P, 1.0); t00.projection_comm(); T.projection_comm()
+    assert common.rel_linf(t00.download(), checker.projection_T00(N, pos, vel, 1e-4, a, phi[0])) <= FIELD_TOL
+    assert common.rel_linf(T.download(), checker.projection_Tij(N, pos, vel, 1e-4, a, phi[0])) <= FIELD_TOL
+    t0i = gevb.Field(c, gevb.REAL, 3)
+    p.projection_T0i_project(t0i, P, 1.0); t0i.projection_comm()
+    assert common.rel_linf(t0i.download(), checker.projection_T0i(N, pos, vel, 1e-4, phi[0])) <= FIELD_TOL
+    params = [a, a * a * N]
+    vmax = p.kick_drift(gevb.UPDATE_Q, 0.03, 3, params, 0.05, 3, params, [P, X, B])
+    rv, rmax = checker.updateVel(N, pos, vel, 0, 0.03, phi, chi, Bi, 3, params)
+    rp = checker.moveParticles(N, pos, rv, 0, 0.05, phi, chi, Bi, 3, params)
+    gid, gpos, gvel = p.download()
+    o = np.argsort(gid)
+    assert common.rel_linf(gvel[o], rv) <= PCL_TOL and np.abs(gpos[o] - rp).max() <= 1e-14 and abs(vmax - rmax) <= 1e-12 * rmax
+    cell = np.minimum(np.floor(gpos[o] * N).astype(np.int64), N - 1)
+    assert np.array_equal(p.cell_counts(), np.bincount((cell[:, 2] * N + cell[:, 1]) * N + cell[:, 0], minlength=N ** 3).astype(np.uint32))
+    for f in (P, X, B, t00, T, t0i):
+        f.close()
+    p.close()
