@@ -12,7 +12,13 @@
 
 namespace {
 
-struct RGeom { int N, nzl; size_t plane; };
+struct RGeom { int N, nzl; size_t plane; uint64_t mhalf, mN; };   // mhalf = ceil(2^40 / (N/2)), mN = ceil(2^40 / N): quotients by multiply-shift
+__host__ __device__ __forceinline__ uint32_t mdiv(uint32_t i, uint64_t m) { return (uint32_t) (((uint64_t) i * m) >> 40); }
+static RGeom make_rgeom(const gevb_ctx * c)
+{
+	RGeom G = {c->N, c->nzl, c->plane(), ((1ull << 40) + (uint64_t) (c->N / 2) - 1) / (uint64_t) (c->N / 2), ((1ull << 40) + (uint64_t) c->N - 1) / (uint64_t) c->N};
+	return G;
+}
 
 // Two x-adjacent sites per thread: every stream (phi rows, the six T / S components, source, chi) moves as 16-byte
 // accesses, which halves the number of memory requests in flight per byte; the arithmetic per site is unchanged.
@@ -44,8 +50,9 @@ __global__ void __launch_bounds__(256) k_prepare_scalar(RGeom G, const double * 
 	double acc = 0.;
 	for (size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x; j < pairs; j += (size_t) gridDim.x * blockDim.x)
 	{
-		const int x = 2 * (int) (j % half); const size_t r = j / half;
-		const int y = (int) (r % N); const int zl = (int) (r / N);
+		const uint32_t r = mdiv((uint32_t) j, G.mhalf), zq = mdiv(r, G.mN);          // pairs < 2^31 (checked by the launcher)
+		const int x = 2 * (int) ((uint32_t) j - r * (uint32_t) half);
+		const int y = (int) (r - zq * (uint32_t) N); const int zl = (int) zq;
 		const size_t row = ((size_t) (zl + 1) * N + y) * N;
 		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 2 ? 0 : x + 2;
 		const size_t rowm = ((size_t) (zl + 1) * N + (y == 0 ? N - 1 : y - 1)) * N;
@@ -114,8 +121,9 @@ __global__ void __launch_bounds__(256) k_prepare_tensor(RGeom G, const double * 
 	const size_t pl = G.plane;
 	for (size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x; j < pairs; j += (size_t) gridDim.x * blockDim.x)
 	{
-		const int x = 2 * (int) (j % half); const size_t r = j / half;
-		const int y = (int) (r % N); const int zl = (int) (r / N);
+		const uint32_t r = mdiv((uint32_t) j, G.mhalf), zq = mdiv(r, G.mN);          // pairs < 2^31 (checked by the launcher)
+		const int x = 2 * (int) ((uint32_t) j - r * (uint32_t) half);
+		const int y = (int) (r - zq * (uint32_t) N); const int zl = (int) zq;
 		const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 2 ? 0 : x + 2;
 		const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
 		const size_t row = ((size_t) (zl + 1) * N + y) * N, rowm = ((size_t) (zl + 1) * N + ym) * N, rowp = ((size_t) (zl + 1) * N + yp) * N;
@@ -157,7 +165,8 @@ static int prepare_scalar(gevb_field * phi, gevb_field * chi, gevb_field * sourc
 	gevb_ctx * c = phi->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	Timed timed_(c, CLS_PREP_SCALAR);
-	RGeom G = {c->N, c->nzl, c->plane()};
+	RGeom G = make_rgeom(c);
+	GEVB_CHECK_ARG((size_t) c->nzl * c->plane() / 2 < (1ull << 31), "prepareFTsource: too many sites per rank for the 32-bit index decode (use more ranks)");
 	const int grid = gevb_grid(c, (size_t) c->nzl * c->plane() / 2, 256);      // <= 8 blocks per SM: the partials fit d_red[0..2048)
 	GEVB_CHECK_ARG(sum_source == NULL || grid <= 2048, "prepareFTsource: reduction buffer too small for %d blocks", grid);
 	k_prepare_scalar<<<grid, 256, 0, c->stream>>>(G, phi->data, chi->data, source->data, bgmodel, result->data, coeff, coeff2, coeff3, sum_source ? c->d_red : NULL);
@@ -193,7 +202,8 @@ extern "C" int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, g
 	gevb_ctx * c = phi->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	Timed timed_(c, CLS_PREP_TENSOR);
-	RGeom G = {c->N, c->nzl, c->plane()};
+	RGeom G = make_rgeom(c);
+	GEVB_CHECK_ARG((size_t) c->nzl * c->plane() / 2 < (1ull << 31), "prepareFTsource: too many sites per rank for the 32-bit index decode (use more ranks)");
 	k_prepare_tensor<<<gevb_grid(c, (size_t) c->nzl * c->plane() / 2, 256), 256, 0, c->stream>>>(G, phi->data, Tij->data, Sij->data, Sij->comp_stride, coeff);
 	KERNEL_CHECK(c);
 	return 0;
