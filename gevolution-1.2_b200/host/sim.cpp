@@ -285,9 +285,16 @@ extern "C" int gevb_sim_hibernate(gevb_sim * s, const char * filebase)
 	return bad == 0. ? 0 : 1;
 }
 
+static int sim_restore(gevb_sim * s, const char * filebase);
 extern "C" int gevb_sim_restore(gevb_sim * s, const char * filebase)
 {
 	if (s == NULL || filebase == NULL) return 1;
+	try { return sim_restore(s, filebase); }
+	catch (...) { return 1; }                                 // allocation failure and the like never cross the C boundary
+}
+
+static int sim_restore(gevb_sim * s, const char * filebase)
+{
 	gevb_ctx * ctx = s->lat.ctx();
 	int rank = 0, nranks = 1, n, z0, nzl, ky0, nky;
 	gevb_ctx_ranks(ctx, &rank, &nranks);
@@ -297,6 +304,17 @@ extern "C" int gevb_sim_restore(gevb_sim * s, const char * filebase)
 	FILE * f = std::fopen(name, "rb");
 	HibHeader h;
 	bool ok = f != NULL && get(f, &h, sizeof(h)) && std::memcmp(h.magic, HIB_MAGIC, 8) == 0;
+	// the particle counts must fit the file (a truncated or foreign file must not drive the allocations below)
+	if (ok)
+	{
+		long here = std::ftell(f);
+		std::fseek(f, 0, SEEK_END);
+		const long size = std::ftell(f);
+		std::fseek(f, here, SEEK_SET);
+		int64_t total = 0;
+		for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) if (h.npart[i] > 0) total += h.npart[i];
+		ok = here > 0 && size > here && total >= 0 && total <= (int64_t) ((size - here) / 56);
+	}
 	// a restart must use the decomposition the state was written with (the reference has the same restriction per file set)
 	ok = ok && h.ngrid == n && h.nranks == nranks && h.rank == rank && h.z0 == z0 && h.nzl == nzl && h.gr_flag == s->gr_flag && h.vector_flag == s->vector_flag
 		&& h.num_ncdm == s->cosmo.num_ncdm;

@@ -79,3 +79,31 @@ def test_host_background_matches_reference(gevb, ref):
     # non-relativistic limit: bg_ncdm -> Omega_ncdm (background.hpp:78 with w >> 1)
     g = gevb.background_eval(c2, 1.0, fourpiG, 0.0, m, T, Om)
     assert abs(g["bg_ncdm"] - Om.sum()) < 2e-4 * Om.sum()
+
+
+def test_power_spectrum_file_format_needs_no_device(gevb, tmp_path):
+    """host logic of the spectra writer (tools.hpp:268-346): header, one line per occupied bin, rescaling, and the
+    EXACT_OUTPUT_REDSHIFTS interpolation between the stored spectrum and the current one"""
+    import numpy as np
+    k = np.array([1.0, 2.0, 3.0, 4.0]); p = np.array([10.0, 20.0, 0.0, 40.0])
+    ks = np.array([0.1, 0.2, 0.0, 0.4]); ps = np.array([1.0, 2.0, 0.0, 4.0])
+    occ = np.array([3, 5, 0, 7], dtype=np.int32)
+    fn = str(tmp_path / "pk.dat")
+    gevb.writePowerSpectrum(k, p, ks, ps, occ, 2.0, 5.0, fn, "power spectrum of phi", 1.0 / 11.0, 9.5)   # z = 10, above the target
+    lines = open(fn).read().splitlines()
+    assert lines[:3] == ["# power spectrum of phi", "# redshift z=10.000000", "# k              Pk             sigma(k)       sigma(Pk)      count"]
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[3:]])
+    assert rows.shape == (3, 5)                                             # the empty bin is skipped
+    assert np.allclose(rows[:, 0], k[occ > 0] / 2.0) and np.allclose(rows[:, 1], p[occ > 0] / 5.0)
+    assert np.allclose(rows[:, 2], ks[occ > 0] / 2.0) and np.allclose(rows[:, 3], ps[occ > 0] / 5.0 / np.sqrt(occ[occ > 0]), rtol=1e-6)
+    assert np.array_equal(rows[:, 4].astype(int), occ[occ > 0])
+    # next cycle, z = 9 < 9.5: weight = (10 - 9.5) / (1 + 10 - 10) = 0.5 -> mean of the stored and the new spectrum, labelled z = 9.5
+    gevb.writePowerSpectrum(k, 3.0 * p, ks, ps, occ, 2.0, 5.0, fn, "power spectrum of phi", 1.0 / 10.0, 9.5)
+    lines = open(fn).read().splitlines()
+    assert lines[1] == "# redshift z=9.500000"
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[3:]])
+    assert np.allclose(rows[:, 1], 2.0 * p[occ > 0] / 5.0, rtol=1e-6)
+    # a target that is not reached yet (or disabled): plain overwrite
+    gevb.writePowerSpectrum(k, p, ks, ps, occ, 2.0, 5.0, fn, "power spectrum of phi", 1.0 / 10.0, -1.0)
+    rows = np.array([[float(v) for v in ln.split()] for ln in open(fn).read().splitlines()[3:]])
+    assert np.allclose(rows[:, 1], p[occ > 0] / 5.0)
