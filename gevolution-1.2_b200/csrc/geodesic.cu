@@ -293,10 +293,11 @@ __device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint3
 // (2 blocks of 256 threads per SM).  NBUF == 1: one tile buffer per block and twice as many, smaller blocks per SM --
 // a block that waits for its tile leaves the SM to the others.  In both forms the first particle of the next brick is
 // requested before the current brick's closing barrier, so no DRAM latency is exposed at a brick boundary.
-// PREF: the next particle of every thread (the next of this brick, else the first of the next brick) is fetched by
+// PREF 1: the next particle of every thread (the next of this brick, else the first of the next brick) is fetched by
 // asynchronous copies into a private shared-memory slot while the current one is processed -- a register prefetch at
-// the bottom of the loop is consumed immediately at its top and hides nothing within the warp.
-template <int MODE, int THREADS, int NBUF, int MINB, bool PREF>
+// the bottom of the loop is consumed immediately at its top and hides nothing within the warp.  PREF 2: the same
+// through a second set of registers, loaded at the top of the iteration.
+template <int MODE, int THREADS, int NBUF, int MINB, int PREF>
 __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 {
 	extern __shared__ double smem[];
@@ -336,7 +337,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 			{
 				uint32_t inext = i + THREADS;
 				bool fetched = false;
-				if (PREF)
+				double pn[3] = {0., 0., 0.}, qn[3] = {0., 0., 0.};
+				if (PREF == 2)
+				{
+					const uint32_t j = inext < last ? inext : nfirst + threadIdx.x;
+					fetched = inext < last || j < nlast;
+					if (fetched) { pn[0] = __ldcv(P.x + j); pn[1] = __ldcv(P.y + j); pn[2] = __ldcv(P.z + j); qn[0] = __ldcv(P.qx + j); qn[1] = __ldcv(P.qy + j); qn[2] = __ldcv(P.qz + j); }
+				}
+				if (PREF == 1)
 				{
 					// next particle of this brick, else this thread's first particle of the next brick
 					const uint32_t j = inext < last ? inext : nfirst + threadIdx.x;
@@ -398,9 +406,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 				if (PREF)
 				{
 					// the copies were issued at the top of this iteration; only this thread reads its slot, so no barrier
-					cp_async_wait<0>();
+					if (PREF == 1) cp_async_wait<0>();
 					i = inext;
-					if (fetched) { pos[0] = slot[0]; pos[1] = slot[THREADS]; pos[2] = slot[2 * THREADS]; q[0] = slot[3 * THREADS]; q[1] = slot[4 * THREADS]; q[2] = slot[5 * THREADS]; }
+					if (fetched)
+					{
+						if (PREF == 1) { pos[0] = slot[0]; pos[1] = slot[THREADS]; pos[2] = slot[2 * THREADS]; q[0] = slot[3 * THREADS]; q[1] = slot[4 * THREADS]; q[2] = slot[5 * THREADS]; }
+						else { pos[0] = pn[0]; pos[1] = pn[1]; pos[2] = pn[2]; q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; }
+					}
 					have_next = fetched && i >= last;
 					if (have_next) i = nfirst + threadIdx.x;
 				}
@@ -485,12 +497,12 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
 }
 
-template <int MODE, int THREADS, int NBUF, int MINB, bool PREF>
+template <int MODE, int THREADS, int NBUF, int MINB, int PREF>
 int launch_variant(gevb_pcls * p, const GParams & P)
 {
 	gevb_ctx * c = p->ctx;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
-	const size_t smem = ((size_t) NBUF * ncomp * TILE_SITES + (PREF ? 6 * THREADS : 0)) * sizeof(double);
+	const size_t smem = ((size_t) NBUF * ncomp * TILE_SITES + (PREF == 1 ? 6 * THREADS : 0)) * sizeof(double);
 	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE, THREADS, NBUF, MINB, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	const uint32_t persistent = (uint32_t) c->num_sms * MINB;
 	k_geodesic<MODE, THREADS, NBUF, MINB, PREF><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P);
@@ -498,18 +510,21 @@ int launch_variant(gevb_pcls * p, const GParams & P)
 	return 0;
 }
 
-// tuning knob geodesic_variant: 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 (default) = 128 threads, single
+// tuning knob geodesic_variant (default 6, measured in profiles/r2c): 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 = 128 threads, single
 // tile buffer, 4 blocks per SM; 4 = the same with the next particle fetched by cp.async into shared memory (measured slower:
-// 10.4 vs 7.7 ms at 512^3, profiles/r1q); 2 = 256 threads, single buffer, 2 blocks per SM
+// 10.4 vs 7.7 ms at 512^3, profiles/r1q); 5 / 6 = the next particle in a second set of registers, 4 / 3 blocks per SM; 2 = 256 threads, single buffer, 2 blocks per SM
 template <int MODE>
 int launch_geodesic(gevb_pcls * p, const GParams & P)
 {
 	switch (gevb_tune(TUNE_GEODESIC_VARIANT))
 	{
-		case 0: return launch_variant<MODE, 256, 2, 2, false>(p, P);
-		case 2: return launch_variant<MODE, 256, 1, 2, false>(p, P);
-		case 4: return launch_variant<MODE, 128, 1, 4, true>(p, P);
-		default: return launch_variant<MODE, 128, 1, 4, false>(p, P);
+		case 0: return launch_variant<MODE, 256, 2, 2, 0>(p, P);
+		case 2: return launch_variant<MODE, 256, 1, 2, 0>(p, P);
+		case 4: return launch_variant<MODE, 128, 1, 4, 1>(p, P);
+		case 5: return launch_variant<MODE, 128, 1, 4, 2>(p, P);
+		case 1: return launch_variant<MODE, 128, 1, 4, 0>(p, P);
+		case 7: return launch_variant<MODE, 96, 1, 4, 2>(p, P);
+		default: return launch_variant<MODE, 128, 1, 3, 2>(p, P);     // 6
 	}
 }
 
