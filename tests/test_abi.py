@@ -107,3 +107,12 @@ def test_power_spectrum_file_format_needs_no_device(gevb, tmp_path):
     gevb.writePowerSpectrum(k, p, ks, ps, occ, 2.0, 5.0, fn, "power spectrum of phi", 1.0 / 10.0, -1.0)
     rows = np.array([[float(v) for v in ln.split()] for ln in open(fn).read().splitlines()[3:]])
     assert np.allclose(rows[:, 1], p[occ > 0] / 5.0)
+
+
+def test_reference_shaped_loop_compiles_against_the_drop_in_header():
+    """a main.cpp-shaped loop (same names, argument order and types as the reference's statements) compiles
+    against include/gevolution_b200.hpp -- syntax and overload resolution only, nothing is executed"""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "dropin", "main_loop_shape.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
