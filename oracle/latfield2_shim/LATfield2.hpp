@@ -54,6 +54,39 @@ typedef int MPI_Op;
 #define MPI_SUM 1
 static inline int MPI_Reduce(const void *, void *, int, MPI_Datatype, MPI_Op, int, MPI_Comm) { return 0; }
 
+// ---- MPI-IO vocabulary used by Particles_gevolution.hpp:30-400 (saveGadget2 / loadGadget2), on one rank: plain
+//      positioned stdio.  MPI_MODE_CREATE does not truncate, as in MPI.
+#include <cstdio>
+#include <unistd.h>
+#define MPI_UNSIGNED 4
+#define MPI_BYTE 5
+#define MPI_MODE_RDONLY 1
+#define MPI_MODE_WRONLY 2
+#define MPI_MODE_CREATE 4
+#define MPI_INFO_NULL 0
+#define MPI_SEEK_SET 0
+typedef long long MPI_Offset;
+typedef FILE * MPI_File;
+struct MPI_Status { int unused; };
+static inline size_t lf2_mpi_size(MPI_Datatype t) { return t == MPI_DOUBLE ? 8 : (t == MPI_BYTE ? 1 : 4); }
+static inline int MPI_File_open(MPI_Comm, const char * name, int amode, int, MPI_File * fh)
+{
+	if (amode & MPI_MODE_RDONLY) { *fh = std::fopen(name, "rb"); return *fh ? 0 : 1; }
+	*fh = std::fopen(name, "r+b");
+	if (*fh == NULL && (amode & MPI_MODE_CREATE)) *fh = std::fopen(name, "w+b");
+	return *fh ? 0 : 1;
+}
+static inline int MPI_File_set_size(MPI_File fh, MPI_Offset size) { std::fflush(fh); return ftruncate(fileno(fh), (off_t) size); }
+static inline int MPI_File_write_at(MPI_File fh, MPI_Offset off, const void * buf, int count, MPI_Datatype t, MPI_Status *)
+{
+	if (fseeko(fh, (off_t) off, SEEK_SET) != 0) return 1;
+	return std::fwrite(buf, lf2_mpi_size(t), (size_t) count, fh) == (size_t) count ? 0 : 1;
+}
+static inline int MPI_File_write_at_all(MPI_File fh, MPI_Offset off, const void * buf, int count, MPI_Datatype t, MPI_Status * st) { return MPI_File_write_at(fh, off, buf, count, t, st); }
+static inline int MPI_File_seek(MPI_File fh, MPI_Offset off, int) { return fseeko(fh, (off_t) off, SEEK_SET); }
+static inline int MPI_File_read_all(MPI_File fh, void * buf, int count, MPI_Datatype t, MPI_Status *) { return std::fread(buf, lf2_mpi_size(t), (size_t) count, fh) == (size_t) count ? 0 : 1; }
+static inline int MPI_File_close(MPI_File * fh) { int r = std::fclose(*fh); *fh = NULL; return r; }
+
 namespace lf2 {
 // per-thread restriction of Site iteration to z in [zlo, zhi) (default: all)
 struct ZRange { int zlo, zhi; };
@@ -120,6 +153,8 @@ class Parallel2d
 {
 	int grid_rank_[2];
 	int grid_size_[2];
+	MPI_Comm comms_[1] = {0};
+	std::vector<char> mailbox_;
 public:
 	Parallel2d() { grid_rank_[0] = grid_rank_[1] = 0; grid_size_[0] = grid_size_[1] = 1; }
 	void initialize(int, int) {}
@@ -130,8 +165,14 @@ public:
 	int * grid_rank() { return grid_rank_; }
 	int * grid_size() { return grid_size_; }
 	MPI_Comm lat_world_comm() const { return 0; }
-	MPI_Comm dim0_comm() const { return 0; }
-	MPI_Comm dim1_comm() const { return 0; }
+	MPI_Comm * dim0_comm() { return comms_; }
+	MPI_Comm * dim1_comm() { return comms_; }
+	// point-to-point on one rank: the ring of size one that saveGadget2 builds (Particles_gevolution.hpp:86-116)
+	// sends to "the next rank" and receives from "the previous one" -- both are this rank, so a mailbox does it
+	template <class T> void send(T & v, int) { mailbox_.assign((const char *) &v, (const char *) &v + sizeof(T)); }
+	template <class T> void receive(T & v, int) { if (mailbox_.size() == sizeof(T)) std::memcpy(&v, mailbox_.data(), sizeof(T)); }
+	template <class T> void send_dim0(T & v, int to) { send(v, to); }
+	template <class T> void receive_dim0(T & v, int from) { receive(v, from); }
 	void abortForce() { std::cerr << "parallel.abortForce()" << std::endl; std::exit(-1); }
 	void barrier() {}
 	template <class T> void sum(T &) {}

@@ -66,6 +66,9 @@ _SIGS = {
     "sim_set_state": (None, [_vp, _dp]),
     "sim_get_timers": (None, [_vp, _dp]),
     "sim_step": (None, [_vp]),
+    "sim_create_from_settings": (_vp, [_i, _i, _i]),
+    "sim_get_config": (None, [_vp, _dp, _dp, _i32p, _dp]),
+    "sim_save_gadget2": (_i, [_vp, _i, C.c_char_p, _i, _d, _d]),
     "sim_set_ncdm": (None, [_vp, _i, _dp, _dp, _dp, _dp, _dp, _d, _d]),
     "sim_set_ncdm_maxvel": (None, [_vp, _dp]),
     "sim_get_ncdm_state": (None, [_vp, _dp, _i32p]),
@@ -235,6 +238,19 @@ class Oracle:
     def sim(self, N, gr_flag, vector_flag, dsettings, cosmo):
         return Sim(self, N, gr_flag, vector_flag, dsettings, cosmo)
 
+    def sim_from_settings(self, ngrid=0, tiling=0, seed=-1):
+        """the reference's shipped settings.ini run from its own seed: its parser and generateIC_basic (compiled reference
+        only); ngrid / tiling factor / seed override the file's values when given"""
+        h = self.fn["sim_create_from_settings"](ngrid, tiling, seed)
+        if not h:
+            raise RuntimeError("reference IC generation failed")
+        s = Sim.__new__(Sim)
+        s.o, s.h = self, h
+        cosmo, ds, flags, mass = np.zeros(11), np.zeros(5), np.zeros(4, dtype=np.int32), np.zeros(2)
+        self.fn["sim_get_config"](h, cosmo, ds, flags, mass)
+        s.N, s.cosmo, s.dsettings, s.gr_flag, s.vector_flag, s.baryon_flag, s.mass = int(flags[0]), cosmo, ds, int(flags[1]), int(flags[2]), int(flags[3]), mass
+        return s
+
 
 class Sim:
     """main.cpp:217-246 state + one-cycle stepping, on the CPU checker."""
@@ -290,6 +306,10 @@ class Sim:
         v, n = np.zeros(4), np.zeros(4, dtype=np.int32)
         self.o.fn["sim_get_ncdm_state"](self.h, v, n)
         return v, n
+
+    def save_gadget2(self, species, filename, tracer_factor=1, dtau_pos=0.0, dtau_vel=0.0):
+        """the reference's own saveGadget2 (Particles_gevolution.hpp:30-251)"""
+        return self.o.fn["sim_save_gadget2"](self.h, species, filename.encode(), tracer_factor, dtau_pos, dtau_vel)
 
     def timers(self):
         t = np.zeros(6)

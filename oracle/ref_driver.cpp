@@ -15,24 +15,37 @@
 //   symmetric tensor component order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
 //
 // The time-loop restatement in ref_sim_step() follows main.cpp:372-879 call by
-// call (main.cpp itself cannot be compiled here: it needs HDF5, GSL splines,
-// the parser and the I/O modules).
+// call (main.cpp itself cannot be compiled here: it needs HDF5 and the I/O
+// modules).  The reference's own parser (parser.hpp), IC generator
+// (ic_basic.hpp: generateIC_basic) and snapshot writer (Particles_gevolution.hpp:
+// saveGadget2) ARE compiled in, over stand-ins for the GSL spline and MPI-IO
+// calls they make (latfield2_shim/gsl/gsl_spline.h, LATfield2.hpp), so the shipped
+// settings.ini can be run from its own seed: ref_sim_create_from_settings().
 // =============================================================================
 #include <stdint.h>
 #include <stdlib.h>
 #include <chrono>
 #include <set>
 #include <vector>
+#include <unistd.h>
+#include <fstream>
+#include <iostream>
+#include <string>
 #include "LATfield2.hpp"
 #include "metadata.hpp"
+#include "class_tools.hpp"
 #include "tools.hpp"
 #include "background.hpp"
+#include "Particles_gevolution.hpp"
 #include "gevolution.hpp"
+#include "ic_basic.hpp"
+#include "parser.hpp"
+#include "_ref/embedded_data.h"
 
 using namespace std;
 using namespace LATfield2;
 
-typedef Particles<part_simple, part_simple_info, part_simple_dataType> Pcls;
+typedef Particles_gevolution<part_simple, part_simple_info, part_simple_dataType> Pcls;
 
 namespace {
 
@@ -445,6 +458,125 @@ void * ref_sim_create(int N, int gr_flag, int vector_flag, const double * dsetti
 }
 
 void ref_sim_destroy(void * h) { delete (RefSim *) h; }
+
+// ---- the shipped configuration from its own seed -------------------------------------------------------------------
+// settings.ini, the transfer-function table and the particle template of the reference (embedded at build time) are
+// written to a scratch directory, parsed by the reference's parser (main.cpp:184-186), Ngrid / tiling factor / seed are
+// overridden on request, and the reference's generateIC_basic (ic_basic.hpp:1626; call main.cpp:300) fills particles
+// and metric fields.  Loop scalars as main.cpp:278-297,325-333.
+static std::string write_embedded(const std::string & dir, const char * name, const unsigned char * data, unsigned long len)
+{
+	std::string path = dir + "/" + name;
+	std::ofstream f(path.c_str(), std::ios::binary);
+	f.write((const char *) data, (std::streamsize) len);
+	return path;
+}
+
+void * ref_sim_create_from_settings(int ngrid, int tiling, int seed)
+{
+	char tmpl[] = "/tmp/gevref_XXXXXX";
+	if (mkdtemp(tmpl) == NULL) return NULL;
+	const std::string dir(tmpl);
+	const std::string settings = write_embedded(dir, "settings.ini", ref_settings_ini, ref_settings_ini_len);
+	const std::string tkfile = write_embedded(dir, "class_tk.dat", ref_class_tk_dat, ref_class_tk_dat_len);
+	const std::string pclfile = write_embedded(dir, "sc1_crystal.dat", ref_sc1_crystal_dat, ref_sc1_crystal_dat_len);
+	metadata sim;
+	icsettings ic;
+	cosmology cosmo;
+	parameter * params = NULL;
+	int numparam = loadParameterFile(settings.c_str(), params);                       // main.cpp:184
+	if (numparam <= 0) return NULL;
+	std::streambuf * quiet = std::cout.rdbuf(NULL);                                  // the parser and the generator report on stdout
+	parseMetadata(params, numparam, sim, cosmo, ic);                                 // main.cpp:186
+	free(params); params = NULL; numparam = 0;
+	if (ngrid > 0) sim.numpts = ngrid;
+	if (tiling > 0) ic.numtile[0] = tiling;
+	if (seed >= 0) ic.seed = seed;
+	strcpy(ic.tkfile, tkfile.c_str());
+	strcpy(ic.pclfile[0], pclfile.c_str());
+	const int N = sim.numpts;
+	double ds[5] = {sim.boxsize, sim.Cf, sim.steplimit, sim.z_in, ic.z_relax};
+	RefSim * s = new RefSim();
+	s->N = N; s->L = &get_lat(N);
+	s->cosmo = cosmo;
+	bg_ncdm(-1., s->cosmo);
+	s->boxsize = ds[0]; s->Cf = ds[1]; s->steplimit = ds[2]; s->z_in = ds[3]; s->z_relax = ds[4];
+	s->gr_flag = sim.gr_flag; s->vector_flag = sim.vector_flag; s->baryon_flag = 0; s->have_b = false;
+	Lattice & lat = s->L->lat; Lattice & latFT = s->L->latFT;
+	s->source.initialize(lat, 1); s->phi.initialize(lat, 1); s->chi.initialize(lat, 1);
+	s->scalarFT.initialize(latFT, 1);
+	s->plan_source.initialize(&s->source, &s->scalarFT);
+	s->plan_phi.initialize(&s->phi, &s->scalarFT);
+	s->plan_chi.initialize(&s->chi, &s->scalarFT);
+	s->Sij.initialize(lat, 3, 3, symmetric); s->SijFT.initialize(latFT, 3, 3, symmetric);
+	s->plan_Sij.initialize(&s->Sij, &s->SijFT);
+	s->Bi.initialize(lat, 3); s->BiFT.initialize(latFT, 3);
+	s->plan_Bi.initialize(&s->Bi, &s->BiFT);
+	for (int i = 0; i < MAX_PCL_SPECIES; i++) s->maxvel[i] = 0.;
+	for (int i = 0; i < MAX_PCL_SPECIES - 2; i++) { s->have_ncdm[i] = false; s->z_switch_deltancdm[i] = sim.z_switch_deltancdm[i]; s->z_switch_Bncdm[i] = sim.z_switch_Bncdm[i]; s->numsteps_ncdm[i] = 1; }
+	s->z_switch_linearchi = sim.z_switch_linearchi; s->movelimit = sim.movelimit;
+	s->dx = 1.0 / (double) N;
+	s->fourpiG = 1.5 * sim.boxsize * sim.boxsize / C_SPEED_OF_LIGHT / C_SPEED_OF_LIGHT;                      // main.cpp:280
+	s->a = 1. / (1. + sim.z_in);
+	s->tau = particleHorizon(s->a, s->fourpiG, s->cosmo);
+	if (sim.Cf * s->dx < sim.steplimit / Hconf(s->a, s->fourpiG, s->cosmo)) s->dtau = sim.Cf * s->dx;          // main.cpp:292-295
+	else s->dtau = sim.steplimit / Hconf(s->a, s->fourpiG, s->cosmo);
+	s->dtau_old = 0.;
+	s->cycle = 0; s->T00hom = 0.;
+	s->projection_time = s->gravity_solver_time = s->fft_time = s->update_q_time = s->moveParts_time = s->cycle_time = 0.;
+	double maxvel[MAX_PCL_SPECIES] = {0., 0., 0., 0., 0., 0.};
+	generateIC_basic(sim, ic, s->cosmo, s->fourpiG, &s->pcls_cdm, &s->pcls_b, s->pcls_ncdm, maxvel, &s->phi, &s->chi, &s->Bi, &s->source, &s->Sij,
+		&s->scalarFT, &s->BiFT, &s->SijFT, &s->plan_phi, &s->plan_chi, &s->plan_Bi, &s->plan_source, &s->plan_Sij, params, numparam);   // main.cpp:300
+	std::cout.rdbuf(quiet);
+	s->baryon_flag = sim.baryon_flag; s->have_b = sim.baryon_flag > 0;
+	for (int i = 0; i < s->cosmo.num_ncdm; i++) s->have_ncdm[i] = sim.numpcl[1 + sim.baryon_flag + i] > 0;
+	// main.cpp:325-333: maxvel[] in main.cpp's order (cdm, [baryons], ncdm...) -> species slots; gamma factor for GR
+	const int numspecies = 1 + sim.baryon_flag + s->cosmo.num_ncdm;
+	if (sim.gr_flag > 0) for (int i = 0; i < numspecies; i++) maxvel[i] /= sqrt(maxvel[i] * maxvel[i] + 1.0);
+	s->maxvel[0] = maxvel[0];
+	if (sim.baryon_flag) s->maxvel[1] = maxvel[1];
+	for (int i = 0; i < s->cosmo.num_ncdm; i++) s->maxvel[2 + i] = maxvel[1 + sim.baryon_flag + i];
+	std::remove(settings.c_str()); std::remove(tkfile.c_str()); std::remove(pclfile.c_str()); rmdir(dir.c_str());
+	return s;
+}
+
+// configuration of a simulation as the flat arrays the other constructors take
+// cosmo11: Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h
+// ds5: boxsize, Cf, steplimit, z_in, z_relax ; flags4: Ngrid, gr_flag, vector_flag, baryon_flag ; mass[2]: particle masses cdm, baryons
+void ref_sim_get_config(void * h, double * cosmo11, double * ds5, int * flags4, double * mass2)
+{
+	RefSim * s = (RefSim *) h;
+	const cosmology & c = s->cosmo;
+	const double co[11] = {c.Omega_cdm, c.Omega_b, c.Omega_m, c.Omega_Lambda, c.Omega_fld, c.w0_fld, c.wa_fld, c.Omega_g, c.Omega_ur, c.Omega_rad, c.h};
+	for (int i = 0; i < 11; i++) cosmo11[i] = co[i];
+	ds5[0] = s->boxsize; ds5[1] = s->Cf; ds5[2] = s->steplimit; ds5[3] = s->z_in; ds5[4] = s->z_relax;
+	flags4[0] = s->N; flags4[1] = s->gr_flag; flags4[2] = s->vector_flag; flags4[3] = s->baryon_flag;
+	mass2[0] = s->pcls_cdm.parts_info()->mass;
+	mass2[1] = s->have_b ? s->pcls_b.parts_info()->mass : 0.;
+}
+
+// the reference's own Gadget-2 writer (Particles_gevolution.hpp:30-251) with the header of writeSnapshots
+// (output.hpp:360-402, restated: output.hpp itself needs HDF5)
+int ref_sim_save_gadget2(void * h, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel)
+{
+	RefSim * s = (RefSim *) h;
+	Pcls & p = species == 0 ? s->pcls_cdm : (species == 1 ? s->pcls_b : s->pcls_ncdm[species - 2]);
+	gadget2_header hdr;
+	memset(&hdr, 0, sizeof(hdr));
+	hdr.num_files = 1;
+	hdr.Omega0 = s->cosmo.Omega_m; hdr.OmegaLambda = s->cosmo.Omega_Lambda; hdr.HubbleParam = s->cosmo.h;
+	hdr.BoxSize = s->boxsize / GADGET_LENGTH_CONVERSION;
+	hdr.time = s->a; hdr.redshift = (1. / s->a) - 1.;
+	const long n = p.numParticles();
+	const long nsel = (n % tracer_factor) ? (1 + n / tracer_factor) : (n / tracer_factor);
+	hdr.npart[1] = (uint32_t) (nsel % (1ll << 32)); hdr.npartTotal[1] = hdr.npart[1]; hdr.npartTotalHW[1] = (uint32_t) (nsel / (1ll << 32));
+	hdr.mass[1] = (double) tracer_factor * C_RHO_CRIT * p.parts_info()->mass * s->boxsize * s->boxsize * s->boxsize / GADGET_MASS_CONVERSION;
+	std::remove(filename);
+	std::streambuf * quiet = std::cout.rdbuf(NULL);
+	p.saveGadget2(std::string(filename), hdr, tracer_factor, dtau_pos, dtau_vel, &s->phi);
+	std::cout.rdbuf(quiet);
+	return 0;
+}
 
 // ncdm species: cosmo.*_ncdm (metadata.hpp:284-288) and the switches (metadata.hpp:224-238)
 void ref_sim_set_ncdm(void * h, int num_ncdm, const double * m_ncdm, const double * T_ncdm, const double * Omega_ncdm,

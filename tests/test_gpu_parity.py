@@ -550,3 +550,77 @@ def test_extreme_occupancy(gevb, ctx, checker):
     for f in (P, X, B, t00, T, t0i):
         f.close()
     p.close()
+
+
+# ---- BASELINE config 1: the reference's shipped settings.ini from its own seed ------------------------------------------
+def _gpu_sim_like(gevb, c, cosmo, ds, flags, mass, ids, pos, vel, phi, chi, Bi, BiFT, state):
+    gs = gevb.Sim(c, int(flags[1]), int(flags[2]), ds, cosmo)
+    gs.set_particles(0, ids, pos, vel, float(mass[0]))
+    gs.set_field("phi", phi); gs.set_field("chi", chi); gs.set_field("Bi", Bi); gs.set_field("BiFT", BiFT)
+    gs.set_state(state[0], state[1], state[2], state[3], int(state[4]), (state[5], state[6]))
+    return gs
+
+
+def test_shipped_settings_fixture(gevb, ctx):
+    """initial conditions made by the reference's own parser + generateIC_basic from the shipped settings.ini (Ngrid 16,
+    tiling 4; tests/golden/make_golden.py) and the reference's state four cycles later: the device path reproduces it"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "shipped_settings_N16.npz"))
+    N = int(g["flags"][0])
+    gs = _gpu_sim_like(gevb, ctx(N), g["cosmo"], g["dsettings"], g["flags"], g["mass"], g["ic_ids"], g["ic_pos"], g["ic_vel"],
+                       g["ic_phi"], g["ic_chi"], g["ic_Bi"], g["ic_BiFT"], g["ic_state"])
+    ncycles = int(g["ncycles"][0])
+    for _ in range(ncycles):
+        gs.step()
+    tol = FIELD_TOL * ncycles
+    for name in ("phi", "chi", "Bi"):
+        assert common.rel_linf(gs.get_field(name), g["end_" + name]) <= tol, name
+    gid, gpos, gvel = gs.pcls(0).download()
+    o = np.argsort(gid)
+    assert np.array_equal(gid[o], g["end_ids"]) and np.abs(gpos[o] - g["end_pos"]).max() <= 1e-13 and common.rel_linf(gvel[o], g["end_vel"]) <= tol
+    assert np.array_equal(np.floor(gpos[o] * N), np.floor(g["end_pos"] * N))                       # bit-exact binning
+    st, e = gs.state(), g["end_state"]
+    assert st["cycle"] == int(e[4]) and abs(st["a"] - e[0]) <= 1e-14 * e[0] and abs(st["dtau"] - e[2]) <= 1e-13 * e[2]
+    assert abs(st["maxvel"][0] - e[5]) <= 1e-10 * e[5] and abs(st["T00hom"] - e[6]) <= 1e-10 * e[6]
+    gs.close()
+
+
+def test_config1_shipped_settings_and_reference_snapshot(gevb, ctx, ref, tmp_path):
+    """BASELINE config 1 as shipped -- settings.ini unchanged: Ngrid 64, 64^3 particles, GR, parabolic B, seed 42 -- with the
+    initial conditions generated by the reference itself, six cycles on both sides; then the Gadget-2 snapshot of the device
+    path against the file the reference's own saveGadget2 writes"""
+    rs = ref.sim_from_settings()
+    N = rs.N
+    assert N == 64
+    ids, pos, vel = rs.get_particles(0)
+    assert len(ids) == 64 ** 3
+    st = rs.state()
+    state = [st["a"], st["tau"], st["dtau"], st["dtau_old"], st["cycle"], st["maxvel"][0], st["maxvel"][1]]
+    gs = _gpu_sim_like(gevb, ctx(N), rs.cosmo, rs.dsettings, [N, rs.gr_flag, rs.vector_flag, rs.baryon_flag], rs.mass, ids, pos, vel,
+                       rs.get_field("phi"), rs.get_field("chi"), rs.get_field("Bi"), rs.get_field("BiFT"), state)
+    for step in range(6):
+        rs.step(); gs.step()
+        e = _compare_sims(rs, gs, N)
+        tol = FIELD_TOL * (1 + step)
+        bad = {k: v for k, v in e.items() if k not in ("state_tau", "scalarFT") and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= tol))}
+        assert bad == {}, (step, e)
+    # snapshot: same header, same blocks (particle order in the file is free; float32 values within one unit in the last place)
+    fr, fg = str(tmp_path / "ref_snap"), str(tmp_path / "gpu_snap")
+    tracer, dtau_pos, dtau_vel = 4, 0.011, 0.017
+    rs.save_gadget2(0, fr, tracer, dtau_pos, dtau_vel)
+    gs.save_gadget2(0, fg, tracer, dtau_pos, dtau_vel)
+    rawr, rawg = open(fr, "rb").read(), open(fg, "rb").read()
+    assert len(rawr) == len(rawg)
+    hr, pr, vr, ir = _read_gadget2(fr)
+    hg, pg, vg, ig = _read_gadget2(fg)
+    assert hr["npart"] == hg["npart"] and hr["BoxSize"] == hg["BoxSize"]
+    for k in ("time", "redshift"):
+        assert abs(hr[k] - hg[k]) <= 1e-12 * abs(hr[k])
+    assert np.allclose(hr["mass"], hg["mass"], rtol=1e-14, atol=0)
+    import struct
+    assert struct.unpack_from("<2i", rawr, 4 + 24 + 48 + 16 + 8 + 24)[1] == struct.unpack_from("<2i", rawg, 4 + 24 + 48 + 16 + 8 + 24)[1] == 1     # num_files
+    assert struct.unpack_from("<3d", rawr, 4 + 24 + 48 + 16 + 8 + 24 + 8 + 8) == struct.unpack_from("<3d", rawg, 4 + 24 + 48 + 16 + 8 + 24 + 8 + 8)   # Omega0, OmegaLambda, h
+    orr, og = np.argsort(ir), np.argsort(ig)
+    assert np.array_equal(ir[orr], ig[og])
+    assert np.all(np.abs(pg[og] - pr[orr]) <= np.spacing(np.abs(pr[orr]).astype(np.float32)) + 1e-30)
+    assert np.all(np.abs(vg[og] - vr[orr]) <= 4 * np.spacing(np.abs(vr[orr]).astype(np.float32)) + 1e-30)
+    rs.close(); gs.close()

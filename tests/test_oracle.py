@@ -195,3 +195,52 @@ def test_reference_time_loop_runs(ref):
     ids2, pos2, vel2 = sim.get_particles()
     assert sorted(ids2.tolist()) == ids.tolist() and np.all((pos2 >= 0) & (pos2 < 1))
     sim.close()
+
+
+# ---- the reference's shipped configuration from its own seed (parser + generateIC_basic compiled into oracle/_ref) ----
+SHIPPED = os.path.join(os.path.dirname(__file__), "golden", "shipped_settings_N16.npz")
+
+
+def test_shipped_settings_ic_generation(ref):
+    """settings.ini of the reference (GR, parabolic, blend, seed 42) with Ngrid = 16, tiling 4: what the reference's own
+    parser and IC generator produce is deterministic, depends on the seed, conserves mass, and equals the committed fixture"""
+    s = ref.sim_from_settings(16, 4)
+    assert (s.N, s.gr_flag, s.vector_flag, s.baryon_flag) == (16, 1, 0, 0)
+    cosmo = common.shipped_cosmology()
+    assert np.allclose(s.cosmo, cosmo, rtol=1e-12) and np.allclose(s.dsettings, common.shipped_settings(), rtol=0, atol=0)
+    ids, pos, vel = s.get_particles(0)
+    assert len(ids) == 4 ** 3 * 4 ** 3 and sorted(ids.tolist()) == list(range(len(ids)))     # sc1 template: 4^3 points, tiled 4^3 times
+    assert abs(s.mass[0] - (cosmo[0] + cosmo[1]) / len(ids)) <= 1e-15 * s.mass[0]             # baryon treatment = blend
+    assert np.all((pos >= 0) & (pos < 1)) and 1e-5 < np.abs(s.get_field("phi")).max() < 1e-3
+    g = np.load(SHIPPED)
+    o = np.argsort(ids)
+    assert np.array_equal(ids[o], g["ic_ids"][np.argsort(g["ic_ids"])])
+    assert np.abs(pos[o] - g["ic_pos"][np.argsort(g["ic_ids"])]).max() <= 1e-14 and common.rel_linf(vel[o], g["ic_vel"][np.argsort(g["ic_ids"])]) <= 1e-12
+    assert common.rel_linf(s.get_field("phi"), g["ic_phi"]) <= 1e-12
+    st = s.state()
+    assert abs(st["a"] - 1 / 101.0) < 1e-15 and abs(st["dtau"] - g["ic_state"][2]) <= 1e-14 and st["maxvel"][0] > 0
+    # mass conservation through the first cycle, and the state after the fixture's cycles
+    for _ in range(int(g["ncycles"][0])):
+        s.step()
+    assert abs(s.state()["T00hom"] / (cosmo[0] + cosmo[1]) - 1.0) < 1e-3
+    i2, p2, v2 = s.get_particles(0)
+    o2 = np.argsort(i2)
+    assert np.abs(p2[o2] - g["end_pos"]).max() <= 1e-13 and common.rel_linf(s.get_field("phi"), g["end_phi"]) <= 1e-11
+    # another seed gives another realisation
+    s3 = ref.sim_from_settings(16, 4, seed=7)
+    assert np.abs(s3.get_field("phi") - g["ic_phi"]).max() > 1e-6
+    s.close(); s3.close()
+
+
+def test_reference_gadget2_writer_runs(ref, tmp_path):
+    """the reference's own saveGadget2 over the MPI-IO stand-in: file size and block markers of the Gadget-2 layout"""
+    import struct
+    s = ref.sim_from_settings(16, 4)
+    fn = str(tmp_path / "snap")
+    s.save_gadget2(0, fn, 2, 0.01, 0.02)
+    raw = open(fn, "rb").read()
+    n = 4096 // 2
+    assert len(raw) == 264 + (8 + 12 * n) * 2 + 8 + 8 * n
+    assert struct.unpack_from("<I", raw, 0)[0] == 256 and struct.unpack_from("<6I", raw, 4)[1] == n
+    assert struct.unpack_from("<I", raw, 264)[0] == 12 * n and struct.unpack_from("<I", raw, len(raw) - 4)[0] == 8 * n
+    s.close()
