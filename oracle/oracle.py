@@ -66,6 +66,7 @@ _SIGS = {
     "sim_set_state": (None, [_vp, _dp]),
     "sim_get_timers": (None, [_vp, _dp]),
     "sim_step": (None, [_vp]),
+    "writePowerSpectrum": (None, [_dp, _dp, _dp, _dp, _i32p, _i, _d, _d, C.c_char_p, C.c_char_p, _d, _d]),
     "sim_create_from_settings": (_vp, [_i, _i, _i]),
     "sim_get_config": (None, [_vp, _dp, _dp, _i32p, _dp]),
     "sim_save_gadget2": (_i, [_vp, _i, C.c_char_p, _i, _d, _d]),
@@ -209,6 +210,12 @@ class Oracle:
         occ = np.zeros(numbins, dtype=np.int32)
         self.fn["extractPowerSpectrum"](N, fldFT.shape[0], int(symmetric), fldFT, kbin, power, ksc, psc, occ, numbins, int(deconvolve), ktype)
         return kbin, power, ksc, psc, occ
+
+    def writePowerSpectrum(self, kbin, power, kscatter, pscatter, occupation, rescalek, rescalep, filename, description, a, z_target=-1.0):
+        """the reference's own file writer (tools.hpp:268-346)"""
+        arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (kbin, power, kscatter, pscatter)]
+        occ = np.ascontiguousarray(occupation, dtype=np.int32)
+        self.fn["writePowerSpectrum"](*arr, occ, len(occ), rescalek, rescalep, filename.encode(), description.encode(), a, z_target)
 
     def computeVectorDiagnostics(self, Bi):
         a, b = np.zeros(1), np.zeros(1)

@@ -540,6 +540,15 @@ void * ref_sim_create_from_settings(int ngrid, int tiling, int seed)
 	return s;
 }
 
+// the reference's own spectrum file writer (tools.hpp:268-346), EXACT_OUTPUT_REDSHIFTS branch included
+void ref_writePowerSpectrum(const double * kbin, const double * power, const double * kscatter, const double * pscatter, const int * occupation, int numbins,
+                            double rescalek, double rescalep, const char * filename, const char * description, double a, double z_target)
+{
+	std::vector<Real> k(kbin, kbin + numbins), p(power, power + numbins), ks(kscatter, kscatter + numbins), ps(pscatter, pscatter + numbins);
+	std::vector<int> occ(occupation, occupation + numbins);
+	writePowerSpectrum(k.data(), p.data(), ks.data(), ps.data(), occ.data(), numbins, rescalek, rescalep, filename, description, a, z_target);
+}
+
 // configuration of a simulation as the flat arrays the other constructors take
 // cosmo11: Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h
 // ds5: boxsize, Cf, steplimit, z_in, z_relax ; flags4: Ngrid, gr_flag, vector_flag, baryon_flag ; mass[2]: particle masses cdm, baryons

@@ -116,3 +116,19 @@ def test_reference_shaped_loop_compiles_against_the_drop_in_header():
     src = os.path.join(ROOT, "tests", "dropin", "main_loop_shape.cpp")
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_power_spectrum_file_equals_the_reference_writer(gevb, ref, tmp_path):
+    """byte for byte: gevb_writePowerSpectrum against the reference's own writePowerSpectrum (tools.hpp:268-346), first
+    write, interpolated second write past the target redshift, and a later plain overwrite"""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    nb = 24
+    k = np.sort(rng.random(nb)) * 50; p = rng.random(nb) * 1e-9; ks = rng.random(nb) * 0.1; ps = rng.random(nb) * 1e-10
+    occ = rng.integers(0, 40, nb).astype(np.int32); occ[[3, 11]] = 0
+    fa, fb = str(tmp_path / "a.dat"), str(tmp_path / "b.dat")
+    calls = [(p, 1.0 / 11.0, 9.5), (2.5 * p, 1.0 / 10.2, 9.5), (0.7 * p, 1.0 / 4.0, 3.0), (0.9 * p, 1.0 / 3.9, 3.0), (p, 0.5, -1.0)]
+    for pw, a, zt in calls:
+        gevb.writePowerSpectrum(k, pw, ks, ps, occ, 320.0, 7.3e4, fa, "power spectrum of phi", a, zt)
+        ref.writePowerSpectrum(k, pw, ks, ps, occ, 320.0, 7.3e4, fb, "power spectrum of phi", a, zt)
+        assert open(fa, "rb").read() == open(fb, "rb").read(), (a, zt)
