@@ -67,7 +67,7 @@ _SIGS = {
     "sim_get_timers": (None, [_vp, _dp]),
     "sim_step": (None, [_vp]),
     "writePowerSpectrum": (None, [_dp, _dp, _dp, _dp, _i32p, _i, _d, _d, C.c_char_p, C.c_char_p, _d, _d]),
-    "sim_create_from_settings": (_vp, [_i, _i, _i]),
+    "sim_create_from_settings": (_vp, [_i, _i, _i, C.c_char_p]),
     "sim_get_config": (None, [_vp, _dp, _dp, _i32p, _dp]),
     "sim_save_gadget2": (_i, [_vp, _i, C.c_char_p, _i, _d, _d]),
     "sim_set_ncdm": (None, [_vp, _i, _dp, _dp, _dp, _dp, _dp, _d, _d]),
@@ -245,10 +245,11 @@ class Oracle:
     def sim(self, N, gr_flag, vector_flag, dsettings, cosmo):
         return Sim(self, N, gr_flag, vector_flag, dsettings, cosmo)
 
-    def sim_from_settings(self, ngrid=0, tiling=0, seed=-1):
+    def sim_from_settings(self, ngrid=0, tiling=0, seed=-1, overrides=""):
         """the reference's shipped settings.ini run from its own seed: its parser and generateIC_basic (compiled reference
-        only); ngrid / tiling factor / seed override the file's values when given"""
-        h = self.fn["sim_create_from_settings"](ngrid, tiling, seed)
+        only); ngrid / tiling factor / seed override the file's values when given, `overrides` holds further
+        "key = value" lines that replace the file's lines of the same key (e.g. "gravity theory = Newton")"""
+        h = self.fn["sim_create_from_settings"](ngrid, tiling, seed, overrides.encode())
         if not h:
             raise RuntimeError("reference IC generation failed")
         s = Sim.__new__(Sim)

@@ -472,12 +472,38 @@ static std::string write_embedded(const std::string & dir, const char * name, co
 	return path;
 }
 
-void * ref_sim_create_from_settings(int ngrid, int tiling, int seed)
+// settings text with `overrides` applied: every line "key = value" of overrides replaces the line of the same key
+// (or is appended), so the tests can switch e.g. "gravity theory = Newton" or "vector method = elliptic"
+static std::string apply_overrides(const std::string & text, const char * overrides)
+{
+	if (overrides == NULL || overrides[0] == 0) return text;
+	auto key_of = [](const std::string & line) { size_t e = line.find('='); if (e == std::string::npos) return std::string(); std::string k = line.substr(0, e);
+		while (!k.empty() && (k.back() == ' ' || k.back() == '\t')) k.pop_back(); size_t b = k.find_first_not_of(" \t"); return b == std::string::npos ? std::string() : k.substr(b); };
+	std::vector<std::string> lines, extra;
+	std::string cur;
+	for (char ch : text) { if (ch == '\n') { lines.push_back(cur); cur.clear(); } else cur += ch; }
+	if (!cur.empty()) lines.push_back(cur);
+	cur.clear();
+	for (const char * q = overrides; ; q++) { if (*q == '\n' || *q == 0) { if (!cur.empty()) extra.push_back(cur); cur.clear(); if (*q == 0) break; } else cur += *q; }
+	for (const std::string & o : extra)
+	{
+		const std::string k = key_of(o);
+		bool done = false;
+		for (std::string & l : lines) if (!k.empty() && l[0] != '#' && key_of(l) == k) { l = o; done = true; break; }
+		if (!done) lines.push_back(o);
+	}
+	std::string out;
+	for (const std::string & l : lines) out += l + "\n";
+	return out;
+}
+
+void * ref_sim_create_from_settings(int ngrid, int tiling, int seed, const char * overrides)
 {
 	char tmpl[] = "/tmp/gevref_XXXXXX";
 	if (mkdtemp(tmpl) == NULL) return NULL;
 	const std::string dir(tmpl);
-	const std::string settings = write_embedded(dir, "settings.ini", ref_settings_ini, ref_settings_ini_len);
+	const std::string text = apply_overrides(std::string((const char *) ref_settings_ini, ref_settings_ini_len), overrides);
+	const std::string settings = write_embedded(dir, "settings.ini", (const unsigned char *) text.data(), text.size());
 	const std::string tkfile = write_embedded(dir, "class_tk.dat", ref_class_tk_dat, ref_class_tk_dat_len);
 	const std::string pclfile = write_embedded(dir, "sc1_crystal.dat", ref_sc1_crystal_dat, ref_sc1_crystal_dat_len);
 	metadata sim;
@@ -490,10 +516,10 @@ void * ref_sim_create_from_settings(int ngrid, int tiling, int seed)
 	parseMetadata(params, numparam, sim, cosmo, ic);                                 // main.cpp:186
 	free(params); params = NULL; numparam = 0;
 	if (ngrid > 0) sim.numpts = ngrid;
-	if (tiling > 0) ic.numtile[0] = tiling;
+	if (tiling > 0) for (int i = 0; i < MAX_PCL_SPECIES; i++) if (ic.numtile[i] > 0 || i == 0) ic.numtile[i] = tiling;
 	if (seed >= 0) ic.seed = seed;
 	strcpy(ic.tkfile, tkfile.c_str());
-	strcpy(ic.pclfile[0], pclfile.c_str());
+	for (int i = 0; i < MAX_PCL_SPECIES; i++) strcpy(ic.pclfile[i], pclfile.c_str());
 	const int N = sim.numpts;
 	double ds[5] = {sim.boxsize, sim.Cf, sim.steplimit, sim.z_in, ic.z_relax};
 	RefSim * s = new RefSim();

@@ -624,3 +624,28 @@ def test_config1_shipped_settings_and_reference_snapshot(gevb, ctx, ref, tmp_pat
     assert np.all(np.abs(pg[og] - pr[orr]) <= np.spacing(np.abs(pr[orr]).astype(np.float32)) + 1e-30)
     assert np.all(np.abs(vg[og] - vr[orr]) <= 4 * np.spacing(np.abs(vr[orr]).astype(np.float32)) + 1e-30)
     rs.close(); gs.close()
+
+
+@pytest.mark.parametrize("overrides", ["gravity theory = Newton", "vector method = elliptic", "baryon treatment = sample\ntiling factor = 4, 4"],
+                         ids=["newton", "elliptic", "baryons_sampled"])
+def test_shipped_settings_variants_from_reference_ics(gevb, ctx, ref, overrides):
+    """the shipped settings.ini with one line changed (Newtonian gravity; elliptic vector method, which adds the T0i deposit and
+    projectFTvector; baryons as their own species), initial conditions by the reference's generator, three cycles"""
+    rs = ref.sim_from_settings(16, 4, overrides=overrides)
+    N, nsp = rs.N, 1 + rs.baryon_flag
+    st = rs.state()
+    gs = gevb.Sim(ctx(N), rs.gr_flag, rs.vector_flag, rs.dsettings, rs.cosmo)
+    for sp in range(nsp):
+        ids, pos, vel = rs.get_particles(sp)
+        gs.set_particles(sp, ids, pos, vel, float(rs.mass[sp]))
+    for name in ("phi", "chi", "Bi", "BiFT"):
+        gs.set_field(name, rs.get_field(name))
+    gs.set_state(st["a"], st["tau"], st["dtau"], st["dtau_old"], st["cycle"], st["maxvel"])
+    for step in range(3):
+        rs.step(); gs.step()
+        e = _compare_sims(rs, gs, N, nspecies=nsp)
+        skip = ("state_tau", "scalarFT") + (("chi", "Bi", "Sij", "BiFT", "SijFT", "state_T00hom") if rs.gr_flag == 0 else ())
+        tol = FIELD_TOL * (1 + step)
+        bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= tol))}
+        assert bad == {}, (step, e)
+    rs.close(); gs.close()
