@@ -549,7 +549,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replica", action="store_true", help="(internal) one replica of the CPU reference arm")
     ap.add_argument("--ngrid-ref", type=int, default=128)
-    ap.add_argument("--ablate", default="", help="e.g. geodesic_variant=1:0:2,deposit_variant=0:1 -- times 2 cycles per setting (stderr), first value is restored")
+    ap.add_argument("--ablate", default="", help="e.g. geodesic_variant=6:1:0,fft_decomposed=1:0 -- times 2 cycles per setting (stderr), first value is restored")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra lattice / clustered measurements of the particle kernels")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

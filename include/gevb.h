@@ -59,7 +59,7 @@ typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>
 const char * gevb_last_error(void);
 const char * gevb_version(void);
 
-/* kernel-variant knobs for ablation runs ("geodesic_variant", "deposit_variant", "fft_exchange": 1 = transposes pushed
+/* kernel-variant knobs for ablation runs ("geodesic_variant": block shape / prefetch of the kick-drift kernel, see geodesic.cu; "fft_exchange": 1 = transposes pushed
  * over peer memory, 0 = NCCL all-to-all + local transpose; "fft_overlap": 1 = the push of component k overlaps the local transform of
  * component k+1; "fft_decomposed": 1 = single-rank transforms as 2-D per plane + 1-D along z, 0 = cuFFT 3-D plans);
  * results do not depend on them */
