@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GEVB_LIB") or os.path.join(os.path.dirname(_HERE), "libgevb.so")   # GEVB_LIB: experiment builds (scripts/ablate.sh)
+LIB_PATH = os.environ.get("GEVB_LIB") or os.path.join(os.path.dirname(_HERE), "libgevb.so")   # GEVB_LIB: an alternative build of the library
 
 REAL, CPLX = 0, 1
 FFT_FORWARD, FFT_BACKWARD = 1, -1
