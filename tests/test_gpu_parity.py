@@ -626,12 +626,13 @@ def test_config1_shipped_settings_and_reference_snapshot(gevb, ctx, ref, tmp_pat
     rs.close(); gs.close()
 
 
-@pytest.mark.parametrize("overrides", ["gravity theory = Newton", "vector method = elliptic", "baryon treatment = sample\ntiling factor = 4, 4"],
-                         ids=["newton", "elliptic", "baryons_sampled"])
-def test_shipped_settings_variants_from_reference_ics(gevb, ctx, ref, overrides):
+@pytest.mark.parametrize("overrides,ngrid", [("gravity theory = Newton", 16), ("vector method = elliptic", 16), ("baryon treatment = sample\ntiling factor = 4, 4", 16),
+                                             ("", 24)], ids=["newton", "elliptic", "baryons_sampled", "ngrid24_not_power_of_two"])
+def test_shipped_settings_variants_from_reference_ics(gevb, ctx, ref, overrides, ngrid):
     """the shipped settings.ini with one line changed (Newtonian gravity; elliptic vector method, which adds the T0i deposit and
-    projectFTvector; baryons as their own species), initial conditions by the reference's generator, three cycles"""
-    rs = ref.sim_from_settings(16, 4, overrides=overrides)
+    projectFTvector; baryons as their own species; a lattice size that is not a power of two, where pos/dx is a true
+    division and bricks are partial), initial conditions by the reference's generator, three cycles"""
+    rs = ref.sim_from_settings(ngrid, ngrid // 4, overrides=overrides)
     N, nsp = rs.N, 1 + rs.baryon_flag
     st = rs.state()
     gs = gevb.Sim(ctx(N), rs.gr_flag, rs.vector_flag, rs.dsettings, rs.cosmo)
