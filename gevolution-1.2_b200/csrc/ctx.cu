@@ -59,6 +59,22 @@ extern "C" int gevb_tuning(const char * knob, int value)
 	GEVB_FAIL("gevb_tuning: unknown knob '%s'", knob);
 }
 
+// the slab decomposition by itself (pure host arithmetic, no device): rank r owns z-planes [z0, z0 + nzl) of real space
+// and, after a forward transform, ky-rows [ky0, ky0 + nkyl) of Fourier space
+extern "C" int gevb_slab_geometry(int ngrid, int rank, int nranks, int * z0, int * nz_local, int * ky0, int * nky_local)
+{
+	GEVB_CHECK_ARG(ngrid >= 4 && ngrid % 2 == 0, "gevb_slab_geometry: Ngrid must be even and >= 4 (got %d)", ngrid);
+	GEVB_CHECK_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "gevb_slab_geometry: bad rank %d of %d", rank, nranks);
+	GEVB_CHECK_ARG(ngrid % nranks == 0, "gevb_slab_geometry: Ngrid %d not divisible by %d ranks", ngrid, nranks);
+	GEVB_CHECK_ARG(nranks == 1 || ngrid / nranks >= 2, "gevb_slab_geometry: slabs must be at least 2 planes thick");
+	const int n = ngrid / nranks;
+	if (z0) *z0 = rank * n;
+	if (nz_local) *nz_local = n;
+	if (ky0) *ky0 = rank * n;
+	if (nky_local) *nky_local = n;
+	return 0;
+}
+
 extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank, int nranks, const void * nccl_id)
 {
 	GEVB_CHECK_ARG(out != NULL, "gevb_ctx_create: NULL output");
@@ -77,8 +93,7 @@ extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank,
 	memset(c, 0, sizeof(*c));
 	c->N = ngrid; c->nh = ngrid / 2 + 1;
 	c->device = device; c->rank = rank; c->nranks = nranks;
-	c->nzl = ngrid / nranks; c->z0 = rank * c->nzl;
-	c->nkyl = ngrid / nranks; c->ky0 = rank * c->nkyl;
+	GEVB_TRY(gevb_slab_geometry(ngrid, rank, nranks, &c->z0, &c->nzl, &c->ky0, &c->nkyl));
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
 	c->num_sms = prop.multiProcessorCount;

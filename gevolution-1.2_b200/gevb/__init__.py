@@ -26,7 +26,7 @@ FIELD_COMPS = {"phi": 1, "chi": 1, "Bi": 3, "source": 1, "Sij": 6, "scalarFT": 1
 
 # every symbol include/gevb.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "gevb_last_error", "gevb_version", "gevb_tuning", "gevb_nccl_unique_id", "gevb_ctx_create", "gevb_ctx_destroy", "gevb_ctx_sync",
+    "gevb_last_error", "gevb_version", "gevb_tuning", "gevb_nccl_unique_id", "gevb_ctx_create", "gevb_slab_geometry", "gevb_ctx_destroy", "gevb_ctx_sync",
     "gevb_ctx_geometry", "gevb_ctx_stream", "gevb_ctx_launch_count",
     "gevb_ctx_timing", "gevb_ctx_timing_read", "gevb_timing_num_classes", "gevb_timing_class_name", "gevb_parallel_sum", "gevb_parallel_max",
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
@@ -89,6 +89,7 @@ def _declare(L):
         "gevb_nccl_unique_id": [vp], "gevb_tuning": [C.c_char_p, i],
         "gevb_ctx_create": [C.POINTER(vp), i, i, i, i, vp],
         "gevb_ctx_destroy": [vp], "gevb_ctx_sync": [vp],
+        "gevb_slab_geometry": [i, i, i] + [C.POINTER(i)] * 4,
         "gevb_ctx_geometry": [vp] + [C.POINTER(i)] * 5,
         "gevb_ctx_timing": [vp, i], "gevb_ctx_timing_read": [vp, pd, C.POINTER(C.c_int64)],
         "gevb_parallel_sum": [vp, pd, i], "gevb_parallel_max": [vp, pd, i],
@@ -132,6 +133,13 @@ def writePowerSpectrum(kbin, power, kscatter, pscatter, occupation, rescalek, re
     occ = np.ascontiguousarray(occupation, dtype=np.int32)
     arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (kbin, power, kscatter, pscatter)]
     _ck(lib().gevb_writePowerSpectrum(*[_ptr(v) for v in arrs], _ptr(occ), len(occ), rescalek, rescalep, filename.encode(), description.encode(), a, z_target), "gevb_writePowerSpectrum")
+
+
+def slab_geometry(ngrid, rank, nranks):
+    """(z0, nz_local, ky0, nky_local) of `rank` -- host arithmetic only, no device"""
+    v = [C.c_int() for _ in range(4)]
+    _ck(lib().gevb_slab_geometry(ngrid, rank, nranks, *[C.byref(x) for x in v]), "gevb_slab_geometry")
+    return tuple(x.value for x in v)
 
 
 def tuning(knob, value):

@@ -72,6 +72,9 @@ int gevb_tuning(const char * knob, int value);
  * gevb_nccl_unique_id() on rank 0 and distributed by the host program.       */
 int gevb_nccl_unique_id(void * out128);
 int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank, int nranks, const void * nccl_id);
+/* the slab decomposition gevb_ctx_create uses, by itself (no device needed): z-planes of real space and ky-rows of
+ * Fourier space owned by `rank` */
+int gevb_slab_geometry(int ngrid, int rank, int nranks, int * z0, int * nz_local, int * ky0, int * nky_local);
 int gevb_ctx_destroy(gevb_ctx * ctx);
 int gevb_ctx_sync(gevb_ctx * ctx);                         /* cudaStreamSynchronize                */
 int gevb_ctx_geometry(gevb_ctx * ctx, int * ngrid, int * z0, int * nz_local, int * ky0, int * nky_local);
