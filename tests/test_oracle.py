@@ -244,3 +244,29 @@ def test_reference_gadget2_writer_runs(ref, tmp_path):
     assert struct.unpack_from("<I", raw, 0)[0] == 256 and struct.unpack_from("<6I", raw, 4)[1] == n
     assert struct.unpack_from("<I", raw, 264)[0] == 12 * n and struct.unpack_from("<I", raw, len(raw) - 4)[0] == 8 * n
     s.close()
+
+
+def test_restatement_on_reference_made_ics(ora, ref):
+    """the plain-C restatement against the compiled reference on physical initial conditions (the reference generator's
+    particles and metric fields for the shipped settings.ini), not only on the seeded synthetic inputs"""
+    s = ref.sim_from_settings(16, 4)
+    N, a = s.N, s.state()["a"]
+    ids, pos, vel = s.get_particles(0)
+    phi, chi, Bi = s.get_field("phi"), s.get_field("chi"), s.get_field("Bi")
+    mass = float(s.mass[0])
+    for name, args in (("projection_T00", (N, pos, vel, mass, a, phi[0])), ("projection_Tij", (N, pos, vel, mass, a, phi[0])), ("projection_T0i", (N, pos, vel, mass, phi[0]))):
+        assert common.rel_linf(getattr(ora, name)(*args), getattr(ref, name)(*args)) <= 1e-12, name
+    params = [a, a * a * N]
+    vo, mo = ora.updateVel(N, pos, vel, 0, 0.05, phi, chi, Bi, 3, params)
+    vr, mr = ref.updateVel(N, pos, vel, 0, 0.05, phi, chi, Bi, 3, params)
+    assert common.rel_linf(vo, vr) <= 1e-13 and abs(mo - mr) <= 1e-13 * mr
+    po = ora.moveParticles(N, pos, vr, 0, 0.07, phi, chi, Bi, 3, params)
+    pr = ref.moveParticles(N, pos, vr, 0, 0.07, phi, chi, Bi, 3, params)
+    assert np.abs(po - pr).max() <= 1e-15
+    T = ref.projection_Tij(N, pos, vel, mass, a, phi[0])
+    assert common.rel_linf(ora.prepareFTsource_tensor(phi[0], T, 0.3), ref.prepareFTsource_tensor(phi[0], T, 0.3)) <= 1e-13
+    SF = ref.fft_forward(ref.prepareFTsource_tensor(phi[0], T, 0.3))
+    assert common.rel_linf(ora.projectFTscalar(SF), ref.projectFTscalar(SF)) <= 1e-12
+    BF = s.get_field("BiFT")
+    assert common.rel_linf(ora.evolveFTvector(SF, BF, 0.02), ref.evolveFTvector(SF, BF, 0.02)) <= 1e-12
+    s.close()
