@@ -38,7 +38,7 @@ SYMBOLS = [
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTscalar_evolveFTvector", "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
-    "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
+    "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_sim_run", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
     "gevb_sim_set_fused", "gevb_sim_step",
 ]
@@ -123,6 +123,7 @@ def _declare(L):
         "gevb_sim_write_spectra": [vp, C.c_char_p, i, i, i, d],
         "gevb_sim_save_gadget2": [vp, i, C.c_char_p, i, d, d],
         "gevb_sim_hibernate": [vp, C.c_char_p], "gevb_sim_restore": [vp, C.c_char_p],
+        "gevb_sim_run": [vp, pd, i, i, i, C.c_char_p, pd, i, i, C.c_char_p, i, C.POINTER(i)],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -517,6 +518,14 @@ class Sim:
 
     def save_gadget2(self, species, filename, tracer_factor=1, dtau_pos=0.0, dtau_vel=0.0):
         _ck(lib().gevb_sim_save_gadget2(self.h, species, filename.encode(), tracer_factor, dtau_pos, dtau_vel), "gevb_sim_save_gadget2")
+
+    def run(self, z_pk, pk_mask, numbins, pk_prefix, z_snapshot, tracer_factor, snap_prefix, max_cycles=100000):
+        """the main loop with its outputs (gevb_sim_run); returns (cycles, spectra sets, snapshots)"""
+        zp, zpp = _darr(z_pk)
+        zs, zsp = _darr(z_snapshot)
+        out = (C.c_int * 3)()
+        _ck(lib().gevb_sim_run(self.h, zpp, len(zp), pk_mask, numbins, pk_prefix.encode(), zsp, len(zs), tracer_factor, snap_prefix.encode(), max_cycles, out), "gevb_sim_run")
+        return tuple(out)
 
     def hibernate(self, filebase):
         _ck(lib().gevb_sim_hibernate(self.h, filebase.encode()), "gevb_sim_hibernate")

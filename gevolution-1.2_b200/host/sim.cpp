@@ -214,7 +214,9 @@ extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
 	return 0;
 }
 
-static int sim_step(gevb_sim * s);
+static int sim_solve(gevb_sim * s);
+static int sim_update(gevb_sim * s);
+static int sim_step(gevb_sim * s) { int r = sim_solve(s); return r ? r : sim_update(s); }
 
 // ---- hibernation / restart (hibernation.hpp:38-611 writes, ic_read.hpp:58-400 reads) -----------------------------
 // The state set is the reference's: the particles of every species, phi, chi, the vector potential, and the scalars
@@ -407,7 +409,16 @@ extern "C" int gevb_sim_write_spectra(gevb_sim * s, const char * prefix, int pkc
 
 // snapshot of one species in Gadget-2 format (writeSnapshots, output.hpp:62-470 -> saveGadget2): the header is filled
 // as output.hpp:360-402 does (mass in 1e10 M_sun/h from the critical density, box in kpc/h)
+static int sim_save_gadget2(gevb_sim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel, double time, double redshift);
+
 extern "C" int gevb_sim_save_gadget2(gevb_sim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel)
+{
+	if (s == NULL) return 1;
+	return sim_save_gadget2(s, species, filename, tracer_factor, dtau_pos, dtau_vel, s->a, (1. / s->a) - 1.);      // stamped with the current scale factor (output.hpp:390-391)
+}
+
+// `time`: the scale factor the file is stamped with and the velocities are scaled by (the target of the half-step corrections)
+static int sim_save_gadget2(gevb_sim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel, double time, double redshift)
 {
 	if (s == NULL || filename == NULL) return 1;
 	gevb_pcls * p = gevb_sim_pcls(s, species);
@@ -419,7 +430,7 @@ extern "C" int gevb_sim_save_gadget2(gevb_sim * s, int species, const char * fil
 	hdr.num_files = 1;
 	hdr.Omega0 = s->cosmo.Omega_m; hdr.OmegaLambda = s->cosmo.Omega_Lambda; hdr.HubbleParam = s->cosmo.h;
 	hdr.BoxSize = s->boxsize / 0.001;                                                        // GADGET_LENGTH_CONVERSION, output.hpp:369
-	hdr.time = s->a; hdr.redshift = (1. / s->a) - 1.;
+	hdr.time = time; hdr.redshift = redshift;
 	int64_t n_local = 0;
 	gevb_pcls_count(p, &n_local);
 	double ntot = (double) n_local;
@@ -431,6 +442,60 @@ extern "C" int gevb_sim_save_gadget2(gevb_sim * s, int species, const char * fil
 	return gevb_pcls_saveGadget2(p, filename, &hdr, tracer_factor, dtau_pos, dtau_vel, s->phi.handle());
 }
 
+// the main loop with its snapshot and power-spectrum outputs (main.cpp:372-879; lightcones and HDF5 dumps are not built):
+// cycles run until every requested output is written (main.cpp:685-693) or max_cycles is reached.  Outputs sit between the
+// metric solve and the particle update, as in the reference:
+//   snapshot when 1/a < z_snapshot + 1 (:617-633): Gadget-2 file <snap_prefix><count %03d>_cdm (and _b), stamped with the
+//     target redshift and drifted / kicked to it (EXACT_OUTPUT_REDSHIFTS, output.hpp:384-388,409);
+//   spectra when 1/a < z_pk + 1 (:641-659), and once more one cycle before the target is passed (:661-679) so that
+//     writePowerSpectrum can interpolate to the exact redshift.
+extern "C" int gevb_sim_run(gevb_sim * s, const double * z_pk, int num_pk, int pk_mask, int numbins, const char * pk_prefix,
+                            const double * z_snapshot, int num_snapshot, int tracer_factor, const char * snap_prefix, int max_cycles, int * counts3)
+{
+	if (s == NULL || !s->pcls_cdm.initialized() || (num_pk > 0 && (z_pk == NULL || pk_prefix == NULL)) || (num_snapshot > 0 && (z_snapshot == NULL || snap_prefix == NULL))) return 1;
+	int pkcount = 0, snapcount = 0, cycles = 0;
+	try
+	{
+		while (cycles < max_cycles)
+		{
+			if (sim_solve(s) != 0) return 1;
+			const double a = s->a;
+			if (snapcount < num_snapshot && 1. / a < z_snapshot[snapcount] + 1.)                                     // main.cpp:617
+			{
+				const double time = 1. / (z_snapshot[snapcount] + 1.);                                               // output.hpp:386
+				const double dtau_pos = (time - a) / a / Hconf(a, s->fourpiG, s->cosmo);                             // output.hpp:388
+				char name[1024];
+				for (int sp = 0; sp < 2 + s->cosmo.num_ncdm; sp++)
+				{
+					Particles_gevolution & p = sp == 0 ? s->pcls_cdm : (sp == 1 ? s->pcls_b : s->pcls_ncdm[sp - 2]);
+					if (!p.initialized()) continue;
+					if (sp == 0) std::snprintf(name, sizeof(name), "%s%03d_cdm", snap_prefix, snapcount);
+					else if (sp == 1) std::snprintf(name, sizeof(name), "%s%03d_b", snap_prefix, snapcount);
+					else std::snprintf(name, sizeof(name), "%s%03d_ncdm%d", snap_prefix, snapcount, sp - 2);
+					if (sim_save_gadget2(s, sp, name, tracer_factor, dtau_pos, dtau_pos + 0.5 * s->dtau_old, time, z_snapshot[snapcount]) != 0) return 1;   // output.hpp:386-387,409,423,439
+				}
+				snapcount++;
+			}
+			if (pkcount < num_pk && 1. / a < z_pk[pkcount] + 1.)                                                     // main.cpp:641
+			{
+				if (write_spectra(s, pk_prefix, pkcount, numbins, pk_mask, z_pk[pkcount]) != 0) return 1;
+				pkcount++;
+			}
+			double tmp = a;                                                                                          // main.cpp:661-664
+			rungekutta4bg(tmp, s->fourpiG, s->cosmo, 0.5 * s->dtau);
+			rungekutta4bg(tmp, s->fourpiG, s->cosmo, 0.5 * s->dtau);
+			if (pkcount < num_pk && 1. / tmp < z_pk[pkcount] + 1.)                                                   // main.cpp:666
+				if (write_spectra(s, pk_prefix, pkcount, numbins, pk_mask, z_pk[pkcount]) != 0) return 1;
+			if (pkcount >= num_pk && snapcount >= num_snapshot) break;                                               // main.cpp:685-693: simulation complete
+			if (sim_update(s) != 0) return 1;
+			cycles++;
+		}
+	}
+	catch (const gevb_error &) { return 1; }
+	if (counts3) { counts3[0] = cycles; counts3[1] = pkcount; counts3[2] = snapcount; }
+	return 0;
+}
+
 // one cycle of the main loop (main.cpp:372-879 without outputs); errors come back as a status
 extern "C" int gevb_sim_step(gevb_sim * s)
 {
@@ -439,17 +504,17 @@ extern "C" int gevb_sim_step(gevb_sim * s)
 	catch (const gevb_error &) { return 1; }
 }
 
-static int sim_step(gevb_sim * s)
+// first half of a cycle: stress-energy projections and the metric solve (main.cpp:378-599); the outputs of the reference sit
+// between the two halves (main.cpp:605-679)
+static int sim_solve(gevb_sim * s)
 {
 	const double dx = s->dx, fourpiG = s->fourpiG;
 	cosmology & cosmo = s->cosmo;
-	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
+	double & a = s->a; double & dtau_old = s->dtau_old;
 	Field<Real> & phi = s->phi, & chi = s->chi, & source = s->source, & Sij = s->Sij, & Bi = s->Bi;
 	Field<Cplx> & scalarFT = s->scalarFT, & SijFT = s->SijFT, & BiFT = s->BiFT;
 	Particles_gevolution & pcls_cdm = s->pcls_cdm, & pcls_b = s->pcls_b;
 	Particles_gevolution * pcls_ncdm = s->pcls_ncdm;
-	Field<Real> * update_cdm_fields[3] = {&phi, &chi, &Bi};
-	Field<Real> ** update_ncdm_fields = update_cdm_fields;                                    // main.cpp:255-261: the same three fields
 	bool ncdm_T00[GEVB_MAX_NCDM], ncdm_Tij[GEVB_MAX_NCDM];                                    // which ncdm species deposit this cycle
 	for (int i = 0; i < GEVB_MAX_NCDM; i++)
 	{
@@ -457,7 +522,6 @@ static int sim_step(gevb_sim * s)
 		ncdm_T00[i] = have && a >= 1. / (s->z_switch_deltancdm[i] + 1.);                      // :390
 		ncdm_Tij[i] = have && a >= 1. / (s->z_switch_linearchi + 1.);                         // :442-447
 	}
-	double f_params[5];
 	const bool fuse = s->fused && s->gr_flag > 0;
 
 	// construct stress-energy tensor (main.cpp:378-450)
@@ -564,6 +628,23 @@ static int sim_step(gevb_sim * s)
 		s->plan_Bi.execute(FFT_BACKWARD);                                                     // :593
 		Bi.updateHalo();                                                                      // :598
 	}
+
+	return 0;
+}
+
+// second half of a cycle: particle updates, background, next time step (main.cpp:696-875)
+static int sim_update(gevb_sim * s)
+{
+	const double dx = s->dx, fourpiG = s->fourpiG;
+	cosmology & cosmo = s->cosmo;
+	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
+	Field<Real> & phi = s->phi, & chi = s->chi, & Bi = s->Bi;
+	Particles_gevolution & pcls_cdm = s->pcls_cdm, & pcls_b = s->pcls_b;
+	Particles_gevolution * pcls_ncdm = s->pcls_ncdm;
+	Field<Real> * update_cdm_fields[3] = {&phi, &chi, &Bi};
+	Field<Real> ** update_ncdm_fields = update_cdm_fields;                                    // main.cpp:255-261: the same three fields
+	double f_params[5];
+	const bool fuse = s->fused && s->gr_flag > 0;
 
 	// number of step subdivisions for the ncdm particle updates (main.cpp:696-701)
 	for (int i = 0; i < cosmo.num_ncdm; i++)

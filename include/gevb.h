@@ -249,6 +249,12 @@ int gevb_sim_save_gadget2(gevb_sim * sim, int species, const char * filename, in
  * restore needs a sim created with the same lattice, decomposition and flags.  Both are collective.            */
 int gevb_sim_hibernate(gevb_sim * sim, const char * filebase);
 int gevb_sim_restore(gevb_sim * sim, const char * filebase);
+/* the main loop with its power-spectrum and Gadget-2 snapshot outputs at the requested redshifts (main.cpp:372-879:
+ * output scheduling :617-679 with the EXACT_OUTPUT_REDSHIFTS logic, termination :685-693); files
+ * <pk_prefix><count %03d>_<phi|chi|hij|B>.dat and <snap_prefix><count %03d>_cdm (_b, _ncdm<i>).  Redshift lists in
+ * descending order as the parser leaves them.  counts3 (may be NULL) = cycles run, spectra sets, snapshots written. */
+int gevb_sim_run(gevb_sim * sim, const double * z_pk, int num_pk, int pk_mask, int numbins, const char * pk_prefix,
+                 const double * z_snapshot, int num_snapshot, int tracer_factor, const char * snap_prefix, int max_cycles, int * counts3);
 int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
 
 #ifdef __cplusplus

@@ -70,6 +70,7 @@ _SIGS = {
     "sim_create_from_settings": (_vp, [_i, _i, _i, C.c_char_p]),
     "sim_get_config": (None, [_vp, _dp, _dp, _i32p, _dp]),
     "sim_save_gadget2": (_i, [_vp, _i, C.c_char_p, _i, _d, _d]),
+    "sim_run": (_i, [_vp, _dp, _i, _i, _i, C.c_char_p, _dp, _i, _i, C.c_char_p, _i, _i32p]),
     "sim_set_ncdm": (None, [_vp, _i, _dp, _dp, _dp, _dp, _dp, _d, _d]),
     "sim_set_ncdm_maxvel": (None, [_vp, _dp]),
     "sim_get_ncdm_state": (None, [_vp, _dp, _i32p]),
@@ -314,6 +315,13 @@ class Sim:
         v, n = np.zeros(4), np.zeros(4, dtype=np.int32)
         self.o.fn["sim_get_ncdm_state"](self.h, v, n)
         return v, n
+
+    def run(self, z_pk, pk_mask, numbins, pk_prefix, z_snapshot, tracer_factor, snap_prefix, max_cycles=100000):
+        """the reference's main loop with its spectrum / Gadget-2 outputs at the requested redshifts (main.cpp:605-693)"""
+        zp, zs = np.ascontiguousarray(z_pk, dtype=np.float64), np.ascontiguousarray(z_snapshot, dtype=np.float64)
+        out = np.zeros(3, dtype=np.int32)
+        self.o.fn["sim_run"](self.h, zp, len(zp), pk_mask, numbins, pk_prefix.encode(), zs, len(zs), tracer_factor, snap_prefix.encode(), max_cycles, out)
+        return tuple(int(v) for v in out)
 
     def save_gadget2(self, species, filename, tracer_factor=1, dtau_pos=0.0, dtau_vel=0.0):
         """the reference's own saveGadget2 (Particles_gevolution.hpp:30-251)"""

@@ -592,16 +592,23 @@ void ref_sim_get_config(void * h, double * cosmo11, double * ds5, int * flags4, 
 
 // the reference's own Gadget-2 writer (Particles_gevolution.hpp:30-251) with the header of writeSnapshots
 // (output.hpp:360-402, restated: output.hpp itself needs HDF5)
+static void ref_save_gadget2_at(RefSim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel, double time, double redshift);
 int ref_sim_save_gadget2(void * h, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel)
 {
 	RefSim * s = (RefSim *) h;
+	ref_save_gadget2_at(s, species, filename, tracer_factor, dtau_pos, dtau_vel, s->a, (1. / s->a) - 1.);   // output.hpp:390-391
+	return 0;
+}
+
+static void ref_save_gadget2_at(RefSim * s, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel, double time, double redshift)
+{
 	Pcls & p = species == 0 ? s->pcls_cdm : (species == 1 ? s->pcls_b : s->pcls_ncdm[species - 2]);
 	gadget2_header hdr;
 	memset(&hdr, 0, sizeof(hdr));
 	hdr.num_files = 1;
 	hdr.Omega0 = s->cosmo.Omega_m; hdr.OmegaLambda = s->cosmo.Omega_Lambda; hdr.HubbleParam = s->cosmo.h;
 	hdr.BoxSize = s->boxsize / GADGET_LENGTH_CONVERSION;
-	hdr.time = s->a; hdr.redshift = (1. / s->a) - 1.;
+	hdr.time = time; hdr.redshift = redshift;
 	const long n = p.numParticles();
 	const long nsel = (n % tracer_factor) ? (1 + n / tracer_factor) : (n / tracer_factor);
 	hdr.npart[1] = (uint32_t) (nsel % (1ll << 32)); hdr.npartTotal[1] = hdr.npart[1]; hdr.npartTotalHW[1] = (uint32_t) (nsel / (1ll << 32));
@@ -610,7 +617,6 @@ int ref_sim_save_gadget2(void * h, int species, const char * filename, int trace
 	std::streambuf * quiet = std::cout.rdbuf(NULL);
 	p.saveGadget2(std::string(filename), hdr, tracer_factor, dtau_pos, dtau_vel, &s->phi);
 	std::cout.rdbuf(quiet);
-	return 0;
 }
 
 // ncdm species: cosmo.*_ncdm (metadata.hpp:284-288) and the switches (metadata.hpp:224-238)
@@ -721,14 +727,16 @@ void ref_sim_get_timers(void * h, double * out)
 }
 
 // one cycle of the main loop, outputs stripped (main.cpp:372-879)
-void ref_sim_step(void * h)
+static void ref_sim_solve(RefSim * s);
+static void ref_sim_update(RefSim * s);
+void ref_sim_step(void * h) { ref_sim_solve((RefSim *) h); ref_sim_update((RefSim *) h); }
+
+// first half of the cycle: projections and metric solve (main.cpp:378-599)
+static void ref_sim_solve(RefSim * s)
 {
-	RefSim * s = (RefSim *) h;
 	const double dx = s->dx, fourpiG = s->fourpiG;
 	cosmology & cosmo = s->cosmo;
-	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
-	Field<Real> * update_cdm_fields[3] = {&s->phi, &s->chi, &s->Bi};
-	double f_params[5];
+	double & a = s->a; double & dtau_old = s->dtau_old;
 	Site x(s->L->lat);
 	double t0 = now_s(), t1, t2;
 
@@ -830,6 +838,18 @@ void ref_sim_step(void * h)
 	}
 
 	t2 = now_s(); s->gravity_solver_time += t2 - t1;
+	s->cycle_time += now_s() - t0;
+}
+
+// second half of the cycle: particle updates, background, next time step (main.cpp:696-875)
+static void ref_sim_update(RefSim * s)
+{
+	const double dx = s->dx, fourpiG = s->fourpiG;
+	cosmology & cosmo = s->cosmo;
+	double & a = s->a; double & dtau = s->dtau; double & dtau_old = s->dtau_old;
+	Field<Real> * update_cdm_fields[3] = {&s->phi, &s->chi, &s->Bi};
+	double f_params[5];
+	double t0 = now_s(), t1, t2 = t0;
 
 	// main.cpp:696-701  step subdivisions for the ncdm updates
 	for (int i = 0; i < cosmo.num_ncdm; i++)
@@ -906,6 +926,91 @@ void ref_sim_step(void * h)
 	else dtau = s->steplimit / Hconf(a, fourpiG, cosmo);
 	s->cycle++;
 	s->cycle_time += now_s() - t0;
+}
+
+// ---- the main loop with its outputs (main.cpp:605-693), as far as they can be produced without HDF5 ---------------------
+// writeSpectra's phi / chi / hij / B branches (output.hpp:1945-1981,2151-2155; output.hpp itself needs HDF5, so the call
+// sequence is restated here around the reference's own extractPowerSpectrum and writePowerSpectrum)
+static void ref_write_spectra(RefSim * s, const char * prefix, int pkcount, int numbins, int mask, double z_target)
+{
+	const double a = s->a, fourpiG = s->fourpiG;
+	const Real numpts3d = (Real) s->N * (Real) s->N * (Real) s->N;
+	std::vector<Real> kbin(numbins), power(numbins), kscatter(numbins), pscatter(numbins);
+	std::vector<int> occupation(numbins);
+	char filename[1024];
+	if (mask & MASK_PHI)
+	{
+		s->plan_phi.execute(FFT_FORWARD);
+		extractPowerSpectrum(s->scalarFT, kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, false, KTYPE_LINEAR);
+		sprintf(filename, "%s%03d_phi.dat", prefix, pkcount);
+		writePowerSpectrum(kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, s->boxsize, (Real) numpts3d * (Real) numpts3d * 2. * M_PI * M_PI, filename, "power spectrum of phi", a, z_target);
+	}
+	if (mask & MASK_CHI)
+	{
+		s->plan_chi.execute(FFT_FORWARD);
+		extractPowerSpectrum(s->scalarFT, kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, false, KTYPE_LINEAR);
+		sprintf(filename, "%s%03d_chi.dat", prefix, pkcount);
+		writePowerSpectrum(kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, s->boxsize, (Real) numpts3d * (Real) numpts3d * 2. * M_PI * M_PI, filename, "power spectrum of chi", a, z_target);
+	}
+	if (mask & MASK_HIJ)
+	{
+		projection_init(&s->Sij);
+		projection_Tij_project(&s->pcls_cdm, &s->Sij, a, &s->phi);
+		if (s->baryon_flag) projection_Tij_project(&s->pcls_b, &s->Sij, a, &s->phi);
+		for (int i = 0; i < s->cosmo.num_ncdm; i++) if (s->have_ncdm[i]) projection_Tij_project(s->pcls_ncdm + i, &s->Sij, a, &s->phi);
+		projection_Tij_comm(&s->Sij);
+		prepareFTsource<Real>(s->phi, s->Sij, s->Sij, 2. * fourpiG / (double) s->N / (double) s->N / a);
+		s->plan_Sij.execute(FFT_FORWARD);
+		projectFTtensor(s->SijFT, s->SijFT);
+		extractPowerSpectrum(s->SijFT, kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, false, KTYPE_LINEAR);
+		sprintf(filename, "%s%03d_hij.dat", prefix, pkcount);
+		writePowerSpectrum(kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, s->boxsize, 2. * M_PI * M_PI, filename, "power spectrum of hij", a, z_target);
+	}
+	if (mask & MASK_B)
+	{
+		extractPowerSpectrum(s->BiFT, kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, false, KTYPE_LINEAR);
+		sprintf(filename, "%s%03d_B.dat", prefix, pkcount);
+		writePowerSpectrum(kbin.data(), power.data(), kscatter.data(), pscatter.data(), occupation.data(), numbins, s->boxsize, a * a * a * a * s->N * s->N * 2. * M_PI * M_PI, filename, "power spectrum of B", a, z_target);
+	}
+}
+
+int ref_sim_run(void * h, const double * z_pk, int num_pk, int pk_mask, int numbins, const char * pk_prefix,
+                const double * z_snapshot, int num_snapshot, int tracer_factor, const char * snap_prefix, int max_cycles, int * counts3)
+{
+	RefSim * s = (RefSim *) h;
+	int pkcount = 0, snapcount = 0, cycles = 0;
+	std::streambuf * quiet = std::cout.rdbuf(NULL);
+	while (cycles < max_cycles)
+	{
+		ref_sim_solve(s);
+		const double a = s->a;
+		if (snapcount < num_snapshot && 1. / a < z_snapshot[snapcount] + 1.)                     // main.cpp:617
+		{
+			const double time = 1. / (z_snapshot[snapcount] + 1.);                               // output.hpp:386
+			const double dtau_pos = (time - a) / a / Hconf(a, s->fourpiG, s->cosmo);             // output.hpp:388
+			char name[1024];
+			sprintf(name, "%s%03d_cdm", snap_prefix, snapcount);
+			ref_save_gadget2_at(s, 0, name, tracer_factor, dtau_pos, dtau_pos + 0.5 * s->dtau_old, time, z_snapshot[snapcount]);   // output.hpp:409
+			if (s->baryon_flag) { sprintf(name, "%s%03d_b", snap_prefix, snapcount); ref_save_gadget2_at(s, 1, name, tracer_factor, dtau_pos, dtau_pos + 0.5 * s->dtau_old, time, z_snapshot[snapcount]); }
+			snapcount++;
+		}
+		if (pkcount < num_pk && 1. / a < z_pk[pkcount] + 1.)                                     // main.cpp:641
+		{
+			ref_write_spectra(s, pk_prefix, pkcount, numbins, pk_mask, z_pk[pkcount]);
+			pkcount++;
+		}
+		double tmp = a;                                                                          // main.cpp:661-664
+		rungekutta4bg(tmp, s->fourpiG, s->cosmo, 0.5 * s->dtau);
+		rungekutta4bg(tmp, s->fourpiG, s->cosmo, 0.5 * s->dtau);
+		if (pkcount < num_pk && 1. / tmp < z_pk[pkcount] + 1.)                                   // main.cpp:666
+			ref_write_spectra(s, pk_prefix, pkcount, numbins, pk_mask, z_pk[pkcount]);
+		if (pkcount >= num_pk && snapcount >= num_snapshot) break;                               // main.cpp:685-693
+		ref_sim_update(s);
+		cycles++;
+	}
+	std::cout.rdbuf(quiet);
+	if (counts3) { counts3[0] = cycles; counts3[1] = pkcount; counts3[2] = snapcount; }
+	return 0;
 }
 
 } // extern "C"

@@ -650,3 +650,51 @@ def test_shipped_settings_variants_from_reference_ics(gevb, ctx, ref, overrides,
         bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= tol))}
         assert bad == {}, (step, e)
     rs.close(); gs.close()
+
+
+def test_shipped_run_to_z0_output_files(gevb, ctx, ref, tmp_path):
+    """the whole shipped run in small (settings.ini at Ngrid 16, reference-made initial conditions) from z = 100 to z = 0 through
+    gevb_sim_run and through the reference's loop, with the file's own output lists: every power-spectrum file (phi, chi, hij, B
+    at z = 50, 30, 10, 3, 1, 0) and every Gadget-2 snapshot (z = 30, 10, 3, 0) is compared -- the north-star 1e-5 criterion on
+    the spectra and the snapshots at z = 0, on the files a user would read"""
+    rs = ref.sim_from_settings(16, 4)
+    N = rs.N
+    ids, pos, vel = rs.get_particles(0)
+    st = rs.state()
+    gs = _gpu_sim_like(gevb, ctx(N), rs.cosmo, rs.dsettings, [N, rs.gr_flag, rs.vector_flag, rs.baryon_flag], rs.mass, ids, pos, vel,
+                       rs.get_field("phi"), rs.get_field("chi"), rs.get_field("Bi"), rs.get_field("BiFT"),
+                       [st["a"], st["tau"], st["dtau"], st["dtau_old"], st["cycle"], st["maxvel"][0], st["maxvel"][1]])
+    z_pk, z_snap, mask, numbins, tracer = [50., 30., 10., 3., 1., 0.], [30., 10., 3., 0.], 1 | 2 | 8 | 128, 16, 2
+    rdir, gdir = tmp_path / "ref", tmp_path / "gpu"
+    rdir.mkdir(); gdir.mkdir()
+    rc = rs.run(z_pk, mask, numbins, str(rdir / "pk"), z_snap, tracer, str(rdir / "snap"))
+    gc = gs.run(z_pk, mask, numbins, str(gdir / "pk"), z_snap, tracer, str(gdir / "snap"))
+    assert rc == gc and rc[1:] == (6, 4), (rc, gc)
+    worst = 0.0
+    for k in range(len(z_pk)):
+        for tag in ("phi", "chi", "hij", "B"):
+            lr = open(str(rdir / f"pk{k:03d}_{tag}.dat")).read().splitlines()
+            lg = open(str(gdir / f"pk{k:03d}_{tag}.dat")).read().splitlines()
+            assert lr[:3] == lg[:3] and len(lr) == len(lg), (k, tag)
+            a = np.array([[float(v) for v in ln.split()] for ln in lr[3:]])
+            b = np.array([[float(v) for v in ln.split()] for ln in lg[3:]])
+            assert np.array_equal(a[:, 4], b[:, 4]) and np.allclose(a[:, 0], b[:, 0], rtol=2e-6)
+            err = np.max(np.abs(b[:, 1] - a[:, 1]) / np.abs(a[:, 1]))
+            worst = max(worst, err)
+            assert err <= 1e-5, (k, tag, err)
+            assert np.allclose(a[:, 3], b[:, 3], rtol=1e-3, atol=1e-5 * np.abs(a[:, 1]).max())
+    for k, z in enumerate(z_snap):
+        hr, pr, vr, ir = _read_gadget2(str(rdir / f"snap{k:03d}_cdm"))
+        hg, pg, vg, ig = _read_gadget2(str(gdir / f"snap{k:03d}_cdm"))
+        assert hr["npart"] == hg["npart"] and hr["redshift"] == hg["redshift"] == z and hr["time"] == hg["time"] and hr["BoxSize"] == hg["BoxSize"]
+        orr, og = np.argsort(ir), np.argsort(ig)
+        assert np.array_equal(ir[orr], ig[og])
+        d = np.abs(pg[og] - pr[orr])
+        d = np.minimum(d, hr["BoxSize"] - d)                                     # a particle may sit on either side of the periodic boundary
+        assert d.max() <= 1e-5 * hr["BoxSize"] * (1 + k), (k, d.max())
+        assert np.abs(vg[og] - vr[orr]).max() <= 1e-4 * np.abs(vr).max(), k
+        # snapshot statistics (north star: 1e-5): rms velocity, extent of the displacements from the lattice
+        sr, sg = np.sqrt((vr.astype(np.float64) ** 2).mean()), np.sqrt((vg.astype(np.float64) ** 2).mean())
+        assert abs(sg - sr) <= 1e-5 * sr
+    print("shipped run: cycles", rc[0], "worst spectrum rel err", worst)
+    rs.close(); gs.close()

@@ -270,3 +270,22 @@ def test_restatement_on_reference_made_ics(ora, ref):
     BF = s.get_field("BiFT")
     assert common.rel_linf(ora.evolveFTvector(SF, BF, 0.02), ref.evolveFTvector(SF, BF, 0.02)) <= 1e-12
     s.close()
+
+
+def test_reference_run_with_outputs(ref, tmp_path):
+    """the shipped settings.ini at Ngrid 16 to z = 0 with its own output lists (Pk at z = 50, 30, 10, 3, 1, 0; snapshots at
+    z = 30, 10, 3, 0): every file appears, stamped with the exact target redshift (EXACT_OUTPUT_REDSHIFTS)"""
+    s = ref.sim_from_settings(16, 4)
+    z_pk, z_snap = [50., 30., 10., 3., 1., 0.], [30., 10., 3., 0.]
+    cycles, npk, nsnap = s.run(z_pk, 1 | 2 | 8 | 128, 16, str(tmp_path / "pk"), z_snap, 2, str(tmp_path / "snap"))
+    assert (npk, nsnap) == (6, 4) and 40 < cycles < 400 and s.state()["a"] >= 1.0
+    for k, z in enumerate(z_pk):
+        for tag in ("phi", "chi", "hij", "B"):
+            lines = open(str(tmp_path / f"pk{k:03d}_{tag}.dat")).read().splitlines()
+            assert lines[0] == f"# power spectrum of {tag}" and lines[1] == "# redshift z=%f" % z and len(lines) > 8
+    import struct
+    for k, z in enumerate(z_snap):
+        raw = open(str(tmp_path / f"snap{k:03d}_cdm"), "rb").read()
+        time, redshift = struct.unpack_from("<2d", raw, 4 + 24 + 48)
+        assert redshift == z and abs(time - 1. / (1. + z)) < 1e-15 and struct.unpack_from("<6I", raw, 4)[1] == 2048
+    s.close()
