@@ -34,8 +34,8 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
-static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed"};
-static int tune_values[GEVB_NTUNE] = {6, 1, 1, 1};
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused"};
+static int tune_values[GEVB_NTUNE] = {6, 1, 1, 1, 0, 0, 0, 1};
 static bool tune_env_read = false;
 static void tune_read_env()
 {
@@ -413,5 +413,46 @@ extern "C" int gevb_field_add_constant(gevb_field * f, int comp, double value)
 	const size_t n = (size_t) c->nzl * c->plane();
 	k_add_constant<<<gevb_grid(c, n, 256), 256, 0, c->stream>>>(f->data + comp * f->comp_stride + c->plane(), n, value);
 	KERNEL_CHECK(c);
+	return 0;
+}
+
+__global__ void k_scale(double * __restrict__ v, size_t n, double factor)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) v[i] *= factor;
+}
+
+// the site loops that rescale the stored vector potential around an output (output.hpp:212-218, hibernation.hpp:533-538,
+// ic_read.hpp:312-317): every component of the local bulk times `factor`; the ghost planes are left to updateHalo
+extern "C" int gevb_field_scale(gevb_field * f, double factor)
+{
+	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL, "gevb_field_scale: needs a real field");
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t n = (size_t) c->nzl * c->plane();
+	for (int k = 0; k < f->ncomp; k++)
+	{
+		k_scale<<<gevb_grid(c, n, 256), 256, 0, c->stream>>>(f->data + k * f->comp_stride + c->plane(), n, factor);
+		KERNEL_CHECK(c);
+	}
+	return 0;
+}
+
+extern "C" gevb_ctx * gevb_field_ctx(gevb_field * f) { return f ? f->ctx : NULL; }
+
+// individual sites of one component (the IC generator's convolution kernel lives on 27 sites, ic_basic.hpp:737-1052)
+extern "C" int gevb_field_set_sites(gevb_field * f, int comp, int n, const int * xyz, const double * values)
+{
+	GEVB_CHECK_ARG(f != NULL && f->kind == GEVB_REAL && n >= 0 && (n == 0 || (xyz != NULL && values != NULL)), "gevb_field_set_sites: bad arguments");
+	GEVB_CHECK_ARG(comp >= 0 && comp < f->ncomp, "gevb_field_set_sites: component %d out of range", comp);
+	gevb_ctx * c = f->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	for (int i = 0; i < n; i++)
+	{
+		const int x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+		GEVB_CHECK_ARG(x >= 0 && x < c->N && y >= 0 && y < c->N && z >= 0 && z < c->N, "gevb_field_set_sites: site (%d, %d, %d) outside the lattice", x, y, z);
+		if (z < c->z0 || z >= c->z0 + c->nzl) continue;
+		CUDA_TRY(cudaMemcpyAsync(f->data + comp * f->comp_stride + ((size_t) (z - c->z0 + 1) * c->N + y) * c->N + x, values + i, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return 0;
 }

@@ -185,11 +185,12 @@ __host__ __device__ constexpr int phase_comp(int what, int K, int j)
 }
 
 // contributions of one particle to corner K of its cell, in the order of phase_comp()
-template <int WHAT, bool HAS_PHI, int K>
+// ph: the phi tile at the particle's cell (corner k at ph[corner_offset(k)]), or, with CORNERS, the eight corner values themselves
+template <int WHAT, bool HAS_PHI, int K, bool CORNERS = false>
 __device__ __forceinline__ void phase_values(const PInv & I, const double * ph, double * v)
 {
 	constexpr int X = (K >> 2) & 1, Y = (K >> 1) & 1, Z = K & 1;
-	#define PHI(k) (HAS_PHI ? ph[corner_offset(k)] : 0.)
+	#define PHI(k) (HAS_PHI ? ph[CORNERS ? (k) : corner_offset(k)] : 0.)
 	int n = 0;
 	if (WHAT == DEP_T0I)
 	{
@@ -390,6 +391,308 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 	}
 }
 
+// =====================================================================================================================
+// k_deposit_cells (tuning knob deposit_variant = 1, the default): the same projections without corner phases.
+//
+// The old kernel above updates a tile of lattice SITES, so two particles of neighbouring cells can meet on a site and
+// every batch needs eight barrier-separated corner phases plus shared-memory CAS loops for cells split between warps
+// (profiles/r1k: 4.7 barrier stalls per issue, 704 ATOMS.CAST.SPIN sites).  Here a block accumulates per CELL: every cell
+// of the unit (half a brick: 16 x 8 x 2 cells) owns NACC private accumulators in shared memory, one per (corner,
+// component) pair it deposits to -- the reference's localCube / localEdge arrays (gevolution.hpp:953,1075,1199-1200)
+// kept for all cells of the unit at once.  Particles of different cells never touch the same word, so the accumulation
+// needs no barrier and no atomic:
+//
+//   accumulate  each warp owns a contiguous slice of the unit's (cell-sorted) particles, one particle per lane per step.
+//               Lanes that share a cell are neighbours: a segmented shuffle sum (only in warps that hold such lanes)
+//               leaves the cell's contribution in the first lane of the segment, which adds it to the cell's
+//               accumulators with a plain read-add-write.  A cell cut by the boundary between two warps' slices is
+//               accumulated in a private column of the warp (one "head" and one "tail" column per warp) instead.
+//   gather      one thread per tile site sums the up to eight cells around it, clears what it read, and issues one FP64
+//               reduction (RED.ADD.F64) per component into the field in HBM; the at most 16 head / tail columns are
+//               reduced into HBM directly, value by value.
+//
+// Two barriers per unit (about 256 particles at one particle per cell) instead of eight per batch of 256 particles, and
+// they separate phases of the whole unit, not corner phases of a batch.
+#define UZ 2                                           // z-layers of a unit
+#define UCELLS (GEVB_BX * GEVB_BY * UZ)                // 256 cells
+#define UT_SITES (DX * DY * (UZ + 1))                  // 459 tile sites (upper apron included)
+#define DEP_WARPS (DEP_THREADS / 32)
+#define ACC_COLS (UCELLS + 2 * DEP_WARPS)              // one column per cell + head / tail column per warp; 272 = 17 x 16: column c lives in bank pair c % 16
+#define UCELLTAB (UCELLS + 4)                          // 257 prefix sums, padded
+#define USTAGE_DOUBLES (UT_SITES + 1 + UCELLTAB / 2)   // one pipeline stage: phi tile, cell table
+
+__host__ __device__ constexpr int dep_nacc(int what) { int n = 0; for (int K = 0; K < 8; K++) n += phase_comp(what, K, -1); return n; }
+// accumulator of the j-th contribution of corner K: they are numbered corner by corner
+__host__ __device__ constexpr int acc_index(int what, int K, int j) { int n = 0; for (int k = 0; k < K; k++) n += phase_comp(what, k, -1); return n + j; }
+
+struct CWriter
+{
+	double * col;                  // acc + column of the particle's cell (or of the warp's head / tail column)
+	int after;                     // lanes after this one in the same cell (within the warp step)
+	bool write;                    // first lane of its cell's segment
+};
+
+template <int WHAT, bool HAS_PHI, int K, int STEPS>
+__device__ __forceinline__ void cell_corner(const PInv & I, const CWriter & W, const double * ph)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	if (NV == 0) return;
+	double v[NV > 0 ? NV : 1];
+	phase_values<WHAT, HAS_PHI, K, true>(I, ph, v);
+	#pragma unroll
+	for (int s = 0; s < STEPS; s++)
+	{
+		#pragma unroll
+		for (int j = 0; j < NV; j++)
+		{
+			const double t = __shfl_down_sync(0xffffffffu, v[j], 1 << s);
+			if ((1 << s) <= W.after) v[j] += t;
+		}
+	}
+	if (W.write)
+	{
+		double * p = W.col + acc_index(WHAT, K, 0) * ACC_COLS;
+		#pragma unroll
+		for (int j = 0; j < NV; j++) p[j * ACC_COLS] += v[j];
+	}
+}
+
+template <int WHAT, bool HAS_PHI, int STEPS>
+__device__ __forceinline__ void cell_corners(const PInv & I, const CWriter & W, const double * ph)
+{
+	cell_corner<WHAT, HAS_PHI, 0, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 1, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 2, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 3, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 4, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 5, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 6, STEPS>(I, W, ph);
+	cell_corner<WHAT, HAS_PHI, 7, STEPS>(I, W, ph);
+}
+
+// what the cell at (sx - X, sy - Y, sz - Z) deposited on corner K = 4X + 2Y + Z, i.e. on site (sx, sy, sz); read and cleared
+template <int WHAT, int K>
+__device__ __forceinline__ void gather_corner(double * acc, int sx, int sy, int sz, double * sum)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	if (NV == 0) return;
+	const int cx = sx - ((K >> 2) & 1), cy = sy - ((K >> 1) & 1), cz = sz - (K & 1);
+	if ((unsigned) cx >= GEVB_BX || (unsigned) cy >= GEVB_BY || (unsigned) cz >= UZ) return;
+	double * p = acc + acc_index(WHAT, K, 0) * ACC_COLS + ((cz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (cy << GEVB_BX_BITS) | cx);
+	#pragma unroll
+	for (int j = 0; j < NV; j++)
+	{
+		sum[phase_comp(WHAT, K, j)] += p[j * ACC_COLS];
+		p[j * ACC_COLS] = 0.;
+	}
+}
+
+// corner and target component of accumulator a (all comparisons are against compile-time constants)
+template <int WHAT>
+__device__ __forceinline__ void acc_target(int a, int & corner, int & comp)
+{
+	corner = 0; comp = 0;
+	#pragma unroll
+	for (int K = 0; K < 8; K++)
+	{
+		#pragma unroll
+		for (int j = 0; j < phase_comp(WHAT, K, -1); j++)
+			if (a == acc_index(WHAT, K, j)) { corner = K; comp = phase_comp(WHAT, K, j); }
+	}
+}
+
+// particle range of unit u = (brick, half)
+__device__ __forceinline__ void unit_range(const DParams & D, uint32_t u, uint32_t & first, uint32_t & last)
+{
+	first = last = 0;
+	if (u < 2 * D.G.nbricks) { first = __ldg(D.cell_start + (size_t) u * UCELLS); last = __ldg(D.cell_start + (size_t) (u + 1) * UCELLS); }
+}
+
+// slice of the unit's particles that warp w works on: equal shares, a multiple of the warp size
+__device__ __forceinline__ void warp_slice(uint32_t first, uint32_t last, int w, uint32_t & wlo, uint32_t & whi)
+{
+	const uint32_t m = (((last - first + DEP_WARPS - 1) / DEP_WARPS) + 31u) & ~31u;
+	wlo = first + (uint32_t) w * m; wlo = wlo < last ? wlo : last;
+	whi = wlo + m; whi = whi < last ? whi : last;
+}
+
+template <bool HAS_PHI>
+__device__ __forceinline__ void stage_unit(const DParams & D, uint32_t unit, uint32_t first, uint32_t last, double * stage)
+{
+	const BrickGeom & G = D.G;
+	double * tphi = stage;
+	uint32_t * ctab = (uint32_t *) (stage + UT_SITES + 1);
+	if (first == last) return;
+	const uint32_t * src = D.cell_start + (size_t) unit * UCELLS;
+	for (int k = threadIdx.x; k <= UCELLS; k += DEP_THREADS) cp_async4(ctab + k, src + k);
+	if (HAS_PHI && threadIdx.x < DX * DY)
+	{
+		int x0, y0, zl0;
+		brick_origin(G, unit >> 1, x0, y0, zl0);
+		zl0 += (int) (unit & 1) * UZ;
+		const int tx = threadIdx.x % DX, ty = threadIdx.x / DX;
+		const size_t gcol = (size_t) wrap_up(y0 + ty, G.N) * G.N + wrap_up(x0 + tx, G.N);
+		#pragma unroll
+		for (int tz = 0; tz <= UZ; tz++)
+		{
+			const int plane = zl0 + tz + 1;
+			if (plane > G.nzl + 1) break;                       // past the top of the slab: never read
+			cp_async8(tphi + (tz * DY + ty) * DX + tx, D.phi + (size_t) plane * G.N * G.N + gcol);
+		}
+	}
+}
+
+template <int WHAT, bool HAS_PHI>
+__global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit_cells(DParams D)
+{
+	constexpr int NCOMP = dep_ncomp(WHAT), NACC = dep_nacc(WHAT);
+	extern __shared__ double smem[];
+	double * acc = smem;                                    // [NACC][ACC_COLS]
+	double * stages = smem + NACC * ACC_COLS;               // [2][USTAGE_DOUBLES]
+	int * slotcell = (int *) (stages + 2 * USTAGE_DOUBLES); // [2 * DEP_WARPS] cell of each head / tail column in use, else -1
+
+	const BrickGeom & G = D.G;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int idx = threadIdx.x; idx < NACC * ACC_COLS + 2 * USTAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
+	if (threadIdx.x < 2 * DEP_WARPS) slotcell[threadIdx.x] = -1;
+	__syncthreads();
+	const uint32_t nunits = 2 * G.nbricks;
+	uint32_t unit = blockIdx.x;
+	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
+	unit_range(D, unit, first, last);
+	unit_range(D, unit + gridDim.x, nfirst, nlast);
+	stage_unit<HAS_PHI>(D, unit, first, last, stages);
+	cp_async_commit();
+	double pv[6] = {0., 0., 0., 0., 0., 0.};
+	{
+		uint32_t wlo, whi;
+		warp_slice(first, last, w, wlo, whi);
+		if (wlo + lane < whi) load_particle(D, wlo + lane, pv);
+	}
+	int cur = 0;
+	while (unit < nunits)
+	{
+		const uint32_t nunit = unit + gridDim.x;
+		unit_range(D, nunit + gridDim.x, nnfirst, nnlast);                   // consumed at the end of this iteration
+		if (nunit < nunits) stage_unit<HAS_PHI>(D, nunit, nfirst, nlast, stages + (cur ^ 1) * USTAGE_DOUBLES);
+		cp_async_commit();
+		uint32_t nwlo, nwhi;                                                 // this warp's slice of the next unit
+		warp_slice(nfirst, nlast, w, nwlo, nwhi);
+		if (first != last)                                                   // block-uniform
+		{
+			int x0, y0, zl0;
+			brick_origin(G, unit >> 1, x0, y0, zl0);
+			zl0 += (int) (unit & 1) * UZ;
+			cp_async_wait<1>();                             // everything but the newest group: this unit's stage has landed
+			__syncthreads();                                // ... for all threads; also: the previous unit's gather has cleared acc
+			const double * tphi = stages + cur * USTAGE_DOUBLES;
+			const uint32_t * ctab = (const uint32_t *) (tphi + UT_SITES + 1);
+			uint32_t wlo, whi;
+			warp_slice(first, last, w, wlo, whi);
+			if (lane < 2) slotcell[2 * w + lane] = -1;      // only this warp writes its two entries
+			__syncwarp();
+
+			// ---- accumulate: no barrier in here
+			for (uint32_t base = wlo; base < whi; base += 32)
+			{
+				const uint32_t i = base + lane;
+				const bool valid = i < whi;
+				PInv I;
+				CWriter W;
+				double phc[8];                              // phi at the eight corners of the particle's cell (index 4X + 2Y + Z)
+				int steps;
+				{
+					int cx = 0, cy = 0, cz = 0, site = 0, cu = 0;
+					uint32_t cfirst = i, clast = i + 1;
+					if (valid)
+					{
+						cx = cell_scaled(D, pv[0]); cy = cell_scaled(D, pv[1]); cz = cell_scaled(D, pv[2]);
+						// the particle lies in this unit (the storage order is maintained by the re-bin); the masks only keep a broken order memory-safe
+						const int sx = (cx - x0) & (GEVB_BX - 1), sy = (cy - y0) & (GEVB_BY - 1), sz = (cz - G.z0 - zl0) & (UZ - 1);
+						site = (sz * DY + sy) * DX + sx;
+						cu = (sz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (sy << GEVB_BX_BITS) | sx;
+						cfirst = ctab[cu]; clast = ctab[cu + 1];
+					}
+					if (HAS_PHI)
+					{
+						#pragma unroll
+						for (int k = 0; k < 8; k++) phc[k] = tphi[site + corner_offset(k)];
+					}
+					particle_factors<WHAT, HAS_PHI>(I, D, pv, cx, cy, cz);
+					// lanes of this step that share the cell form a contiguous segment [seg_lo, seg_hi)
+					const uint32_t step_hi = base + 32 < whi ? base + 32 : whi;
+					const uint32_t seg_lo = cfirst > base ? cfirst : base, seg_hi = clast < step_hi ? clast : step_hi;
+					const int maxlen = __reduce_max_sync(0xffffffffu, valid ? (int) (seg_hi - seg_lo) : 0);
+					steps = maxlen > 1 ? 32 - __clz(maxlen - 1) : 0;
+					W.after = valid ? (int) (seg_hi - 1 - i) : 0;
+					W.write = valid && i == seg_lo;
+					// a cell that reaches out of this warp's slice is accumulated in the warp's head (it began before the slice) or
+					// tail column; everything else belongs to this warp alone
+					int col = cu;
+					if (cfirst < wlo) col = UCELLS + 2 * w; else if (clast > whi) col = UCELLS + 2 * w + 1;
+					if (W.write && col >= UCELLS) slotcell[col - UCELLS] = cu;
+					W.col = acc + col;
+				}
+				// request the next step's particle (of this slice, else of this warp's slice of the next unit) while this one is processed
+				{
+					const uint32_t nb = base + 32;
+					const uint32_t j = nb < whi ? nb + lane : nwlo + lane;
+					if (j < (nb < whi ? whi : nwhi)) load_particle(D, j, pv);
+				}
+				// shuffle steps of the segmented sum are warp-uniform: 0 when no two lanes of the step share a cell
+				if (steps == 0) cell_corners<WHAT, HAS_PHI, 0>(I, W, phc);
+				else if (steps == 1) cell_corners<WHAT, HAS_PHI, 1>(I, W, phc);
+				else if (steps == 2) cell_corners<WHAT, HAS_PHI, 2>(I, W, phc);
+				else cell_corners<WHAT, HAS_PHI, 5>(I, W, phc);
+				__syncwarp();                               // the next step of this warp may add to the same cell
+			}
+			if (wlo >= whi && nwlo + lane < nwhi) load_particle(D, nwlo + lane, pv);   // idle warp: nothing was prefetched
+			__syncthreads();
+
+			// ---- gather + flush: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row; acc is left zeroed
+			for (int s = threadIdx.x; s < UT_SITES; s += DEP_THREADS)
+			{
+				const int sz = s / (DX * DY), r = s - sz * (DX * DY), sy = r / DX, sx = r - sy * DX;
+				double sum[NCOMP];
+				#pragma unroll
+				for (int k = 0; k < NCOMP; k++) sum[k] = 0.;
+				gather_corner<WHAT, 0>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 1>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 2>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 3>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 4>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 5>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 6>(acc, sx, sy, sz, sum);
+				gather_corner<WHAT, 7>(acc, sx, sy, sz, sum);
+				const size_t off = (size_t) (zl0 + sz + 1) * G.N * G.N + (size_t) wrap_up(y0 + sy, G.N) * G.N + wrap_up(x0 + sx, G.N);
+				#pragma unroll
+				for (int k = 0; k < NCOMP; k++)
+					if (sum[k] != 0.) atomicAdd(D.out[k] + off, sum[k]);
+			}
+			// the head / tail columns in use go to HBM value by value: accumulator a of the column's cell belongs to the site at
+			// that cell + its corner offset
+			for (int t = threadIdx.x; t < 2 * DEP_WARPS * NACC; t += DEP_THREADS)
+			{
+				const int slot = t / NACC, a = t - slot * NACC;
+				const int c = slotcell[slot];
+				if (c < 0) continue;
+				double * p = acc + a * ACC_COLS + UCELLS + slot;
+				const double v = *p;
+				*p = 0.;
+				if (v == 0.) continue;
+				int K, comp;
+				acc_target<WHAT>(a, K, comp);
+				const int sx = (c & (GEVB_BX - 1)) + ((K >> 2) & 1), sy = ((c >> GEVB_BX_BITS) & (GEVB_BY - 1)) + ((K >> 1) & 1), sz = (c >> (GEVB_BX_BITS + GEVB_BY_BITS)) + (K & 1);
+				const size_t off = (size_t) (zl0 + sz + 1) * G.N * G.N + (size_t) wrap_up(y0 + sy, G.N) * G.N + wrap_up(x0 + sx, G.N);
+				atomicAdd(D.out[comp] + off, v);
+			}
+		}
+		else if (nwlo + lane < nwhi) load_particle(D, nwlo + lane, pv);      // empty unit: nothing was prefetched
+		unit = nunit; cur ^= 1;
+		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
+	}
+}
+
 int check_real(const gevb_field * f, int ncomp, const char * who, const char * name)
 {
 	GEVB_CHECK_ARG(f != NULL, "%s: %s is NULL", who, name);
@@ -411,6 +714,25 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 	D.x = p->x[b]; D.y = p->y[b]; D.z = p->z[b]; D.qx = p->qx[b]; D.qy = p->qy[b]; D.qz = p->qz[b];
 	D.phi = phi ? phi->data : NULL;
 	for (int k = 0; k < 7; k++) D.out[k] = k < dep_ncomp(WHAT) ? out[k] : NULL;
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) != 0)
+	{
+		// per-cell accumulators (k_deposit_cells): two blocks per SM, one unit (half a brick) at a time
+		const size_t smem = ((size_t) dep_nacc(WHAT) * ACC_COLS + 2 * USTAGE_DOUBLES) * sizeof(double) + 2 * DEP_WARPS * sizeof(int);
+		const uint32_t persistent = (uint32_t) c->num_sms * 2, nunits = 2 * D.G.nbricks;
+		const uint32_t grid = nunits < persistent ? nunits : persistent;
+		if (phi)
+		{
+			CUDA_TRY(cudaFuncSetAttribute(k_deposit_cells<WHAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_deposit_cells<WHAT, true><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+		}
+		else
+		{
+			CUDA_TRY(cudaFuncSetAttribute(k_deposit_cells<WHAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_deposit_cells<WHAT, false><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+		}
+		KERNEL_CHECK(c);
+		return 0;
+	}
 	const size_t smem = ((size_t) dep_ncomp(WHAT) * DT_SITES + 2 * DEP_STAGE_DOUBLES) * sizeof(double);
 	const uint32_t persistent = (uint32_t) c->num_sms * 3;
 	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;

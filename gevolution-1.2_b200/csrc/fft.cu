@@ -254,6 +254,26 @@ void gevb_xchg_release(gevb_ctx * c)
 	if (c->xchg_state == 1) c->xchg_state = 0;
 }
 
+// tuning knob fft_l2_planes = L > 0 (single rank): the 2-D transforms run L planes at a time, so that cuFFT's x-pass and
+// y-pass of a chunk follow each other while the chunk (L N^2 reals in, L N nh complex out) is still in the 126 MB L2 and
+// the intermediate never travels to HBM; 0: all planes in one batched call (two HBM passes).  Returns the chunk in use.
+static int chunked_planes(gevb_plan * p)
+{
+	const int L = gevb_tune(TUNE_FFT_L2_PLANES);
+	const int N = p->ctx->N, nh = p->ctx->nh;
+	if (L <= 0 || L >= N || N % L != 0) return 0;
+	if (p->chunk_planes != L)
+	{
+		if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); p->chunk_planes = 0; }
+		int n2[2] = {N, N}, r2[2] = {N, N}, k2[2] = {N, nh};
+		if (cufftPlanMany(&p->f2d_c, 2, n2, r2, 1, N * N, k2, 1, N * nh, CUFFT_D2Z, L) != CUFFT_SUCCESS) return 0;
+		if (cufftPlanMany(&p->b2d_c, 2, n2, k2, 1, N * nh, r2, 1, N * N, CUFFT_Z2D, L) != CUFFT_SUCCESS) { cufftDestroy(p->f2d_c); return 0; }
+		cufftSetStream(p->f2d_c, p->ctx->stream); cufftSetStream(p->b2d_c, p->ctx->stream);
+		p->chunk_planes = L;
+	}
+	return L;
+}
+
 extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * cf)
 {
 	GEVB_CHECK_ARG(out != NULL && rf != NULL && cf != NULL, "gevb_plan_create: NULL argument");
@@ -313,7 +333,7 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	if (p == NULL) return 0;
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
-	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); }
+	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); } }
 	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); }
 	delete p;
 	return 0;
@@ -344,13 +364,17 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		if (direction == GEVB_FFT_FORWARD)
 		{
 			if (!decomposed) { CUFFT_TRY(cufftExecD2Z(p->fwd, rbulk, (cufftDoubleComplex *) cf->data)); c->launches++; return 0; }
+			const int L = chunked_planes(p);
 			for (int k = 0; k < nc; k++)
 			{
 				cufftDoubleComplex * out = (cufftDoubleComplex *) cf->data + k * cf->comp_stride;
-				CUFFT_TRY(cufftExecD2Z(p->f2d, rbulk + k * rf->comp_stride, out));
+				if (L == 0) CUFFT_TRY(cufftExecD2Z(p->f2d, rbulk + k * rf->comp_stride, out));
+				else
+					for (int z = 0; z < N; z += L)          // x-pass and y-pass of L planes back to back: the intermediate stays in L2
+						CUFFT_TRY(cufftExecD2Z(p->f2d_c, rbulk + k * rf->comp_stride + (size_t) z * N * N, out + (size_t) z * N * nh));
 				CUFFT_TRY(cufftExecZ2Z(p->bz1d, out, out, CUFFT_FORWARD));
 			}
-			c->launches += 2 * nc;
+			c->launches += (L ? N / L + 1 : 2) * nc;
 		}
 		else
 		{
@@ -358,25 +382,33 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 			{
 				// the Fourier field is scratch for the caller
 				if (!decomposed) { CUFFT_TRY(cufftExecZ2D(p->bwd, (cufftDoubleComplex *) cf->data, rbulk)); c->launches++; return 0; }
+				const int L = chunked_planes(p);
 				for (int k = 0; k < nc; k++)
 				{
 					cufftDoubleComplex * in = (cufftDoubleComplex *) cf->data + k * cf->comp_stride;
 					CUFFT_TRY(cufftExecZ2Z(p->bz1d, in, in, CUFFT_INVERSE));
-					CUFFT_TRY(cufftExecZ2D(p->b2d, in, rbulk + k * rf->comp_stride));
+					if (L == 0) CUFFT_TRY(cufftExecZ2D(p->b2d, in, rbulk + k * rf->comp_stride));
+					else
+						for (int z = 0; z < N; z += L)
+							CUFFT_TRY(cufftExecZ2D(p->b2d_c, in + (size_t) z * N * nh, rbulk + k * rf->comp_stride + (size_t) z * N * N));
 				}
-				c->launches += 2 * nc;
+				c->launches += (L ? N / L + 1 : 2) * nc;
 			}
 			else
 			{
 				void * stage;
 				GEVB_TRY(gevb_ctx_scratch2(c, cf->bytes, &stage));
+				const int L = chunked_planes(p);
 				for (int k = 0; k < nc; k++)
 				{
 					cufftDoubleComplex * in = (cufftDoubleComplex *) cf->data + k * cf->comp_stride, * tmp = (cufftDoubleComplex *) stage + k * cf->comp_stride;
 					CUFFT_TRY(cufftExecZ2Z(p->bz1d, in, tmp, CUFFT_INVERSE));
-					CUFFT_TRY(cufftExecZ2D(p->b2d, tmp, rbulk + k * rf->comp_stride));
+					if (L == 0) CUFFT_TRY(cufftExecZ2D(p->b2d, tmp, rbulk + k * rf->comp_stride));
+					else
+						for (int z = 0; z < N; z += L)
+							CUFFT_TRY(cufftExecZ2D(p->b2d_c, tmp + (size_t) z * N * nh, rbulk + k * rf->comp_stride + (size_t) z * N * N));
 				}
-				c->launches += 2 * nc;
+				c->launches += (L ? N / L + 1 : 2) * nc;
 			}
 		}
 		return 0;

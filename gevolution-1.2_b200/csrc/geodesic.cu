@@ -41,6 +41,7 @@ struct GParams
 	// particles
 	int64_t n;
 	double * x, * y, * z, * qx, * qy, * qz; int64_t * id; uint32_t * key;
+	uint32_t * rank;                     // rank of every particle inside its new cell (NULL: the histogram is only counted, rebin_variant 0)
 	const uint32_t * cell_start; uint32_t * cell_count;
 	unsigned long long * maxv2;          // bit pattern of the running max of v^2 (>= 0)
 	// migration
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 	cp_async_commit();
 	int cur = 0;
 	double vmax = 0.;
+	uint32_t pend_i = 0xffffffffu, pend_rank = 0;                       // rank returned by the histogram's atomic, stored one particle later
 	uint32_t i = first + threadIdx.x;
 	double pos[3] = {0., 0., 0.}, q[3] = {0., 0., 0.};
 	if (i < last) { pos[0] = P.x[i]; pos[1] = P.y[i]; pos[2] = P.z[i]; q[0] = P.qx[i]; q[1] = P.qy[i]; q[2] = P.qz[i]; }
@@ -356,6 +358,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 					}
 					cp_async_commit();
 				}
+				// the previous particle's rank has had a whole iteration to come back from L2
+				if ((MODE == 1 || MODE == 2) && pend_i != 0xffffffffu) { P.rank[pend_i] = pend_rank; pend_i = 0xffffffffu; }
 				// the particle's cell and ref_dist = frac(pos/dx) (LATfield2 updateVel / moveParticles drivers)
 				double r[3];
 				const double * t;
@@ -398,7 +402,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 					else
 					{
 						key = brick_key(G, cx, cy, zl);
-						atomicAdd(P.cell_count + key, 1u);              // histogram of the counting sort (particles.cu)
+						// histogram of the counting sort (particles.cu); what the atomic returns is the particle's slot inside its new cell
+						if (P.rank) { pend_rank = atomicAdd(P.cell_count + key, 1u); pend_i = i; }
+						else atomicAdd(P.cell_count + key, 1u);
 					}
 					P.x[i] = pos[0]; P.y[i] = pos[1]; P.z[i] = pos[2];
 					P.key[i] = key;
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 		}
 		brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1;
 	}
+	if ((MODE == 1 || MODE == 2) && pend_i != 0xffffffffu) P.rank[pend_i] = pend_rank;
 	{
 		for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_down_sync(0xffffffffu, vmax, o));
 		if ((threadIdx.x & 31) == 0 && vmax > 0.) atomicMax(P.maxv2, (unsigned long long) __double_as_longlong(vmax));
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 // received particles (7 x cap SoA staging) appended behind the live ones, keys computed and histogrammed
 __global__ void k_append_received(int64_t nrecv, const double * __restrict__ rb, int64_t cap, int64_t at,
                                   double * x, double * y, double * z, double * qx, double * qy, double * qz, int64_t * id, uint32_t * key,
-                                  BrickGeom G, double dx, uint32_t * cell_count, unsigned long long * lost)
+                                  BrickGeom G, double dx, uint32_t * cell_count, unsigned long long * lost, uint32_t * rank)
 {
 	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < nrecv; i += (int64_t) gridDim.x * blockDim.x)
 	{
@@ -460,7 +467,8 @@ __global__ void k_append_received(int64_t nrecv, const double * __restrict__ rb,
 		if (cz < 0 || cz >= G.nzl) { atomicAdd(lost, 1ull); cz = cz < 0 ? 0 : G.nzl - 1; }   // moved farther than one slab: reported by the host
 		const uint32_t k = brick_key(G, cx, cy, cz);
 		key[at + i] = k;
-		atomicAdd(cell_count + k, 1u);
+		const uint32_t r = atomicAdd(cell_count + k, 1u);
+		if (rank) rank[at + i] = r;
 	}
 }
 
@@ -493,6 +501,7 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.n = p->n;
 	P.x = p->x[b]; P.y = p->y[b]; P.z = p->z[b]; P.qx = p->qx[b]; P.qy = p->qy[b]; P.qz = p->qz[b]; P.id = p->id[b]; P.key = p->key;
 	P.cell_start = p->cell_start; P.cell_count = p->cell_count;
+	P.rank = gevb_tune(TUNE_REBIN_VARIANT) != 0 ? p->rank : NULL;
 	P.maxv2 = (unsigned long long *) (c->d_red + 4008);
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
 }
@@ -568,12 +577,12 @@ int finish_move(gevb_pcls * p, GParams & P)
 	const double dx = 1.0 / (double) c->N;
 	if (h[2])
 	{
-		k_append_received<<<gevb_grid(c, h[2], 256), 256, 0, c->stream>>>((int64_t) h[2], rb_up, P.sendcap, p->n, p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4);
+		k_append_received<<<gevb_grid(c, h[2], 256), 256, 0, c->stream>>>((int64_t) h[2], rb_up, P.sendcap, p->n, p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4, P.rank ? p->rank : NULL);
 		KERNEL_CHECK(c);
 	}
 	if (h[3])
 	{
-		k_append_received<<<gevb_grid(c, h[3], 256), 256, 0, c->stream>>>((int64_t) h[3], rb_dn, P.sendcap, p->n + (int64_t) h[2], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4);
+		k_append_received<<<gevb_grid(c, h[3], 256), 256, 0, c->stream>>>((int64_t) h[3], rb_dn, P.sendcap, p->n + (int64_t) h[2], p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx, p->cell_count, cnt + 4, P.rank ? p->rank : NULL);
 		KERNEL_CHECK(c);
 	}
 	// the departed carry GEVB_INVALID_KEY and are dropped by the scatter

@@ -13,7 +13,7 @@
 void gevb_set_error(const char * fmt, ...);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -136,6 +136,8 @@ struct gevb_plan
 	cufftHandle f2d, bz1d, b2d; // nranks == 1, one component: 2-D D2Z per plane, 1-D Z2Z along z (stride N*nh), 2-D Z2D per plane
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
 	cufftHandle z1d_one;             // 1-D along z for one component (component-pipelined backward transform)
+	cufftHandle f2d_c, b2d_c;        // nranks == 1: the 2-D transforms of `chunk_planes` planes at a time (tuning knob fft_l2_planes)
+	int chunk_planes;                // 0: not created
 	bool multi;
 	bool preserve;             // backward execute keeps the Fourier field intact (default)
 };
@@ -207,6 +209,7 @@ struct gevb_pcls
 	double * x[2], * y[2], * z[2], * qx[2], * qy[2], * qz[2];
 	int64_t * id[2];
 	uint32_t * key;            // sort key of each live particle after a drift (input of the re-bin)
+	uint32_t * rank;           // its rank among the particles of the same new cell (what the histogram's atomicAdd returned)
 	uint32_t * cell_count;     // [ncells + 1] histogram of keys; all zero between re-bins
 	uint32_t * cell_start;     // [ncells + 1] exclusive prefix sum; cell_start[ncells] == n
 	BrickGeom geom;
@@ -216,6 +219,8 @@ struct gevb_pcls
 int gevb_pcls_reserve(gevb_pcls * p, int64_t cap);
 // counting sort of the first n_in live particles by p->key (entries with GEVB_INVALID_KEY are dropped);
 // hist_valid: cell_count already holds the histogram of the keys (the drift kernel accumulates it)
+// (with tuning knob rebin_variant = 1 the producers of the histogram also keep the value each atomicAdd returned in
+// p->rank, and the move needs no atomic: slot = cell_start[key] + rank)
 int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid);
 
 // Fourier-space index decode shared by all k-kernels

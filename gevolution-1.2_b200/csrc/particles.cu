@@ -53,16 +53,61 @@ __global__ void k_count_local(int64_t n, const double * __restrict__ pos, int N,
 	if ((threadIdx.x & 31) == 0 && mine) atomicAdd(counter, mine);
 }
 
+#define SCATTER_ILP 4
 // keys of particles [first, first + n) from their positions, accumulated into the histogram
 __global__ void k_make_keys(BrickGeom G, int64_t first, int64_t n, const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
-                            double dx, uint32_t * __restrict__ key, uint32_t * count)
+                            double dx, uint32_t * __restrict__ key, uint32_t * count, uint32_t * __restrict__ rank)
 {
 	for (int64_t i = first + blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < first + n; i += (int64_t) gridDim.x * blockDim.x)
 	{
 		const int cx = cell_of(x[i], dx, G.N), cy = cell_of(y[i], dx, G.N), cz = cell_of(z[i], dx, G.N) - G.z0;
 		const uint32_t k = brick_key(G, cx, cy, cz);
 		key[i] = k;
-		atomicAdd(count + k, 1u);
+		const uint32_t r = atomicAdd(count + k, 1u);
+		if (rank) rank[i] = r;
+	}
+}
+
+// the move of the counting sort when every particle knows its rank inside its new cell (rebin_variant = 1): no atomic,
+// two independent streaming loads (key, rank), one dependent lookup of cell_start (L2: neighbours share lines), seven
+// independent record loads, seven stores
+__global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank, const uint32_t * __restrict__ cell_start,
+                          const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
+                          const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
+                          double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
+                          double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t i0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i0 < n; i0 += SCATTER_ILP * stride)
+	{
+		uint32_t k[SCATTER_ILP], d[SCATTER_ILP];
+		double v[SCATTER_ILP][6];
+		int64_t vid[SCATTER_ILP];
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+		{
+			const int64_t i = i0 + u * stride;
+			k[u] = GEVB_INVALID_KEY; d[u] = 0;
+			if (i < n) { k[u] = __ldcs(key + i); d[u] = __ldcs(rank + i); }
+		}
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+		{
+			const int64_t i = i0 + u * stride;
+			if (k[u] == GEVB_INVALID_KEY) continue;
+			d[u] += __ldg(cell_start + k[u]);
+			v[u][0] = __ldcs(x + i); v[u][1] = __ldcs(y + i); v[u][2] = __ldcs(z + i);
+			v[u][3] = __ldcs(qx + i); v[u][4] = __ldcs(qy + i); v[u][5] = __ldcs(qz + i);
+			vid[u] = __ldcs(id + i);
+		}
+		#pragma unroll
+		for (int u = 0; u < SCATTER_ILP; u++)
+		{
+			if (k[u] == GEVB_INVALID_KEY) continue;
+			ox[d[u]] = v[u][0]; oy[d[u]] = v[u][1]; oz[d[u]] = v[u][2];
+			oqx[d[u]] = v[u][3]; oqy[d[u]] = v[u][4]; oqz[d[u]] = v[u][5];
+			oid[d[u]] = vid[u];
+		}
 	}
 }
 
@@ -70,7 +115,6 @@ __global__ void k_make_keys(BrickGeom G, int64_t first, int64_t n, const double 
 // Counting down leaves cell_count all zero again, ready for the next histogram.  Four particles per thread and
 // iteration, all loads and atomics of the four issued before the first dependent store (the chain key -> atomic ->
 // slot -> stores is latency bound otherwise).
-#define SCATTER_ILP 4
 __global__ void __launch_bounds__(256) k_scatter(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ cell_start, uint32_t * count,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
@@ -134,6 +178,7 @@ void free_arrays(gevb_pcls * p)
 		p->x[b] = p->y[b] = p->z[b] = p->qx[b] = p->qy[b] = p->qz[b] = NULL; p->id[b] = NULL;
 	}
 	cudaFree(p->key); p->key = NULL;
+	cudaFree(p->rank); p->rank = NULL;
 }
 
 } // namespace
@@ -205,6 +250,7 @@ int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)
 		CUDA_TRY(cudaMalloc(&p->id[b], sizeof(int64_t) * cap));
 	}
 	CUDA_TRY(cudaMalloc(&p->key, sizeof(uint32_t) * cap));
+	CUDA_TRY(cudaMalloc(&p->rank, sizeof(uint32_t) * cap));
 	if (old.cap > 0)
 	{
 		// the live arrays may hold more than n records (received particles appended behind them)
@@ -231,9 +277,12 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	const BrickGeom & G = p->geom;
 	const int s = p->cur, d = 1 - p->cur;
 	const double dx = 1.0 / (double) c->N;
+	// the histogram's producers (here, the drift kernel, the append of received particles) all follow the knob, so a
+	// histogram passed in as valid comes with ranks exactly when the knob is on; it must not change between a drift and its re-bin
+	const bool ranked = gevb_tune(TUNE_REBIN_VARIANT) != 0;
 	if (!hist_valid && n_in > 0)
 	{
-		k_make_keys<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(G, 0, n_in, p->x[s], p->y[s], p->z[s], dx, p->key, p->cell_count);
+		k_make_keys<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(G, 0, n_in, p->x[s], p->y[s], p->z[s], dx, p->key, p->cell_count, ranked ? p->rank : NULL);
 		KERNEL_CHECK(c);
 	}
 	size_t temp_bytes = 0;
@@ -243,7 +292,19 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	GEVB_TRY(gevb_ctx_scratch(c, temp_bytes, &temp));
 	CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, p->cell_count, p->cell_start, items, c->stream));
 	c->launches += 2;
-	if (n_in > 0)
+	if (ranked)
+	{
+		// nothing counts the histogram down: clear it for the next one
+		CUDA_TRY(cudaMemsetAsync(p->cell_count, 0, ((size_t) G.ncells + 1) * sizeof(uint32_t), c->stream));
+		if (n_in > 0)
+		{
+			k_scatter_ranked<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->key, p->rank, p->cell_start,
+				p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+				p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+			KERNEL_CHECK(c);
+		}
+	}
+	else if (n_in > 0)
 	{
 		k_scatter<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->key, p->cell_start, p->cell_count,
 			p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],

@@ -31,16 +31,18 @@ SYMBOLS = [
     "gevb_ctx_timing", "gevb_ctx_timing_read", "gevb_timing_num_classes", "gevb_timing_class_name", "gevb_parallel_sum", "gevb_parallel_max",
     "gevb_field_create", "gevb_field_destroy", "gevb_field_upload", "gevb_field_download", "gevb_field_components",
     "gevb_field_device_ptr", "gevb_projection_init", "gevb_field_updateHalo", "gevb_projection_comm", "gevb_field_sum",
-    "gevb_field_add_constant", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_plan_set_preserve_input", "gevb_pcls_create",
+    "gevb_field_add_constant", "gevb_field_scale", "gevb_field_ctx", "gevb_field_save_raw", "gevb_field_load_raw", "gevb_plan_create", "gevb_plan_destroy", "gevb_plan_execute", "gevb_plan_set_preserve_input", "gevb_pcls_create",
     "gevb_pcls_destroy", "gevb_pcls_reset", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
     "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTscalar_evolveFTvector", "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
-    "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_sim_run", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
+    "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_write_field_snapshot", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_sim_run", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
     "gevb_sim_get_field", "gevb_sim_field", "gevb_sim_pcls", "gevb_sim_get_state", "gevb_sim_set_state",
     "gevb_sim_set_fused", "gevb_sim_step",
+    "gevb_settings_read", "gevb_sim_create_from_settings", "gevb_sim_run_settings", "gevb_ic_cic_kernel", "gevb_ic_displacement_field",
+    "gevb_ic_load_template", "gevb_field_set_sites",
 ]
 
 _lib = None
@@ -122,8 +124,14 @@ def _declare(L):
         "gevb_ctx_ranks": [vp, C.POINTER(i), C.POINTER(i)],
         "gevb_sim_write_spectra": [vp, C.c_char_p, i, i, i, d],
         "gevb_sim_save_gadget2": [vp, i, C.c_char_p, i, d, d],
-        "gevb_sim_hibernate": [vp, C.c_char_p], "gevb_sim_restore": [vp, C.c_char_p],
+        "gevb_sim_hibernate": [vp, C.c_char_p], "gevb_sim_restore": [vp, C.c_char_p], "gevb_sim_write_field_snapshot": [vp, C.c_char_p, i],
+        "gevb_field_scale": [vp, d], "gevb_field_save_raw": [vp, C.c_char_p], "gevb_field_load_raw": [vp, C.c_char_p],
         "gevb_sim_run": [vp, pd, i, i, i, C.c_char_p, pd, i, i, C.c_char_p, i, C.POINTER(i)],
+        "gevb_settings_read": [C.c_char_p, C.c_char_p, vp], "gevb_sim_create_from_settings": [C.POINTER(vp), vp, vp],
+        "gevb_sim_run_settings": [vp, vp, i, C.POINTER(i)],
+        "gevb_ic_cic_kernel": [i, i64, vp, i, pd], "gevb_ic_displacement_field": [i, pd, d, i, pd, pd, C.c_uint, i, i],
+        "gevb_ic_load_template": [C.c_char_p, C.POINTER(i64), C.POINTER(C.POINTER(C.c_float))],
+        "gevb_field_set_sites": [vp, i, i, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -533,8 +541,82 @@ class Sim:
     def restore(self, filebase):
         _ck(lib().gevb_sim_restore(self.h, filebase.encode()), "gevb_sim_restore")
 
+    def write_field_snapshot(self, prefix, mask):
+        """writeSnapshots' field dumps (output.hpp:98-300): <prefix>_<T00|B|phi|chi|hij>.bin"""
+        _ck(lib().gevb_sim_write_field_snapshot(self.h, prefix.encode(), int(mask)), "gevb_sim_write_field_snapshot")
+
     def set_fused(self, fused):
         lib().gevb_sim_set_fused(self.h, int(bool(fused)))
 
     def step(self):
         _ck(lib().gevb_sim_step(self.h), "gevb_sim_step")
+
+
+def read_raw_field(filename):
+    """the flat binary field file of gevb_field_save_raw: float64 [comp][z][y][x] behind a 32-byte header"""
+    with open(filename, "rb") as f:
+        hdr = f.read(32)
+        if hdr[:8] != b"GEVBFLD1":
+            raise GevbError(f"{filename}: not a gevb field file")
+        n, ncomp = np.frombuffer(hdr[8:16], dtype=np.int32)
+        return np.fromfile(f, dtype=np.float64, count=int(ncomp) * int(n) ** 3).reshape(int(ncomp), int(n), int(n), int(n))
+
+
+# ---- settings.ini + basic IC generator (host side of the product; no device needed for the pieces) -------------------
+MAX_OUTPUTS, PATH_MAX = 32, 512
+
+
+class Settings(C.Structure):
+    """gevb_settings (include/gevb.h): the subset of the reference's settings.ini the hot path needs"""
+    _fields_ = [("ngrid", C.c_int), ("gr_flag", C.c_int), ("vector_flag", C.c_int), ("baryon_flag", C.c_int), ("seed", C.c_int), ("ksphere", C.c_int),
+                ("correct_displacement", C.c_int), ("tiling", C.c_int * 2), ("tracer_factor", C.c_int * 2), ("numbins", C.c_int), ("pk_mask", C.c_int),
+                ("snapshot_mask", C.c_int), ("num_pk", C.c_int), ("num_snapshot", C.c_int),
+                ("boxsize", C.c_double), ("Cf", C.c_double), ("steplimit", C.c_double), ("movelimit", C.c_double), ("z_in", C.c_double), ("z_relax", C.c_double),
+                ("A_s", C.c_double), ("n_s", C.c_double), ("k_pivot", C.c_double), ("cosmo", C.c_double * 11),
+                ("z_pk", C.c_double * MAX_OUTPUTS), ("z_snapshot", C.c_double * MAX_OUTPUTS),
+                ("template_file", (C.c_char * PATH_MAX) * 2), ("tk_file", C.c_char * PATH_MAX), ("output_path", C.c_char * PATH_MAX),
+                ("basename_generic", C.c_char * 128), ("basename_pk", C.c_char * 128), ("basename_snapshot", C.c_char * 128)]
+
+
+def settings_read(filename, overrides=""):
+    st = Settings()
+    _ck(lib().gevb_settings_read(str(filename).encode(), overrides.encode(), C.byref(st)), "gevb_settings_read")
+    return st
+
+
+def ic_cic_kernel(N, pcldata=None, numtile=1):
+    """generateCICKernel on its 27 sites: array [dz+1][dy+1][dx+1]"""
+    out = np.zeros(27)
+    if pcldata is None:
+        _ck(lib().gevb_ic_cic_kernel(N, 0, None, 1, out.ctypes.data_as(C.POINTER(C.c_double))), "gevb_ic_cic_kernel")
+    else:
+        p = np.ascontiguousarray(pcldata, dtype=np.float32)
+        _ck(lib().gevb_ic_cic_kernel(N, len(p), p.ctypes.data_as(C.c_void_p), numtile, out.ctypes.data_as(C.POINTER(C.c_double))), "gevb_ic_cic_kernel")
+    return out.reshape(3, 3, 3)
+
+
+def ic_displacement_field(potFT, coeff, spline_x, spline_y, seed, ksphere=0, deconvolve_f=1):
+    out = np.ascontiguousarray(potFT, dtype=np.float64).copy()
+    x, y = np.ascontiguousarray(spline_x, dtype=np.float64), np.ascontiguousarray(spline_y, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    _ck(lib().gevb_ic_displacement_field(out.shape[0], out.ctypes.data_as(dp), coeff, len(x), x.ctypes.data_as(dp), y.ctypes.data_as(dp), seed, ksphere, deconvolve_f),
+        "gevb_ic_displacement_field")
+    return out
+
+
+def ic_load_template(filename):
+    n, ptr = C.c_int64(0), C.POINTER(C.c_float)()
+    _ck(lib().gevb_ic_load_template(str(filename).encode(), C.byref(n), C.byref(ptr)), "gevb_ic_load_template")
+    out = np.ctypeslib.as_array(ptr, shape=(n.value, 3)).copy()
+    C.CDLL(None).free(ptr)
+    return out
+
+
+def sim_from_settings(ctx, settings):
+    """main.cpp:184-340 with IC generator = basic: a Sim with particles and metric fields from the settings' own seed"""
+    h = C.c_void_p()
+    _ck(lib().gevb_sim_create_from_settings(C.byref(h), ctx.h, C.byref(settings)), "gevb_sim_create_from_settings")
+    s = Sim.__new__(Sim)
+    s.ctx, s.h = ctx, h
+    s.settings = settings
+    return s

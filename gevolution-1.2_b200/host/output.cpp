@@ -100,7 +100,13 @@ extern "C" int gevb_pcls_saveGadget2(gevb_pcls * p, const char * filename, void 
 	if (gevb_parallel_sum(ctx, counts.data(), nranks) != 0) return 1;
 	uint64_t before = 0, total = 0;
 	for (int r = 0; r < nranks; r++) { if (r < rank) before += (uint64_t) counts[r]; total += (uint64_t) counts[r]; }
+	// one file with 32-bit block markers (MASK_MULTI is not built): the reference refuses such a write too (output.hpp:404)
+	if (12 * total >= (1ull << 32)) { std::fprintf(stderr, " error: %llu particles do not fit one Gadget-2 file (32-bit block markers)\n", (unsigned long long) total); return 1; }
 	const uint32_t npart1 = (uint32_t) total;
+	uint32_t requested;
+	std::memcpy(&requested, hdr + 4, 4);
+	// the reference reports the mismatch and writes what it found (Particles_gevolution.hpp:90,108); npartTotal stays the caller's
+	if (rank == 0 && requested != npart1) std::fprintf(stderr, " error: number of particles in saveGadget2 does not match request!\n");
 	std::memcpy(hdr + 4, &npart1, 4);                                                     // hdr.npart[1]
 	// [4][hdr 256][4] [4][pos 12 n][4] [4][vel 12 n][4] [4][ids 8 n][4]
 	const uint64_t off_pos = 4 + 256 + 4 + 4, off_vel = off_pos + 12 * total + 4 + 4, off_id = off_vel + 12 * total + 4 + 4;
@@ -136,4 +142,75 @@ extern "C" int gevb_pcls_saveGadget2(gevb_pcls * p, const char * filename, void 
 	double done = ok ? 0. : 1.;
 	if (gevb_parallel_sum(ctx, &done, 1) != 0) return 1;
 	return done == 0. ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Field::saveHDF5 / loadHDF5 stand-ins (output.hpp:98-300; hibernation.hpp:588-600; ic_read.hpp:310,326).  HDF5 is not
+// available in this image, so the dataset is a flat binary file: a 32-byte header, then the whole lattice as
+// float64 [comp][z][y][x].  Every rank writes / reads the planes of its own slab at their global offsets.
+namespace {
+struct RawHeader { char magic[8]; int32_t ngrid, ncomp; char pad[16]; };
+const char RAW_MAGIC[8] = {'G', 'E', 'V', 'B', 'F', 'L', 'D', '1'};
+}
+
+extern "C" int gevb_field_save_raw(gevb_field * f, const char * filename)
+{
+	if (f == NULL || filename == NULL) return 1;
+	gevb_ctx * ctx = gevb_field_ctx(f);
+	int rank = 0, nranks = 1, n, z0, nzl;
+	gevb_ctx_ranks(ctx, &rank, &nranks);
+	gevb_ctx_geometry(ctx, &n, &z0, &nzl, NULL, NULL);
+	const int ncomp = gevb_field_components(f);
+	const size_t slab = (size_t) nzl * n * n, comp_sites = (size_t) n * n * n;
+	bool ok = true;
+	std::vector<double> buf;
+	try { buf.resize(slab * ncomp); } catch (...) { ok = false; }
+	ok = ok && gevb_field_download(f, buf.data()) == 0;
+	if (rank == 0 && ok)
+	{
+		FILE * h = std::fopen(filename, "wb");
+		RawHeader hd;
+		std::memset(&hd, 0, sizeof(hd));
+		std::memcpy(hd.magic, RAW_MAGIC, 8); hd.ngrid = n; hd.ncomp = ncomp;
+		ok = h != NULL && std::fwrite(&hd, 1, sizeof(hd), h) == sizeof(hd);
+		if (h) ok = std::fclose(h) == 0 && ok;
+		if (!ok) std::fprintf(stderr, " error opening %s for field output\n", filename);
+	}
+	double created = ok ? 0. : 1.;
+	if (gevb_parallel_sum(ctx, &created, 1) != 0 || created != 0.) return 1;             // the file exists for every rank from here on
+	FILE * h = std::fopen(filename, "r+b");
+	ok = h != NULL;
+	for (int k = 0; k < ncomp && ok; k++)
+		ok = fseeko(h, (off_t) (sizeof(RawHeader) + ((size_t) k * comp_sites + (size_t) z0 * n * n) * sizeof(double)), SEEK_SET) == 0
+			&& std::fwrite(buf.data() + (size_t) k * slab, sizeof(double), slab, h) == slab;
+	if (h) ok = std::fclose(h) == 0 && ok;
+	double done = ok ? 0. : 1.;
+	if (gevb_parallel_sum(ctx, &done, 1) != 0) return 1;
+	return done == 0. ? 0 : 1;
+}
+
+extern "C" int gevb_field_load_raw(gevb_field * f, const char * filename)
+{
+	if (f == NULL || filename == NULL) return 1;
+	gevb_ctx * ctx = gevb_field_ctx(f);
+	int n, z0, nzl;
+	gevb_ctx_geometry(ctx, &n, &z0, &nzl, NULL, NULL);
+	const int ncomp = gevb_field_components(f);
+	const size_t slab = (size_t) nzl * n * n, comp_sites = (size_t) n * n * n;
+	// read and validate everything on the host first; the ranks agree before anyone touches the device (no rank may
+	// skip a collective the others enter)
+	bool ok = true;
+	std::vector<double> buf;
+	try { buf.resize(slab * ncomp); } catch (...) { ok = false; }
+	FILE * h = ok ? std::fopen(filename, "rb") : NULL;
+	RawHeader hd;
+	ok = ok && h != NULL && std::fread(&hd, 1, sizeof(hd), h) == sizeof(hd) && std::memcmp(hd.magic, RAW_MAGIC, 8) == 0 && hd.ngrid == n && hd.ncomp == ncomp;
+	for (int k = 0; k < ncomp && ok; k++)
+		ok = fseeko(h, (off_t) (sizeof(RawHeader) + ((size_t) k * comp_sites + (size_t) z0 * n * n) * sizeof(double)), SEEK_SET) == 0
+			&& std::fread(buf.data() + (size_t) k * slab, sizeof(double), slab, h) == slab;
+	if (h) std::fclose(h);
+	double bad = ok ? 0. : 1.;
+	if (gevb_parallel_sum(ctx, &bad, 1) != 0 || bad != 0.) return 1;
+	if (gevb_field_upload(f, buf.data()) != 0) return 1;
+	return gevb_field_updateHalo(f);
 }

@@ -4,44 +4,43 @@
 // (main.cpp:372-879) with the output / hibernation branches stripped, written
 // against include/gevolution_b200.hpp so that it reads like the reference's own
 // loop.  Exposed through the C ABI as gevb_sim_* (include/gevb.h).
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <new>
-#include <vector>
-#define GEVB_THROW_ON_ERROR
-#include "../../include/gevolution_b200.hpp"
-#include "background.hpp"
+#include "sim_internal.hpp"
 
-using namespace gevb200;
+// No exception crosses the C boundary: every gevb_sim_* body that can allocate or call into the library runs inside
+// GEVB_C_BOUNDARY, which turns gevb_error (message already in gevb_last_error) and anything else into status 1.
+#define GEVB_C_BOUNDARY(body) try { body } catch (const gevb_error &) { return 1; } catch (...) { return 1; }
 
-#define VECTOR_PARABOLIC 0      // metadata.hpp:92
-#define VECTOR_ELLIPTIC 1       // metadata.hpp:93
+static int sim_create(gevb_sim * s, int gr_flag, int vector_flag, const double * ds, const double * c);
 
-struct gevb_sim
+// main.cpp:281-286: no particle may move farther than the thinnest local domain minus one cell per update (the migration
+// reaches the adjacent slab only); with z-slabs that is nz_local - 1 (N - 1 on one rank)
+static double clamp_movelimit(gevb_sim * s, double movelimit)
 {
-	Lattice lat;
-	cosmology cosmo;
-	int numpts, gr_flag, vector_flag, baryon_flag, fused;
-	double boxsize, Cf, steplimit, z_in, z_relax;
-	double fourpiG, a, tau, dtau, dtau_old, dx, T00hom;
-	int cycle;
-	double maxvel[2 + GEVB_MAX_NCDM];                 // by species slot: cdm, baryons, ncdm 0..3 (main.cpp indexes [i+1+baryon_flag])
-	Particles_gevolution pcls_cdm, pcls_b;
-	Particles_gevolution pcls_ncdm[GEVB_MAX_NCDM];    // main.cpp:219
-	double z_switch_deltancdm[GEVB_MAX_NCDM], z_switch_Bncdm[GEVB_MAX_NCDM], z_switch_linearchi, movelimit;   // metadata.hpp:224-238
-	int numsteps_ncdm[GEVB_MAX_NCDM];
-	Field<Real> phi, source, chi, Sij, Bi;
-	Field<Cplx> scalarFT, SijFT, BiFT;
-	PlanFFT<Cplx> plan_source, plan_phi, plan_chi, plan_Sij, plan_Bi;
-	explicit gevb_sim(gevb_ctx * ctx) : lat(ctx) {}
-};
+	int rank = 0, nranks = 1, n = 0, nzl = 0;
+	gevb_ctx_ranks(s->lat.ctx(), &rank, &nranks);
+	gevb_ctx_geometry(s->lat.ctx(), &n, NULL, &nzl, NULL, NULL);
+	const double lim = (double) ((nranks > 1 ? nzl : n) - 1);
+	return movelimit < lim ? movelimit : lim;
+}
 
 extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int vector_flag, const double * ds, const double * c)
 {
 	if (out == NULL || ctx == NULL || ds == NULL || c == NULL) return 1;
-	gevb_sim * s = new (std::nothrow) gevb_sim(ctx);
-	if (s == NULL) return 1;
+	gevb_sim * s = NULL;
+	// a failed field / plan allocation (the Sij and SijFT fields are 13 GB at 512^3) throws from the wrappers: the partly
+	// built simulation is destroyed (the field destructors release what was allocated) and the status reports it
+	try
+	{
+		s = new gevb_sim(ctx);
+		if (sim_create(s, gr_flag, vector_flag, ds, c) != 0) { delete s; return 1; }
+	}
+	catch (...) { delete s; return 1; }
+	*out = s;
+	return 0;
+}
+
+static int sim_create(gevb_sim * s, int gr_flag, int vector_flag, const double * ds, const double * c)
+{
 	s->numpts = s->lat.size(0);
 	s->gr_flag = gr_flag; s->vector_flag = vector_flag; s->baryon_flag = 0; s->fused = 1;
 	s->boxsize = ds[0]; s->Cf = ds[1]; s->steplimit = ds[2]; s->z_in = ds[3]; s->z_relax = ds[4];
@@ -50,7 +49,8 @@ extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int
 	co.Omega_cdm = c[0]; co.Omega_b = c[1]; co.Omega_m = c[2]; co.Omega_Lambda = c[3]; co.Omega_fld = c[4]; co.w0_fld = c[5]; co.wa_fld = c[6];
 	co.Omega_g = c[7]; co.Omega_ur = c[8]; co.Omega_rad = c[9]; co.h = c[10]; co.num_ncdm = 0;
 	s->cosmo = co;
-	s->z_switch_linearchi = 0.; s->movelimit = 1.e10;
+	s->z_switch_linearchi = 0.;
+	s->movelimit = clamp_movelimit(s, 1.e10);
 	for (int i = 0; i < GEVB_MAX_NCDM; i++) { s->z_switch_deltancdm[i] = s->z_switch_Bncdm[i] = 0.; s->numsteps_ncdm[i] = 1; }
 	Lattice & lat = s->lat;
 	// main.cpp:234-246
@@ -80,7 +80,6 @@ extern "C" int gevb_sim_create(gevb_sim ** out, gevb_ctx * ctx, int gr_flag, int
 	s->dtau_old = 0.;
 	s->cycle = 0; s->T00hom = 0.;
 	for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) s->maxvel[i] = 0.;
-	*out = s;
 	return 0;
 }
 
@@ -96,7 +95,7 @@ extern "C" int gevb_sim_set_ncdm(gevb_sim * s, int num_ncdm, const double * m_nc
 		s->cosmo.m_ncdm[i] = m_ncdm[i]; s->cosmo.T_ncdm[i] = T_ncdm[i]; s->cosmo.Omega_ncdm[i] = Omega_ncdm[i];
 		s->z_switch_deltancdm[i] = z_switch_deltancdm[i]; s->z_switch_Bncdm[i] = z_switch_Bncdm[i];
 	}
-	s->z_switch_linearchi = z_switch_linearchi; s->movelimit = movelimit;
+	s->z_switch_linearchi = z_switch_linearchi; s->movelimit = clamp_movelimit(s, movelimit);
 	if (s->cycle == 0)
 	{
 		// the background changed: redo main.cpp:289-295 at the initial redshift
@@ -146,7 +145,7 @@ extern "C" int gevb_sim_set_particles(gevb_sim * s, int species, int64_t n, cons
 	part_simple_info info;
 	info.mass = mass; info.relativistic = species >= 2; std::strcpy(info.type_name, "part_simple");
 	Particles_gevolution & p = species == 0 ? s->pcls_cdm : (species == 1 ? s->pcls_b : s->pcls_ncdm[species - 2]);
-	p.initialize(info, &s->lat);
+	GEVB_C_BOUNDARY(p.initialize(info, &s->lat);)
 	if (species == 1) s->baryon_flag = 1;
 	return gevb_pcls_add(p.handle(), n, id, pos, vel);
 }
@@ -207,10 +206,10 @@ extern "C" int gevb_sim_set_ncdm_maxvel(gevb_sim * s, const double * maxvel)
 
 extern "C" int gevb_sim_set_fused(gevb_sim * s, int fused)
 {
+	if (s == NULL) return 1;
 	s->fused = fused;
 	// fused mode treats scalarFT as scratch (its backward transforms may clobber it); unfused keeps LATfield2's semantics
-	s->plan_phi.preserveInput(!fused);
-	s->plan_chi.preserveInput(!fused);
+	GEVB_C_BOUNDARY(s->plan_phi.preserveInput(!fused); s->plan_chi.preserveInput(!fused);)
 	return 0;
 }
 
@@ -218,14 +217,15 @@ static int sim_solve(gevb_sim * s);
 static int sim_update(gevb_sim * s);
 static int sim_step(gevb_sim * s) { int r = sim_solve(s); return r ? r : sim_update(s); }
 
-// ---- hibernation / restart (hibernation.hpp:38-611 writes, ic_read.hpp:58-400 reads) -----------------------------
-// The state set is the reference's: the particles of every species, phi, chi, the vector potential, and the scalars
-// a, tau, dtau, dtau_old, cycle, maxvel[] (+ the ncdm sub-stepping inputs).  The reference stores the fields and
-// particles as HDF5 (absent here) and rebuilds BiFT from Bi by a forward FFT at restart; this writer keeps one
-// self-describing binary file per rank, <filebase>.<rank>.gevb, and stores BiFT itself so that a restart continues
-// from exactly the state that was left.
+// ---- hibernation / restart (hibernation.hpp:512-611 writes, ic_read.hpp:290-330 reads) ---------------------------
+// The state set and the arithmetic are the reference's: the particles of every species, phi, chi, and the vector
+// potential in REAL space divided by a^2 N (hibernation.hpp:533-538), plus the scalars a, tau, dtau, dtau_old, cycle,
+// maxvel[] that it keeps in the restart settings file (writeRestartSettings).  At restart the stored B is multiplied
+// by a^2 / N^2 and BiFT is rebuilt from it by a forward transform (ic_read.hpp:305-319).  The reference stores fields
+// and particles as HDF5 (absent here): the fields go to flat binary files <filebase>_phi.bin, _chi.bin, _B.bin
+// (gevb_field_save_raw), the particles and scalars of a rank to <filebase>.<rank>.gevb.
 namespace {
-const char HIB_MAGIC[8] = {'G', 'E', 'V', 'B', 'H', 'I', 'B', '1'};
+const char HIB_MAGIC[8] = {'G', 'E', 'V', 'B', 'H', 'I', 'B', '2'};
 struct HibHeader
 {
 	char magic[8];
@@ -238,11 +238,11 @@ struct HibHeader
 bool put(FILE * f, const void * p, size_t bytes) { return bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes; }
 bool get(FILE * f, void * p, size_t bytes) { return bytes == 0 || std::fread(p, 1, bytes, f) == bytes; }
 Particles_gevolution * species_of(gevb_sim * s, int sp) { return sp == 0 ? &s->pcls_cdm : (sp == 1 ? &s->pcls_b : &s->pcls_ncdm[sp - 2]); }
+struct FileCloser { FILE * f; ~FileCloser() { if (f) std::fclose(f); } };
 }
 
-extern "C" int gevb_sim_hibernate(gevb_sim * s, const char * filebase)
+static int sim_hibernate(gevb_sim * s, const char * filebase)
 {
-	if (s == NULL || filebase == NULL) return 1;
 	gevb_ctx * ctx = s->lat.ctx();
 	int rank = 0, nranks = 1, n, z0, nzl, ky0, nky;
 	gevb_ctx_ranks(ctx, &rank, &nranks);
@@ -261,38 +261,60 @@ extern "C" int gevb_sim_hibernate(gevb_sim * s, const char * filebase)
 		h.mass[i] = p->initialized() ? gevb_pcls_mass(p->handle()) : 0.;
 	}
 	char name[1024];
-	std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
-	FILE * f = std::fopen(name, "wb");
-	bool ok = f != NULL && put(f, &h, sizeof(h));
-	const size_t bulk = (size_t) nzl * n * n, ksites = nranks == 1 ? (size_t) n * n * (n / 2 + 1) : (size_t) nky * (n / 2 + 1) * n;
-	std::vector<double> buf;
-	struct { gevb_field * f; size_t doubles; } fields[3] = {{s->phi.handle(), bulk}, {s->chi.handle(), bulk}, {s->BiFT.handle(), 3 * 2 * ksites}};
-	for (int k = 0; k < 3 && ok; k++)
+	bool ok = true;
 	{
-		buf.resize(fields[k].doubles);
-		ok = gevb_field_download(fields[k].f, buf.data()) == 0 && put(f, buf.data(), buf.size() * sizeof(double));
+		std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
+		FileCloser fc = {std::fopen(name, "wb")};
+		ok = fc.f != NULL && put(fc.f, &h, sizeof(h));
+		for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
+		{
+			if (h.npart[i] <= 0) continue;
+			const size_t np = (size_t) h.npart[i];
+			std::vector<int64_t> id(np);
+			std::vector<double> pos(3 * np), vel(3 * np);
+			ok = gevb_pcls_download(species_of(s, i)->handle(), id.data(), pos.data(), vel.data()) == 0
+				&& put(fc.f, id.data(), np * 8) && put(fc.f, pos.data(), np * 24) && put(fc.f, vel.data(), np * 24);
+		}
+		if (fc.f) { ok = std::fclose(fc.f) == 0 && ok; fc.f = NULL; }
 	}
-	for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
-	{
-		if (h.npart[i] <= 0) continue;
-		const size_t np = (size_t) h.npart[i];
-		std::vector<int64_t> id(np);
-		std::vector<double> pos(3 * np), vel(3 * np);
-		ok = gevb_pcls_download(species_of(s, i)->handle(), id.data(), pos.data(), vel.data()) == 0
-			&& put(f, id.data(), np * 8) && put(f, pos.data(), np * 24) && put(f, vel.data(), np * 24);
-	}
-	if (f) ok = std::fclose(f) == 0 && ok;
 	double bad = ok ? 0. : 1.;
-	if (gevb_parallel_sum(ctx, &bad, 1) != 0) return 1;
-	return bad == 0. ? 0 : 1;
+	if (gevb_parallel_sum(ctx, &bad, 1) != 0 || bad != 0.) return 1;              // every rank enters the collective field writes below, or none
+	// hibernation.hpp:533-538: the stored vector potential is Bi / (a^2 N).  As in the reference it is not scaled back: Bi is
+	// derived state that the next metric solve rebuilds from BiFT (main.cpp:593) before anything reads it.
+	if (s->vector_flag == VECTOR_PARABOLIC)
+	{
+		if (s->gr_flag == 0) s->plan_Bi.execute(FFT_BACKWARD);                    // main.cpp:837,850
+		check(gevb_field_scale(s->Bi.handle(), 1. / (s->a * s->a * s->numpts)), "hibernate");
+		std::snprintf(name, sizeof(name), "%s_B.bin", filebase);
+		if (gevb_field_save_raw(s->Bi.handle(), name) != 0) return 1;             // hibernation.hpp:597
+	}
+	if (s->gr_flag > 0)
+	{
+		std::snprintf(name, sizeof(name), "%s_phi.bin", filebase);
+		if (gevb_field_save_raw(s->phi.handle(), name) != 0) return 1;            // hibernation.hpp:591
+		std::snprintf(name, sizeof(name), "%s_chi.bin", filebase);
+		if (gevb_field_save_raw(s->chi.handle(), name) != 0) return 1;            // hibernation.hpp:592
+	}
+	else
+	{
+		// Newtonian runs recompute phi from the particles every cycle; it is written all the same so that a restart begins from the state left
+		std::snprintf(name, sizeof(name), "%s_phi.bin", filebase);
+		if (gevb_field_save_raw(s->phi.handle(), name) != 0) return 1;
+	}
+	return 0;
+}
+
+extern "C" int gevb_sim_hibernate(gevb_sim * s, const char * filebase)
+{
+	if (s == NULL || filebase == NULL) return 1;
+	GEVB_C_BOUNDARY(return sim_hibernate(s, filebase);)
 }
 
 static int sim_restore(gevb_sim * s, const char * filebase);
 extern "C" int gevb_sim_restore(gevb_sim * s, const char * filebase)
 {
 	if (s == NULL || filebase == NULL) return 1;
-	try { return sim_restore(s, filebase); }
-	catch (...) { return 1; }                                 // allocation failure and the like never cross the C boundary
+	GEVB_C_BOUNDARY(return sim_restore(s, filebase);)         // allocation failure and the like never cross the C boundary
 }
 
 static int sim_restore(gevb_sim * s, const char * filebase)
@@ -301,57 +323,115 @@ static int sim_restore(gevb_sim * s, const char * filebase)
 	int rank = 0, nranks = 1, n, z0, nzl, ky0, nky;
 	gevb_ctx_ranks(ctx, &rank, &nranks);
 	gevb_ctx_geometry(ctx, &n, &z0, &nzl, &ky0, &nky);
-	char name[1024];
-	std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
-	FILE * f = std::fopen(name, "rb");
+	// 1. every rank reads and validates its whole particle file on the host; the ranks agree on the outcome before any
+	//    device work or collective starts (a rank with a truncated file must not leave the others inside an exchange)
 	HibHeader h;
-	bool ok = f != NULL && get(f, &h, sizeof(h)) && std::memcmp(h.magic, HIB_MAGIC, 8) == 0;
-	// the particle counts must fit the file (a truncated or foreign file must not drive the allocations below)
-	if (ok)
+	std::vector<int64_t> id[2 + GEVB_MAX_NCDM];
+	std::vector<double> pos[2 + GEVB_MAX_NCDM], vel[2 + GEVB_MAX_NCDM];
+	bool ok = true;
+	try
 	{
-		long here = std::ftell(f);
-		std::fseek(f, 0, SEEK_END);
-		const long size = std::ftell(f);
-		std::fseek(f, here, SEEK_SET);
-		int64_t total = 0;
-		for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) if (h.npart[i] > 0) total += h.npart[i];
-		ok = here > 0 && size > here && total >= 0 && total <= (int64_t) ((size - here) / 56);
-	}
-	// a restart must use the decomposition the state was written with (the reference has the same restriction per file set)
-	ok = ok && h.ngrid == n && h.nranks == nranks && h.rank == rank && h.z0 == z0 && h.nzl == nzl && h.gr_flag == s->gr_flag && h.vector_flag == s->vector_flag
-		&& h.num_ncdm == s->cosmo.num_ncdm;
-	if (ok)
-	{
-		const size_t bulk = (size_t) nzl * n * n, ksites = nranks == 1 ? (size_t) n * n * (n / 2 + 1) : (size_t) nky * (n / 2 + 1) * n;
-		std::vector<double> buf;
-		const int which[3] = {0, 1, 11};
-		const size_t doubles[3] = {bulk, bulk, 3 * 2 * ksites};
-		for (int k = 0; k < 3 && ok; k++)
-		{
-			buf.resize(doubles[k]);
-			ok = get(f, buf.data(), buf.size() * sizeof(double)) && gevb_sim_set_field(s, which[k], buf.data()) == 0;     // fills the ghost planes too
-		}
-		for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
-		{
-			if (h.npart[i] < 0) continue;
-			const size_t np = (size_t) h.npart[i];
-			std::vector<int64_t> id(np);
-			std::vector<double> pos(3 * np), vel(3 * np);
-			ok = get(f, id.data(), np * 8) && get(f, pos.data(), np * 24) && get(f, vel.data(), np * 24)
-				&& gevb_sim_set_particles(s, i, (int64_t) np, id.data(), pos.data(), vel.data(), h.mass[i]) == 0;
-		}
+		char name[1024];
+		std::snprintf(name, sizeof(name), "%s.%d.gevb", filebase, rank);
+		FileCloser fc = {std::fopen(name, "rb")};
+		ok = fc.f != NULL && get(fc.f, &h, sizeof(h)) && std::memcmp(h.magic, HIB_MAGIC, 8) == 0;
 		if (ok)
 		{
-			s->a = h.a; s->tau = h.tau; s->dtau = h.dtau; s->dtau_old = h.dtau_old; s->cycle = h.cycle; s->T00hom = h.T00hom;
-			for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) s->maxvel[i] = h.maxvel[i];
-			// Bi in real space is derived state (main.cpp:593-598)
-			if (s->gr_flag > 0) { try { s->plan_Bi.execute(FFT_BACKWARD); s->Bi.updateHalo(); } catch (const gevb_error &) { ok = false; } }
+			// the particle counts must fit the file (a truncated or foreign file must not drive the allocations below)
+			const long here = std::ftell(fc.f);
+			std::fseek(fc.f, 0, SEEK_END);
+			const long size = std::ftell(fc.f);
+			std::fseek(fc.f, here, SEEK_SET);
+			int64_t total = 0;
+			for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) if (h.npart[i] > 0) total += h.npart[i];
+			ok = here > 0 && size >= here && total >= 0 && total <= (int64_t) ((size - here) / 56);
+		}
+		// a restart must use the decomposition the state was written with (the reference has the same restriction per file set)
+		ok = ok && h.ngrid == n && h.nranks == nranks && h.rank == rank && h.z0 == z0 && h.nzl == nzl && h.gr_flag == s->gr_flag && h.vector_flag == s->vector_flag
+			&& h.num_ncdm == s->cosmo.num_ncdm;
+		for (int i = 0; i < 2 + GEVB_MAX_NCDM && ok; i++)
+		{
+			if (h.npart[i] <= 0) continue;
+			const size_t np = (size_t) h.npart[i];
+			id[i].resize(np); pos[i].resize(3 * np); vel[i].resize(3 * np);
+			ok = get(fc.f, id[i].data(), np * 8) && get(fc.f, pos[i].data(), np * 24) && get(fc.f, vel[i].data(), np * 24);
 		}
 	}
-	if (f) std::fclose(f);
+	catch (...) { ok = false; }
 	double bad = ok ? 0. : 1.;
-	if (gevb_parallel_sum(ctx, &bad, 1) != 0) return 1;
-	return bad == 0. ? 0 : 1;
+	if (gevb_parallel_sum(ctx, &bad, 1) != 0 || bad != 0.) return 1;
+	// 2. fields (each load validates on the host and agrees across ranks before it uploads)
+	char name[1024];
+	std::snprintf(name, sizeof(name), "%s_phi.bin", filebase);
+	if (gevb_field_load_raw(s->phi.handle(), name) != 0) return 1;                // ic_read.hpp (metricfile[0]) + updateHalo :288
+	if (s->gr_flag > 0)
+	{
+		std::snprintf(name, sizeof(name), "%s_chi.bin", filebase);
+		if (gevb_field_load_raw(s->chi.handle(), name) != 0) return 1;            // ic_read.hpp:323-327
+	}
+	s->a = h.a; s->tau = h.tau; s->dtau = h.dtau; s->dtau_old = h.dtau_old; s->cycle = h.cycle; s->T00hom = h.T00hom;
+	for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++) s->maxvel[i] = h.maxvel[i];
+	if (s->vector_flag == VECTOR_PARABOLIC)
+	{
+		std::snprintf(name, sizeof(name), "%s_B.bin", filebase);
+		if (gevb_field_load_raw(s->Bi.handle(), name) != 0) return 1;             // ic_read.hpp:309-310
+		check(gevb_field_scale(s->Bi.handle(), s->a * s->a / ((double) s->numpts * (double) s->numpts)), "restore");   // :312-317
+		s->plan_Bi.execute(FFT_FORWARD);                                          // :318: BiFT is rebuilt from the stored real-space field
+	}
+	// Bi in real space is derived state (main.cpp:593-598)
+	if (s->gr_flag > 0) { s->plan_Bi.execute(FFT_BACKWARD); s->Bi.updateHalo(); }
+	// 3. particles
+	for (int i = 0; i < 2 + GEVB_MAX_NCDM; i++)
+	{
+		if (h.npart[i] < 0) continue;
+		if (gevb_sim_set_particles(s, i, h.npart[i], id[i].data(), pos[i].data(), vel[i].data(), h.mass[i]) != 0) return 1;
+	}
+	return 0;
+}
+
+// writeSnapshots' field dumps (output.hpp:98-300) as flat binary files <prefix>_<T00|B|phi|chi|hij>.bin
+static int write_field_snapshot(gevb_sim * s, const char * prefix, int mask)
+{
+	const double a = s->a;
+	char name[1024];
+	auto file = [&](const char * tag) { std::snprintf(name, sizeof(name), "%s_%s.bin", prefix, tag); return name; };
+	if (mask & 16)                                                                           // MASK_T00, output.hpp:155-193
+	{
+		projection_init(&s->source);
+		for (int sp = 0; sp < 2 + s->cosmo.num_ncdm; sp++)
+		{
+			Particles_gevolution * p = species_of(s, sp);
+			if (!p->initialized()) continue;
+			if (s->gr_flag > 0) projection_T00_project(p, &s->source, a, &s->phi);           // :160-167
+			else scalarProjectionCIC_project(p, &s->source);                                 // :171-178
+		}
+		projection_T00_comm(&s->source);                                                     // :181
+		if (gevb_field_save_raw(s->source.handle(), file("T00")) != 0) return 1;
+	}
+	if (mask & 8)                                                                            // MASK_B, output.hpp:206-237
+	{
+		if (s->gr_flag == 0) s->plan_Bi.execute(FFT_BACKWARD);                               // :210
+		check(gevb_field_scale(s->Bi.handle(), 1. / (a * a * s->numpts)), "writeSnapshots"); // :212-217
+		s->Bi.updateHalo();                                                                  // :218
+		if (gevb_field_save_raw(s->Bi.handle(), file("B")) != 0) return 1;                   // :229
+		if (s->gr_flag > 0) { s->plan_Bi.execute(FFT_BACKWARD); s->Bi.updateHalo(); }        // :232-236: restored from BiFT
+	}
+	if ((mask & 1) && gevb_field_save_raw(s->phi.handle(), file("phi")) != 0) return 1;      // MASK_PHI, :239-247
+	if ((mask & 2) && gevb_field_save_raw(s->chi.handle(), file("chi")) != 0) return 1;      // MASK_CHI, :249-257
+	if (mask & 128)                                                                          // MASK_HIJ, :259-277 (done_hij == 0)
+	{
+		projectFTtensor(s->SijFT, s->SijFT);
+		s->plan_Sij.execute(FFT_BACKWARD);
+		s->Sij.updateHalo();
+		if (gevb_field_save_raw(s->Sij.handle(), file("hij")) != 0) return 1;
+	}
+	return 0;
+}
+
+extern "C" int gevb_sim_write_field_snapshot(gevb_sim * s, const char * prefix, int mask)
+{
+	if (s == NULL || prefix == NULL) return 1;
+	GEVB_C_BOUNDARY(return write_field_snapshot(s, prefix, mask);)
 }
 
 // the phi / chi / hij / B part of writeSpectra (output.hpp:1945-1981,2151-2155; call main.cpp:639-679): forward
@@ -403,8 +483,7 @@ static int write_spectra(gevb_sim * s, const char * prefix, int pkcount, int num
 extern "C" int gevb_sim_write_spectra(gevb_sim * s, const char * prefix, int pkcount, int numbins, int mask, double z_target)
 {
 	if (s == NULL || prefix == NULL || numbins < 1) return 1;
-	try { return write_spectra(s, prefix, pkcount, numbins, mask, z_target); }
-	catch (const gevb_error &) { return 1; }
+	GEVB_C_BOUNDARY(return write_spectra(s, prefix, pkcount, numbins, mask, z_target);)
 }
 
 // snapshot of one species in Gadget-2 format (writeSnapshots, output.hpp:62-470 -> saveGadget2): the header is filled
@@ -492,6 +571,7 @@ extern "C" int gevb_sim_run(gevb_sim * s, const double * z_pk, int num_pk, int p
 		}
 	}
 	catch (const gevb_error &) { return 1; }
+	catch (...) { return 1; }                                                                                    // std::bad_alloc of the output buffers and the like
 	if (counts3) { counts3[0] = cycles; counts3[1] = pkcount; counts3[2] = snapcount; }
 	return 0;
 }
@@ -500,8 +580,7 @@ extern "C" int gevb_sim_run(gevb_sim * s, const double * z_pk, int num_pk, int p
 extern "C" int gevb_sim_step(gevb_sim * s)
 {
 	if (s == NULL || !s->pcls_cdm.initialized()) return 1;
-	try { return sim_step(s); }
-	catch (const gevb_error &) { return 1; }
+	GEVB_C_BOUNDARY(return sim_step(s);)
 }
 
 // first half of a cycle: stress-energy projections and the metric solve (main.cpp:378-599); the outputs of the reference sit

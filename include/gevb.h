@@ -111,6 +111,15 @@ int gevb_projection_comm(gevb_field * f);
 int gevb_field_sum(gevb_field * f, int comp, double * out);
 /* result(x) += value on the bulk of comp (the bg_ncdm add, main.cpp:394-397) */
 int gevb_field_add_constant(gevb_field * f, int comp, double value);
+/* every component of the local bulk times factor: the site loops that rescale the stored vector potential around an
+ * output or a restart (output.hpp:212-218, hibernation.hpp:533-538, ic_read.hpp:312-317)                             */
+int gevb_field_scale(gevb_field * f, double factor);
+gevb_ctx * gevb_field_ctx(gevb_field * f);
+/* Field::saveHDF5 / loadHDF5 (output.hpp:98-300, hibernation.hpp:588-600, ic_read.hpp:310,326): HDF5 is not in this
+ * image, so the dataset is written as a flat binary file -- 32-byte header {"GEVBFLD1", int32 ngrid, ncomp, 16 bytes 0},
+ * then float64 [comp][z][y][x] of the whole lattice.  Collective: every rank writes / reads the planes of its slab.   */
+int gevb_field_save_raw(gevb_field * f, const char * filename);
+int gevb_field_load_raw(gevb_field * f, const char * filename);
 
 /* ---- FFT ---------------------------------------------------------------------
  * PlanFFT<Cplx>(&real,&cplx) + execute(dir) (main.cpp:238-246,477,488,544,563,575,593):
@@ -244,9 +253,17 @@ int gevb_sim_set_fused(gevb_sim * sim, int fused);          /* 1 (default): fuse
 int gevb_sim_write_spectra(gevb_sim * sim, const char * prefix, int pkcount, int numbins, int mask, double z_target);
 /* writeSnapshots' Gadget-2 branch for one species (output.hpp:95-131 header, then saveGadget2) */
 int gevb_sim_save_gadget2(gevb_sim * sim, int species, const char * filename, int tracer_factor, double dtau_pos, double dtau_vel);
-/* hibernation / restart (hibernation.hpp:38-611, ic_read.hpp:58-400): particles of every species, phi, chi, BiFT and the
- * loop scalars, one binary file <filebase>.<rank>.gevb per rank (the reference's HDF5 container is not available);
- * restore needs a sim created with the same lattice, decomposition and flags.  Both are collective.            */
+/* hibernation / restart with the reference's state set and arithmetic (hibernation.hpp:512-611, ic_read.hpp:290-330):
+ * the particles of every species (<filebase>.<rank>.gevb, with the loop scalars a, tau, dtau, dtau_old, cycle, maxvel),
+ * phi and chi (<filebase>_phi.bin, _chi.bin) and the vector potential in REAL space divided by a^2 N (<filebase>_B.bin,
+ * hibernation.hpp:533-538).  Restore multiplies B by a^2 / N^2 and rebuilds BiFT by a forward transform
+ * (ic_read.hpp:305-319).  HDF5 is not in this image: the field files are flat binary (gevb_field_save_raw).  Restore
+ * needs a sim created with the same lattice, decomposition and flags.  Both are collective.                     */
+/* writeSnapshots' field dumps (output.hpp:98-300) as raw binary files <prefix>_<T00|B|phi|chi|hij>.bin (see
+ * gevb_field_save_raw): mask = MASK_PHI 1 | MASK_CHI 2 | MASK_B 8 | MASK_T00 16 | MASK_HIJ 128.  B is written divided by
+ * a^2 N and restored afterwards by a backward transform of BiFT, exactly the reference's sequence (output.hpp:212-236);
+ * hij is the TT projection of SijFT transformed back (output.hpp:259-265), T00 a fresh projection (:155-182).          */
+int gevb_sim_write_field_snapshot(gevb_sim * sim, const char * prefix, int mask);
 int gevb_sim_hibernate(gevb_sim * sim, const char * filebase);
 int gevb_sim_restore(gevb_sim * sim, const char * filebase);
 /* the main loop with its power-spectrum and Gadget-2 snapshot outputs at the requested redshifts (main.cpp:372-879:
@@ -256,6 +273,51 @@ int gevb_sim_restore(gevb_sim * sim, const char * filebase);
 int gevb_sim_run(gevb_sim * sim, const double * z_pk, int num_pk, int pk_mask, int numbins, const char * pk_prefix,
                  const double * z_snapshot, int num_snapshot, int tracer_factor, const char * snap_prefix, int max_cycles, int * counts3);
 int gevb_sim_step(gevb_sim * sim);                          /* one cycle; asynchronous except the maxvel / T00hom reads */
+
+/* ---- settings.ini and the basic IC generator: a run starts from the reference's own settings file ---------------
+ * gevb_settings_read restates the subset of the reference's parser (parser.hpp:40-105 readline, :122 loadParameterFile,
+ * :759-1800 parseMetadata) that the hot path, its outputs and "IC generator = basic" need; keys, defaults and derived
+ * cosmological parameters are the reference's.  `overrides` (may be NULL) holds further "key = value" lines that replace
+ * the file's lines of the same key.  Not supported (reported as errors): mPk file, IC generator other than basic,
+ * ncdm particle species from the generator, CLASS, lightcones.                                                       */
+#define GEVB_MAX_OUTPUTS 32
+#define GEVB_PATH_MAX 512
+typedef struct gevb_settings
+{
+	int ngrid, gr_flag, vector_flag;        /* Ngrid; gravity theory GR = 1 / Newton = 0; vector method parabolic = 0 / elliptic = 1 */
+	int baryon_flag;                        /* baryon treatment: ignore 0, sample 1, blend 2, hybrid 3 (parser.hpp:928-960)            */
+	int seed, ksphere, correct_displacement;/* seed; k-domain sphere; correct displacement                                             */
+	int tiling[2];                          /* tiling factor of the cdm (and baryon) template                                          */
+	int tracer_factor[2];
+	int numbins, pk_mask, snapshot_mask;    /* Pk bins; Pk outputs / snapshot outputs as MASK_* bits (metadata.hpp:56-70)              */
+	int num_pk, num_snapshot;
+	double boxsize, Cf, steplimit, movelimit, z_in, z_relax;
+	double A_s, n_s, k_pivot;
+	double cosmo[11];                       /* Omega_cdm, Omega_b, Omega_m, Omega_Lambda, Omega_fld, w0_fld, wa_fld, Omega_g, Omega_ur, Omega_rad, h */
+	double z_pk[GEVB_MAX_OUTPUTS], z_snapshot[GEVB_MAX_OUTPUTS];   /* descending, as the parser leaves them                           */
+	char template_file[2][GEVB_PATH_MAX], tk_file[GEVB_PATH_MAX];
+	char output_path[GEVB_PATH_MAX], basename_generic[128], basename_pk[128], basename_snapshot[128];
+} gevb_settings;
+int gevb_settings_read(const char * filename, const char * overrides, gevb_settings * out);
+/* main.cpp:184-340 for IC generator = basic: a simulation with the file's lattice, flags and cosmology (ctx must have been
+ * created with settings->ngrid), particles and metric fields from generateIC_basic (ic_basic.hpp:1626-2259; Threefry
+ * realisation prng_engine.hpp, transfer-function splines, template tiling, displacement / velocity callbacks, phi, chi, B). */
+int gevb_sim_create_from_settings(gevb_sim ** out, gevb_ctx * ctx, const gevb_settings * settings);
+/* the main loop with the file's outputs (gevb_sim_run with the settings' redshift lists, masks and file names under
+ * output_path)                                                                                                          */
+int gevb_sim_run_settings(gevb_sim * sim, const gevb_settings * settings, int max_cycles, int * counts3);
+/* host-side pieces of the generator by themselves (no device): the CIC convolution kernel on its 3 x 3 x 3 support around the
+ * origin (generateCICKernel, ic_basic.hpp:737-1052; out27[(dz+1)*9 + (dy+1)*3 + (dx+1)], numpcl = 0 gives the standard kernel)
+ * and the Gaussian realisation of one Fourier field (generateDisplacementField, ic_basic.hpp:1090-1379) on the host layout
+ * double[kz][ky][kx][2] of a whole lattice; potFT holds the kernel's transform on entry.                                */
+int gevb_ic_cic_kernel(int ngrid, int64_t numpcl, const float * pcldata, int numtile, double * out27);
+int gevb_ic_displacement_field(int ngrid, double * potFT, double coeff, int nspline, const double * spline_x, const double * spline_y,
+                               unsigned int seed, int ksphere, int deconvolve_f);
+/* loadHomogeneousTemplate (ic_basic.hpp:191-330): positions of a Gadget-2 template in box units; *numpart particles, pcldata
+ * (3 floats each) is allocated with malloc and owned by the caller                                                      */
+int gevb_ic_load_template(const char * filename, int64_t * numpart, float ** pcldata);
+/* sets individual sites of one component of a real field (global coordinates; sites outside this rank's slab are skipped) */
+int gevb_field_set_sites(gevb_field * f, int comp, int n, const int * xyz, const double * values);
 
 #ifdef __cplusplus
 }

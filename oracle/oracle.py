@@ -75,6 +75,9 @@ _SIGS = {
     "sim_set_ncdm_maxvel": (None, [_vp, _dp]),
     "sim_get_ncdm_state": (None, [_vp, _dp, _i32p]),
     "bg_ncdm": (_d, [_d, _dp, _i, _dp, _dp, _dp]),
+    "generateCICKernel": (None, [_i, _l, _vp, _i, _dp]),
+    "generateDisplacementField": (None, [_i, _dp, _d, _i, _dp, _dp, C.c_uint, _i, _i]),
+    "dump_shipped_files": (_l, [C.c_char_p, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS"), _l]),
 }
 
 FIELD_IDS = {"phi": 0, "chi": 1, "Bi": 2, "source": 3, "Sij": 4, "scalarFT": 10, "BiFT": 11, "SijFT": 12}
@@ -241,6 +244,31 @@ class Oracle:
 
     def particleHorizon(self, a, fourpiG, cosmo):
         return self.fn["particleHorizon"](a, fourpiG, np.ascontiguousarray(cosmo, dtype=np.float64))
+
+    # ---- pieces of the IC generator (compiled reference only) ---------------------------
+    def generateCICKernel(self, N, pcldata=None, numtile=1):
+        """generateCICKernel (ic_basic.hpp:737): the kernel field [z][y][x]; pcldata (n, 3) float32 template or None (standard kernel)"""
+        out = np.zeros((N, N, N))
+        if pcldata is None:
+            self.fn["generateCICKernel"](N, 0, None, 1, out)
+        else:
+            p = np.ascontiguousarray(pcldata, dtype=np.float32)
+            self.fn["generateCICKernel"](N, len(p), p.ctypes.data_as(C.c_void_p), numtile, out)
+        return out
+
+    def generateDisplacementField(self, potFT, coeff, spline_x, spline_y, seed, ksphere=0, deconvolve_f=1):
+        """generateDisplacementField (ic_basic.hpp:1090) applied to a copy of potFT [kz][ky][kx][2]"""
+        out = np.ascontiguousarray(potFT, dtype=np.float64).copy()
+        x, y = np.ascontiguousarray(spline_x, dtype=np.float64), np.ascontiguousarray(spline_y, dtype=np.float64)
+        self.fn["generateDisplacementField"](out.shape[0], out, coeff, len(x), x, y, seed, ksphere, deconvolve_f)
+        return out
+
+    def dump_shipped_files(self, directory):
+        """settings.ini, class_tk.dat, sc1_crystal.dat of the reference written to `directory`; returns the template's
+        positions as loadHomogeneousTemplate (ic_basic.hpp:191) delivers them"""
+        buf = np.zeros((4096, 3), dtype=np.float32)
+        n = self.fn["dump_shipped_files"](str(directory).encode(), buf, len(buf))
+        return buf[:n].copy()
 
     # ---- stateful simulation -----------------------------------------------------------
     def sim(self, N, gr_flag, vector_flag, dsettings, cosmo):

@@ -566,6 +566,49 @@ void * ref_sim_create_from_settings(int ngrid, int tiling, int seed, const char 
 	return s;
 }
 
+// ---- the IC generator's pieces by themselves (checkers of gevb_ic_cic_kernel / gevb_ic_displacement_field / gevb_ic_load_template)
+// generateCICKernel (ic_basic.hpp:737): the whole kernel field, flat [z][y][x]
+void ref_generateCICKernel(int N, long numpcl, float * pcldata, int numtile, double * out)
+{
+	Lat & L = get_lat(N);
+	Field<Real> ker;
+	ker.initialize(L.lat, 1); ker.alloc();
+	if (numpcl > 0) generateCICKernel(ker, numpcl, pcldata, numtile); else generateCICKernel(ker);
+	store_real(ker, out);
+}
+
+// generateDisplacementField (ic_basic.hpp:1090) on a Fourier field given and returned as flat [kz][ky][kx][2]; the spline is
+// built from (x, y) with the shim's gsl_interp_cspline
+void ref_generateDisplacementField(int N, double * potFT, double coeff, int n, const double * x, const double * y, unsigned int seed, int ksphere, int deconvolve_f)
+{
+	Lat & L = get_lat(N);
+	Field<Cplx> f;
+	f.initialize(L.latFT, 1); f.alloc();
+	load_cplx(f, potFT);
+	gsl_spline * sp = gsl_spline_alloc(gsl_interp_cspline, n);
+	gsl_spline_init(sp, x, y, n);
+	generateDisplacementField(f, coeff, sp, seed, ksphere, deconvolve_f);
+	gsl_spline_free(sp);
+	store_cplx(f, potFT);
+}
+
+// loadHomogeneousTemplate (ic_basic.hpp:191) of the embedded sc1_crystal.dat; the files the shipped configuration reads are
+// written to `dir` (settings.ini, class_tk.dat, sc1_crystal.dat) so that a product run can start from them on a box
+// without the reference tree.  Returns the template's particle count; positions (box units) go to out[3 * cap].
+long ref_dump_shipped_files(const char * dir, float * out, long cap)
+{
+	const std::string d(dir);
+	write_embedded(d, "settings.ini", ref_settings_ini, ref_settings_ini_len);
+	write_embedded(d, "class_tk.dat", ref_class_tk_dat, ref_class_tk_dat_len);
+	const std::string pclfile = write_embedded(d, "sc1_crystal.dat", ref_sc1_crystal_dat, ref_sc1_crystal_dat_len);
+	long numpart = 0;
+	float * data = NULL;
+	loadHomogeneousTemplate(pclfile.c_str(), numpart, data);
+	for (long i = 0; i < 3 * numpart && i < 3 * cap; i++) out[i] = data[i];
+	free(data);
+	return numpart;
+}
+
 // the reference's own spectrum file writer (tools.hpp:268-346), EXACT_OUTPUT_REDSHIFTS branch included
 void ref_writePowerSpectrum(const double * kbin, const double * power, const double * kscatter, const double * pscatter, const int * occupation, int numbins,
                             double rescalek, double rescalep, const char * filename, const char * description, double a, double z_target)

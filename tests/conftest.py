@@ -46,6 +46,14 @@ def gevb():
     return g
 
 
+@pytest.fixture(scope="session")
+def gevb_host():
+    """libgevb.so for its host-only entry points (settings reader, IC generator pieces, file writers): loads without a GPU"""
+    import gevb as g
+    g.lib()
+    return g
+
+
 @pytest.fixture()
 def ctx(gevb, request):
     """A single-rank device context for lattice size given by the `ngrid` marker/param (default 16)."""

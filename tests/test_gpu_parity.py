@@ -61,10 +61,8 @@ def test_against_checker(gevb, ctx, checker, N, seed):
     assert np.abs(out["fused_pos"] - pos).max() <= 1e-14
     assert abs(out["fused_max"][0] - vmax) <= 1e-12 * vmax
     # bit-exact re-binning after the drift
-    _, counts = checker.cell_index(N, ref_out["drift_nf3"])
-    moved_same_cell = np.array_equal(np.floor(out["drift_nf3"] * N), np.floor(ref_out["drift_nf3"] * N))
-    if moved_same_cell:
-        assert np.array_equal(out["drift_nf3_counts"], counts)
+    ok, flipped = common.counts_bit_exact(N, out["drift_nf3"], ref_out["drift_nf3"], out["drift_nf3_counts"], checker.cell_index)
+    assert ok, f"per-cell counts differ from the reference's ({flipped} particles on a cell face)"
 
 
 def test_empty_and_single_particle(gevb, ctx, checker):
@@ -94,6 +92,12 @@ def test_error_behaviour(gevb, ctx):
     k1 = gevb.Field(c, gevb.CPLX, 1)
     with pytest.raises(gevb.GevbError):
         gevb.projectFTscalar(k1, k1)
+
+
+def _cell_index_numpy(N, pos):
+    c = np.minimum(np.floor(pos * N).astype(np.int64), N - 1)
+    lin = (c[:, 2] * N + c[:, 1]) * N + c[:, 0]
+    return lin, np.bincount(lin, minlength=N ** 3).astype(np.uint32)
 
 
 def _make_sims(gevb, c, checker, N, seed, vector_flag=0, gr=1, baryons=False):
@@ -139,6 +143,9 @@ def _compare_sims(rs, gs, N, nspecies=1):
         rc = np.floor(rpos[ro] * N).astype(np.int64)
         gc = np.floor(gpos[go] * N).astype(np.int64)
         errs[f"cells{sp}"] = int(np.count_nonzero(rc != gc))
+        # ... and the container's own per-cell counts are the histogram of floor(pos/dx) (always compared)
+        ok, _ = common.counts_bit_exact(N, gpos[go], rpos[ro], gs.pcls(sp).cell_counts(), _cell_index_numpy)
+        errs[f"cells_counts{sp}"] = 0 if ok else 1
     r, g = rs.state(), gs.state()
     for k in ("a", "dtau", "dtau_old", "T00hom"):
         errs["state_" + k] = abs(r[k] - g[k]) / abs(r[k]) if r[k] != 0 else abs(g[k])
@@ -162,6 +169,21 @@ def test_time_loop_one_and_more_steps(gevb, ctx, ref, fused, vector_flag):
         bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= tol))}
         assert bad == {}, (step, e)
         assert e["state_tau"] < 1e-6    # tau offset comes from the reference's 1e-7 quadrature (bookkeeping only)
+    rs.close(); gs.close()
+
+
+def test_time_loop_N128_many_super_bricks(gevb, ctx, ref):
+    """One and two cycles at N = 128 against the compiled reference: 2 x 4 x 4 super-bricks of 64 x 32 x 32 cells, so the
+    super-brick index arithmetic in x (sx_shift), k_decode at scale and the multi-brick flush paths are compared with the
+    oracle, not just with invariants."""
+    N = 128
+    rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=128)
+    for step in range(2):
+        rs.step(); gs.step()
+        e = _compare_sims(rs, gs, N)
+        skip = ("state_tau", "scalarFT")
+        bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= FIELD_TOL * (1 + step)))}
+        assert bad == {}, (step, e)
     rs.close(); gs.close()
 
 
@@ -419,38 +441,77 @@ def test_spectra_files_and_gadget2_snapshot(gevb, ctx, ref, tmp_path):
 
 
 def test_hibernate_and_restart(gevb, ctx, ref, tmp_path):
-    """a run continued from a hibernation file reproduces the uninterrupted run (hibernation.hpp, ic_read.hpp)"""
+    """a run continued from a hibernation point is compared with the REFERENCE running on from the same state
+    (hibernation.hpp:512-611, ic_read.hpp:290-330).  The files hold the reference's state set: particles, phi, chi and the
+    real-space vector potential divided by a^2 N; the restart multiplies it by a^2 / N^2 and rebuilds BiFT by a forward FFT."""
     N = 16
     rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=61, baryons=True)
-    rs.close()
     for _ in range(2):
-        gs.step()
+        rs.step(); gs.step()
     base = str(tmp_path / "hib")
+    a_hib = gs.state()["a"]
     gs.hibernate(base)
-    for _ in range(2):
-        gs.step()
+    # what the reference writes: B / (a^2 N) (hibernation.hpp:533-538), phi, chi
+    B_file = gevb.read_raw_field(base + "_B.bin")
+    assert common.rel_linf(B_file, rs.get_field("Bi") / (a_hib * a_hib * N)) <= 2 * FIELD_TOL
+    assert common.rel_linf(gevb.read_raw_field(base + "_phi.bin"), rs.get_field("phi")) <= 2 * FIELD_TOL
+    assert common.rel_linf(gevb.read_raw_field(base + "_chi.bin"), rs.get_field("chi")) <= 2 * FIELD_TOL
+    # the reference runs on uninterrupted; the device run is thrown away and continued from the files in a new simulation
+    gs.close()
     cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
-    g2 = gevb.Sim(gs.ctx, 1, 0, ds, cosmo)
+    g2 = gevb.Sim(ctx(N), 1, 0, ds, cosmo)
     g2.restore(base)
     assert g2.state()["cycle"] == 2
+    # BiFT rebuilt by the forward transform of the stored field (ic_read.hpp:305-319) is the reference's persistent BiFT
+    assert common.rel_linf(g2.get_field("BiFT"), rs.get_field("BiFT")) <= 2 * FIELD_TOL
     for _ in range(2):
-        g2.step()
-    a, b = gs.state(), g2.state()
-    for k in ("a", "tau", "dtau", "dtau_old"):
-        assert a[k] == b[k], k
-    assert a["cycle"] == b["cycle"] == 4 and abs(a["T00hom"] - b["T00hom"]) <= 1e-13 * abs(a["T00hom"])
-    for name in ("phi", "chi", "Bi", "BiFT"):
-        assert common.rel_linf(g2.get_field(name), gs.get_field(name)) <= 1e-12, name
-    for sp in (0, 1):
-        i1, p1, v1 = gs.pcls(sp).download()
-        i2, p2, v2 = g2.pcls(sp).download()
-        o1, o2 = np.argsort(i1), np.argsort(i2)
-        assert np.array_equal(i1[o1], i2[o2]) and np.abs(p1[o1] - p2[o2]).max() <= 1e-14 and common.rel_linf(v2[o2], v1[o1]) <= 1e-12
-    # a file written for another lattice is refused
+        rs.step(); g2.step()
+    e = _compare_sims(rs, g2, N, nspecies=2)
+    skip = ("state_tau", "scalarFT")
+    bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= 5 * FIELD_TOL))}
+    assert bad == {}, e
+    assert g2.state()["cycle"] == rs.state()["cycle"] == 4
+    # a file written for another lattice is refused; so is a truncated particle file (no rank is left inside a collective)
     g3 = gevb.Sim(ctx(8), 1, 0, ds, cosmo)
     with pytest.raises(gevb.GevbError):
         g3.restore(base)
-    gs.close(); g2.close(); g3.close()
+    with open(base + ".0.gevb", "r+b") as f:
+        f.truncate(600)
+    g4 = gevb.Sim(ctx(N), 1, 0, ds, cosmo)
+    with pytest.raises(gevb.GevbError):
+        g4.restore(base)
+    rs.close(); g2.close(); g3.close(); g4.close()
+
+
+def test_field_snapshot_dumps(gevb, ctx, ref, tmp_path):
+    """writeSnapshots' field dumps (output.hpp:98-300) against the reference's fields: phi, chi, T00 as projected
+    for the output, B divided by a^2 N with the stored field restored afterwards (output.hpp:212-236), hij = TT projection of
+    SijFT transformed back (output.hpp:259-265)"""
+    N = 16
+    rs, gs = _make_sims(gevb, ctx(N), ref, N, seed=62)
+    for _ in range(2):
+        rs.step(); gs.step()
+    a = gs.state()["a"]
+    Bi_before = gs.get_field("Bi")
+    prefix = str(tmp_path / "snap000")
+    gs.write_field_snapshot(prefix, 1 | 2 | 8 | 16 | 128)
+    rd = gevb.read_raw_field
+    assert common.rel_linf(rd(prefix + "_phi.bin"), rs.get_field("phi")) <= 2 * FIELD_TOL
+    assert common.rel_linf(rd(prefix + "_chi.bin"), rs.get_field("chi")) <= 2 * FIELD_TOL
+    assert common.rel_linf(rd(prefix + "_B.bin"), rs.get_field("Bi") / (a * a * N)) <= 2 * FIELD_TOL
+    # the rescale is undone by the backward transform of BiFT (output.hpp:232-236)
+    assert common.rel_linf(gs.get_field("Bi"), Bi_before) <= 1e-12
+    # T00 as output.hpp:155-182 projects it: the current particles with the current phi
+    ids, pos, vel = rs.get_particles(0)
+    cosmo = common.shipped_cosmology()
+    mass = (cosmo[0] + cosmo[1]) / len(ids)
+    T00 = ref.projection_T00(N, pos, vel, mass, a, rs.get_field("phi")[0], 1.0)
+    assert common.rel_linf(rd(prefix + "_T00.bin"), T00) <= 2 * FIELD_TOL
+    # hij: TT projection of the reference's SijFT, transformed back (unnormalised c2r)
+    hijFT = ref.projectFTtensor(rs.get_field("SijFT"))
+    hij = np.stack([ref.fft_backward(hijFT[c:c + 1])[0] for c in range(6)])
+    assert common.rel_linf(rd(prefix + "_hij.bin"), hij) <= 5 * FIELD_TOL
+    rs.close(); gs.close()
 
 
 def _cic_gradient(field, pos, N):
@@ -623,6 +684,40 @@ def test_config1_shipped_settings_and_reference_snapshot(gevb, ctx, ref, tmp_pat
     assert np.array_equal(ir[orr], ig[og])
     assert np.all(np.abs(pg[og] - pr[orr]) <= np.spacing(np.abs(pr[orr]).astype(np.float32)) + 1e-30)
     assert np.all(np.abs(vg[og] - vr[orr]) <= 4 * np.spacing(np.abs(vr[orr]).astype(np.float32)) + 1e-30)
+    rs.close(); gs.close()
+
+
+@pytest.mark.parametrize("overrides,ngrid,tiling", [("", 64, 16), ("", 16, 4), ("gravity theory = Newton", 16, 4), ("baryon treatment = sample", 16, 4),
+                                                    ("baryon treatment = hybrid", 16, 4), ("baryon treatment = ignore\ncorrect displacement = no\nk-domain = cube", 16, 4),
+                                                    ("", 24, 6)],
+                         ids=["config1_as_shipped", "ngrid16", "newton", "baryons_sampled", "baryons_hybrid", "ignore_cube_uncorrected", "ngrid24"])
+def test_product_starts_from_settings_ini(gevb, ctx, ref, tmp_path, overrides, ngrid, tiling):
+    """SURVEY 8f-2 / VERDICT r1 missing 2-3: the product reads the reference's settings.ini and generates its own initial
+    conditions (host/settings.cpp, host/ic_basic.cpp: template, CIC kernel, Threefry realisation, transfer-function splines on
+    the host; FFTs, displacement / momentum callbacks, phi, chi, B on the device) -- no oracle in the product's loop.  Compared
+    with the reference's own parser + generateIC_basic from the same file and seed: identical IDs and per-cell counts,
+    positions / momenta / fields to round-off; then both sides run three cycles."""
+    d = tmp_path
+    ref.dump_shipped_files(d)                                          # the three files the shipped run reads (test infrastructure provides the inputs)
+    ov = f"Ngrid = {ngrid}\ntiling factor = {tiling}\ntemplate file = {d}/sc1_crystal.dat\nTk file = {d}/class_tk.dat\n" + overrides
+    st = gevb.settings_read(d / "settings.ini", ov)
+    assert st.ngrid == ngrid
+    gs = gevb.sim_from_settings(ctx(ngrid), st)
+    rs = ref.sim_from_settings(ngrid=ngrid, tiling=tiling, overrides=overrides)
+    N = ngrid
+    nspecies = 2 if "sample" in overrides else 1
+    e = _compare_sims(rs, gs, N, nspecies=nspecies)
+    # the realisation is bit-identical; what differs is the device's FFT / summation order: particle displacements are O(1e-3) box
+    # units from gradients of fields that agree to 1e-10 relative
+    skip = ("state_tau", "scalarFT", "source", "Sij", "SijFT", "state_T00hom", "state_dtau_old")
+    bad = {k: v for k, v in e.items() if k not in skip and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= 5 * FIELD_TOL))}
+    assert bad == {}, e
+    assert abs(rs.state()["maxvel"][0] - gs.state()["maxvel"][0]) <= 1e-9 * rs.state()["maxvel"][0]
+    for step in range(3):
+        rs.step(); gs.step()
+    e = _compare_sims(rs, gs, N, nspecies=nspecies)
+    bad = {k: v for k, v in e.items() if k not in ("state_tau", "scalarFT") and ((k.startswith("cells") and v != 0) or (not k.startswith("cells") and not v <= 20 * FIELD_TOL))}
+    assert bad == {}, e
     rs.close(); gs.close()
 
 
