@@ -37,6 +37,18 @@ import numpy as np  # noqa: E402
 METRIC = "particle-steps/s (GR, 512^3)"
 UNIT = "particle-steps/s"
 
+# BASELINE.json configs (1-based as in SURVEY 8d; config 1 is the shipped settings.ini run, covered by tests/ and
+# scripts/run_settings.py).  The bench line is quoted on config 3; the others are run on request (--config) and their
+# lines are kept under profiles/.
+CONFIGS = {
+    2: dict(ngrid=256, species=("cdm",), vector_flag=0, hij=False, what="256^3 grid / 256^3 CDM particles, GR (phi, chi, B_i, Tij sources)"),
+    3: dict(ngrid=512, species=("cdm",), vector_flag=0, hij=False, what="512^3 grid / 512^3 particles, GR, parabolic B"),
+    4: dict(ngrid=512, species=("cdm", "b", "ncdm0", "ncdm1"), vector_flag=0, hij=False,
+            what="512^3 grid, cdm + baryon + 2 massive-neutrino (0.1, 0.2 eV) species of 512^3 particles each, GR; synthetic ICs: the ncdm species are "
+                 "a jittered lattice with Fermi-Dirac thermal momenta (the shipped class_tk.dat has no ncdm columns and CLASS is unavailable, SURVEY 8d)"),
+    5: dict(ngrid=1024, species=("cdm",), vector_flag=1, hij=True, what="1024^3 grid / 1024^3 particles, GR with elliptic vector method (T0i deposit + projectFTvector) and an hij spectrum call"),
+}
+
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
@@ -61,6 +73,24 @@ def local_particles(N, z0, nzl, a, seed):
     vel *= 1e-3 * a
     ids = np.arange(z0 * N * N, z0 * N * N + n, dtype=np.int64)
     return ids, pos, vel
+
+
+def fermi_dirac_momenta(n, T_over_m, seed):
+    """q/m of n particles drawn from the relativistic Fermi-Dirac distribution q^2 / (e^q + 1) (isotropic), the distribution
+    applyMomentumDistribution samples (ic_basic.hpp:1460-1585): Gamma(3) proposals accepted with probability 1 / (1 + e^-q)"""
+    rng = np.random.default_rng(seed)
+    q = np.empty(n)
+    todo = np.arange(n)
+    while len(todo):
+        prop = rng.gamma(3.0, 1.0, len(todo))
+        ok = rng.random(len(todo)) < 1.0 / (1.0 + np.exp(-prop))
+        q[todo[ok]] = prop[ok]
+        todo = todo[~ok]
+    mu = 2.0 * rng.random(n) - 1.0
+    ph = 2.0 * np.pi * rng.random(n)
+    st = np.sqrt(1.0 - mu * mu)
+    q *= T_over_m
+    return np.stack([q * st * np.cos(ph), q * st * np.sin(ph), q * mu], axis=1)
 
 
 def analytic_field(N, z0, nzl, rms, seed, ncomp=1):
@@ -292,6 +322,48 @@ def particle_regime(gevb, ctx, common, N, label, ds, cosmo, mass, phi, chi):
     return out
 
 
+# ----------------------------------------------------------------------------- multi-rank parity (checker use of oracle/)
+def multi_rank_parity(gevb, dist, rank, world, local_rank):
+    """The decomposition-versus-oracle checks of tests/multigpu_worker.py (deposit + fold, halo, kick, drift with slab
+    migration, whole cycles of the time loop) at N = 32 on the ranks of this run, before anything is timed: the scaling lease
+    is the only multi-GPU box the driver runs, so the parity of the slab-decomposed path is established there.  oracle/ is
+    used here strictly as the checker (tier rule 3); a failure aborts the run."""
+    import multigpu_worker as mw
+    N = 32
+    if N % world != 0 or N // world < 2:
+        return {"skipped": f"N = {N} does not divide into {world} slabs"}
+    chk = None
+    if rank == 0:
+        import oracle
+        chk = oracle.load_ref() or oracle.load_ora()
+        if chk is None:
+            raise RuntimeError("multi-rank parity: no CPU checker library (oracle/_ref or oracle/libgev_oracle.so) in the snapshot")
+    box = [gevb.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = gevb.Context(N, device=local_rank, rank=rank, nranks=world, nccl_id=box[0])
+    failures = []
+    mw.RESULTS.clear()
+    mw.QUIET = True
+    mw.case_fft(ctx, N, failures)
+    mw.case_particles(ctx, chk, N, failures)
+    mw.case_time_loop(ctx, chk, N, 0, 1, failures, nsteps=2)
+    mw.case_time_loop(ctx, chk, N, 1, 1, failures, nsteps=1)
+    ctx.close()
+    allf = [None] * world
+    dist.all_gather_object(allf, failures)
+    bad = [f for fl in allf for f in fl]
+    out = None
+    if rank == 0:
+        worst = max(mw.RESULTS, key=lambda r: r[1] / r[2] if r[2] > 0 else (float("inf") if r[1] > 0 else 0.0))
+        cells = [r for r in mw.RESULTS if "cells" in r[0] or "counts" in r[0] or "ids" in r[0] or "conservation" in r[0]]
+        out = {"checker": chk.description, "ngrid": N, "ranks": world, "checks": len(mw.RESULTS), "failed": len(bad),
+               "worst_field": {"name": worst[0], "error": worst[1], "tolerance": worst[2]},
+               "cells_mismatch": int(sum(r[1] for r in cells)), "integer_checks": len(cells)}
+    if bad:
+        raise RuntimeError(f"multi-rank parity check failed: {bad}")
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import torch                      # first: its bundled NCCL must be the one mapped into the process
@@ -305,26 +377,66 @@ def run_ours(args, rank, world, local_rank):
     nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        box = [gevb.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nccl_id = box[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    N = args.ngrid
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_rank_parity(gevb, dist, rank, world, local_rank)
+    if world > 1:
+        box = [gevb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+
+    cfg = CONFIGS[args.config]
+    N = args.ngrid if args.ngrid else cfg["ngrid"]
+    species = cfg["species"]
     ctx = gevb.Context(N, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
     cosmo, ds = common.shipped_cosmology(), common.shipped_settings()
+    ncdm = None
+    if "ncdm0" in species:
+        cosmo, m_ncdm, T_ncdm, Om_ncdm = common.ncdm_model(cosmo)
+        ncdm = (m_ncdm, T_ncdm, Om_ncdm)
     a0 = 1.0 / (1.0 + ds[3])
     t_setup = time.perf_counter()
-    ids, pos, vel = local_particles(N, ctx.z0, ctx.nzl, a0, 42)
-    np_local, np_total = len(ids), N ** 3
-    mass = (cosmo[0] + cosmo[1]) / np_total
+    sim = gevb.Sim(ctx, 1, cfg["vector_flag"], ds, cosmo)
+    if ncdm:
+        # deposits of the ncdm species on from the start; move limit as the parser's default (Ngrid, clamped to the slab by the library)
+        sim.set_ncdm(m_ncdm, T_ncdm, Om_ncdm, [1e4, 1e4], [1e4, 1e4], 1e4, float(N))
+    np_local_total, masses = 0, {}
+    for sp_index, name in enumerate(species):
+        slot = {"cdm": 0, "b": 1, "ncdm0": 2, "ncdm1": 3}[name]
+        ids, pos, vel = local_particles(N, ctx.z0, ctx.nzl, a0, 42 + 17 * sp_index)
+        if name.startswith("ncdm"):
+            k = int(name[-1])
+            # q/m scale of the species: (Omega_g h^2 / C_PLANCK_LAW)^(1/4) T_ncdm k_B / m_ncdm  (ic_basic.hpp:2218)
+            T_over_m = (cosmo[7] * cosmo[10] ** 2 / 4.48147e-7) ** 0.25 * T_ncdm[k] * 8.61733e-5 / m_ncdm[k]
+            vel = fermi_dirac_momenta(len(ids), T_over_m, 4242 + 1000 * ctx.z0 + k)
+            mass = Om_ncdm[k] / N ** 3
+        else:
+            mass = {"cdm": cosmo[0] if "b" in species else cosmo[0] + cosmo[1], "b": cosmo[1]}[name] / N ** 3
+        masses[slot] = mass
+        sim.set_particles(slot, ids, pos, vel, mass)
+        np_local_total += len(ids)
+        if sp_index == 0:
+            np_local = len(ids)
+        del ids, pos, vel
+    if ncdm:
+        # the first cycle's sub-stepping needs the largest ncdm velocity (the IC generator returns it, main.cpp:330-340)
+        vmax = []
+        for k in range(2):
+            _, _, v = sim.pcls(2 + k).download()
+            q = float(np.sqrt((v * v).sum(axis=1).max())) if len(v) else 0.0
+            vmax.append(q / a0 / np.sqrt((q / a0) ** 2 + 1.0))
+            del v
+        vmax = ctx.parallel_max(vmax)
+        sim.set_ncdm_maxvel(vmax)
+    np_total = N ** 3 * len(species)
+    mass = masses[0]
     phi = analytic_field(N, ctx.z0, ctx.nzl, 1e-5, 1)
     chi = analytic_field(N, ctx.z0, ctx.nzl, 1e-7, 2)
-    sim = gevb.Sim(ctx, 1, 0, ds, cosmo)
-    sim.set_particles(0, ids, pos, vel, mass)
     sim.set_field("phi", phi)
     sim.set_field("chi", chi)
     t_setup = time.perf_counter() - t_setup
@@ -358,14 +470,37 @@ def run_ours(args, rank, world, local_rank):
     value = np_total * args.steps / (ms * 1e-3)
     state = sim.state()
     # size-independent invariants of the timed run (full benchmark size): no particle lost in re-binning / migration,
-    # mass conservation of the deposit (T00hom = Omega_cdm + Omega_b up to the O(phi) metric correction)
-    n_now = torch.tensor([float(sim.pcls(0).count())], dtype=torch.float64, device="cuda")
+    # mass conservation of the deposit (T00hom = Omega_m up to the O(phi) metric and O(q^2) kinetic corrections)
+    n_now = torch.tensor([float(sum(sim.pcls({"cdm": 0, "b": 1, "ncdm0": 2, "ncdm1": 3}[nm]).count() for nm in species))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(n_now)
+    Omega_dep = cosmo[0] + cosmo[1] + (float(np.sum(ncdm[2])) if ncdm else 0.0)
     invariants = {"particles_after": int(n_now.item()), "particles_conserved": int(n_now.item()) == np_total,
-                  "T00hom_over_Omega_m_minus_1": state["T00hom"] / (cosmo[0] + cosmo[1]) - 1.0}
-    if not invariants["particles_conserved"] or abs(invariants["T00hom_over_Omega_m_minus_1"]) > 1e-3:
+                  "T00hom_over_Omega_m_minus_1": state["T00hom"] / Omega_dep - 1.0}
+    # the relativistic ncdm species carry kinetic energy: T00hom exceeds Omega_m by <q^2>/2a^2-ish for them (a few per cent of Omega_ncdm)
+    tol_T00 = 1e-3 if not ncdm else 2e-2
+    if not invariants["particles_conserved"] or abs(invariants["T00hom_over_Omega_m_minus_1"]) > tol_T00:
         raise RuntimeError(f"benchmark run violates an invariant: {invariants}")
+    mem_gb = torch.cuda.mem_get_info(local_rank)
+    mem_used_gb = (mem_gb[1] - mem_gb[0]) / 2 ** 30
+    ncdm_steps = None
+    if ncdm:
+        ncdm_steps = [int(x) for x in sim.ncdm_state()[1][:2]]
+
+    # ---- config 5: the hij spectrum call of output.hpp:1961-1981 once, outside the timed region (Tij deposit, 6 FFTs, TT projection, binning)
+    hij_ms = None
+    if cfg["hij"]:
+        import tempfile
+        tmpd = tempfile.mkdtemp()
+        ctx.sync(); barrier()
+        t0 = time.perf_counter()
+        sim.write_spectra(os.path.join(tmpd, "pk"), 0, 1024, 128)
+        ctx.sync(); barrier()
+        hij_ms = 1e3 * (time.perf_counter() - t0)
+        if rank == 0:
+            pk = np.loadtxt(os.path.join(tmpd, "pk000_hij.dat"))
+            invariants["hij_spectrum_bins"] = int(len(pk))
+            invariants["hij_spectrum_finite"] = bool(np.all(np.isfinite(pk)))
 
     # ---- the FFT exchange by itself: two more cycles with the component pipeline off, so that the time of the pushes is
     #      not hidden behind the local transforms (the timed run above keeps the overlap on)
@@ -396,67 +531,51 @@ def run_ours(args, rank, world, local_rank):
                     print(json.dumps({"ablate": knob, "value": int(v), "ms": {k: round(t / 2, 3) for k, (t, n) in per.items() if t / 2 > 0.1}}), file=sys.stderr, flush=True)
             gevb.tuning(knob, int(vals.split(":")[0]))
 
-    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    # ---- end to end through the C ABI with host buffers (species 0 and the metric state; config 3 is the quoted one) ----
+    e2e_value, h2d, d2h = None, 0, 0
     e2e_steps = max(1, min(args.steps, env_int("GEVB_E2E_STEPS", 2)))
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    gid, gpos, gvel = sim.pcls(0).download()
-    h_id, h_pos, h_vel = pin(gid), pin(gpos), pin(gvel)
-    h_phi, h_chi, h_bft = pin(sim.get_field("phi")), pin(sim.get_field("chi")), pin(sim.get_field("BiFT"))
-    pc = sim.pcls(0)
-    h2d = h_id.nbytes + h_pos.nbytes + h_vel.nbytes + h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
-    d2h = h_id.nbytes + h_pos.nbytes + h_vel.nbytes + h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
+    if len(species) == 1 and not args.no_e2e:
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        gid, gpos, gvel = sim.pcls(0).download()
+        h_phi, h_chi, h_bft = pin(sim.get_field("phi")), pin(sim.get_field("chi")), pin(sim.get_field("BiFT"))
+        # slab counts change as particles migrate; host buffers are sized once with head-room
+        cap = len(gid) if world == 1 else int(np_local * 1.1) + 1024
+        h_id, h_pos, h_vel = pin(np.resize(gid, cap)), pin(np.resize(gpos, (cap, 3))), pin(np.resize(gvel, (cap, 3)))
+        nloc = [len(gid)]
+        del gid, gpos, gvel
+        fbytes = h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
 
-    def e2e_step():
-        sim.set_particles(0, h_id, h_pos, h_vel, mass)          # host -> device: particle state
-        sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
-        sim.step()
-        p = sim.pcls(0)
-        n = p.count()
-        L = gevb.lib()
-        gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:n]), gevb._ptr(h_pos[:n]), gevb._ptr(h_vel[:n])), "download")
-        for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
-            gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
+        def e2e_step():
+            n = nloc[0]
+            sim.set_particles(0, h_id[:n], h_pos[:n], h_vel[:n], mass)          # host -> device: particle state
+            sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
+            sim.step()
+            p = sim.pcls(0)
+            m = p.count()
+            L = gevb.lib()
+            gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:m]), gevb._ptr(h_pos[:m]), gevb._ptr(h_vel[:m])), "download")
+            for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
+                gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
+            nloc[0] = m
+            return 56 * n + fbytes, 56 * m + fbytes
 
-    e2e_value = None
-    if world == 1:
         e2e_step()                                              # warm-up (allocations)
         ctx.sync(); barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            e2e_step()
+            up, down = e2e_step()
+            h2d += up; d2h += down
         ctx.sync(); barrier()
         e2e_s = time.perf_counter() - t0
+        h2d //= e2e_steps; d2h //= e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+            hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            dist.all_reduce(hb)
+            h2d, d2h = int(hb[0].item()), int(hb[1].item())
         e2e_value = np_total * e2e_steps / e2e_s
-    else:
-        # slab counts change as particles migrate; host buffers are sized once with head-room
-        cap = int(np_local * 1.1) + 1024
-        h_id, h_pos, h_vel = pin(np.resize(gid, cap)), pin(np.resize(gpos, (cap, 3))), pin(np.resize(gvel, (cap, 3)))
-        nloc = [len(gid)]
-
-        def e2e_step_multi():
-            n = nloc[0]
-            sim.set_particles(0, h_id[:n], h_pos[:n], h_vel[:n], mass)
-            sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
-            sim.step()
-            p = sim.pcls(0)
-            n = p.count()
-            L = gevb.lib()
-            gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:n]), gevb._ptr(h_pos[:n]), gevb._ptr(h_vel[:n])), "download")
-            for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
-                gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
-            nloc[0] = n
-        e2e_step_multi()
-        ctx.sync(); barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step_multi()
-        ctx.sync(); barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = np_total * e2e_steps / float(t.item())
-        hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
-        dist.all_reduce(hb)
-        h2d, d2h = int(hb[0].item()), int(hb[1].item())
 
     # ---- roofline of the dominant own kernel ---------------------------------------------------
     peak, peak_src = measured_peak()
@@ -475,15 +594,16 @@ def run_ours(args, rank, world, local_rank):
             gbs = b * cnt / (kms * 1e-3) / 1e9
             entry.update({"bytes_per_launch": b, "achieved_gbs": gbs, "frac": gbs / peak})
         kernels[name] = entry
-    # FFT: 12 component transforms per step in 6 forward + 6 backward component-units (1+6 fwd, 1+1+3 bwd + ...)
-    for name, ncomp_per_step in (("fft_forward", 7), ("fft_backward", 5)):
+    # FFT: 12 component transforms per step (parabolic): 1 + 6 forward, 1 + 1 + 3 backward; the elliptic method adds 3 forward
+    nfwd = 7 + (3 if cfg["vector_flag"] else 0)
+    for name, ncomp_per_step in (("fft_forward", nfwd), ("fft_backward", 5)):
         if name in kernels and per_class[name][0] > 0:
             gbs = 16 * ctx.nzl * N * N * ncomp_per_step * args.steps / (per_class[name][0] * 1e-3) / 1e9
             kernels[name].update({"bytes_per_launch": 16 * ctx.nzl * N * N, "achieved_gbs": gbs, "frac": gbs / peak, "note": "cuFFT; ideal 16 B per site and component"})
     nvlink = None
     if world > 1 and "fft_alltoall" in per_class and per_class["fft_alltoall"][0] > 0:
-        # bytes one rank puts on NVLink per step: 12 component transforms x 16 B x local k-sites x (P-1)/P
-        sent = 12 * 16 * (N // 2 + 1) * N * (N // world) * (world - 1) / world
+        # bytes one rank puts on NVLink per step: component transforms x 16 B x local k-sites x (P-1)/P
+        sent = (nfwd + 5) * 16 * (N // 2 + 1) * N * (N // world) * (world - 1) / world
         exposed_ms = per_class["fft_alltoall"][0] / args.steps
         a2a_ms = exchange_ms if exchange_ms else exposed_ms
         nvlink = {"bound": "nvlink", "kernel": "k_push_fwd / k_push_bwd (FFT transposes stored straight into peer memory over NVLink) + barrier", "achieved": sent / (a2a_ms * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s per direction per GPU",
@@ -491,16 +611,22 @@ def run_ours(args, rank, world, local_rank):
                   "exposed_ms_per_step_in_timed_run": exposed_ms, "note": "ms_per_step: exchange measured with the component pipeline off; exposed: what the main stream still waited for in the timed run (pushes overlap the local transforms)"}
     own = {k: v for k, v in kernels.items() if not k.startswith("fft_") and "frac" in v}
     top = max(own, key=lambda k: own[k]["ms_per_step"]) if own else None
-    traffic = ncu_traffic().get(top) if top else None
     roofline = None
     if top:
+        # DRAM traffic of that kernel from the committed ncu --set full capture of the SAME regime (the timed run's: synthetic ICs
+        # evolved by >= 10 cycles) and configuration (512^3, one species); scaled by this rank's share of the work, else null
+        traffic, traffic_src = None, None
+        tj = ncu_traffic().get(top)
+        if isinstance(tj, dict) and args.config == 3 and N == 512:
+            traffic = tj["dram_bytes_per_launch"] * np_local / float(N ** 3)
+            traffic_src = tj.get("capture")
         roofline = {"kernel": top, "bound": "hbm", "achieved": own[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": own[top]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "frac": own[top]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "ms_per_launch": own[top]["ms_per_step"] / max(own[top]["calls_per_step"], 1e-9), "share_of_step": own[top]["share"]}
 
     # ---- the particle kernels in the other occupancy regimes (report lattice-like and clustered) ---
     regimes = None
-    if world == 1 and not args.no_regimes:
+    if world == 1 and not args.no_regimes and len(species) == 1:
         regimes = {"timed_run": "quasi-uniform ICs evolved by warmup+steps cycles (hot synthetic velocities: cell occupancy drifts from exactly 1 towards Poisson)"}
         for label in ("lattice", "clustered"):
             regimes[label] = particle_regime(gevb, ctx, common, N, label, ds, cosmo, mass, phi, chi)
@@ -511,22 +637,24 @@ def run_ours(args, rank, world, local_rank):
         ngrid_cpu, nst = env_int("GEVB_REF_NGRID", 128), env_int("GEVB_REF_STEPS", 6)
         r = reference_replicas(ngrid_cpu, nst, 1, env_int("GEVB_REF_PROCS", os.cpu_count() or 1))
         cpu = {"value": r["particles"] * nst / r["seconds"], "unit": UNIT, "cores": r["replicas"], "kind": r["kind"],
-               "sample": f"{nst} cycles of the reference main loop (gevolution.hpp over the single-rank LATfield2 shim) at {ngrid_cpu}^3 grid / {ngrid_cpu}^3 "
+               "sample": f"{nst} cycles of the reference main loop (gevolution.hpp over the single-rank LATfield2 shim; the reference's MPI build cannot be produced: mpic++ / LATfield2 / FFTW absent) at {ngrid_cpu}^3 grid / {ngrid_cpu}^3 "
                          f"particles in {r['replicas']} independent single-threaded replicas run concurrently, one per host core"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.config == 3 and N == 512 else f"particle-steps/s (config {args.config}, {N}^3)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"GR {N}^3 grid / {N}^3 particles, parabolic B, one cycle of main.cpp:372-879 per step (fused T00+Tij deposit, fused kick+drift, 12 FFTs)",
-                       "ngrid": N, "particles": np_total, "slabs": world, "parallelism": f"z-slab x{world}",
+            "config": {"workload": f"BASELINE config {args.config}: {cfg['what']}; one cycle of main.cpp:372-879 per step (fused T00+Tij deposit, fused kick+drift, {nfwd + 5} FFTs)",
+                       "ngrid": N, "particles": np_total, "species": list(species), "slabs": world, "parallelism": f"z-slab x{world}",
                        "l2_policy": "inputs larger than L2: every pass streams >= 1 GB per rank (126 MB L2)",
-                       "e2e_steps": e2e_steps, "z": 1.0 / state["a"] - 1.0, "setup_s": t_setup},
+                       "e2e_steps": e2e_steps, "z": 1.0 / state["a"] - 1.0, "setup_s": t_setup, "device_memory_used_gb_rank0": mem_used_gb,
+                       "ncdm_substeps": ncdm_steps, "hij_spectrum_call_ms": hij_ms},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "invariants": invariants,
+            "parity_check": parity,
             "roofline": roofline,
             "nvlink": nvlink,
             "regimes": regimes,
@@ -545,7 +673,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 512))
+    ap.add_argument("--ngrid", type=int, default=env_int("GEVB_BENCH_NGRID", 0), help="override the configuration's lattice size (parity / smoke runs)")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json configuration (SURVEY 8d numbering); the bench line is quoted on 3")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity check that precedes the timed region when WORLD_SIZE > 1")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replica", action="store_true", help="(internal) one replica of the CPU reference arm")
     ap.add_argument("--ngrid-ref", type=int, default=128)

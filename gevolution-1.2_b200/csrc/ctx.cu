@@ -34,8 +34,8 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
-static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused"};
-static int tune_values[GEVB_NTUNE] = {6, 1, 1, 1, 0, 0, 0, 1};
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused", "peer_comm"};
+static int tune_values[GEVB_NTUNE] = {6, 1, 1, 1, 0, 0, 0, 1, 1};
 static bool tune_env_read = false;
 static void tune_read_env()
 {
@@ -121,6 +121,7 @@ extern "C" int gevb_ctx_create(gevb_ctx ** out, int ngrid, int device, int rank,
 		GEVB_TRY(gevb_nccl_load());
 		NCCL_TRY(ncclCommInitRank(&c->comm, nranks, id, rank));
 		c->have_comm = true;
+		GEVB_TRY(gevb_peer_setup(c));
 	}
 	*out = c;
 	return 0;
@@ -132,6 +133,7 @@ extern "C" int gevb_ctx_destroy(gevb_ctx * c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	gevb_xchg_release(c);
+	gevb_peer_release(c);
 	if (c->d_barrier)
 	{
 		cudaFree(c->d_barrier);
@@ -308,6 +310,7 @@ extern "C" int gevb_field_updateHalo(gevb_field * f)
 		}
 		return 0;
 	}
+	if (gevb_peer_on(c) && (size_t) f->ncomp * pl * 2 <= c->pc_plane_doubles) return gevb_peer_halo(f);
 	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
 	NCCL_TRY(ncclGroupStart());
 	for (int k = 0; k < f->ncomp; k++)
@@ -341,6 +344,7 @@ extern "C" int gevb_projection_comm(gevb_field * f)
 	const size_t pl = c->plane();
 	const double * src = f->data + (size_t) (c->nzl + 1) * pl;
 	size_t src_stride = f->comp_stride;
+	if (c->nranks > 1 && gevb_peer_on(c) && (size_t) f->ncomp * pl <= c->pc_plane_doubles) return gevb_peer_fold(f);
 	if (c->nranks > 1)
 	{
 		void * stage;

@@ -516,7 +516,7 @@ __device__ __forceinline__ void warp_slice(uint32_t first, uint32_t last, int w,
 	whi = wlo + m; whi = whi < last ? whi : last;
 }
 
-template <bool HAS_PHI>
+template <bool HAS_PHI, int THREADS = DEP_THREADS>
 __device__ __forceinline__ void stage_unit(const DParams & D, uint32_t unit, uint32_t first, uint32_t last, double * stage)
 {
 	const BrickGeom & G = D.G;
@@ -524,7 +524,7 @@ __device__ __forceinline__ void stage_unit(const DParams & D, uint32_t unit, uin
 	uint32_t * ctab = (uint32_t *) (stage + UT_SITES + 1);
 	if (first == last) return;
 	const uint32_t * src = D.cell_start + (size_t) unit * UCELLS;
-	for (int k = threadIdx.x; k <= UCELLS; k += DEP_THREADS) cp_async4(ctab + k, src + k);
+	for (int k = threadIdx.x; k <= UCELLS; k += THREADS) cp_async4(ctab + k, src + k);
 	if (HAS_PHI && threadIdx.x < DX * DY)
 	{
 		int x0, y0, zl0;
@@ -693,6 +693,310 @@ __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit_cells(DParams D)
 	}
 }
 
+// =====================================================================================================================
+// k_deposit_percell (tuning knob deposit_variant = 2): one thread per CELL, accumulators in registers.
+//
+// What the profiles of the two kernels above say (profiles/round2_v03): both are bound by the shared-memory data pipe
+// (l1tex wavefronts at 71-77 % of peak) and by instruction issue (1455 warp instructions per 32 particles), because every
+// particle's 38 contributions are read-added-written in shared memory, shuffled for the segmented sums, and -- in the
+// per-cell form -- read and cleared again by the gather.  The reference keeps the contributions of a cell's particles in
+// local accumulators (localCube / localEdge, gevolution.hpp:953,1075,1199-1200) and touches the field once per cell; so
+// does this kernel: a thread owns a cell, walks the cell's particles (they are contiguous in the sorted order) and
+// accumulates in registers -- no shuffle, no shared-memory traffic per particle.  The cell's sums are stored once
+// (38 plain stores), a barrier, then the site gather of k_deposit_cells (read-only here) reduces into HBM.
+//
+//   balance   cells hold different numbers of particles; a warp runs as long as its fullest cell.  The block therefore
+//             sorts the unit's 256 cells by particle count first (one shared-memory counting sort over the counts), so the
+//             cells of a warp hold about equally many particles; cells above ZC_HEAVY particles are left to whole warps
+//             (lanes stride over the cell, one warp reduction per cell).
+//   staging   the unit's particles (six contiguous ranges of the SoA arrays) arrive by TMA bulk copies
+//             (cp.async.bulk, UBLKCP) that are issued a unit ahead and complete on an mbarrier; units above ZC_PMAX
+//             particles are read from global memory directly (their latency is amortised over long loops).
+#define ZC_PMAX 320                                    // particles of a unit that the shared-memory stage holds
+#define ZC_HEAVY 64                                    // cells with more particles are processed by whole warps
+#define ZC_CLASSES 32                                  // count classes of the balance sort (the last one takes 31 .. ZC_HEAVY)
+#define ZC_THREADS 192                                 // 2 blocks of 192 threads per SM: 170 registers per thread for the 38 accumulators
+#define ZC_PSTRIDE (ZC_PMAX + 2)                       // one staged array (the range is widened to 16-byte boundaries)
+
+__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long * bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long * bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long * bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gmem_src, uint32_t bytes, unsigned long long * bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// contributions of one particle added to the register accumulators A[] of its cell (corner K)
+template <int WHAT, bool HAS_PHI, int K>
+__device__ __forceinline__ void accumulate_corner(const PInv & I, const double * phc, double * A)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	if (NV == 0) return;
+	double v[NV > 0 ? NV : 1];
+	phase_values<WHAT, HAS_PHI, K, true>(I, phc, v);
+	#pragma unroll
+	for (int j = 0; j < NV; j++) A[acc_index(WHAT, K, 0) + j] += v[j];
+}
+
+template <int WHAT, bool HAS_PHI>
+__device__ __forceinline__ void accumulate_particle(const DParams & D, const double * pv, int cx, int cy, int cz, const double * phc, double * A)
+{
+	PInv I;
+	particle_factors<WHAT, HAS_PHI>(I, D, pv, cx, cy, cz);
+	accumulate_corner<WHAT, HAS_PHI, 0>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 1>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 2>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 3>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 4>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 5>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 6>(I, phc, A);
+	accumulate_corner<WHAT, HAS_PHI, 7>(I, phc, A);
+}
+
+// where the unit's particles are read from: the shared-memory stage (index relative to the widened start) or global memory
+struct PSource { const double * a[6]; uint32_t base; };
+__device__ __forceinline__ void fetch(const PSource & S, uint32_t i, double * pv)
+{
+	const uint32_t j = i - S.base;
+	#pragma unroll
+	for (int k = 0; k < 6; k++) pv[k] = S.a[k][j];
+}
+
+// gather_corner without the clearing store (every cell of the unit is rewritten before the next gather)
+template <int WHAT, int K>
+__device__ __forceinline__ void gather_corner_ro(const double * acc, int sx, int sy, int sz, double * sum)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	if (NV == 0) return;
+	const int cx = sx - ((K >> 2) & 1), cy = sy - ((K >> 1) & 1), cz = sz - (K & 1);
+	if ((unsigned) cx >= GEVB_BX || (unsigned) cy >= GEVB_BY || (unsigned) cz >= UZ) return;
+	const double * p = acc + acc_index(WHAT, K, 0) * UCELLS + ((cz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (cy << GEVB_BX_BITS) | cx);
+	#pragma unroll
+	for (int j = 0; j < NV; j++) sum[phase_comp(WHAT, K, j)] += p[j * UCELLS];
+}
+
+// thread 0: request the particles of a unit into the stage (nothing for empty or oversized units); returns whether it did
+__device__ __forceinline__ bool request_particles(const DParams & D, uint32_t first, uint32_t last, double * pstage, unsigned long long * bar)
+{
+	if (first == last || last - first > ZC_PMAX) return false;
+	if (threadIdx.x == 0)
+	{
+		const uint32_t astart = first & ~1u, count = (last - astart + 1u) & ~1u;     // whole 16-byte pieces (the arrays are padded by two elements)
+		const double * src[6] = {D.x, D.y, D.z, D.qx, D.qy, D.qz};
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                 // the stage was read through the generic proxy until now
+		mbar_expect(bar, 6u * count * (uint32_t) sizeof(double));
+		#pragma unroll
+		for (int k = 0; k < 6; k++) bulk_g2s(pstage + k * ZC_PSTRIDE, src[k] + astart, count * (uint32_t) sizeof(double), bar);
+	}
+	return true;
+}
+
+template <int WHAT, bool HAS_PHI>
+__global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
+{
+	constexpr int NCOMP = dep_ncomp(WHAT), NACC = dep_nacc(WHAT);
+	extern __shared__ __align__(16) double smem[];
+	double * acc = smem;                                    // [NACC][UCELLS] sums of every cell of the unit
+	double * stages = acc + NACC * UCELLS;                  // [2][USTAGE_DOUBLES] phi tile + cell table, one unit ahead
+	double * pstage = stages + 2 * USTAGE_DOUBLES;          // [6][ZC_PSTRIDE] the unit's particles
+	unsigned long long * bar = (unsigned long long *) (pstage + 6 * ZC_PSTRIDE);
+	int * hist = (int *) (bar + 1);                         // [ZC_CLASSES] cells per count class, then their first slots
+	int * nheavy = hist + ZC_CLASSES;
+	unsigned char * order = (unsigned char *) (nheavy + 1); // [UCELLS] cells in order of decreasing particle count
+	unsigned char * heavy = order + UCELLS;                 // [UCELLS] cells above ZC_HEAVY
+
+	const BrickGeom & G = D.G;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int idx = threadIdx.x; idx < 2 * USTAGE_DOUBLES; idx += ZC_THREADS) stages[idx] = 0.;
+	if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;
+	if (threadIdx.x == 0) { *nheavy = 0; mbar_init(bar, 1); }
+	__syncthreads();
+	const uint32_t nunits = 2 * G.nbricks;
+	uint32_t unit = blockIdx.x;
+	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
+	unit_range(D, unit, first, last);
+	unit_range(D, unit + gridDim.x, nfirst, nlast);
+	stage_unit<HAS_PHI, ZC_THREADS>(D, unit, first, last, stages);
+	cp_async_commit();
+	bool staged = request_particles(D, first, last, pstage, bar);
+	uint32_t parity = 0;
+	int cur = 0;
+	while (unit < nunits)
+	{
+		const uint32_t nunit = unit + gridDim.x;
+		unit_range(D, nunit + gridDim.x, nnfirst, nnlast);                   // consumed at the end of this iteration
+		if (nunit < nunits) stage_unit<HAS_PHI, ZC_THREADS>(D, nunit, nfirst, nlast, stages + (cur ^ 1) * USTAGE_DOUBLES);
+		cp_async_commit();
+		bool nstaged = false;
+		if (first != last)                                                   // block-uniform
+		{
+			int x0, y0, zl0;
+			brick_origin(G, unit >> 1, x0, y0, zl0);
+			zl0 += (int) (unit & 1) * UZ;
+			cp_async_wait<1>();                             // everything but the newest group: this unit's phi tile and cell table have landed
+			__syncthreads();                                // ... for all threads; also: the previous unit's gather is done with acc
+			const double * tphi = stages + cur * USTAGE_DOUBLES;
+			const uint32_t * ctab = (const uint32_t *) (tphi + UT_SITES + 1);
+
+			// ---- balance: cells sorted by decreasing particle count (counting sort over the count classes)
+			{
+				int kc[2] = {0, 0}, rc[2] = {0, 0};
+				#pragma unroll
+				for (int q = 0; q < 2; q++)
+				{
+					const int c = threadIdx.x + q * ZC_THREADS;
+					if (c >= UCELLS) break;
+					const uint32_t cnt = ctab[c + 1] - ctab[c];
+					const bool is_heavy = cnt > ZC_HEAVY;
+					kc[q] = is_heavy ? 0 : (int) (cnt < ZC_CLASSES - 1 ? cnt : ZC_CLASSES - 1);
+					rc[q] = atomicAdd(hist + kc[q], 1);
+					if (is_heavy) heavy[atomicAdd(nheavy, 1)] = (unsigned char) c;
+				}
+				__syncthreads();
+				int s = 0, h = 0;
+				if (w == 0)
+				{
+					h = s = hist[lane];                     // cells of class `lane`; s becomes the number of cells in classes >= lane
+					#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, s, o); if (lane + o < 32) s += t; }
+				}
+				__syncthreads();
+				if (w == 0) hist[lane] = s - h;             // first slot of the class
+				__syncthreads();
+				#pragma unroll
+				for (int q = 0; q < 2; q++)
+				{
+					const int c = threadIdx.x + q * ZC_THREADS;
+					if (c < UCELLS) order[hist[kc[q]] + rc[q]] = (unsigned char) c;
+				}
+			}
+			__syncthreads();
+			if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;   // for the next unit (nobody reads hist again before the next unit's barrier)
+			const int numheavy = *nheavy;
+
+			PSource S;
+			if (staged)
+			{
+				mbar_wait(bar, parity);                     // the bulk copies of this unit have completed
+				for (int k = 0; k < 6; k++) S.a[k] = pstage + k * ZC_PSTRIDE;
+				S.base = first & ~1u;
+			}
+			else
+			{
+				S.a[0] = D.x; S.a[1] = D.y; S.a[2] = D.z; S.a[3] = D.qx; S.a[4] = D.qy; S.a[5] = D.qz;
+				S.base = 0;
+			}
+
+			// ---- one cell per thread: the cell's particles are accumulated in registers, the sums stored once
+			for (int slot = threadIdx.x; slot < UCELLS; slot += ZC_THREADS)       // slots in order of decreasing count: the second round holds the emptiest cells
+			{
+				const int c = order[slot];
+				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
+				if (clast - cfirst <= ZC_HEAVY)
+				{
+					const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
+					const int site = (sz * DY + sy) * DX + sx;
+					double phc[8];
+					if (HAS_PHI)
+					{
+						#pragma unroll
+						for (int k = 0; k < 8; k++) phc[k] = tphi[site + corner_offset(k)];
+					}
+					double A[NACC];
+					#pragma unroll
+					for (int a = 0; a < NACC; a++) A[a] = 0.;
+					double pv[6];
+					if (cfirst < clast) fetch(S, cfirst, pv);
+					for (uint32_t i = cfirst; i < clast; i++)
+					{
+						double cur_pv[6];
+						#pragma unroll
+						for (int k = 0; k < 6; k++) cur_pv[k] = pv[k];
+						if (i + 1 < clast) fetch(S, i + 1, pv);         // the next particle of the cell is requested before this one is processed
+						accumulate_particle<WHAT, HAS_PHI>(D, cur_pv, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
+					}
+					#pragma unroll
+					for (int a = 0; a < NACC; a++) acc[a * UCELLS + c] = A[a];
+				}
+			}
+			// ---- cells above ZC_HEAVY: a warp per cell, lanes stride over its particles, one warp reduction per cell
+			for (int hc = w; hc < numheavy; hc += ZC_THREADS / 32)
+			{
+				const int c = heavy[hc];
+				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
+				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
+				const int site = (sz * DY + sy) * DX + sx;
+				double phc[8];
+				if (HAS_PHI)
+				{
+					#pragma unroll
+					for (int k = 0; k < 8; k++) phc[k] = tphi[site + corner_offset(k)];
+				}
+				double A[NACC];
+				#pragma unroll
+				for (int a = 0; a < NACC; a++) A[a] = 0.;
+				for (uint32_t i = cfirst + lane; i < clast; i += 32)
+				{
+					double pv[6];
+					fetch(S, i, pv);
+					accumulate_particle<WHAT, HAS_PHI>(D, pv, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
+				}
+				#pragma unroll
+				for (int a = 0; a < NACC; a++)
+				{
+					double v = A[a];
+					#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+					if (lane == 0) acc[a * UCELLS + c] = v;
+				}
+			}
+			__syncthreads();                                // every cell's sums are in acc; the particle stage is free
+			if (threadIdx.x == 0) *nheavy = 0;
+			if (staged) parity ^= 1;
+			nstaged = request_particles(D, nfirst, nlast, pstage, bar);      // arrives while this unit is gathered
+
+			// ---- gather + flush: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row
+			for (int s = threadIdx.x; s < UT_SITES; s += ZC_THREADS)
+			{
+				const int sz = s / (DX * DY), r = s - sz * (DX * DY), sy = r / DX, sx = r - sy * DX;
+				double sum[NCOMP];
+				#pragma unroll
+				for (int k = 0; k < NCOMP; k++) sum[k] = 0.;
+				gather_corner_ro<WHAT, 0>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 1>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 2>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 3>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 4>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 5>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 6>(acc, sx, sy, sz, sum);
+				gather_corner_ro<WHAT, 7>(acc, sx, sy, sz, sum);
+				const size_t off = (size_t) (zl0 + sz + 1) * G.N * G.N + (size_t) wrap_up(y0 + sy, G.N) * G.N + wrap_up(x0 + sx, G.N);
+				#pragma unroll
+				for (int k = 0; k < NCOMP; k++)
+					if (sum[k] != 0.) atomicAdd(D.out[k] + off, sum[k]);
+			}
+		}
+		else nstaged = request_particles(D, nfirst, nlast, pstage, bar);     // empty unit: the stage is free anyway
+		staged = nstaged;
+		unit = nunit; cur ^= 1;
+		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
+	}
+}
+
 int check_real(const gevb_field * f, int ncomp, const char * who, const char * name)
 {
 	GEVB_CHECK_ARG(f != NULL, "%s: %s is NULL", who, name);
@@ -714,6 +1018,25 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 	D.x = p->x[b]; D.y = p->y[b]; D.z = p->z[b]; D.qx = p->qx[b]; D.qy = p->qy[b]; D.qz = p->qz[b];
 	D.phi = phi ? phi->data : NULL;
 	for (int k = 0; k < 7; k++) D.out[k] = k < dep_ncomp(WHAT) ? out[k] : NULL;
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 2)
+	{
+		// one thread per cell, register accumulators (k_deposit_percell): two blocks per SM, one unit (half a brick) at a time
+		const size_t smem = ((size_t) dep_nacc(WHAT) * UCELLS + 2 * USTAGE_DOUBLES + 6 * ZC_PSTRIDE) * sizeof(double) + 8 + (ZC_CLASSES + 1) * sizeof(int) + 2 * UCELLS;
+		const uint32_t persistent = (uint32_t) c->num_sms * 2, nunits = 2 * D.G.nbricks;
+		const uint32_t grid = nunits < persistent ? nunits : persistent;
+		if (phi)
+		{
+			CUDA_TRY(cudaFuncSetAttribute(k_deposit_percell<WHAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_deposit_percell<WHAT, true><<<grid, ZC_THREADS, smem, c->stream>>>(D);
+		}
+		else
+		{
+			CUDA_TRY(cudaFuncSetAttribute(k_deposit_percell<WHAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_deposit_percell<WHAT, false><<<grid, ZC_THREADS, smem, c->stream>>>(D);
+		}
+		KERNEL_CHECK(c);
+		return 0;
+	}
 	if (gevb_tune(TUNE_DEPOSIT_VARIANT) != 0)
 	{
 		// per-cell accumulators (k_deposit_cells): two blocks per SM, one unit (half a brick) at a time

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A
 // completed before any rank's later work starts
 int rank_barrier(gevb_ctx * c, cudaStream_t stream)
 {
+	if (gevb_peer_on(c)) return gevb_peer_barrier(c, stream);       // flags in peer memory: one 32-thread kernel instead of a collective
 	NCCL_TRY(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, stream));
 	return 0;
 }

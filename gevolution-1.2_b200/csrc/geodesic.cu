@@ -451,11 +451,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 	}
 }
 
-// received particles (7 x cap SoA staging) appended behind the live ones, keys computed and histogrammed
+// received particles (7 x cap SoA staging) appended behind the live ones, keys computed and histogrammed.
+// cnt != NULL (peer-memory migration): the number received is cnt[which], the records go behind the cnt[0] received
+// before them when which == 1, never beyond `room` slots of the arrays (lost[2] counts what did not fit)
 __global__ void k_append_received(int64_t nrecv, const double * __restrict__ rb, int64_t cap, int64_t at,
                                   double * x, double * y, double * z, double * qx, double * qy, double * qz, int64_t * id, uint32_t * key,
-                                  BrickGeom G, double dx, uint32_t * cell_count, unsigned long long * lost, uint32_t * rank)
+                                  BrickGeom G, double dx, uint32_t * cell_count, unsigned long long * lost, uint32_t * rank,
+                                  const unsigned long long * cnt = NULL, int which = 0, int64_t room = 0)
 {
+	if (cnt)
+	{
+		nrecv = (int64_t) cnt[which];
+		if (nrecv > cap) nrecv = cap;
+		if (which == 1) at += (int64_t) (cnt[0] < (unsigned long long) cap ? cnt[0] : (unsigned long long) cap);
+		if (at + nrecv > room)
+		{
+			if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(lost + 2, (unsigned long long) (at + nrecv - room));
+			nrecv = room > at ? room - at : 0;
+		}
+	}
 	for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < nrecv; i += (int64_t) gridDim.x * blockDim.x)
 	{
 		const double px = rb[i], py = rb[cap + i], pz = rb[2 * cap + i];
@@ -537,11 +551,73 @@ int launch_geodesic(gevb_pcls * p, const GParams & P)
 	}
 }
 
+// what the ranks tell each other after a drift over peer memory: how many records they stored into the neighbour's slot.
+// cnt (this rank's d_red area): [0,1] = my sends (down, up).  The receiver's slot ends with two counters: [0] what its
+// upper neighbour sent down, [1] what its lower neighbour sent up.  The last thread also leaves the number of records the
+// re-bin has to look at (live + received, clamped as k_append_received clamps) in cnt[5].
+__global__ void k_publish_counts(const unsigned long long * cnt, unsigned long long * dn_counts, unsigned long long * up_counts)
+{
+	if (threadIdx.x == 0) dn_counts[0] = cnt[0];             // I am the upper neighbour of `dn`
+	if (threadIdx.x == 1) up_counts[1] = cnt[1];             // ... and the lower neighbour of `up`
+}
+__global__ void k_total_records(unsigned long long * cnt, const unsigned long long * mine, unsigned long long n_live, unsigned long long cap, unsigned long long room)
+{
+	unsigned long long a = __ldcg(mine), b = __ldcg(mine + 1);
+	a = a < cap ? a : cap; b = b < cap ? b : cap;
+	cnt[2] = a; cnt[3] = b;
+	unsigned long long total = n_live + a + b;
+	cnt[5] = total < room ? total : room;
+}
+
+// migration over peer memory: the drift kernel stored the leavers straight into the neighbours' slots; publish the
+// counts, barrier, append what arrived (counts stay on the device), re-file, then ONE read-back for the host
+int finish_move_peer(gevb_pcls * p, GParams & P, int slot)
+{
+	gevb_ctx * c = p->ctx;
+	Timed timed_mig_(c, CLS_MIGRATE);
+	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+	const int64_t cap = (int64_t) c->pc_mig_cap;
+	unsigned long long * cnt = P.nsend;
+	auto counters = [&](int r) { return (unsigned long long *) (gevb_peer_slot(c, r, slot) + c->pc_plane_doubles + 2 * 7 * c->pc_mig_cap); };
+	k_publish_counts<<<1, 32, 0, c->stream>>>(cnt, counters(dn), counters(up));
+	KERNEL_CHECK(c);
+	GEVB_TRY(gevb_peer_barrier(c, c->stream));
+	const int b = p->cur;
+	const double dx = 1.0 / (double) c->N;
+	const double * mig = gevb_peer_slot(c, c->rank, slot) + c->pc_plane_doubles;
+	k_total_records<<<1, 1, 0, c->stream>>>(cnt, counters(c->rank), (unsigned long long) p->n, (unsigned long long) cap, (unsigned long long) p->cap);
+	KERNEL_CHECK(c);
+	const int grid = gevb_grid(c, (size_t) (cap < p->cap - p->n ? cap : (p->cap - p->n > 0 ? p->cap - p->n : 1)), 256, 4);
+	for (int which = 0; which < 2; which++)
+	{
+		k_append_received<<<grid, 256, 0, c->stream>>>(0, mig + (size_t) which * 7 * cap, cap, p->n, p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], p->key, p->geom, dx,
+			p->cell_count, cnt + 4, P.rank ? p->rank : NULL, counters(c->rank), which, p->cap);
+		KERNEL_CHECK(c);
+	}
+	// the departed carry GEVB_INVALID_KEY and are dropped by the move; it reads the number of records from the device
+	p->d_nin = cnt + 5;
+	const int64_t n_upper = p->n + 2 * cap < p->cap ? p->n + 2 * cap : p->cap;
+	const int r = gevb_pcls_rebin(p, n_upper, p->n, true);
+	p->d_nin = NULL;
+	GEVB_TRY(r);
+	// one read-back: sends, receives, lost, overflow
+	CUDA_TRY(cudaMemcpyAsync(c->h_red + 16, cnt, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	const unsigned long long * h = (const unsigned long long *) (c->h_red + 16);
+	GEVB_TRY(gevb_peer_check(c));
+	GEVB_CHECK_ARG((int64_t) h[0] <= cap && (int64_t) h[1] <= cap, "moveParticles: migration buffer overflow (%llu / %llu sent, capacity %lld per direction; set GEVB_MIGRATION_CAP)", h[0], h[1], (long long) cap);
+	GEVB_CHECK_ARG(h[4] == 0, "moveParticles: %llu particles moved farther than the adjacent slab (move limit, main.cpp:281-286)", h[4]);
+	GEVB_CHECK_ARG(h[6] == 0 && p->n + (int64_t) (h[2] + h[3]) <= p->cap, "moveParticles: received particles do not fit the particle arrays (%lld + %llu > %lld)", (long long) p->n, h[2] + h[3], (long long) p->cap);
+	p->n = p->n + (int64_t) (h[2] + h[3]) - (int64_t) (h[0] + h[1]);
+	return 0;
+}
+
 // after a drift: exchange slab-crossing particles with the ring neighbours, then re-file (counting sort)
-int finish_move(gevb_pcls * p, GParams & P)
+int finish_move(gevb_pcls * p, GParams & P, int peer_slot)
 {
 	gevb_ctx * c = p->ctx;
 	if (c->nranks == 1) { Timed timed_(c, CLS_SORT); return gevb_pcls_rebin(p, p->n, p->n, true); }
+	if (peer_slot >= 0) return finish_move_peer(p, P, peer_slot);
 	Timed timed_mig_(c, CLS_MIGRATE);
 	const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
 	unsigned long long * cnt = P.nsend;                 // [0,1] = my sends (down, up); [2,3] = what I receive (from up, from down)
@@ -594,10 +670,28 @@ int finish_move(gevb_pcls * p, GParams & P)
 	return 0;
 }
 
-int setup_migration(gevb_pcls * p, GParams & P)
+// returns in *peer_slot the slot of the peer buffers the leavers are stored into, or -1 (NCCL messages from local buffers)
+int setup_migration(gevb_pcls * p, GParams & P, int * peer_slot)
 {
 	gevb_ctx * c = p->ctx;
+	*peer_slot = -1;
 	if (c->nranks == 1) return 0;
+	if (gevb_peer_on(c))
+	{
+		// the drift kernel stores straight into the neighbours' memory: moving down -> region 0 of the lower neighbour's slot
+		// ("what my upper neighbour sent down"), moving up -> region 1 of the upper neighbour's slot
+		const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+		const int slot = (int) (c->pc_seq++ & 1);
+		P.sendcap = (int64_t) c->pc_mig_cap;
+		P.sendbuf[0] = gevb_peer_slot(c, dn, slot) + c->pc_plane_doubles;
+		P.sendbuf[1] = gevb_peer_slot(c, up, slot) + c->pc_plane_doubles + 7 * c->pc_mig_cap;
+		// room for what may arrive (the counts stay on the device until the end of the call)
+		const int64_t want = p->n + p->n / 4 + 131072;
+		if (p->cap < want) { GEVB_TRY(gevb_pcls_reserve(p, want)); P.x = p->x[p->cur]; P.y = p->y[p->cur]; P.z = p->z[p->cur]; P.qx = p->qx[p->cur]; P.qy = p->qy[p->cur]; P.qz = p->qz[p->cur]; P.id = p->id[p->cur]; P.key = p->key; if (P.rank) P.rank = p->rank; }
+		CUDA_TRY(cudaMemsetAsync(P.nsend, 0, 7 * sizeof(unsigned long long), c->stream));
+		*peer_slot = slot;
+		return 0;
+	}
 	int64_t cap = p->n / 8 + 65536;
 	void * buf;
 	GEVB_TRY(gevb_ctx_scratch2(c, (size_t) cap * 7 * 4 * sizeof(double), &buf));
@@ -667,14 +761,15 @@ static int move_particles(gevb_pcls * p, int fn, double dtau, gevb_field * const
 	GParams P;
 	base_params(P, p, fields, nfields);
 	P.fn = fn; P.nf_drift = nfields; P.dtau_drift = dtau; P.a_drift = params[0]; P.bscale_drift = params[1]; P.binv_drift = 1.0 / params[1];
-	GEVB_TRY(setup_migration(p, P));
+	int peer_slot = -1;
+	GEVB_TRY(setup_migration(p, P, &peer_slot));
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
 		Timed timed_(c, CLS_DRIFT);
 		GEVB_TRY(launch_geodesic<1>(p, P));
 	}
-	GEVB_TRY(finish_move(p, P));
+	GEVB_TRY(finish_move(p, P, peer_slot));
 	if (output_max)
 	{
 		// the callback's reduction output (largest displacement, ic_basic.hpp:88-89) of the LOCAL particles; the caller reduces over ranks
@@ -702,7 +797,8 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 	P.fn = fn;
 	P.nf_kick = nfields_kick; P.dtau_kick = dtau_kick; P.a_kick = params_kick[0]; P.bscale_kick = params_kick[1]; P.binv_kick = 1.0 / params_kick[1];
 	P.nf_drift = nfields_drift; P.dtau_drift = dtau_drift; P.a_drift = params_drift[0]; P.bscale_drift = params_drift[1]; P.binv_drift = 1.0 / params_drift[1];
-	GEVB_TRY(setup_migration(p, P));
+	int peer_slot = -1;
+	GEVB_TRY(setup_migration(p, P, &peer_slot));
 	CUDA_TRY(cudaMemsetAsync(P.maxv2, 0, sizeof(unsigned long long), c->stream));
 	if (p->n > 0)
 	{
@@ -710,7 +806,7 @@ extern "C" int gevb_kick_drift(gevb_pcls * p, int fn, double dtau_kick, int nfie
 		GEVB_TRY(launch_geodesic<2>(p, P));
 	}
 	// the max lives in its own reduction slot, untouched by finish_move
-	GEVB_TRY(finish_move(p, P));
+	GEVB_TRY(finish_move(p, P, peer_slot));
 	if (maxvel)
 	{
 		CUDA_TRY(cudaMemcpyAsync(c->h_red, P.maxv2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

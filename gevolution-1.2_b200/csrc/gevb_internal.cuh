@@ -13,7 +13,7 @@
 void gevb_set_error(const char * fmt, ...);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, TUNE_PEER_COMM, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -106,12 +106,31 @@ struct gevb_ctx
 	int * d_barrier;
 	cudaStream_t xstream;      // the pushes of component k run here while the local transform of component k+1 runs on `stream`
 	cudaEvent_t xev[8];        // [0..6] component k's local transform is done; [7] exchange + barrier are done
+	// ghost planes, deposit folds, particle migration and rank barriers over peer memory (peer.cu): pc[r] is the
+	// communication buffer of rank r as mapped into this process (cudaIpc), pf[r] its flag page
+	void * pc[GEVB_MAX_RANKS];
+	unsigned long long * pf[GEVB_MAX_RANKS];
+	size_t pc_bytes, pc_plane_doubles, pc_mig_cap;     // whole buffer; doubles of the plane region of one slot; particles per direction of a slot
+	uint64_t pc_seq, pf_epoch;                         // collective operations so far (slot = pc_seq & 1); barriers so far
+	int peer_state;                                    // 0 not tried, 1 mapped, -1 unavailable (NCCL point-to-point is used)
+	int * d_peer_err;                                  // set by a barrier that timed out
 	size_t plane() const { return (size_t) N * N; }
 	size_t real_comp_stride() const { return (size_t) (nzl + 2) * N * N; }
 	size_t cplx_comp_stride() const { return nranks == 1 ? (size_t) N * N * nh : (size_t) nkyl * nh * N; }
 };
 
 int gevb_ctx_scratch(gevb_ctx * ctx, size_t bytes, void ** out);
+// ---- peer.cu: communication over peer memory (one node, NVLink / NVSwitch) ---------------------------------------
+int gevb_peer_setup(gevb_ctx * ctx);                       // collective; falls back silently (peer_state = -1) where peer mapping is unavailable
+void gevb_peer_release(gevb_ctx * ctx);
+bool gevb_peer_on(const gevb_ctx * ctx);                   // mapped and not switched off by the tuning knob peer_comm
+int gevb_peer_barrier(gevb_ctx * ctx, cudaStream_t stream);   // stream-ordered barrier of all ranks: flags in peer memory, one small kernel
+int gevb_peer_share(gevb_ctx * ctx, void * mine, void ** all, cudaStream_t stream);   // collective: IPC handles of `mine` to every rank, mapped into all[r]
+int gevb_peer_halo(gevb_field * f);                        // Field::updateHalo across ranks
+int gevb_peer_fold(gevb_field * f);                        // *_comm: upper ghost plane added into the next rank's first bulk plane
+struct PeerSlot { double * base[GEVB_MAX_RANKS]; };        // the current slot of every rank's buffer
+double * gevb_peer_slot(gevb_ctx * ctx, int rank, int slot);
+int gevb_peer_check(gevb_ctx * ctx);                       // after a host synchronisation: did a barrier time out?
 void gevb_xchg_release(gevb_ctx * ctx);      // fft.cu: unmap / free the peer exchange buffers
 int gevb_ctx_scratch2(gevb_ctx * ctx, size_t bytes, void ** out);
 
@@ -214,6 +233,7 @@ struct gevb_pcls
 	uint32_t * cell_start;     // [ncells + 1] exclusive prefix sum; cell_start[ncells] == n
 	BrickGeom geom;
 	int cur;
+	const unsigned long long * d_nin;   // when set, the re-bin's move reads the number of records from here (the host passes an upper bound)
 };
 
 int gevb_pcls_reserve(gevb_pcls * p, int64_t cap);

@@ -71,13 +71,14 @@ __global__ void k_make_keys(BrickGeom G, int64_t first, int64_t n, const double 
 // the move of the counting sort when every particle knows its rank inside its new cell (rebin_variant = 1): no atomic,
 // two independent streaming loads (key, rank), one dependent lookup of cell_start (L2: neighbours share lines), seven
 // independent record loads, seven stores
-__global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank, const uint32_t * __restrict__ cell_start,
+__global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const unsigned long long * __restrict__ n_dev, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank, const uint32_t * __restrict__ cell_start,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
                           double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
                           double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
 {
 	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	if (n_dev) n = (int64_t) *n_dev;                            // after a migration over peer memory the count lives on the device
 	for (int64_t i0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i0 < n; i0 += SCATTER_ILP * stride)
 	{
 		uint32_t k[SCATTER_ILP], d[SCATTER_ILP];
@@ -115,13 +116,14 @@ __global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const uint32_
 // Counting down leaves cell_count all zero again, ready for the next histogram.  Four particles per thread and
 // iteration, all loads and atomics of the four issued before the first dependent store (the chain key -> atomic ->
 // slot -> stores is latency bound otherwise).
-__global__ void __launch_bounds__(256) k_scatter(int64_t n, const uint32_t * __restrict__ key, const uint32_t * __restrict__ cell_start, uint32_t * count,
+__global__ void __launch_bounds__(256) k_scatter(int64_t n, const unsigned long long * __restrict__ n_dev, const uint32_t * __restrict__ key, const uint32_t * __restrict__ cell_start, uint32_t * count,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
                           double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
                           double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
 {
 	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	if (n_dev) n = (int64_t) *n_dev;
 	for (int64_t i0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i0 < n; i0 += SCATTER_ILP * stride)
 	{
 		uint32_t k[SCATTER_ILP], d[SCATTER_ILP];
@@ -246,7 +248,7 @@ int gevb_pcls_reserve(gevb_pcls * p, int64_t cap)
 	for (int b = 0; b < 2; b++)
 	{
 		double ** arrs[6] = {&p->x[b], &p->y[b], &p->z[b], &p->qx[b], &p->qy[b], &p->qz[b]};
-		for (int a = 0; a < 6; a++) CUDA_TRY(cudaMalloc(arrs[a], sizeof(double) * cap));
+		for (int a = 0; a < 6; a++) CUDA_TRY(cudaMalloc(arrs[a], sizeof(double) * (cap + 2)));   // + 2: the deposit's bulk copies round a range out to 16-byte boundaries
 		CUDA_TRY(cudaMalloc(&p->id[b], sizeof(int64_t) * cap));
 	}
 	CUDA_TRY(cudaMalloc(&p->key, sizeof(uint32_t) * cap));
@@ -298,7 +300,7 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 		CUDA_TRY(cudaMemsetAsync(p->cell_count, 0, ((size_t) G.ncells + 1) * sizeof(uint32_t), c->stream));
 		if (n_in > 0)
 		{
-			k_scatter_ranked<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->key, p->rank, p->cell_start,
+			k_scatter_ranked<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->d_nin, p->key, p->rank, p->cell_start,
 				p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
 				p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
 			KERNEL_CHECK(c);
@@ -306,7 +308,7 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	}
 	else if (n_in > 0)
 	{
-		k_scatter<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->key, p->cell_start, p->cell_count,
+		k_scatter<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->d_nin, p->key, p->cell_start, p->cell_count,
 			p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
 			p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
 		KERNEL_CHECK(c);

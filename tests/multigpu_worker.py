@@ -37,10 +37,15 @@ def slab(a, ctx, axis=1):
     return np.ascontiguousarray(np.take(a, range(ctx.z0, ctx.z0 + ctx.nzl), axis=axis))
 
 
+RESULTS = []          # (name, error, tolerance) of every check made on this rank (bench.py reports the worst one)
+QUIET = False         # bench.py: no line per check
+
+
 def check(name, err, tol, failures):
     ok = err <= tol
-    if dist.get_rank() == 0:
-        print(f"  {'ok ' if ok else 'BAD'} {name}: {err:.3e} (tol {tol:.1e})", flush=True)
+    RESULTS.append((name, float(err), float(tol)))
+    if dist.get_rank() == 0 and not (QUIET and ok):
+        print(f"  {'ok ' if ok else 'BAD'} {name}: {err:.3e} (tol {tol:.1e})", flush=True, file=sys.stderr if QUIET else sys.stdout)
     if not ok:
         failures.append((name, float(err)))
 
