@@ -512,7 +512,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(2):
             sim.step()
         per_x = ctx.timing_read(); ctx.timing(False)
-        gevb.tuning("fft_overlap", 1)
+        gevb.tuning("fft_overlap", 2)
         if "fft_alltoall" in per_x:
             exchange_ms = per_x["fft_alltoall"][0] / 2
 

@@ -93,45 +93,47 @@ struct PeerPtrs { double2 * p[GEVB_MAX_RANKS]; };
 // forward exchange: local A [c][ky][zl][kx]  ->  rank d = ky / nkyl : X_d [c][kyl][kx][kz = rank * nzl + zl]
 // Blocks walk the 32 x 32 tiles with stride gridDim.x: the launch decides how much of the machine the exchange takes
 // (all of it when it runs alone, a few hundred resident blocks when it shares the SMs with the next local transform).
-__global__ void __launch_bounds__(256) k_push_fwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp)
+// (zb, zn): only the local planes [zb, zb + zn) -- one chunk of the plane pipeline (zn is a multiple of 32 or the whole slab)
+__global__ void __launch_bounds__(256) k_push_fwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp, int zb, int zn)
 {
 	__shared__ double2 tile[32][33];
-	const int tkx = (nh + 31) / 32, tz = (nzl + 31) / 32;
+	const int tkx = (nh + 31) / 32, tz = (zn + 31) / 32;
 	const long ntiles = (long) tkx * tz * ncomp * N;
 	for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
 		const int kx0 = (int) (t % tkx) * 32; long r = t / tkx;
-		const int zl0 = (int) (r % tz) * 32; r /= tz;
+		const int zl0 = zb + (int) (r % tz) * 32; r /= tz;
 		const int c = c0 + (int) (r / N), ky = (int) (r % N);
 		const int d = ky / nkyl, kyl = ky % nkyl;
 		const double2 * src = A + ((size_t) c * N + ky) * nzl * nh;
 		for (int j = threadIdx.y; j < 32; j += blockDim.y)
 		{
 			const int zl = zl0 + j, kx = kx0 + threadIdx.x;
-			if (zl < nzl && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) zl * nh + kx);
+			if (zl < zb + zn && kx < nh) tile[j][threadIdx.x] = __ldcs(src + (size_t) zl * nh + kx);
 		}
 		__syncthreads();
 		double2 * dst = X.p[d] + ((size_t) c * nkyl + kyl) * nh * N + (size_t) rank * nzl;
 		for (int j = threadIdx.y; j < 32; j += blockDim.y)
 		{
 			const int kx = kx0 + j, zl = zl0 + threadIdx.x;
-			if (zl < nzl && kx < nh) dst[(size_t) kx * N + zl] = tile[threadIdx.x][j];
+			if (zl < zb + zn && kx < nh) dst[(size_t) kx * N + zl] = tile[threadIdx.x][j];
 		}
 		__syncthreads();
 	}
 }
 
 // backward exchange: local A [c][kyl][kx][z]  ->  rank d = z / nzl : X_d [c][ky = rank * nkyl + kyl][zl][kx]
-__global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp)
+// (yb, yn): only the local rows kyl in [yb, yb + yn) -- one chunk of the row pipeline
+__global__ void __launch_bounds__(256) k_push_bwd(const double2 * __restrict__ A, PeerPtrs X, int N, int nh, int nzl, int nkyl, int rank, int c0, int ncomp, int yb, int yn)
 {
 	__shared__ double2 tile[32][33];
 	const int tkx = (nh + 31) / 32, tz = (N + 31) / 32;
-	const long ntiles = (long) tkx * tz * ncomp * nkyl;
+	const long ntiles = (long) tkx * tz * ncomp * yn;
 	for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
 		const int kx0 = (int) (t % tkx) * 32; long r = t / tkx;
 		const int z0 = (int) (r % tz) * 32; r /= tz;
-		const int c = c0 + (int) (r / nkyl), kyl = (int) (r % nkyl);
+		const int c = c0 + (int) (r / yn), kyl = yb + (int) (r % yn);
 		const double2 * src = A + ((size_t) c * nkyl + kyl) * nh * N;
 		for (int j = threadIdx.y; j < 32; j += blockDim.y)
 		{
@@ -175,7 +177,7 @@ int xchg_ensure(gevb_ctx * c, size_t bytes)
 		int prio_lo = 0, prio_hi = 0;
 		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 		CUDA_TRY(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, prio_hi));     // its blocks are placed before the local transform's
-		for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreateWithFlags(&c->xev[k], cudaEventDisableTiming));
+		for (int k = 0; k <= GEVB_NXEV; k++) CUDA_TRY(cudaEventCreateWithFlags(&c->xev[k], cudaEventDisableTiming));
 	}
 	int ok = 1;
 	cudaIpcMemHandle_t mine[2], all[GEVB_MAX_RANKS][2];
@@ -321,6 +323,18 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 		CUFFT_TRY(cufftSetStream(p->z1d, c->stream));
 		CUFFT_TRY(cufftPlanMany(&p->z1d_one, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, c->nkyl * nh));
 		CUFFT_TRY(cufftSetStream(p->z1d_one, c->stream));
+		// pipeline inside a component: the slab's planes (forward) / rows (backward) are transformed in `chunks` pieces and the
+		// push of a piece overlaps the local transform of the next, so that a one-component transform hides its exchange too
+		p->chunks = 1;
+		for (int ch = 4; ch > 1; ch >>= 1)
+			if (c->nzl % (32 * ch) == 0 && c->nkyl % ch == 0) { p->chunks = ch; break; }
+		if (p->chunks > 1)
+		{
+			CUFFT_TRY(cufftPlanMany(&p->fwd2d_c, 2, n2, rembed, 1, N * N, kembed, 1, nh, CUFFT_D2Z, c->nzl / p->chunks));
+			CUFFT_TRY(cufftPlanMany(&p->z1d_c, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, (c->nkyl / p->chunks) * nh));
+			CUFFT_TRY(cufftSetStream(p->fwd2d_c, c->stream));
+			CUFFT_TRY(cufftSetStream(p->z1d_c, c->stream));
+		}
 		// exchange buffers large enough for this field (collective; grow-only)
 		// (sized for six components from the start -- the largest field of the time loop -- so that they are mapped once)
 		GEVB_TRY(xchg_ensure(c, (size_t) (rf->ncomp > 6 ? rf->ncomp : 6) * c->nzl * N * nh * sizeof(double2)));
@@ -335,7 +349,7 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
 	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); } }
-	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); }
+	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); if (p->chunks > 1) { cufftDestroy(p->fwd2d_c); cufftDestroy(p->z1d_c); } }
 	delete p;
 	return 0;
 }
@@ -432,49 +446,64 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		double2 * Xl = (double2 *) c->xchg[buf][c->rank];
 		// component pipeline: the push of component k (xstream) overlaps the local transform of component k+1 (stream);
 		// the time the main stream then still waits for the exchange is what CLS_FFT_A2A measures
-		const bool overlap = gevb_tune(TUNE_FFT_OVERLAP) != 0 && nc > 1 && nc <= 7;
+		const int chunks = gevb_tune(TUNE_FFT_OVERLAP) >= 2 ? p->chunks : 1;       // fft_overlap: 0 off, 1 component pipeline, 2 (default) also pieces inside a component
+		const bool overlap = gevb_tune(TUNE_FFT_OVERLAP) != 0 && (nc > 1 || chunks > 1) && nc <= 7;
 		cudaStream_t xs = overlap ? c->xstream : c->stream;
 		// resident blocks of the exchange: two per SM when it shares the machine with a local transform, else eight
 		const long pcap = (long) c->num_sms * (overlap ? 2 : 8);
 		if (direction == GEVB_FFT_FORWARD)
 		{
-			const long ntiles = (long) ((nh + 31) / 32) * ((c->nzl + 31) / 32) * (overlap ? 1 : nc) * N;
+			const int zn = c->nzl / (overlap ? chunks : 1);
+			const long ntiles = (long) ((nh + 31) / 32) * ((zn + 31) / 32) * (overlap ? 1 : nc) * N;
 			const int pg = (int) (ntiles < pcap ? ntiles : pcap);
 			for (int k = 0; k < nc; k++)
 			{
-				CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * comp_sites)));
-				c->launches++;
-				if (overlap)
+				if (!overlap || chunks == 1)
 				{
-					CUDA_TRY(cudaEventRecord(c->xev[k], c->stream));
-					CUDA_TRY(cudaStreamWaitEvent(xs, c->xev[k], 0));
-					k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1);
+					CUFFT_TRY(cufftExecD2Z(p->fwd2d, rbulk + k * rf->comp_stride, (cufftDoubleComplex *) (A + (size_t) k * comp_sites)));
+					c->launches++;
+				}
+				for (int ch = 0; overlap && ch < chunks; ch++)
+				{
+					if (chunks > 1)
+					{
+						CUFFT_TRY(cufftExecD2Z(p->fwd2d_c, rbulk + k * rf->comp_stride + (size_t) ch * zn * N * N, (cufftDoubleComplex *) (A + (size_t) k * comp_sites + (size_t) ch * zn * nh)));
+						c->launches++;
+					}
+					cudaEvent_t ev = c->xev[(k * chunks + ch) % GEVB_NXEV];
+					CUDA_TRY(cudaEventRecord(ev, c->stream));
+					CUDA_TRY(cudaStreamWaitEvent(xs, ev, 0));
+					k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1, ch * zn, zn);
 					KERNEL_CHECK(c);
 				}
 			}
 			{
 				Timed t_(c, CLS_FFT_A2A);
-				if (!overlap) { k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc); KERNEL_CHECK(c); }
+				if (!overlap) { k_push_fwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc, 0, c->nzl); KERNEL_CHECK(c); }
 				GEVB_TRY(rank_barrier(c, xs));
-				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[7], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[7], 0)); }
+				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[GEVB_NXEV], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[GEVB_NXEV], 0)); }
 			}
 			CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) Xl, (cufftDoubleComplex *) cf->data, CUFFT_FORWARD));
 			c->launches++;
 		}
 		else
 		{
-			const long ntiles = (long) ((nh + 31) / 32) * ((N + 31) / 32) * (overlap ? 1 : nc) * c->nkyl;
+			const int yn = c->nkyl / (overlap ? chunks : 1);
+			const long ntiles = (long) ((nh + 31) / 32) * ((N + 31) / 32) * (overlap ? 1 : nc) * yn;
 			const int pg = (int) (ntiles < pcap ? ntiles : pcap);
 			if (overlap)
 				for (int k = 0; k < nc; k++)
-				{
-					CUFFT_TRY(cufftExecZ2Z(p->z1d_one, (cufftDoubleComplex *) cf->data + (size_t) k * comp_sites, (cufftDoubleComplex *) (A + (size_t) k * comp_sites), CUFFT_INVERSE));
-					c->launches++;
-					CUDA_TRY(cudaEventRecord(c->xev[k], c->stream));
-					CUDA_TRY(cudaStreamWaitEvent(xs, c->xev[k], 0));
-					k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1);
-					KERNEL_CHECK(c);
-				}
+					for (int ch = 0; ch < chunks; ch++)
+					{
+						const size_t off = (size_t) k * comp_sites + (size_t) ch * yn * nh * N;
+						CUFFT_TRY(cufftExecZ2Z(chunks > 1 ? p->z1d_c : p->z1d_one, (cufftDoubleComplex *) cf->data + off, (cufftDoubleComplex *) (A + off), CUFFT_INVERSE));
+						c->launches++;
+						cudaEvent_t ev = c->xev[(k * chunks + ch) % GEVB_NXEV];
+						CUDA_TRY(cudaEventRecord(ev, c->stream));
+						CUDA_TRY(cudaStreamWaitEvent(xs, ev, 0));
+						k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, k, 1, ch * yn, yn);
+						KERNEL_CHECK(c);
+					}
 			else
 			{
 				CUFFT_TRY(cufftExecZ2Z(p->z1d, (cufftDoubleComplex *) cf->data, (cufftDoubleComplex *) A, CUFFT_INVERSE));
@@ -482,9 +511,9 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 			}
 			{
 				Timed t_(c, CLS_FFT_A2A);
-				if (!overlap) { k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc); KERNEL_CHECK(c); }
+				if (!overlap) { k_push_bwd<<<pg, tb, 0, xs>>>(A, X, N, nh, c->nzl, c->nkyl, c->rank, 0, nc, 0, c->nkyl); KERNEL_CHECK(c); }
 				GEVB_TRY(rank_barrier(c, xs));
-				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[7], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[7], 0)); }
+				if (overlap) { CUDA_TRY(cudaEventRecord(c->xev[GEVB_NXEV], xs)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c->xev[GEVB_NXEV], 0)); }
 			}
 			for (int k = 0; k < nc; k++)
 				CUFFT_TRY(cufftExecZ2D(p->bwd2d, (cufftDoubleComplex *) (Xl + (size_t) k * comp_sites), rbulk + k * rf->comp_stride));

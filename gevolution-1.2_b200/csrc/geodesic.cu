@@ -686,8 +686,9 @@ int setup_migration(gevb_pcls * p, GParams & P, int * peer_slot)
 		P.sendbuf[0] = gevb_peer_slot(c, dn, slot) + c->pc_plane_doubles;
 		P.sendbuf[1] = gevb_peer_slot(c, up, slot) + c->pc_plane_doubles + 7 * c->pc_mig_cap;
 		// room for what may arrive (the counts stay on the device until the end of the call)
-		const int64_t want = p->n + p->n / 4 + 131072;
-		if (p->cap < want) { GEVB_TRY(gevb_pcls_reserve(p, want)); P.x = p->x[p->cur]; P.y = p->y[p->cur]; P.z = p->z[p->cur]; P.qx = p->qx[p->cur]; P.qy = p->qy[p->cur]; P.qz = p->qz[p->cur]; P.id = p->id[p->cur]; P.key = p->key; if (P.rank) P.rank = p->rank; }
+		// (grown with hysteresis: the slab population drifts by a few particles per step, which must not reallocate every step)
+		const int64_t need = p->n + p->n / 8 + 65536, want = p->n + p->n / 4 + 131072;
+		if (p->cap < need) { GEVB_TRY(gevb_pcls_reserve(p, want)); P.x = p->x[p->cur]; P.y = p->y[p->cur]; P.z = p->z[p->cur]; P.qx = p->qx[p->cur]; P.qy = p->qy[p->cur]; P.qz = p->qz[p->cur]; P.id = p->id[p->cur]; P.key = p->key; if (P.rank) P.rank = p->rank; }
 		CUDA_TRY(cudaMemsetAsync(P.nsend, 0, 7 * sizeof(unsigned long long), c->stream));
 		*peer_slot = slot;
 		return 0;

@@ -65,6 +65,7 @@ struct GevbTimer
 	size_t used = 0;
 };
 #define GEVB_MAX_RANKS 16
+#define GEVB_NXEV 32
 struct gevb_ctx;
 struct gevb_plan;
 void gevb_timer_begin(gevb_ctx * c, int cls);
@@ -105,7 +106,7 @@ struct gevb_ctx
 	int xchg_state;            // 0 not tried, 1 mapped, -1 unavailable (NCCL exchange is used)
 	int * d_barrier;
 	cudaStream_t xstream;      // the pushes of component k run here while the local transform of component k+1 runs on `stream`
-	cudaEvent_t xev[8];        // [0..6] component k's local transform is done; [7] exchange + barrier are done
+	cudaEvent_t xev[GEVB_NXEV + 1];   // [0..GEVB_NXEV) a piece's local transform is done (used round robin); [GEVB_NXEV] exchange + barrier are done
 	// ghost planes, deposit folds, particle migration and rank barriers over peer memory (peer.cu): pc[r] is the
 	// communication buffer of rank r as mapped into this process (cudaIpc), pf[r] its flag page
 	void * pc[GEVB_MAX_RANKS];
@@ -155,6 +156,8 @@ struct gevb_plan
 	cufftHandle f2d, bz1d, b2d; // nranks == 1, one component: 2-D D2Z per plane, 1-D Z2Z along z (stride N*nh), 2-D Z2D per plane
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
 	cufftHandle z1d_one;             // 1-D along z for one component (component-pipelined backward transform)
+	cufftHandle fwd2d_c, z1d_c;      // nranks > 1: the same for one piece of a component (chunks > 1)
+	int chunks;                      // pieces per component of the exchange pipeline
 	cufftHandle f2d_c, b2d_c;        // nranks == 1: the 2-D transforms of `chunk_planes` planes at a time (tuning knob fft_l2_planes)
 	int chunk_planes;                // 0: not created
 	bool multi;

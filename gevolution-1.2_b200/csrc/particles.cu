@@ -13,6 +13,7 @@
 // slots.  Particles move by a fraction of a cell per step, so source and
 // destination order are almost the same and both sides of the move stay coalesced.
 #include <cub/device/device_scan.cuh>
+#include <thread>
 #include "gevb_internal.cuh"
 
 namespace {
@@ -332,6 +333,40 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 	const int64_t n_before = p->n;
 	unsigned long long * counter = (unsigned long long *) (c->d_red + 4000);
 	if (c->nranks == 1) GEVB_TRY(gevb_pcls_reserve(p, p->n + n));
+	int64_t nloc_host = 0;
+	if (c->nranks > 1)
+	{
+		// which of the offered particles are filed in this rank's slab is decided by the same floor(pos/dx) the device uses; counting
+		// them on the host first (a few threads over the z coordinates) sizes the arrays once, so that the upload below runs
+		// chunk after chunk at PCIe speed without a count-and-synchronise round trip per chunk
+		const int nthreads = n > (1 << 20) ? 4 : 1;
+		std::vector<int64_t> part(nthreads, 0);
+		auto count = [&](int t)
+		{
+			int64_t mine = 0;
+			for (int64_t i = n * t / nthreads; i < n * (t + 1) / nthreads; i++)
+			{
+				int cz = (int) floor(pos[3 * i + 2] / dx);
+				cz = cz >= c->N ? c->N - 1 : (cz < 0 ? 0 : cz);
+				mine += (cz >= c->z0 && cz < c->z0 + c->nzl);
+			}
+			part[t] = mine;
+		};
+		if (nthreads == 1) count(0);
+		else
+		{
+			std::vector<std::thread> pool;
+			for (int t = 0; t < nthreads; t++) pool.emplace_back(count, t);
+			for (std::thread & th : pool) th.join();
+		}
+		for (int t = 0; t < nthreads; t++) nloc_host += part[t];
+		if (nloc_host == 0) return 0;
+		GEVB_TRY(gevb_pcls_reserve(p, p->n + nloc_host));
+		c->h_red[8] = 0.;
+		unsigned long long start = (unsigned long long) p->n;
+		memcpy(c->h_red + 8, &start, sizeof(start));                                  // pinned: stays valid while the copy is in flight
+		CUDA_TRY(cudaMemcpyAsync(counter, c->h_red + 8, sizeof(start), cudaMemcpyHostToDevice, c->stream));
+	}
 	for (int64_t off = 0; off < n; off += chunk)
 	{
 		const int64_t m = (n - off < chunk) ? n - off : chunk;
@@ -351,29 +386,20 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 			p->n += m;
 			continue;
 		}
-		// several ranks: how many of this chunk are filed in this rank's slab?
-		CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
-		k_count_local<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, dpos, c->N, c->z0, c->nzl, dx, counter);
-		KERNEL_CHECK(c);
-		unsigned long long nloc = 0;
-		CUDA_TRY(cudaMemcpyAsync(&nloc, counter, sizeof(nloc), cudaMemcpyDeviceToHost, c->stream));
-		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		if (nloc == 0) continue;
-		if (p->n + (int64_t) nloc > p->cap)
-		{
-			int64_t want = p->n + (int64_t) nloc;
-			if (off + m < n) want += want / 4;      // more chunks to come
-			// scratch holds the staged chunk; reserve() syncs but does not touch scratch
-			GEVB_TRY(gevb_pcls_reserve(p, want + want / 8 + 65536));
-		}
+		// several ranks: the chunk's local particles are appended behind the ones kept so far (the device counter runs on from
+		// chunk to chunk; room for all of them was reserved from the host-side count above), no host synchronisation in the loop
 		const int b = p->cur;
-		unsigned long long start = (unsigned long long) p->n;
-		CUDA_TRY(cudaMemcpyAsync(counter, &start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
 		k_append<<<gevb_grid(c, (size_t) m, 256), 256, 0, c->stream>>>(m, did, dpos, dvel, c->N, c->z0, c->nzl, dx,
 			p->x[b], p->y[b], p->z[b], p->qx[b], p->qy[b], p->qz[b], p->id[b], counter, p->cap);
 		KERNEL_CHECK(c);
-		CUDA_TRY(cudaStreamSynchronize(c->stream));     // `start` lives on this stack frame
-		p->n += (int64_t) nloc;
+	}
+	if (c->nranks > 1)
+	{
+		unsigned long long total = 0;
+		CUDA_TRY(cudaMemcpyAsync(&total, counter, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		GEVB_CHECK_ARG((int64_t) total == n_before + nloc_host, "gevb_pcls_add: the device kept %llu particles, the host counted %lld", total, (long long) (n_before + nloc_host));
+		p->n = (int64_t) total;
 	}
 	if (p->n == n_before) return 0;
 	// keys + histogram of everything (old particles included: their keys are not kept between calls)

@@ -541,6 +541,12 @@ class Sim:
     def restore(self, filebase):
         _ck(lib().gevb_sim_restore(self.h, filebase.encode()), "gevb_sim_restore")
 
+    def run_settings(self, settings, max_cycles=100000):
+        """the main loop with the outputs of a settings file (gevb_sim_run_settings); returns (cycles, spectra sets, snapshots)"""
+        out = (C.c_int * 3)()
+        _ck(lib().gevb_sim_run_settings(self.h, C.byref(settings), max_cycles, out), "gevb_sim_run_settings")
+        return tuple(out)
+
     def write_field_snapshot(self, prefix, mask):
         """writeSnapshots' field dumps (output.hpp:98-300): <prefix>_<T00|B|phi|chi|hij>.bin"""
         _ck(lib().gevb_sim_write_field_snapshot(self.h, prefix.encode(), int(mask)), "gevb_sim_write_field_snapshot")
