@@ -767,28 +767,6 @@ __device__ __forceinline__ void accumulate_particle(const DParams & D, const dou
 	accumulate_corner<WHAT, HAS_PHI, 7>(I, phc, A);
 }
 
-// where the unit's particles are read from: the shared-memory stage (index relative to the widened start) or global memory
-struct PSource { const double * a[6]; uint32_t base; };
-__device__ __forceinline__ void fetch(const PSource & S, uint32_t i, double * pv)
-{
-	const uint32_t j = i - S.base;
-	#pragma unroll
-	for (int k = 0; k < 6; k++) pv[k] = S.a[k][j];
-}
-
-// gather_corner without the clearing store (every cell of the unit is rewritten before the next gather)
-template <int WHAT, int K>
-__device__ __forceinline__ void gather_corner_ro(const double * acc, int sx, int sy, int sz, double * sum)
-{
-	constexpr int NV = phase_comp(WHAT, K, -1);
-	if (NV == 0) return;
-	const int cx = sx - ((K >> 2) & 1), cy = sy - ((K >> 1) & 1), cz = sz - (K & 1);
-	if ((unsigned) cx >= GEVB_BX || (unsigned) cy >= GEVB_BY || (unsigned) cz >= UZ) return;
-	const double * p = acc + acc_index(WHAT, K, 0) * UCELLS + ((cz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (cy << GEVB_BX_BITS) | cx);
-	#pragma unroll
-	for (int j = 0; j < NV; j++) sum[phase_comp(WHAT, K, j)] += p[j * UCELLS];
-}
-
 // thread 0: request the particles of a unit into the stage (nothing for empty or oversized units); returns whether it did
 __device__ __forceinline__ bool request_particles(const DParams & D, uint32_t first, uint32_t last, double * pstage, unsigned long long * bar)
 {
@@ -805,6 +783,89 @@ __device__ __forceinline__ bool request_particles(const DParams & D, uint32_t fi
 	return true;
 }
 
+// one (x, y) column of tile sites gathers the cells around it: every accumulator of the unit is read exactly once
+template <int WHAT, int K>
+__device__ __forceinline__ void corner_into(const double * p, double * sum)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	#pragma unroll
+	for (int j = 0; j < NV; j++) sum[phase_comp(WHAT, K, j)] += p[(acc_index(WHAT, K, 0) + j) * UCELLS];
+}
+template <int WHAT, int X, int Y>
+__device__ __forceinline__ void column_from(const double * acc, int sx, int sy, double (* sum)[7])
+{
+	const int cx = sx - X, cy = sy - Y;
+	if ((unsigned) cx >= GEVB_BX || (unsigned) cy >= GEVB_BY) return;
+	#pragma unroll
+	for (int cz = 0; cz < UZ; cz++)
+	{
+		const double * p = acc + ((cz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (cy << GEVB_BX_BITS) | cx);
+		corner_into<WHAT, 4 * X + 2 * Y>(p, sum[cz]);            // Z = 0: the cell's own plane
+		corner_into<WHAT, 4 * X + 2 * Y + 1>(p, sum[cz + 1]);    // Z = 1: the plane above
+	}
+}
+
+// the particles of one cell accumulated in registers (the thread's cell, or a lane's share of a heavy cell)
+template <int WHAT, bool HAS_PHI, bool STAGED>
+__device__ __forceinline__ void cell_particles(const DParams & D, const double * pstage, uint32_t base, uint32_t ibegin, uint32_t iend, uint32_t istep,
+                                               int cx, int cy, int cz, const double * phc, double * A)
+{
+	auto fetch = [&](uint32_t i, double * pv)
+	{
+		if (STAGED)
+		{
+			const uint32_t j = i - base;
+			#pragma unroll
+			for (int k = 0; k < 6; k++) pv[k] = pstage[k * ZC_PSTRIDE + j];
+		}
+		else load_particle(D, i, pv);
+	};
+	double pv[6];
+	if (ibegin < iend) fetch(ibegin, pv);
+	for (uint32_t i = ibegin; i < iend; i += istep)
+	{
+		double cur_pv[6];
+		#pragma unroll
+		for (int k = 0; k < 6; k++) cur_pv[k] = pv[k];
+		if (i + istep < iend) fetch(i + istep, pv);             // the next particle is requested before this one is processed
+		accumulate_particle<WHAT, HAS_PHI>(D, cur_pv, cx, cy, cz, phc, A);
+	}
+}
+
+// counting sort of the unit's cells by particle count, first half: class and rank of this thread's cells
+__device__ __forceinline__ void sort_count(const uint32_t * ctab, int * hist, int * nheavy, unsigned char * heavy, int * kc, int * rc)
+{
+	#pragma unroll
+	for (int q = 0; q < 2; q++)
+	{
+		const int c = threadIdx.x + q * ZC_THREADS;
+		kc[q] = rc[q] = 0;
+		if (c >= UCELLS) break;
+		const uint32_t cnt = ctab[c + 1] - ctab[c];
+		const bool is_heavy = cnt > ZC_HEAVY;
+		kc[q] = is_heavy ? 0 : (int) (cnt < ZC_CLASSES - 1 ? cnt : ZC_CLASSES - 1);
+		rc[q] = atomicAdd(hist + kc[q], 1);
+		if (is_heavy) heavy[atomicAdd(nheavy, 1)] = (unsigned char) c;
+	}
+}
+// second half (after a barrier): every warp forms the first slot of each class for itself, then files its cells
+__device__ __forceinline__ void sort_place(const int * hist, unsigned char * order, const int * kc, const int * rc)
+{
+	const int lane = threadIdx.x & 31;
+	const int h = hist[lane];
+	int s = h;                                              // becomes the number of cells in classes >= lane
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, s, o); if (lane + o < 32) s += t; }
+	const int start = s - h;
+	#pragma unroll
+	for (int q = 0; q < 2; q++)
+	{
+		const int c = threadIdx.x + q * ZC_THREADS;
+		const int first_slot = __shfl_sync(0xffffffffu, start, kc[q]);
+		if (c < UCELLS) order[first_slot + rc[q]] = (unsigned char) c;
+	}
+}
+
 template <int WHAT, bool HAS_PHI>
 __global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
 {
@@ -814,16 +875,16 @@ __global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
 	double * stages = acc + NACC * UCELLS;                  // [2][USTAGE_DOUBLES] phi tile + cell table, one unit ahead
 	double * pstage = stages + 2 * USTAGE_DOUBLES;          // [6][ZC_PSTRIDE] the unit's particles
 	unsigned long long * bar = (unsigned long long *) (pstage + 6 * ZC_PSTRIDE);
-	int * hist = (int *) (bar + 1);                         // [ZC_CLASSES] cells per count class, then their first slots
-	int * nheavy = hist + ZC_CLASSES;
-	unsigned char * order = (unsigned char *) (nheavy + 1); // [UCELLS] cells in order of decreasing particle count
-	unsigned char * heavy = order + UCELLS;                 // [UCELLS] cells above ZC_HEAVY
+	int * hist = (int *) (bar + 1);                         // [ZC_CLASSES] cells per count class
+	int * nheavy = hist + ZC_CLASSES;                       // [2] heavy cells of the unit in work / of the next one
+	unsigned char * order = (unsigned char *) (nheavy + 2); // [UCELLS] cells in order of decreasing particle count
+	unsigned char * heavy = order + UCELLS;                 // [2][UCELLS] cells above ZC_HEAVY
 
 	const BrickGeom & G = D.G;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int idx = threadIdx.x; idx < 2 * USTAGE_DOUBLES; idx += ZC_THREADS) stages[idx] = 0.;
 	if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;
-	if (threadIdx.x == 0) { *nheavy = 0; mbar_init(bar, 1); }
+	if (threadIdx.x == 0) { nheavy[0] = nheavy[1] = 0; mbar_init(bar, 1); }
 	__syncthreads();
 	const uint32_t nunits = 2 * G.nbricks;
 	uint32_t unit = blockIdx.x;
@@ -834,109 +895,60 @@ __global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
 	cp_async_commit();
 	bool staged = request_particles(D, first, last, pstage, bar);
 	uint32_t parity = 0;
-	int cur = 0;
+	int cur = 0, hb = 0;                                    // pipeline stage in work; heavy-list buffer of the unit in work
+	int kc[2], rc[2];
+	// the first unit's cells are sorted before the loop; inside the loop the sort of unit k+1 rides behind the gather of unit k
+	cp_async_wait<0>();
+	__syncthreads();
+	if (first != last) sort_count((const uint32_t *) (stages + UT_SITES + 1), hist, nheavy + hb, heavy + hb * UCELLS, kc, rc);
+	__syncthreads();
+	if (first != last) sort_place(hist, order, kc, rc);
+	__syncthreads();
+	if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;
 	while (unit < nunits)
 	{
 		const uint32_t nunit = unit + gridDim.x;
 		unit_range(D, nunit + gridDim.x, nnfirst, nnlast);                   // consumed at the end of this iteration
 		if (nunit < nunits) stage_unit<HAS_PHI, ZC_THREADS>(D, nunit, nfirst, nlast, stages + (cur ^ 1) * USTAGE_DOUBLES);
 		cp_async_commit();
-		bool nstaged = false;
+		int x0 = 0, y0 = 0, zl0 = 0;
 		if (first != last)                                                   // block-uniform
 		{
-			int x0, y0, zl0;
 			brick_origin(G, unit >> 1, x0, y0, zl0);
 			zl0 += (int) (unit & 1) * UZ;
-			cp_async_wait<1>();                             // everything but the newest group: this unit's phi tile and cell table have landed
-			__syncthreads();                                // ... for all threads; also: the previous unit's gather is done with acc
 			const double * tphi = stages + cur * USTAGE_DOUBLES;
 			const uint32_t * ctab = (const uint32_t *) (tphi + UT_SITES + 1);
+			const int numheavy = nheavy[hb];
+			const unsigned char * hlist = heavy + hb * UCELLS;
+			if (staged) mbar_wait(bar, parity);             // the bulk copies of this unit have completed
+			const uint32_t pbase = first & ~1u;
 
-			// ---- balance: cells sorted by decreasing particle count (counting sort over the count classes)
-			{
-				int kc[2] = {0, 0}, rc[2] = {0, 0};
-				#pragma unroll
-				for (int q = 0; q < 2; q++)
-				{
-					const int c = threadIdx.x + q * ZC_THREADS;
-					if (c >= UCELLS) break;
-					const uint32_t cnt = ctab[c + 1] - ctab[c];
-					const bool is_heavy = cnt > ZC_HEAVY;
-					kc[q] = is_heavy ? 0 : (int) (cnt < ZC_CLASSES - 1 ? cnt : ZC_CLASSES - 1);
-					rc[q] = atomicAdd(hist + kc[q], 1);
-					if (is_heavy) heavy[atomicAdd(nheavy, 1)] = (unsigned char) c;
-				}
-				__syncthreads();
-				int s = 0, h = 0;
-				if (w == 0)
-				{
-					h = s = hist[lane];                     // cells of class `lane`; s becomes the number of cells in classes >= lane
-					#pragma unroll
-					for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, s, o); if (lane + o < 32) s += t; }
-				}
-				__syncthreads();
-				if (w == 0) hist[lane] = s - h;             // first slot of the class
-				__syncthreads();
-				#pragma unroll
-				for (int q = 0; q < 2; q++)
-				{
-					const int c = threadIdx.x + q * ZC_THREADS;
-					if (c < UCELLS) order[hist[kc[q]] + rc[q]] = (unsigned char) c;
-				}
-			}
-			__syncthreads();
-			if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;   // for the next unit (nobody reads hist again before the next unit's barrier)
-			const int numheavy = *nheavy;
-
-			PSource S;
-			if (staged)
-			{
-				mbar_wait(bar, parity);                     // the bulk copies of this unit have completed
-				for (int k = 0; k < 6; k++) S.a[k] = pstage + k * ZC_PSTRIDE;
-				S.base = first & ~1u;
-			}
-			else
-			{
-				S.a[0] = D.x; S.a[1] = D.y; S.a[2] = D.z; S.a[3] = D.qx; S.a[4] = D.qy; S.a[5] = D.qz;
-				S.base = 0;
-			}
-
-			// ---- one cell per thread: the cell's particles are accumulated in registers, the sums stored once
-			for (int slot = threadIdx.x; slot < UCELLS; slot += ZC_THREADS)       // slots in order of decreasing count: the second round holds the emptiest cells
+			// ---- one cell per thread (slots in order of decreasing count: the second round holds the emptiest cells)
+			for (int slot = threadIdx.x; slot < UCELLS; slot += ZC_THREADS)
 			{
 				const int c = order[slot];
 				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
-				if (clast - cfirst <= ZC_HEAVY)
+				if (clast - cfirst > ZC_HEAVY) continue;
+				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
+				const int site = (sz * DY + sy) * DX + sx;
+				double phc[8];
+				if (HAS_PHI)
 				{
-					const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
-					const int site = (sz * DY + sy) * DX + sx;
-					double phc[8];
-					if (HAS_PHI)
-					{
-						#pragma unroll
-						for (int k = 0; k < 8; k++) phc[k] = tphi[site + corner_offset(k)];
-					}
-					double A[NACC];
 					#pragma unroll
-					for (int a = 0; a < NACC; a++) A[a] = 0.;
-					double pv[6];
-					if (cfirst < clast) fetch(S, cfirst, pv);
-					for (uint32_t i = cfirst; i < clast; i++)
-					{
-						double cur_pv[6];
-						#pragma unroll
-						for (int k = 0; k < 6; k++) cur_pv[k] = pv[k];
-						if (i + 1 < clast) fetch(S, i + 1, pv);         // the next particle of the cell is requested before this one is processed
-						accumulate_particle<WHAT, HAS_PHI>(D, cur_pv, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
-					}
-					#pragma unroll
-					for (int a = 0; a < NACC; a++) acc[a * UCELLS + c] = A[a];
+					for (int k = 0; k < 8; k++) phc[k] = tphi[site + corner_offset(k)];
 				}
+				double A[NACC];
+				#pragma unroll
+				for (int a = 0; a < NACC; a++) A[a] = 0.;
+				if (staged) cell_particles<WHAT, HAS_PHI, true>(D, pstage, pbase, cfirst, clast, 1, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
+				else cell_particles<WHAT, HAS_PHI, false>(D, pstage, pbase, cfirst, clast, 1, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
+				#pragma unroll
+				for (int a = 0; a < NACC; a++) acc[a * UCELLS + c] = A[a];
 			}
 			// ---- cells above ZC_HEAVY: a warp per cell, lanes stride over its particles, one warp reduction per cell
 			for (int hc = w; hc < numheavy; hc += ZC_THREADS / 32)
 			{
-				const int c = heavy[hc];
+				const int c = hlist[hc];
 				const uint32_t cfirst = ctab[c], clast = ctab[c + 1];
 				const int sx = c & (GEVB_BX - 1), sy = (c >> GEVB_BX_BITS) & (GEVB_BY - 1), sz = c >> (GEVB_BX_BITS + GEVB_BY_BITS);
 				const int site = (sz * DY + sy) * DX + sx;
@@ -949,12 +961,8 @@ __global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
 				double A[NACC];
 				#pragma unroll
 				for (int a = 0; a < NACC; a++) A[a] = 0.;
-				for (uint32_t i = cfirst + lane; i < clast; i += 32)
-				{
-					double pv[6];
-					fetch(S, i, pv);
-					accumulate_particle<WHAT, HAS_PHI>(D, pv, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
-				}
+				if (staged) cell_particles<WHAT, HAS_PHI, true>(D, pstage, pbase, cfirst + lane, clast, 32, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
+				else cell_particles<WHAT, HAS_PHI, false>(D, pstage, pbase, cfirst + lane, clast, 32, x0 + sx, y0 + sy, G.z0 + zl0 + sz, phc, A);
 				#pragma unroll
 				for (int a = 0; a < NACC; a++)
 				{
@@ -964,35 +972,47 @@ __global__ void __launch_bounds__(ZC_THREADS, 2) k_deposit_percell(DParams D)
 					if (lane == 0) acc[a * UCELLS + c] = v;
 				}
 			}
-			__syncthreads();                                // every cell's sums are in acc; the particle stage is free
-			if (threadIdx.x == 0) *nheavy = 0;
-			if (staged) parity ^= 1;
-			nstaged = request_particles(D, nfirst, nlast, pstage, bar);      // arrives while this unit is gathered
-
-			// ---- gather + flush: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row
-			for (int s = threadIdx.x; s < UT_SITES; s += ZC_THREADS)
-			{
-				const int sz = s / (DX * DY), r = s - sz * (DX * DY), sy = r / DX, sx = r - sy * DX;
-				double sum[NCOMP];
-				#pragma unroll
-				for (int k = 0; k < NCOMP; k++) sum[k] = 0.;
-				gather_corner_ro<WHAT, 0>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 1>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 2>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 3>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 4>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 5>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 6>(acc, sx, sy, sz, sum);
-				gather_corner_ro<WHAT, 7>(acc, sx, sy, sz, sum);
-				const size_t off = (size_t) (zl0 + sz + 1) * G.N * G.N + (size_t) wrap_up(y0 + sy, G.N) * G.N + wrap_up(x0 + sx, G.N);
-				#pragma unroll
-				for (int k = 0; k < NCOMP; k++)
-					if (sum[k] != 0.) atomicAdd(D.out[k] + off, sum[k]);
-			}
 		}
-		else nstaged = request_particles(D, nfirst, nlast, pstage, bar);     // empty unit: the stage is free anyway
-		staged = nstaged;
-		unit = nunit; cur ^= 1;
+		cp_async_wait<0>();                                 // the next unit's phi tile and cell table (this thread's copies)
+		__syncthreads();                                    // 1: every cell's sums are in acc; the next stage is visible; the particle stage is free
+		if (threadIdx.x == 0) nheavy[hb] = 0;
+		if (staged) parity ^= 1;
+		staged = request_particles(D, nfirst, nlast, pstage, bar);           // arrives while this unit is gathered
+		const bool next_has = nfirst != nlast;
+		if (next_has) sort_count((const uint32_t *) (stages + (cur ^ 1) * USTAGE_DOUBLES + UT_SITES + 1), hist, nheavy + (hb ^ 1), heavy + (hb ^ 1) * UCELLS, kc, rc);
+
+		// ---- gather + flush: a thread per (x, y) column of the tile sums the cells around its three sites and issues the
+		//      FP64 reductions (RED.ADD.F64) into HBM; consecutive lanes hold consecutive sites of a row
+		if (first != last)
+			for (int col = threadIdx.x; col < DX * DY; col += ZC_THREADS)
+			{
+				const int sy = col / DX, sx = col - sy * DX;
+				double sum[UZ + 1][7];
+				#pragma unroll
+				for (int z = 0; z <= UZ; z++)
+				{
+					#pragma unroll
+					for (int k = 0; k < 7; k++) sum[z][k] = 0.;
+				}
+				column_from<WHAT, 0, 0>(acc, sx, sy, sum);
+				column_from<WHAT, 0, 1>(acc, sx, sy, sum);
+				column_from<WHAT, 1, 0>(acc, sx, sy, sum);
+				column_from<WHAT, 1, 1>(acc, sx, sy, sum);
+				const size_t gcol = (size_t) wrap_up(y0 + sy, G.N) * G.N + wrap_up(x0 + sx, G.N);
+				#pragma unroll
+				for (int z = 0; z <= UZ; z++)
+				{
+					const size_t off = (size_t) (zl0 + z + 1) * G.N * G.N + gcol;
+					#pragma unroll
+					for (int k = 0; k < NCOMP; k++)
+						if (sum[z][k] != 0.) atomicAdd(D.out[k] + off, sum[z][k]);
+				}
+			}
+		__syncthreads();                                    // 2: the histogram of the next unit is complete; acc is free again
+		if (next_has) sort_place(hist, order, kc, rc);
+		__syncthreads();                                    // 3: the next unit's slot order is in place
+		if (threadIdx.x < ZC_CLASSES) hist[threadIdx.x] = 0;
+		unit = nunit; cur ^= 1; hb ^= 1;
 		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
 	}
 }
@@ -1021,7 +1041,7 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 2)
 	{
 		// one thread per cell, register accumulators (k_deposit_percell): two blocks per SM, one unit (half a brick) at a time
-		const size_t smem = ((size_t) dep_nacc(WHAT) * UCELLS + 2 * USTAGE_DOUBLES + 6 * ZC_PSTRIDE) * sizeof(double) + 8 + (ZC_CLASSES + 1) * sizeof(int) + 2 * UCELLS;
+		const size_t smem = ((size_t) dep_nacc(WHAT) * UCELLS + 2 * USTAGE_DOUBLES + 6 * ZC_PSTRIDE) * sizeof(double) + 8 + (ZC_CLASSES + 2) * sizeof(int) + 3 * UCELLS;
 		const uint32_t persistent = (uint32_t) c->num_sms * 2, nunits = 2 * D.G.nbricks;
 		const uint32_t grid = nunits < persistent ? nunits : persistent;
 		if (phi)

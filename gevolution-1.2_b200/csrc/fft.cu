@@ -325,14 +325,20 @@ extern "C" int gevb_plan_create(gevb_plan ** out, gevb_field * rf, gevb_field * 
 		CUFFT_TRY(cufftSetStream(p->z1d_one, c->stream));
 		// pipeline inside a component: the slab's planes (forward) / rows (backward) are transformed in `chunks` pieces and the
 		// push of a piece overlaps the local transform of the next, so that a one-component transform hides its exchange too
-		p->chunks = 1;
+		// (forward pieces are whole 32-plane tiles of the transposing push; backward pieces are rows of the ky-slab)
+		p->chunks = p->chunks_bwd = 1;
 		for (int ch = 4; ch > 1; ch >>= 1)
-			if (c->nzl % (32 * ch) == 0 && c->nkyl % ch == 0) { p->chunks = ch; break; }
+			if (c->nzl % (32 * ch) == 0) { p->chunks = ch; break; }
+		for (int ch = 4; ch > 1; ch >>= 1)
+			if (c->nkyl % ch == 0 && c->nkyl / ch >= 8) { p->chunks_bwd = ch; break; }
 		if (p->chunks > 1)
 		{
 			CUFFT_TRY(cufftPlanMany(&p->fwd2d_c, 2, n2, rembed, 1, N * N, kembed, 1, nh, CUFFT_D2Z, c->nzl / p->chunks));
-			CUFFT_TRY(cufftPlanMany(&p->z1d_c, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, (c->nkyl / p->chunks) * nh));
 			CUFFT_TRY(cufftSetStream(p->fwd2d_c, c->stream));
+		}
+		if (p->chunks_bwd > 1)
+		{
+			CUFFT_TRY(cufftPlanMany(&p->z1d_c, 1, n1, n1, 1, N, n1, 1, N, CUFFT_Z2Z, (c->nkyl / p->chunks_bwd) * nh));
 			CUFFT_TRY(cufftSetStream(p->z1d_c, c->stream));
 		}
 		// exchange buffers large enough for this field (collective; grow-only)
@@ -349,7 +355,7 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
 	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); } }
-	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); if (p->chunks > 1) { cufftDestroy(p->fwd2d_c); cufftDestroy(p->z1d_c); } }
+	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); if (p->chunks > 1) cufftDestroy(p->fwd2d_c); if (p->chunks_bwd > 1) cufftDestroy(p->z1d_c); }
 	delete p;
 	return 0;
 }
@@ -446,7 +452,7 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		double2 * Xl = (double2 *) c->xchg[buf][c->rank];
 		// component pipeline: the push of component k (xstream) overlaps the local transform of component k+1 (stream);
 		// the time the main stream then still waits for the exchange is what CLS_FFT_A2A measures
-		const int chunks = gevb_tune(TUNE_FFT_OVERLAP) >= 2 ? p->chunks : 1;       // fft_overlap: 0 off, 1 component pipeline, 2 (default) also pieces inside a component
+		const int chunks = gevb_tune(TUNE_FFT_OVERLAP) >= 2 ? (direction == GEVB_FFT_FORWARD ? p->chunks : p->chunks_bwd) : 1;   // fft_overlap: 0 off, 1 component pipeline, 2 (default) also pieces inside a component
 		const bool overlap = gevb_tune(TUNE_FFT_OVERLAP) != 0 && (nc > 1 || chunks > 1) && nc <= 7;
 		cudaStream_t xs = overlap ? c->xstream : c->stream;
 		// resident blocks of the exchange: two per SM when it shares the machine with a local transform, else eight

@@ -157,7 +157,7 @@ struct gevb_plan
 	cufftHandle fwd2d, bwd2d, z1d;   // nranks > 1: per-plane 2-D transforms + 1-D along z
 	cufftHandle z1d_one;             // 1-D along z for one component (component-pipelined backward transform)
 	cufftHandle fwd2d_c, z1d_c;      // nranks > 1: the same for one piece of a component (chunks > 1)
-	int chunks;                      // pieces per component of the exchange pipeline
+	int chunks, chunks_bwd;          // pieces per component of the exchange pipeline (forward: planes, backward: rows)
 	cufftHandle f2d_c, b2d_c;        // nranks == 1: the 2-D transforms of `chunk_planes` planes at a time (tuning knob fft_l2_planes)
 	int chunk_planes;                // 0: not created
 	bool multi;
