@@ -364,6 +364,29 @@ def multi_rank_parity(gevb, dist, rank, world, local_rank):
     return out
 
 
+def bind_near_gpu(local_rank):
+    """Bind this rank's host threads (and so the first-touch placement of its pinned buffers) to the cores of the NUMA
+    node its GPU hangs off -- what `mpirun --bind-to` / `numactl` do for the reference's ranks.  Read from sysfs through the
+    GPU's PCI address; a no-op when the box does not expose it (single node, VM without topology)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(path + "/numa_node").read())
+        cpus = set()
+        for part in open(path + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus or cpus == os.sched_getaffinity(0):
+            return {"numa_node": node, "cpus": len(os.sched_getaffinity(0)), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "bound": True}
+    except Exception as e:                                     # placement is an optimisation, never a failure
+        return {"bound": False, "why": str(e)[:80]}
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import torch                      # first: its bundled NCCL must be the one mapped into the process
@@ -373,6 +396,7 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    binding = bind_near_gpu(local_rank) if env_int("GEVB_BIND", 1) else {"bound": False}
     torch.cuda.set_device(local_rank)
     nccl_id = None
     if world > 1:
@@ -532,7 +556,7 @@ def run_ours(args, rank, world, local_rank):
             gevb.tuning(knob, int(vals.split(":")[0]))
 
     # ---- end to end through the C ABI with host buffers (species 0 and the metric state; config 3 is the quoted one) ----
-    e2e_value, h2d, d2h = None, 0, 0
+    e2e_value, h2d, d2h, e2e_parts = None, 0, 0, None
     e2e_steps = max(1, min(args.steps, env_int("GEVB_E2E_STEPS", 2)))
     if len(species) == 1 and not args.no_e2e:
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
@@ -545,21 +569,35 @@ def run_ours(args, rank, world, local_rank):
         del gid, gpos, gvel
         fbytes = h_phi.nbytes + h_chi.nbytes + h_bft.nbytes
 
-        def e2e_step():
+        e2e_parts = {}
+
+        def e2e_step(parts=None):
+            def mark(name, t=[0.0]):                            # untimed warm-up only: where an end-to-end step spends its time
+                if parts is not None:
+                    ctx.sync(); now = time.perf_counter()
+                    if name: parts[name] = round((now - t[0]) * 1e3, 2)
+                    t[0] = now
+            mark(None)
             n = nloc[0]
             sim.set_particles(0, h_id[:n], h_pos[:n], h_vel[:n], mass)          # host -> device: particle state
+            mark("h2d_particles_ms")
             sim.set_field("phi", h_phi); sim.set_field("chi", h_chi); sim.set_field("BiFT", h_bft)
+            mark("h2d_fields_ms")
             sim.step()
+            mark("step_ms")
             p = sim.pcls(0)
             m = p.count()
             L = gevb.lib()
             gevb._ck(L.gevb_pcls_download(p.h, gevb._ptr(h_id[:m]), gevb._ptr(h_pos[:m]), gevb._ptr(h_vel[:m])), "download")
+            mark("d2h_particles_ms")
             for name, buf in (("phi", h_phi), ("chi", h_chi), ("BiFT", h_bft)):
                 gevb._ck(L.gevb_field_download(sim.field(name).h, gevb._ptr(buf)), "download")
+            mark("d2h_fields_ms")
             nloc[0] = m
             return 56 * n + fbytes, 56 * m + fbytes
 
         e2e_step()                                              # warm-up (allocations)
+        e2e_step(e2e_parts)                                     # second warm-up, with a synchronisation after every part
         ctx.sync(); barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -648,7 +686,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"BASELINE config {args.config}: {cfg['what']}; one cycle of main.cpp:372-879 per step (fused T00+Tij deposit, fused kick+drift, {nfwd + 5} FFTs)",
                        "ngrid": N, "particles": np_total, "species": list(species), "slabs": world, "parallelism": f"z-slab x{world}",
                        "l2_policy": "inputs larger than L2: every pass streams >= 1 GB per rank (126 MB L2)",
-                       "e2e_steps": e2e_steps, "z": 1.0 / state["a"] - 1.0, "setup_s": t_setup, "device_memory_used_gb_rank0": mem_used_gb,
+                       "e2e_steps": e2e_steps, "z": 1.0 / state["a"] - 1.0, "setup_s": t_setup, "device_memory_used_gb_rank0": mem_used_gb, "host_binding_rank0": binding, "e2e_parts_rank0": e2e_parts,
                        "ncdm_substeps": ncdm_steps, "hij_spectrum_call_ms": hij_ms},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

@@ -41,6 +41,18 @@ namespace {
 #define DEP_THREADS 256
 
 enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
+// variants of k_deposit (tuning knob deposit_variant = 3 + flags):
+//   DEPF_BULK   the tile is flushed row by row with bulk reductions of the TMA unit (cp.reduce.async.bulk ... add.f64, one per
+//               row of 16 sites and component) instead of one RED per site; rows of the accumulator tile are padded to 18
+//               sites so that each starts on a 16-byte boundary
+//   DEPF_SPLIT  the barrier between corner phases is split (mbarrier arrive / wait): a warp arrives after its updates of phase
+//               k, computes and segment-sums the contributions of phase k + 1 and only then waits for the other warps
+//   DEPF_ROUNDS particles of one cell inside a warp take turns (lane r of a cell's segment updates in round r, plain
+//               read-add-write) instead of being summed by shuffles first; segments longer than four lanes still use the shuffles
+enum { DEPF_BULK = 1, DEPF_SPLIT = 2, DEPF_ROUNDS = 4 };
+__host__ __device__ constexpr int acc_ax(int flags) { return (flags & DEPF_BULK) ? DX + 1 : DX; }         // row stride of the accumulator tile
+__host__ __device__ constexpr int acc_sites(int flags) { return acc_ax(flags) * DY * DZ; }
+__host__ __device__ constexpr int acc_corner(int flags, int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * acc_ax(flags) + (k & 1) * acc_ax(flags) * DY; }
 
 // tile components per projection; Tij components follow the field order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
 __host__ __device__ constexpr int dep_ncomp(int what) { return what == DEP_T00 ? 1 : what == DEP_TIJ ? 6 : what == DEP_T00_TIJ ? 7 : 3; }
@@ -68,6 +80,41 @@ __device__ __forceinline__ void cp_async4(void * smem_dst, const void * gmem_src
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long * bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long * bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long * bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gmem_src, uint32_t bytes, unsigned long long * bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+// bulk reduction (TMA unit, UBLKRED): global[0 .. bytes) += shared[0 .. bytes) as FP64 adds; 16-byte aligned on both sides
+__device__ __forceinline__ void bulk_add_f64(double * gmem_dst, const double * smem_src, uint32_t bytes)
+{
+	asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" :: "l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // periodic wrap of an index in [0, 2N) (a tile reaches one site past the brick; bricks of a partial super-brick lie past N)
 __device__ __forceinline__ int wrap_up(int v, int N) { v = v >= N ? v - N : v; return v >= N ? v % N : v; }
@@ -153,8 +200,11 @@ struct Writer
 {
 	double * tile;                 // tile + site of the particle's cell
 	int after, steps;              // lanes after this one in the same cell (within the warp); shuffle steps of the segmented sum
+	int before;                    // lanes before this one in the same cell (within the warp)
 	bool write;                    // this lane writes: alone in its cell, or first lane of its cell's segment in this warp
 	bool plain;                    // no other warp holds particles of this cell: plain read-add-write is safe
+	unsigned long long * bar;      // DEPF_SPLIT: the block's phase barrier
+	uint32_t parity;               // DEPF_SPLIT: parity of the barrier phase this thread waits for next
 };
 
 // tile component of the j-th contribution of corner K (j = -1: how many contributions corner K has)
@@ -219,8 +269,27 @@ __device__ __forceinline__ void phase_values(const PInv & I, const double * ph, 
 // read-add-write.  Particles of one cell are contiguous lanes: their contributions are summed by a segmented
 // shuffle reduction and the first lane of the segment writes -- with a shared-memory atomic if the cell's
 // particles straddle warps (the only case in which two warps can meet on a site within a phase).
-template <int WHAT, bool HAS_PHI, int K, int STEPS>
-__device__ __forceinline__ void phase(const PInv & I, const Writer & W, const double * ph)
+template <int WHAT, int K, int FLAGS>
+__device__ __forceinline__ void tile_add(const Writer & W, const double * v)
+{
+	constexpr int NV = phase_comp(WHAT, K, -1);
+	constexpr int ASITES = acc_sites(FLAGS);
+	double * p = W.tile + acc_corner(FLAGS, K);
+	if (W.plain)
+	{
+		#pragma unroll
+		for (int j = 0; j < NV; j++) p[phase_comp(WHAT, K, j) * ASITES] += v[j];
+	}
+	else
+	{
+		#pragma unroll
+		for (int j = 0; j < NV; j++) atomicAdd(p + phase_comp(WHAT, K, j) * ASITES, v[j]);
+	}
+}
+
+// STEPS > 0: that many shuffle steps of the segmented sum; STEPS < 0 (DEPF_ROUNDS): -STEPS rounds without shuffles
+template <int WHAT, bool HAS_PHI, int K, int STEPS, int FLAGS>
+__device__ __forceinline__ void phase(const PInv & I, Writer & W, const double * ph)
 {
 	constexpr int NV = phase_comp(WHAT, K, -1);
 	double v[NV > 0 ? NV : 1];
@@ -235,17 +304,26 @@ __device__ __forceinline__ void phase(const PInv & I, const Writer & W, const do
 			if ((1 << s) <= W.after) v[j] += t;
 		}
 	}
-	if (W.write)
+	if (FLAGS & DEPF_SPLIT) { mbar_wait(W.bar, W.parity); W.parity ^= 1; }     // every warp is through the previous phase
+	if (STEPS >= 0)
 	{
-		double * p = W.tile + corner_offset(K);
+		if (W.write) tile_add<WHAT, K, FLAGS>(W, v);
+	}
+	else
+	{
 		#pragma unroll
-		for (int j = 0; j < NV; j++)
+		for (int r = 0; r < -STEPS; r++)
 		{
-			if (W.plain) p[phase_comp(WHAT, K, j) * DT_SITES] += v[j];
-			else atomicAdd(p + phase_comp(WHAT, K, j) * DT_SITES, v[j]);
+			if (W.before == r) tile_add<WHAT, K, FLAGS>(W, v);
+			if (r + 1 < -STEPS) __syncwarp();
 		}
 	}
-	__syncthreads();
+	if (FLAGS & DEPF_SPLIT)
+	{
+		__syncwarp();
+		if ((threadIdx.x & 31) == 0) mbar_arrive(W.bar);                        // one arrival per warp
+	}
+	else __syncthreads();
 }
 
 // cell = floor(pos/dx) clamped into the lattice; pos * N is bit-identical to pos / dx for power-of-two N
@@ -262,42 +340,40 @@ __device__ __forceinline__ void load_particle(const DParams & D, uint32_t i, dou
 }
 
 // the eight corner phases of one batch
-template <int WHAT, bool HAS_PHI, int STEPS>
-__device__ __forceinline__ void phases(const PInv & I, const Writer & W, const double * ph)
+template <int WHAT, bool HAS_PHI, int STEPS, int FLAGS>
+__device__ __forceinline__ void phases(const PInv & I, Writer & W, const double * ph)
 {
-	phase<WHAT, HAS_PHI, 0, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 1, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 2, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 3, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 4, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 5, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 6, STEPS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 7, STEPS>(I, W, ph);
-}
-
-// barrier pattern of phases() for a warp that holds no particle of the batch
-__device__ __forceinline__ void idle_phases()
-{
-	#pragma unroll
-	for (int k = 0; k < 8; k++) __syncthreads();
+	phase<WHAT, HAS_PHI, 0, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 1, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 2, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 3, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 4, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 5, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 6, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 7, STEPS, FLAGS>(I, W, ph);
 }
 
 // Persistent blocks walk the bricks with stride gridDim.x in a software pipeline: while brick k is accumulated and
 // flushed, the cell table and phi tile of brick k+1 are in flight into the other shared-memory stage, the particle
 // range of brick k+2 is being fetched, and the next batch of particles is already requested.
-template <int WHAT, bool HAS_PHI>
+template <int WHAT, bool HAS_PHI, int FLAGS>
 __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 {
 	constexpr int NCOMP = dep_ncomp(WHAT);
-	extern __shared__ double smem[];
-	double * tile = smem;                                   // [NCOMP][DT_SITES] accumulators
-	double * stages = smem + NCOMP * DT_SITES;              // [2][DEP_STAGE_DOUBLES]
+	constexpr int AX = acc_ax(FLAGS), ASITES = acc_sites(FLAGS);
+	extern __shared__ __align__(16) double site_smem[];
+	double * smem = site_smem;
+	double * tile = smem;                                   // [NCOMP][ASITES] accumulators
+	double * stages = smem + NCOMP * ASITES;                // [2][DEP_STAGE_DOUBLES]
+	unsigned long long * bar = (unsigned long long *) (stages + 2 * DEP_STAGE_DOUBLES);
 
 	const BrickGeom & G = D.G;
 	const int tcol = threadIdx.x, ttx = tcol % DX, tty = tcol / DX;      // this thread's column of the tile (flush)
 	const int lane = threadIdx.x & 31;
-	for (int idx = threadIdx.x; idx < NCOMP * DT_SITES + 2 * DEP_STAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
+	for (int idx = threadIdx.x; idx < NCOMP * ASITES + 2 * DEP_STAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
+	if ((FLAGS & DEPF_SPLIT) && threadIdx.x == 0) mbar_init(bar, DEP_THREADS / 32);
 	__syncthreads();
+	uint32_t parity = 0;
 	uint32_t brick = blockIdx.x;
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
 	brick_range(D, brick, first, last);
@@ -319,6 +395,8 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 			brick_origin(G, brick, x0, y0, zl0);
 			cp_async_wait<1>();                             // everything but the newest group: this brick's stage has landed
 			__syncthreads();
+			// split barrier: every phase waits for the arrivals of the one before it; the first phase of a brick finds these
+			if (FLAGS & DEPF_SPLIT) { if (lane == 0) mbar_arrive(bar); }
 			const double * tphi = stages + cur * DEP_STAGE_DOUBLES;
 			const uint32_t * ctab = (const uint32_t *) (tphi + DT_SITES);
 
@@ -331,13 +409,14 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 				const double * ph;
 				{
 					// the particle's cell (it lies in this brick: the storage order is maintained by the re-bin)
-					int cx = 0, cy = 0, cz = 0, site = 0;
+					int cx = 0, cy = 0, cz = 0, site = 0, asite = 0;
 					uint32_t cfirst = i, clast = i + 1;
 					if (valid)
 					{
 						cx = cell_scaled(D, pv[0]); cy = cell_scaled(D, pv[1]); cz = cell_scaled(D, pv[2]);
 						const int sx = cx - x0, sy = cy - y0, sz = cz - G.z0 - zl0;
 						site = (sz * DY + sy) * DX + sx;
+						asite = (sz * DY + sy) * AX + sx;
 						const int c = (sz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (sy << GEVB_BX_BITS) | sx;
 						cfirst = ctab[c]; clast = ctab[c + 1];
 					}
@@ -346,11 +425,14 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 					const uint32_t warp_lo = i - lane, warp_hi = warp_lo + 32;
 					const uint32_t seg_lo = cfirst > warp_lo ? cfirst : warp_lo, seg_hi = clast < warp_hi ? clast : warp_hi;
 					const int maxlen = __reduce_max_sync(0xffffffffu, (int) (seg_hi - seg_lo));
-					W.tile = tile + site; ph = tphi + site;
+					W.tile = tile + asite; ph = tphi + site;
 					W.after = (int) (seg_hi - 1 - i);
+					W.before = valid ? (int) (i - seg_lo) : 32;
 					W.steps = maxlen > 1 ? 32 - __clz(maxlen - 1) : 0;
+					if ((FLAGS & DEPF_ROUNDS) && maxlen > 1) W.steps = maxlen <= 4 ? -maxlen : 5;
 					W.write = valid && i == seg_lo;
 					W.plain = cfirst >= warp_lo && clast <= warp_hi;
+					W.bar = bar; W.parity = parity;
 				}
 				// request the next batch (of this brick, else the first batch of the next brick) while the phases run
 				{
@@ -360,27 +442,57 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 				}
 				// shuffle steps of the segmented sum are a warp-uniform property of the batch: 0 when no two lanes share a cell;
 				// a warp without particles (tail of the brick) only keeps the barriers company
-				if (W.steps == 0) phases<WHAT, HAS_PHI, 0>(I, W, ph);
-				else if (W.steps == 1) phases<WHAT, HAS_PHI, 1>(I, W, ph);
-				else if (W.steps == 2) phases<WHAT, HAS_PHI, 2>(I, W, ph);
-				else phases<WHAT, HAS_PHI, 5>(I, W, ph);
+				if (W.steps == 0) phases<WHAT, HAS_PHI, 0, FLAGS>(I, W, ph);
+				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -2) phases<WHAT, HAS_PHI, -2, FLAGS>(I, W, ph);
+				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -3) phases<WHAT, HAS_PHI, -3, FLAGS>(I, W, ph);
+				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -4) phases<WHAT, HAS_PHI, -4, FLAGS>(I, W, ph);
+				else if (!(FLAGS & DEPF_ROUNDS) && W.steps == 1) phases<WHAT, HAS_PHI, 1, FLAGS>(I, W, ph);
+				else if (!(FLAGS & DEPF_ROUNDS) && W.steps == 2) phases<WHAT, HAS_PHI, 2, FLAGS>(I, W, ph);
+				else phases<WHAT, HAS_PHI, 5, FLAGS>(I, W, ph);
+				parity = W.parity;
 			}
+			if (FLAGS & DEPF_SPLIT) { mbar_wait(bar, parity); parity ^= 1; }       // the last phase of every warp
 
-			// ---- flush the tile: FP64 reductions into HBM, consecutive lanes on consecutive sites of a row;
-			//      the tile is left zeroed for the next brick (stage `cur` is free from here on)
-			if (tcol < DX * DY)
+			// ---- flush the tile into the field in HBM; it is left zeroed for the next brick (stage `cur` is free from here on)
+			if ((FLAGS & DEPF_BULK) && x0 + GEVB_BX <= G.N)
 			{
-				const size_t gcol = (size_t) wrap_up(y0 + tty, G.N) * G.N + wrap_up(x0 + ttx, G.N);
-				#pragma unroll
-				for (int tz = 0; tz < DZ; tz++)
+				// one bulk reduction per row of 16 sites and component (the row does not wrap in x), one RED for the apron site
+				fence_async_proxy();
+				__syncthreads();
+				for (int r = threadIdx.x; r < NCOMP * DZ * DY; r += DEP_THREADS)
 				{
-					const int s = (tz * DY + tty) * DX + ttx;
-					const size_t off = (size_t) (zl0 + tz + 1) * G.N * G.N + gcol;
+					const int k = r / (DZ * DY), rem = r - k * (DZ * DY), tz = rem / DY, ty = rem - tz * DY;
+					const int plane = zl0 + tz + 1;
+					if (plane > G.nzl + 1) continue;                                   // partial brick at the top of the slab
+					const double * row = tile + k * ASITES + (tz * DY + ty) * AX;
+					double * grow = D.out[k] + (size_t) plane * G.N * G.N + (size_t) wrap_up(y0 + ty, G.N) * G.N;
+					bulk_add_f64(grow + x0, row, GEVB_BX * sizeof(double));
+					const double v = row[GEVB_BX];
+					if (v != 0.) atomicAdd(grow + wrap_up(x0 + GEVB_BX, G.N), v);
+				}
+				bulk_commit();
+				bulk_wait_read();                                   // the rows have been read: the tile may be cleared
+				__syncthreads();
+				double2 * t2 = (double2 *) tile;
+				for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
+			}
+			else
+			{
+				// FP64 reductions, consecutive lanes on consecutive sites of a row
+				if (tcol < DX * DY)
+				{
+					const size_t gcol = (size_t) wrap_up(y0 + tty, G.N) * G.N + wrap_up(x0 + ttx, G.N);
 					#pragma unroll
-					for (int k = 0; k < NCOMP; k++)
+					for (int tz = 0; tz < DZ; tz++)
 					{
-						const double v = tile[k * DT_SITES + s];
-						if (v != 0.) { atomicAdd(D.out[k] + off, v); tile[k * DT_SITES + s] = 0.; }
+						const int s = (tz * DY + tty) * AX + ttx;
+						const size_t off = (size_t) (zl0 + tz + 1) * G.N * G.N + gcol;
+						#pragma unroll
+						for (int k = 0; k < NCOMP; k++)
+						{
+							const double v = tile[k * ASITES + s];
+							if (v != 0.) { atomicAdd(D.out[k] + off, v); tile[k * ASITES + s] = 0.; }
+						}
 					}
 				}
 			}
@@ -718,28 +830,6 @@ __global__ void __launch_bounds__(DEP_THREADS, 2) k_deposit_cells(DParams D)
 #define ZC_THREADS 192                                 // 2 blocks of 192 threads per SM: 170 registers per thread for the 38 accumulators
 #define ZC_PSTRIDE (ZC_PMAX + 2)                       // one staged array (the range is widened to 16-byte boundaries)
 
-__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long * bar, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect(unsigned long long * bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long * bar, uint32_t parity)
-{
-	uint32_t done = 0;
-	while (!done)
-		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gmem_src, uint32_t bytes, unsigned long long * bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		:: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
 // contributions of one particle added to the register accumulators A[] of its cell (corner K)
 template <int WHAT, bool HAS_PHI, int K>
 __device__ __forceinline__ void accumulate_corner(const PInv & I, const double * phc, double * A)
@@ -1025,6 +1115,26 @@ int check_real(const gevb_field * f, int ncomp, const char * who, const char * n
 	return 0;
 }
 
+template <int WHAT, int FLAGS>
+int launch_sites(gevb_ctx * c, const DParams & D, bool has_phi)
+{
+	const size_t smem = ((size_t) dep_ncomp(WHAT) * acc_sites(FLAGS) + 2 * DEP_STAGE_DOUBLES) * sizeof(double) + 16;
+	const uint32_t persistent = (uint32_t) c->num_sms * 3;
+	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;
+	if (has_phi)
+	{
+		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, true, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_deposit<WHAT, true, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+	}
+	else
+	{
+		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, false, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_deposit<WHAT, false, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+	}
+	KERNEL_CHECK(c);
+	return 0;
+}
+
 template <int WHAT>
 int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, double mass)
 {
@@ -1057,7 +1167,7 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 		KERNEL_CHECK(c);
 		return 0;
 	}
-	if (gevb_tune(TUNE_DEPOSIT_VARIANT) != 0)
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 1)
 	{
 		// per-cell accumulators (k_deposit_cells): two blocks per SM, one unit (half a brick) at a time
 		const size_t smem = ((size_t) dep_nacc(WHAT) * ACC_COLS + 2 * USTAGE_DOUBLES) * sizeof(double) + 2 * DEP_WARPS * sizeof(int);
@@ -1076,21 +1186,17 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 		KERNEL_CHECK(c);
 		return 0;
 	}
-	const size_t smem = ((size_t) dep_ncomp(WHAT) * DT_SITES + 2 * DEP_STAGE_DOUBLES) * sizeof(double);
-	const uint32_t persistent = (uint32_t) c->num_sms * 3;
-	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;
-	if (phi)
+	// deposit_variant 0: the site-tile kernel as it is; 3 + flags: its variants (DEPF_*)
+	const int variant = gevb_tune(TUNE_DEPOSIT_VARIANT);
+	switch (variant >= 3 ? variant - 3 : 0)
 	{
-		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, true><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+	case 0: return launch_sites<WHAT, 0>(c, D, phi != NULL);
+	case DEPF_BULK: return launch_sites<WHAT, DEPF_BULK>(c, D, phi != NULL);
+	case DEPF_SPLIT: return launch_sites<WHAT, DEPF_SPLIT>(c, D, phi != NULL);
+	case DEPF_ROUNDS: return launch_sites<WHAT, DEPF_ROUNDS>(c, D, phi != NULL);
+	case DEPF_ROUNDS | DEPF_BULK: return launch_sites<WHAT, DEPF_ROUNDS | DEPF_BULK>(c, D, phi != NULL);
+	default: gevb_set_error("deposit_variant %d is not built", variant); return 1;
 	}
-	else
-	{
-		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, false><<<grid, DEP_THREADS, smem, c->stream>>>(D);
-	}
-	KERNEL_CHECK(c);
-	return 0;
 }
 
 } // namespace

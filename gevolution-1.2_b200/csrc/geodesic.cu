@@ -515,7 +515,7 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.n = p->n;
 	P.x = p->x[b]; P.y = p->y[b]; P.z = p->z[b]; P.qx = p->qx[b]; P.qy = p->qy[b]; P.qz = p->qz[b]; P.id = p->id[b]; P.key = p->key;
 	P.cell_start = p->cell_start; P.cell_count = p->cell_count;
-	P.rank = gevb_tune(TUNE_REBIN_VARIANT) != 0 ? p->rank : NULL;
+	P.rank = (gevb_tune(TUNE_REBIN_VARIANT) & 1) != 0 ? p->rank : NULL;
 	P.maxv2 = (unsigned long long *) (c->d_red + 4008);
 	P.nsend = (unsigned long long *) (c->d_red + 4010);
 }

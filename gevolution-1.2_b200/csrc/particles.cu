@@ -113,6 +113,107 @@ __global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const unsigne
 	}
 }
 
+// the move of the counting sort through a shared-memory window (rebin_variant = 2, 3).  The records of a chunk of
+// WIN_CHUNK consecutive particles mostly stay where they are in the sorted order (a particle that keeps its brick moves
+// by at most a few hundred slots), so their new slots fall into a window of WIN_SLOTS consecutive slots around the slot of the
+// chunk's first particle.  The block drops those records into the window in shared memory and writes the window out row by
+// row: consecutive lanes store consecutive slots (whole 128-byte lines but for the few slots other blocks fill) instead of
+// 8-byte stores scattered over a dozen sectors per request.  Records that leave the window are stored directly, as in
+// k_scatter.  Where the window lies only matters for speed.  RANKED: the slot inside the cell comes from the rank the drift
+// kernel recorded (rebin_variant 3), else from counting the histogram down.
+#define WIN_CHUNK 1024
+#define WIN_PAD 128
+#define WIN_SLOTS (WIN_CHUNK + 2 * WIN_PAD)
+#define WIN_THREADS 256
+#define WIN_PER (WIN_CHUNK / WIN_THREADS)
+#define WIN_SMEM (7 * WIN_SLOTS * 8 + WIN_SLOTS)
+template <bool RANKED>
+__global__ void __launch_bounds__(WIN_THREADS, 3) k_scatter_window(int64_t n, const unsigned long long * __restrict__ n_dev, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank,
+                          const uint32_t * __restrict__ cell_start, uint32_t * count,
+                          const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
+                          const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
+                          double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
+                          double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
+{
+	extern __shared__ __align__(16) unsigned char win_smem[];
+	double * buf = (double *) win_smem;                                   // [7][WIN_SLOTS]
+	unsigned char * filled = win_smem + 7 * WIN_SLOTS * sizeof(double);   // [WIN_SLOTS]
+	__shared__ uint32_t base_s;
+	if (n_dev) n = (int64_t) *n_dev;
+	const int64_t nchunks = (n + WIN_CHUNK - 1) / WIN_CHUNK;
+	uint32_t k[WIN_PER], d[WIN_PER];
+	double v[WIN_PER][6];
+	int64_t vid[WIN_PER];
+	// the records, keys and slots of a chunk: issued one chunk ahead, so that they are in flight while the previous window is written out
+	auto fetch = [&](int64_t ch)
+	{
+		const int64_t s0 = ch * WIN_CHUNK;
+		#pragma unroll
+		for (int u = 0; u < WIN_PER; u++)
+		{
+			const int64_t i = s0 + u * WIN_THREADS + threadIdx.x;
+			k[u] = GEVB_INVALID_KEY; d[u] = 0;
+			if (ch < nchunks && i < n) { k[u] = __ldcs(key + i); if (RANKED) d[u] = __ldcs(rank + i); }
+		}
+		#pragma unroll
+		for (int u = 0; u < WIN_PER; u++)
+		{
+			const int64_t i = s0 + u * WIN_THREADS + threadIdx.x;
+			if (k[u] == GEVB_INVALID_KEY) continue;
+			v[u][0] = __ldcs(x + i); v[u][1] = __ldcs(y + i); v[u][2] = __ldcs(z + i);
+			v[u][3] = __ldcs(qx + i); v[u][4] = __ldcs(qy + i); v[u][5] = __ldcs(qz + i);
+			vid[u] = __ldcs(id + i);
+		}
+		#pragma unroll
+		for (int u = 0; u < WIN_PER; u++)
+			if (k[u] != GEVB_INVALID_KEY) d[u] = RANKED ? d[u] + __ldg(cell_start + k[u]) : __ldg(cell_start + k[u]) + atomicSub(count + k[u], 1u) - 1u;
+	};
+	fetch(blockIdx.x);
+	for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+	{
+		for (int w = threadIdx.x; w < WIN_SLOTS / 4; w += WIN_THREADS) ((uint32_t *) filled)[w] = 0u;
+		if (threadIdx.x == 0) base_s = k[0] != GEVB_INVALID_KEY ? (d[0] > WIN_PAD ? d[0] - WIN_PAD : 0u) : 0xffffffffu - WIN_SLOTS;
+		__syncthreads();
+		const uint32_t base = base_s;
+		#pragma unroll
+		for (int u = 0; u < WIN_PER; u++)
+		{
+			if (k[u] == GEVB_INVALID_KEY) continue;
+			const uint32_t off = d[u] - base;                               // unsigned: slots below the window wrap to huge values
+			if (off < WIN_SLOTS)
+			{
+				#pragma unroll
+				for (int a = 0; a < 6; a++) buf[a * WIN_SLOTS + off] = v[u][a];
+				((int64_t *) buf)[6 * WIN_SLOTS + off] = vid[u];
+				filled[off] = 1;
+			}
+			else
+			{
+				ox[d[u]] = v[u][0]; oy[d[u]] = v[u][1]; oz[d[u]] = v[u][2];
+				oqx[d[u]] = v[u][3]; oqy[d[u]] = v[u][4]; oqz[d[u]] = v[u][5];
+				oid[d[u]] = vid[u];
+			}
+		}
+		__syncthreads();
+		fetch(ch + gridDim.x);
+		for (int j = threadIdx.x; j < WIN_SLOTS; j += WIN_THREADS)
+		{
+			if (!filled[j]) continue;
+			const size_t t = (size_t) base + j;
+			ox[t] = buf[j]; oy[t] = buf[WIN_SLOTS + j]; oz[t] = buf[2 * WIN_SLOTS + j];
+			oqx[t] = buf[3 * WIN_SLOTS + j]; oqy[t] = buf[4 * WIN_SLOTS + j]; oqz[t] = buf[5 * WIN_SLOTS + j];
+			oid[t] = ((const int64_t *) buf)[6 * WIN_SLOTS + j];
+		}
+		__syncthreads();
+	}
+}
+
+static unsigned window_grid(gevb_ctx * c, int64_t n)
+{
+	const int64_t chunks = (n + WIN_CHUNK - 1) / WIN_CHUNK, persistent = (int64_t) c->num_sms * 3;
+	return (unsigned) (chunks < persistent ? (chunks > 0 ? chunks : 1) : persistent);
+}
+
 // the move of the counting sort: slot = cell_start[key] + (number of particles of this cell not yet placed) - 1.
 // Counting down leaves cell_count all zero again, ready for the next histogram.  Four particles per thread and
 // iteration, all loads and atomics of the four issued before the first dependent store (the chain key -> atomic ->
@@ -282,7 +383,8 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	const double dx = 1.0 / (double) c->N;
 	// the histogram's producers (here, the drift kernel, the append of received particles) all follow the knob, so a
 	// histogram passed in as valid comes with ranks exactly when the knob is on; it must not change between a drift and its re-bin
-	const bool ranked = gevb_tune(TUNE_REBIN_VARIANT) != 0;
+	const int rebin_variant = gevb_tune(TUNE_REBIN_VARIANT);
+	const bool ranked = (rebin_variant & 1) != 0, windowed = (rebin_variant & 2) != 0;
 	if (!hist_valid && n_in > 0)
 	{
 		k_make_keys<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(G, 0, n_in, p->x[s], p->y[s], p->z[s], dx, p->key, p->cell_count, ranked ? p->rank : NULL);
@@ -299,13 +401,29 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	{
 		// nothing counts the histogram down: clear it for the next one
 		CUDA_TRY(cudaMemsetAsync(p->cell_count, 0, ((size_t) G.ncells + 1) * sizeof(uint32_t), c->stream));
-		if (n_in > 0)
+		if (n_in > 0 && windowed)
+		{
+			CUDA_TRY(cudaFuncSetAttribute(k_scatter_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
+			k_scatter_window<true><<<window_grid(c, n_in), WIN_THREADS, WIN_SMEM, c->stream>>>(n_in, p->d_nin, p->key, p->rank, p->cell_start, p->cell_count,
+				p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+				p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+			KERNEL_CHECK(c);
+		}
+		else if (n_in > 0)
 		{
 			k_scatter_ranked<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(n_in, p->d_nin, p->key, p->rank, p->cell_start,
 				p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
 				p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
 			KERNEL_CHECK(c);
 		}
+	}
+	else if (n_in > 0 && windowed)
+	{
+		CUDA_TRY(cudaFuncSetAttribute(k_scatter_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
+		k_scatter_window<false><<<window_grid(c, n_in), WIN_THREADS, WIN_SMEM, c->stream>>>(n_in, p->d_nin, p->key, NULL, p->cell_start, p->cell_count,
+			p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+			p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+		KERNEL_CHECK(c);
 	}
 	else if (n_in > 0)
 	{

@@ -1,0 +1,27 @@
+#!/bin/bash
+# round-2 visit I (1 GPU): deposit with turn-taking instead of shuffles (variant 7, +bulk flush 8), windowed re-bin move
+# (rebin_variant 2, 3): parity subsets, ablations in the timed regime
+TAG=${1:-r2i}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
+for v in 7 8; do
+GEVB_DEPOSIT_VARIANT=$v timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or checker or extreme or time_loop_one or N128 or empty" > $OUT/pytest_gpu_deposit$v.log 2>&1; echo "pytest deposit variant $v exit $?"; tail -2 $OUT/pytest_gpu_deposit$v.log | cut -c1-300
+done
+for v in 2 3; do
+GEVB_REBIN_VARIANT=$v timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or checker or extreme or time_loop or N128 or empty or full_size" > $OUT/pytest_gpu_rebin$v.log 2>&1; echo "pytest rebin variant $v exit $?"; tail -2 $OUT/pytest_gpu_rebin$v.log | cut -c1-300
+done
+timeout 900 python bench.py --steps 10 --warmup 15 --no-cpu-baseline --no-regimes --no-e2e --ablate deposit_variant=0:4:7:8:0:7:8,rebin_variant=0:2:3:1:0:2 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; tail -c 300 $OUT/bench.err
+grep -h ablate $OUT/bench.err | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); m=d['ms']; print(d['ablate'], d['value'], 'deposit', m.get('projection_T00_Tij_project'), 'kick', m.get('kick_drift'), 'rebin', m.get('rebin_sort'))
+"
+GEVB_DEPOSIT_VARIANT=8 GEVB_REBIN_VARIANT=2 timeout 900 python bench.py --steps 10 --warmup 15 --no-cpu-baseline --no-e2e > $OUT/bench_d8_r2.json 2> $OUT/bench_d8_r2.err; echo "bench d8 r2 exit $?"
+python - <<PY
+import json
+for f in ("bench.json","bench_d8_r2.json"):
+    d=json.load(open("$OUT/"+f))
+    print(f, "ms_per_step", d["ms_per_step"], {k:round(v["ms_per_step"],2) for k,v in d["kernels"].items() if v["ms_per_step"]>0.4})
+    r=d["config"].get("regimes") or d.get("regimes")
+    if r: print("  regimes", {k:(v.get("ms") if isinstance(v,dict) else v) for k,v in r.items()})
+PY
+GEVB_DEPOSIT_VARIANT=8 GEVB_REBIN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_deposit|k_scatter' -s 40 -c 2 -o $OUT/d8_r2 python bench.py --steps 1 --warmup 20 --no-cpu-baseline --no-regimes --no-e2e > $OUT/ncu.log 2>&1; echo "ncu exit $?"
