@@ -24,13 +24,15 @@
 //      (gevolution.hpp:953,1199-1200).  Only a cell whose particles straddle two
 //      warps needs a shared-memory atomic.  Work per thread does not depend on
 //      the clustering state.
-//   3. the tile is flushed to the field in HBM with FP64 reductions (RED.ADD.F64),
-//      one per non-zero tile site and component -- about 5 k per brick instead of
-//      38 per particle; consecutive lanes flush consecutive sites of a row.
+//   3. the tile is flushed to the field in HBM with FP64 reductions: one bulk
+//      reduction of the TMA unit per 16-site row and component (UBLKRED, 315 per
+//      brick) plus one RED.ADD.F64 for the apron site of the row -- instead of 38
+//      reductions per particle; bricks whose rows wrap in x flush site by site.
 //
 // x and y wrap by index arithmetic at flush time; z+1 of the last local plane
 // lands in the upper ghost plane which gevb_projection_comm folds into the next rank.
 #include "gevb_internal.cuh"
+#include <cuda.h>                                          // CUtensorMap (the encoder is fetched from the driver at run time, nothing links libcuda)
 
 namespace {
 
@@ -41,18 +43,29 @@ namespace {
 #define DEP_THREADS 256
 
 enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
-// variants of k_deposit (tuning knob deposit_variant = 3 + flags):
-//   DEPF_BULK   the tile is flushed row by row with bulk reductions of the TMA unit (cp.reduce.async.bulk ... add.f64, one per
-//               row of 16 sites and component) instead of one RED per site; rows of the accumulator tile are padded to 18
-//               sites so that each starts on a 16-byte boundary
-//   DEPF_SPLIT  the barrier between corner phases is split (mbarrier arrive / wait): a warp arrives after its updates of phase
-//               k, computes and segment-sums the contributions of phase k + 1 and only then waits for the other warps
-//   DEPF_ROUNDS particles of one cell inside a warp take turns (lane r of a cell's segment updates in round r, plain
-//               read-add-write) instead of being summed by shuffles first; segments longer than four lanes still use the shuffles
-enum { DEPF_BULK = 1, DEPF_SPLIT = 2, DEPF_ROUNDS = 4 };
-__host__ __device__ constexpr int acc_ax(int flags) { return (flags & DEPF_BULK) ? DX + 1 : DX; }         // row stride of the accumulator tile
-__host__ __device__ constexpr int acc_sites(int flags) { return acc_ax(flags) * DY * DZ; }
-__host__ __device__ constexpr int acc_corner(int flags, int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * acc_ax(flags) + (k & 1) * acc_ax(flags) * DY; }
+// flavours of k_deposit (tuning knob deposit_variant: 4 = DEPF_BULK, the default; 0 = none, the round-1 kernel):
+//   DEPF_BULK   the tile is flushed row by row with bulk reductions of the TMA unit (cp.reduce.async.bulk ... add.f64, UBLKRED: one
+//               per row of 16 sites and component, 315 per brick) instead of one RED per site (5355 per brick); rows of the
+//               accumulator tile are padded to 18 sites so that each starts on a 16-byte boundary.
+// Two more were measured and dropped (profiles/round2_v08): a split phase barrier (mbarrier arrive after the updates of phase k,
+// wait before those of phase k + 1: +7 %) and turn-taking of a cell's lanes instead of the shuffle sum (2 x slower).
+//   DEPF_LOOP   (deposit_variant 6, with DEPF_BULK) the shuffle steps of the segmented sum are a run-time loop: one copy of the
+//               eight phases in the instruction stream instead of four (0, 1, 2, 5 steps)
+//   DEPF_SPILL  (deposit_variant 8 with DEPF_BULK, 10 with both) no shared-memory atomics inside the phases.  The only lanes that could
+//               meet another warp on a site are those whose cell began in the previous warp of the batch; they accumulate into a
+//               spare "cell" of their warp in two extra rows of the tile (y = 9, 10 of planes 0 and 1) with the same plain
+//               read-add-write as everyone else, and one extra step per batch merges the spare cells into the real ones
+//   DEPF_TMA    (deposit_variant 18, with the three above) the whole tile of a component is flushed by ONE tensor reduction of the TMA unit
+//               (cp.reduce.async.bulk.tensor.3d ... add, UTMAREDG) through a 3-D tensor map over the field [nzl+2][N][N]: 7 per brick
+//               instead of 315 row reductions + 315 apron REDs.  Sites past the lattice edge are dropped by the unit (the planes above a
+//               partial brick, by construction never to be flushed -- and the apron of a brick at the upper x or y edge, which wraps
+//               around and is flushed with REDs); the padding column and the (zero) spare rows add 0 to the neighbouring brick's sites
+enum { DEPF_BULK = 1, DEPF_LOOP = 2, DEPF_SPILL = 4, DEPF_TMA = 8 };
+struct DMaps { CUtensorMap m[7]; };                      // one tensor map per target component
+__host__ __device__ constexpr int acc_ax(int flags) { return (flags & DEPF_BULK) ? DX + 1 : DX; }
+__host__ __device__ constexpr int acc_ay(int flags) { return (flags & DEPF_SPILL) ? DY + 2 : DY; }            // rows of a plane of the accumulator tile         // row stride of the accumulator tile
+__host__ __device__ constexpr int acc_sites(int flags) { return (flags & DEPF_TMA) ? (acc_ax(flags) * acc_ay(flags) * DZ + 15) / 16 * 16 : acc_ax(flags) * acc_ay(flags) * DZ; }   // TMA: a component starts on a 128-byte boundary
+__host__ __device__ constexpr int acc_corner(int flags, int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * acc_ax(flags) + (k & 1) * acc_ax(flags) * acc_ay(flags); }
 
 // tile components per projection; Tij components follow the field order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
 __host__ __device__ constexpr int dep_ncomp(int what) { return what == DEP_T00 ? 1 : what == DEP_TIJ ? 6 : what == DEP_T00_TIJ ? 7 : 3; }
@@ -103,14 +116,16 @@ __device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gmem_src,
 		:: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
-}
 // bulk reduction (TMA unit, UBLKRED): global[0 .. bytes) += shared[0 .. bytes) as FP64 adds; 16-byte aligned on both sides
 __device__ __forceinline__ void bulk_add_f64(double * gmem_dst, const double * smem_src, uint32_t bytes)
 {
 	asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" :: "l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+}
+// tensor reduction (TMA unit): the box of the tensor map at (x, y, z) += the dense box at smem_src (128-byte aligned)
+__device__ __forceinline__ void tensor_add_3d(const CUtensorMap * map, const double * smem_src, int x, int y, int z)
+{
+	asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+		:: "l"((unsigned long long) map), "r"(x), "r"(y), "r"(z), "r"(smem_addr(smem_src)) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -200,11 +215,8 @@ struct Writer
 {
 	double * tile;                 // tile + site of the particle's cell
 	int after, steps;              // lanes after this one in the same cell (within the warp); shuffle steps of the segmented sum
-	int before;                    // lanes before this one in the same cell (within the warp)
 	bool write;                    // this lane writes: alone in its cell, or first lane of its cell's segment in this warp
 	bool plain;                    // no other warp holds particles of this cell: plain read-add-write is safe
-	unsigned long long * bar;      // DEPF_SPLIT: the block's phase barrier
-	uint32_t parity;               // DEPF_SPLIT: parity of the barrier phase this thread waits for next
 };
 
 // tile component of the j-th contribution of corner K (j = -1: how many contributions corner K has)
@@ -275,7 +287,7 @@ __device__ __forceinline__ void tile_add(const Writer & W, const double * v)
 	constexpr int NV = phase_comp(WHAT, K, -1);
 	constexpr int ASITES = acc_sites(FLAGS);
 	double * p = W.tile + acc_corner(FLAGS, K);
-	if (W.plain)
+	if ((FLAGS & DEPF_SPILL) || W.plain)
 	{
 		#pragma unroll
 		for (int j = 0; j < NV; j++) p[phase_comp(WHAT, K, j) * ASITES] += v[j];
@@ -287,43 +299,38 @@ __device__ __forceinline__ void tile_add(const Writer & W, const double * v)
 	}
 }
 
-// STEPS > 0: that many shuffle steps of the segmented sum; STEPS < 0 (DEPF_ROUNDS): -STEPS rounds without shuffles
 template <int WHAT, bool HAS_PHI, int K, int STEPS, int FLAGS>
-__device__ __forceinline__ void phase(const PInv & I, Writer & W, const double * ph)
+__device__ __forceinline__ int phase(const PInv & I, const Writer & W, const double * ph, int vote, bool solo)
 {
 	constexpr int NV = phase_comp(WHAT, K, -1);
 	double v[NV > 0 ? NV : 1];
 	phase_values<WHAT, HAS_PHI, K>(I, ph, v);
-	#pragma unroll
-	for (int s = 0; s < STEPS; s++)
-	{
-		#pragma unroll
-		for (int j = 0; j < NV; j++)
-		{
-			const double t = __shfl_down_sync(0xffffffffu, v[j], 1 << s);
-			if ((1 << s) <= W.after) v[j] += t;
-		}
-	}
-	if (FLAGS & DEPF_SPLIT) { mbar_wait(W.bar, W.parity); W.parity ^= 1; }     // every warp is through the previous phase
 	if (STEPS >= 0)
 	{
-		if (W.write) tile_add<WHAT, K, FLAGS>(W, v);
+		// v += take * t with take = 1 or 0 is the same sum as a conditional add (exact products), one DFMA instead of two selects and a DADD
+		#pragma unroll
+		for (int s = 0; s < STEPS; s++)
+		{
+			const double take = (1 << s) <= W.after ? 1. : 0.;
+			#pragma unroll
+			for (int j = 0; j < NV; j++) v[j] = fma(__shfl_down_sync(0xffffffffu, v[j], 1 << s), take, v[j]);
+		}
 	}
 	else
 	{
-		#pragma unroll
-		for (int r = 0; r < -STEPS; r++)
+		#pragma unroll 1
+		for (int s = 0; s < W.steps; s++)
 		{
-			if (W.before == r) tile_add<WHAT, K, FLAGS>(W, v);
-			if (r + 1 < -STEPS) __syncwarp();
+			const double take = (1 << s) <= W.after ? 1. : 0.;
+			#pragma unroll
+			for (int j = 0; j < NV; j++) v[j] = fma(__shfl_down_sync(0xffffffffu, v[j], 1 << s), take, v[j]);
 		}
 	}
-	if (FLAGS & DEPF_SPLIT)
-	{
-		__syncwarp();
-		if ((threadIdx.x & 31) == 0) mbar_arrive(W.bar);                        // one arrival per warp
-	}
-	else __syncthreads();
+	if (W.write) tile_add<WHAT, K, FLAGS>(W, v);
+	if ((FLAGS & DEPF_LOOP) && solo) { __syncwarp(); return 0; }            // the only warp at work: its own order is enough
+	if ((FLAGS & DEPF_SPILL) && K == 7) return __syncthreads_or(vote);      // the barrier also tells whether any warp used its spare cell
+	__syncthreads();
+	return 0;
 }
 
 // cell = floor(pos/dx) clamped into the lattice; pos * N is bit-identical to pos / dx for power-of-two N
@@ -341,39 +348,36 @@ __device__ __forceinline__ void load_particle(const DParams & D, uint32_t i, dou
 
 // the eight corner phases of one batch
 template <int WHAT, bool HAS_PHI, int STEPS, int FLAGS>
-__device__ __forceinline__ void phases(const PInv & I, Writer & W, const double * ph)
+__device__ __forceinline__ int phases(const PInv & I, const Writer & W, const double * ph, int vote, bool solo = false)
 {
-	phase<WHAT, HAS_PHI, 0, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 1, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 2, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 3, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 4, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 5, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 6, STEPS, FLAGS>(I, W, ph);
-	phase<WHAT, HAS_PHI, 7, STEPS, FLAGS>(I, W, ph);
+	phase<WHAT, HAS_PHI, 0, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 1, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 2, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 3, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 4, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 5, STEPS, FLAGS>(I, W, ph, 0, solo);
+	phase<WHAT, HAS_PHI, 6, STEPS, FLAGS>(I, W, ph, 0, solo);
+	return phase<WHAT, HAS_PHI, 7, STEPS, FLAGS>(I, W, ph, vote, solo);
 }
 
 // Persistent blocks walk the bricks with stride gridDim.x in a software pipeline: while brick k is accumulated and
 // flushed, the cell table and phi tile of brick k+1 are in flight into the other shared-memory stage, the particle
 // range of brick k+2 is being fetched, and the next batch of particles is already requested.
 template <int WHAT, bool HAS_PHI, int FLAGS>
-__global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
+__global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __grid_constant__ DMaps maps)
 {
 	constexpr int NCOMP = dep_ncomp(WHAT);
-	constexpr int AX = acc_ax(FLAGS), ASITES = acc_sites(FLAGS);
-	extern __shared__ __align__(16) double site_smem[];
+	constexpr int AX = acc_ax(FLAGS), AY = acc_ay(FLAGS), ASITES = acc_sites(FLAGS);
+	extern __shared__ __align__(128) double site_smem[];
 	double * smem = site_smem;
 	double * tile = smem;                                   // [NCOMP][ASITES] accumulators
 	double * stages = smem + NCOMP * ASITES;                // [2][DEP_STAGE_DOUBLES]
-	unsigned long long * bar = (unsigned long long *) (stages + 2 * DEP_STAGE_DOUBLES);
 
 	const BrickGeom & G = D.G;
 	const int tcol = threadIdx.x, ttx = tcol % DX, tty = tcol / DX;      // this thread's column of the tile (flush)
 	const int lane = threadIdx.x & 31;
 	for (int idx = threadIdx.x; idx < NCOMP * ASITES + 2 * DEP_STAGE_DOUBLES; idx += DEP_THREADS) smem[idx] = 0.;
-	if ((FLAGS & DEPF_SPLIT) && threadIdx.x == 0) mbar_init(bar, DEP_THREADS / 32);
 	__syncthreads();
-	uint32_t parity = 0;
 	uint32_t brick = blockIdx.x;
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
 	brick_range(D, brick, first, last);
@@ -395,8 +399,6 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 			brick_origin(G, brick, x0, y0, zl0);
 			cp_async_wait<1>();                             // everything but the newest group: this brick's stage has landed
 			__syncthreads();
-			// split barrier: every phase waits for the arrivals of the one before it; the first phase of a brick finds these
-			if (FLAGS & DEPF_SPLIT) { if (lane == 0) mbar_arrive(bar); }
 			const double * tphi = stages + cur * DEP_STAGE_DOUBLES;
 			const uint32_t * ctab = (const uint32_t *) (tphi + DT_SITES);
 
@@ -407,6 +409,8 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 				PInv I;
 				Writer W;
 				const double * ph;
+				bool spill = false;
+				int spill_to = -1;                                  // warp-uniform: site of the cell the warp's spare cell stands for
 				{
 					// the particle's cell (it lies in this brick: the storage order is maintained by the re-bin)
 					int cx = 0, cy = 0, cz = 0, site = 0, asite = 0;
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 						cx = cell_scaled(D, pv[0]); cy = cell_scaled(D, pv[1]); cz = cell_scaled(D, pv[2]);
 						const int sx = cx - x0, sy = cy - y0, sz = cz - G.z0 - zl0;
 						site = (sz * DY + sy) * DX + sx;
-						asite = (sz * DY + sy) * AX + sx;
+						asite = (sz * AY + sy) * AX + sx;
 						const int c = (sz << (GEVB_BX_BITS + GEVB_BY_BITS)) | (sy << GEVB_BX_BITS) | sx;
 						cfirst = ctab[c]; clast = ctab[c + 1];
 					}
@@ -426,13 +430,17 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 					const uint32_t seg_lo = cfirst > warp_lo ? cfirst : warp_lo, seg_hi = clast < warp_hi ? clast : warp_hi;
 					const int maxlen = __reduce_max_sync(0xffffffffu, (int) (seg_hi - seg_lo));
 					W.tile = tile + asite; ph = tphi + site;
+					if (FLAGS & DEPF_SPILL)
+					{
+						// the cell began in the previous warp of this batch: accumulate in the warp's spare cell (rows 9 and 10, x = 2 warp)
+						spill = valid && cfirst < warp_lo && (threadIdx.x >> 5) != 0;
+						if (spill) W.tile = tile + (DY * AX + 2 * (threadIdx.x >> 5));
+						spill_to = __shfl_sync(0xffffffffu, spill ? asite : -1, 0);
+					}
 					W.after = (int) (seg_hi - 1 - i);
-					W.before = valid ? (int) (i - seg_lo) : 32;
 					W.steps = maxlen > 1 ? 32 - __clz(maxlen - 1) : 0;
-					if ((FLAGS & DEPF_ROUNDS) && maxlen > 1) W.steps = maxlen <= 4 ? -maxlen : 5;
 					W.write = valid && i == seg_lo;
 					W.plain = cfirst >= warp_lo && clast <= warp_hi;
-					W.bar = bar; W.parity = parity;
 				}
 				// request the next batch (of this brick, else the first batch of the next brick) while the phases run
 				{
@@ -442,19 +450,75 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 				}
 				// shuffle steps of the segmented sum are a warp-uniform property of the batch: 0 when no two lanes share a cell;
 				// a warp without particles (tail of the brick) only keeps the barriers company
-				if (W.steps == 0) phases<WHAT, HAS_PHI, 0, FLAGS>(I, W, ph);
-				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -2) phases<WHAT, HAS_PHI, -2, FLAGS>(I, W, ph);
-				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -3) phases<WHAT, HAS_PHI, -3, FLAGS>(I, W, ph);
-				else if ((FLAGS & DEPF_ROUNDS) && W.steps == -4) phases<WHAT, HAS_PHI, -4, FLAGS>(I, W, ph);
-				else if (!(FLAGS & DEPF_ROUNDS) && W.steps == 1) phases<WHAT, HAS_PHI, 1, FLAGS>(I, W, ph);
-				else if (!(FLAGS & DEPF_ROUNDS) && W.steps == 2) phases<WHAT, HAS_PHI, 2, FLAGS>(I, W, ph);
-				else phases<WHAT, HAS_PHI, 5, FLAGS>(I, W, ph);
-				parity = W.parity;
+				int spilled;
+				if ((FLAGS & DEPF_LOOP) && last - base <= 32)
+				{
+					// the last few particles of a brick (Poisson: half of the bricks hold a little more than two batches): one warp, no barriers
+					if (threadIdx.x < 32) phases<WHAT, HAS_PHI, -1, FLAGS>(I, W, ph, 0, true);
+					__syncthreads();
+					spilled = 0;
+				}
+				else if (FLAGS & DEPF_LOOP) spilled = phases<WHAT, HAS_PHI, -1, FLAGS>(I, W, ph, spill_to >= 0);
+				else if (W.steps == 0) spilled = phases<WHAT, HAS_PHI, 0, FLAGS>(I, W, ph, spill_to >= 0);
+				else if (W.steps == 1) spilled = phases<WHAT, HAS_PHI, 1, FLAGS>(I, W, ph, spill_to >= 0);
+				else if (W.steps == 2) spilled = phases<WHAT, HAS_PHI, 2, FLAGS>(I, W, ph, spill_to >= 0);
+				else spilled = phases<WHAT, HAS_PHI, 5, FLAGS>(I, W, ph, spill_to >= 0);
+				if ((FLAGS & DEPF_SPILL) && spilled)
+				{
+					// merge the spare cells into the cells they stand for (two warps can meet on a site here: atomics, one pass of the warp)
+					if (spill_to >= 0)
+					{
+						double * real = tile + spill_to;
+						double * spare = tile + (DY * AX + 2 * (threadIdx.x >> 5));
+						for (int e = lane; e < 8 * NCOMP; e += 32)
+						{
+							const int k = e / NCOMP, comp = e - k * NCOMP;
+							const int off = ((k >> 2) & 1) + ((k >> 1) & 1) * AX + (k & 1) * AX * AY + comp * ASITES;
+							const double v = spare[off];
+							if (v != 0.) { atomicAdd(real + off, v); spare[off] = 0.; }
+						}
+					}
+					__syncthreads();
+				}
 			}
-			if (FLAGS & DEPF_SPLIT) { mbar_wait(bar, parity); parity ^= 1; }       // the last phase of every warp
 
 			// ---- flush the tile into the field in HBM; it is left zeroed for the next brick (stage `cur` is free from here on)
-			if ((FLAGS & DEPF_BULK) && x0 + GEVB_BX <= G.N)
+			if ((FLAGS & DEPF_TMA) && x0 + GEVB_BX <= G.N && y0 + GEVB_BY <= G.N)
+			{
+				fence_async_proxy();
+				__syncthreads();
+				if (threadIdx.x < NCOMP)
+				{
+					tensor_add_3d(&maps.m[threadIdx.x], tile + threadIdx.x * ASITES, x0, y0, zl0 + 1);
+					bulk_commit();
+				}
+				// the apron of a brick at the upper edge of the lattice wraps around: the unit drops it, REDs take it
+				const bool wrapx = x0 + GEVB_BX == G.N, wrapy = y0 + GEVB_BY == G.N;
+				if (wrapx)
+					for (int r = threadIdx.x; r < NCOMP * DZ * DY; r += DEP_THREADS)
+					{
+						const int k = r / (DZ * DY), rem = r - k * (DZ * DY), tz = rem / DY, ty = rem - tz * DY;
+						const int plane = zl0 + tz + 1;
+						const double v = tile[k * ASITES + (tz * AY + ty) * AX + GEVB_BX];
+						if (plane <= G.nzl + 1 && v != 0.) atomicAdd(D.out[k] + (size_t) plane * G.N * G.N + (size_t) wrap_up(y0 + ty, G.N) * G.N, v);
+					}
+				if (wrapy)
+				{
+					const int nx = wrapx ? GEVB_BX : DX;
+					for (int r = threadIdx.x; r < NCOMP * DZ * nx; r += DEP_THREADS)
+					{
+						const int k = r / (DZ * nx), rem = r - k * (DZ * nx), tz = rem / nx, tx = rem - tz * nx;
+						const int plane = zl0 + tz + 1;
+						const double v = tile[k * ASITES + (tz * AY + GEVB_BY) * AX + tx];
+						if (plane <= G.nzl + 1 && v != 0.) atomicAdd(D.out[k] + (size_t) plane * G.N * G.N + x0 + tx, v);
+					}
+				}
+				if (threadIdx.x < NCOMP) bulk_wait_read();
+				__syncthreads();
+				double2 * t2 = (double2 *) tile;
+				for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
+			}
+			else if ((FLAGS & DEPF_BULK) && x0 + GEVB_BX <= G.N)
 			{
 				// one bulk reduction per row of 16 sites and component (the row does not wrap in x), one RED for the apron site
 				fence_async_proxy();
@@ -464,7 +528,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 					const int k = r / (DZ * DY), rem = r - k * (DZ * DY), tz = rem / DY, ty = rem - tz * DY;
 					const int plane = zl0 + tz + 1;
 					if (plane > G.nzl + 1) continue;                                   // partial brick at the top of the slab
-					const double * row = tile + k * ASITES + (tz * DY + ty) * AX;
+					const double * row = tile + k * ASITES + (tz * AY + ty) * AX;
 					double * grow = D.out[k] + (size_t) plane * G.N * G.N + (size_t) wrap_up(y0 + ty, G.N) * G.N;
 					bulk_add_f64(grow + x0, row, GEVB_BX * sizeof(double));
 					const double v = row[GEVB_BX];
@@ -485,7 +549,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D)
 					#pragma unroll
 					for (int tz = 0; tz < DZ; tz++)
 					{
-						const int s = (tz * DY + tty) * AX + ttx;
+						const int s = (tz * AY + tty) * AX + ttx;
 						const size_t off = (size_t) (zl0 + tz + 1) * G.N * G.N + gcol;
 						#pragma unroll
 						for (int k = 0; k < NCOMP; k++)
@@ -1115,21 +1179,57 @@ int check_real(const gevb_field * f, int ncomp, const char * who, const char * n
 	return 0;
 }
 
+typedef CUresult (* EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled tensor_map_encoder()
+{
+	static EncodeTiled fn = []() -> EncodeTiled
+	{
+		void * p = NULL;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return NULL;
+		return (EncodeTiled) p;
+	}();
+	return fn;
+}
+
+// tensor maps over the target components: double [nzl + 2][N][N], box = one accumulator tile of a component
+template <int WHAT, int FLAGS>
+int make_maps(gevb_ctx * c, const DParams & D, DMaps & M)
+{
+	EncodeTiled encode = tensor_map_encoder();
+	GEVB_CHECK_ARG(encode != NULL, "deposit: the driver does not provide cuTensorMapEncodeTiled");
+	const cuuint64_t dims[3] = {(cuuint64_t) c->N, (cuuint64_t) c->N, (cuuint64_t) c->nzl + 2};
+	const cuuint64_t strides[2] = {(cuuint64_t) c->N * sizeof(double), (cuuint64_t) c->N * c->N * sizeof(double)};
+	const cuuint32_t box[3] = {(cuuint32_t) acc_ax(FLAGS), (cuuint32_t) acc_ay(FLAGS), DZ};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	for (int k = 0; k < dep_ncomp(WHAT); k++)
+	{
+		const CUresult r = encode(&M.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, D.out[k], dims, strides, box, estr,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		GEVB_CHECK_ARG(r == CUDA_SUCCESS, "deposit: cuTensorMapEncodeTiled failed (%d)", (int) r);
+	}
+	return 0;
+}
+
 template <int WHAT, int FLAGS>
 int launch_sites(gevb_ctx * c, const DParams & D, bool has_phi)
 {
-	const size_t smem = ((size_t) dep_ncomp(WHAT) * acc_sites(FLAGS) + 2 * DEP_STAGE_DOUBLES) * sizeof(double) + 16;
+	const size_t smem = ((size_t) dep_ncomp(WHAT) * acc_sites(FLAGS) + 2 * DEP_STAGE_DOUBLES) * sizeof(double);
 	const uint32_t persistent = (uint32_t) c->num_sms * 3;
 	const uint32_t grid = D.G.nbricks < persistent ? D.G.nbricks : persistent;
+	DMaps M;
+	memset(&M, 0, sizeof(M));
+	if (FLAGS & DEPF_TMA) GEVB_TRY((make_maps<WHAT, FLAGS>(c, D, M)));
 	if (has_phi)
 	{
 		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, true, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, true, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+		k_deposit<WHAT, true, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D, M);
 	}
 	else
 	{
 		CUDA_TRY(cudaFuncSetAttribute(k_deposit<WHAT, false, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_deposit<WHAT, false, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D);
+		k_deposit<WHAT, false, FLAGS><<<grid, DEP_THREADS, smem, c->stream>>>(D, M);
 	}
 	KERNEL_CHECK(c);
 	return 0;
@@ -1186,17 +1286,13 @@ int launch(gevb_pcls * p, double * const * out, double a, gevb_field * phi, doub
 		KERNEL_CHECK(c);
 		return 0;
 	}
-	// deposit_variant 0: the site-tile kernel as it is; 3 + flags: its variants (DEPF_*)
-	const int variant = gevb_tune(TUNE_DEPOSIT_VARIANT);
-	switch (variant >= 3 ? variant - 3 : 0)
-	{
-	case 0: return launch_sites<WHAT, 0>(c, D, phi != NULL);
-	case DEPF_BULK: return launch_sites<WHAT, DEPF_BULK>(c, D, phi != NULL);
-	case DEPF_SPLIT: return launch_sites<WHAT, DEPF_SPLIT>(c, D, phi != NULL);
-	case DEPF_ROUNDS: return launch_sites<WHAT, DEPF_ROUNDS>(c, D, phi != NULL);
-	case DEPF_ROUNDS | DEPF_BULK: return launch_sites<WHAT, DEPF_ROUNDS | DEPF_BULK>(c, D, phi != NULL);
-	default: gevb_set_error("deposit_variant %d is not built", variant); return 1;
-	}
+	// the site-tile kernel: deposit_variant 4 flushes with bulk reductions, 0 with one RED per site
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 4) return launch_sites<WHAT, DEPF_BULK>(c, D, phi != NULL);
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 6) return launch_sites<WHAT, DEPF_BULK | DEPF_LOOP>(c, D, phi != NULL);
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 8) return launch_sites<WHAT, DEPF_BULK | DEPF_SPILL>(c, D, phi != NULL);
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 10) return launch_sites<WHAT, DEPF_BULK | DEPF_LOOP | DEPF_SPILL>(c, D, phi != NULL);
+	if (gevb_tune(TUNE_DEPOSIT_VARIANT) == 18) return launch_sites<WHAT, DEPF_BULK | DEPF_LOOP | DEPF_SPILL | DEPF_TMA>(c, D, phi != NULL);
+	return launch_sites<WHAT, 0>(c, D, phi != NULL);
 }
 
 } // namespace

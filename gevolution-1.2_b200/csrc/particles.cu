@@ -121,20 +121,18 @@ __global__ void __launch_bounds__(256) k_scatter_ranked(int64_t n, const unsigne
 // 8-byte stores scattered over a dozen sectors per request.  Records that leave the window are stored directly, as in
 // k_scatter.  Where the window lies only matters for speed.  RANKED: the slot inside the cell comes from the rank the drift
 // kernel recorded (rebin_variant 3), else from counting the histogram down.
-#define WIN_CHUNK 1024
 #define WIN_PAD 128
-#define WIN_SLOTS (WIN_CHUNK + 2 * WIN_PAD)
 #define WIN_THREADS 256
-#define WIN_PER (WIN_CHUNK / WIN_THREADS)
-#define WIN_SMEM (7 * WIN_SLOTS * 8 + WIN_SLOTS)
-template <bool RANKED>
-__global__ void __launch_bounds__(WIN_THREADS, 3) k_scatter_window(int64_t n, const unsigned long long * __restrict__ n_dev, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank,
+#define WIN_SMEM(chunk) (7 * ((chunk) + 2 * WIN_PAD) * 8 + ((chunk) + 2 * WIN_PAD))
+template <bool RANKED, int WIN_CHUNK>
+__global__ void __launch_bounds__(WIN_THREADS, WIN_CHUNK == 1024 ? 3 : 5) k_scatter_window(int64_t n, const unsigned long long * __restrict__ n_dev, const uint32_t * __restrict__ key, const uint32_t * __restrict__ rank,
                           const uint32_t * __restrict__ cell_start, uint32_t * count,
                           const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z,
                           const double * __restrict__ qx, const double * __restrict__ qy, const double * __restrict__ qz, const int64_t * __restrict__ id,
                           double * __restrict__ ox, double * __restrict__ oy, double * __restrict__ oz,
                           double * __restrict__ oqx, double * __restrict__ oqy, double * __restrict__ oqz, int64_t * __restrict__ oid)
 {
+	constexpr int WIN_SLOTS = WIN_CHUNK + 2 * WIN_PAD, WIN_PER = WIN_CHUNK / WIN_THREADS;
 	extern __shared__ __align__(16) unsigned char win_smem[];
 	double * buf = (double *) win_smem;                                   // [7][WIN_SLOTS]
 	unsigned char * filled = win_smem + 7 * WIN_SLOTS * sizeof(double);   // [WIN_SLOTS]
@@ -208,10 +206,21 @@ __global__ void __launch_bounds__(WIN_THREADS, 3) k_scatter_window(int64_t n, co
 	}
 }
 
-static unsigned window_grid(gevb_ctx * c, int64_t n)
+static unsigned window_grid(gevb_ctx * c, int64_t n, int chunk)
 {
-	const int64_t chunks = (n + WIN_CHUNK - 1) / WIN_CHUNK, persistent = (int64_t) c->num_sms * 3;
+	const int64_t chunks = (n + chunk - 1) / chunk, persistent = (int64_t) c->num_sms * (chunk == 1024 ? 3 : 5);
 	return (unsigned) (chunks < persistent ? (chunks > 0 ? chunks : 1) : persistent);
+}
+
+template <bool RANKED, int CHUNK>
+static int launch_window(gevb_ctx * c, int64_t n_in, gevb_pcls * p, int s, int d)
+{
+	CUDA_TRY(cudaFuncSetAttribute(k_scatter_window<RANKED, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM(CHUNK)));
+	k_scatter_window<RANKED, CHUNK><<<window_grid(c, n_in, CHUNK), WIN_THREADS, WIN_SMEM(CHUNK), c->stream>>>(n_in, p->d_nin, p->key, RANKED ? p->rank : NULL, p->cell_start, p->cell_count,
+		p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
+		p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
+	KERNEL_CHECK(c);
+	return 0;
 }
 
 // the move of the counting sort: slot = cell_start[key] + (number of particles of this cell not yet placed) - 1.
@@ -384,7 +393,7 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	// the histogram's producers (here, the drift kernel, the append of received particles) all follow the knob, so a
 	// histogram passed in as valid comes with ranks exactly when the knob is on; it must not change between a drift and its re-bin
 	const int rebin_variant = gevb_tune(TUNE_REBIN_VARIANT);
-	const bool ranked = (rebin_variant & 1) != 0, windowed = (rebin_variant & 2) != 0;
+	const bool ranked = (rebin_variant & 1) != 0, windowed = (rebin_variant & 2) != 0, small_window = (rebin_variant & 4) != 0;
 	if (!hist_valid && n_in > 0)
 	{
 		k_make_keys<<<gevb_grid(c, (size_t) n_in, 256), 256, 0, c->stream>>>(G, 0, n_in, p->x[s], p->y[s], p->z[s], dx, p->key, p->cell_count, ranked ? p->rank : NULL);
@@ -403,11 +412,7 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 		CUDA_TRY(cudaMemsetAsync(p->cell_count, 0, ((size_t) G.ncells + 1) * sizeof(uint32_t), c->stream));
 		if (n_in > 0 && windowed)
 		{
-			CUDA_TRY(cudaFuncSetAttribute(k_scatter_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
-			k_scatter_window<true><<<window_grid(c, n_in), WIN_THREADS, WIN_SMEM, c->stream>>>(n_in, p->d_nin, p->key, p->rank, p->cell_start, p->cell_count,
-				p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
-				p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
-			KERNEL_CHECK(c);
+			GEVB_TRY((small_window ? launch_window<true, 512> : launch_window<true, 1024>)(c, n_in, p, s, d));
 		}
 		else if (n_in > 0)
 		{
@@ -419,11 +424,7 @@ int gevb_pcls_rebin(gevb_pcls * p, int64_t n_in, int64_t n_out, bool hist_valid)
 	}
 	else if (n_in > 0 && windowed)
 	{
-		CUDA_TRY(cudaFuncSetAttribute(k_scatter_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
-		k_scatter_window<false><<<window_grid(c, n_in), WIN_THREADS, WIN_SMEM, c->stream>>>(n_in, p->d_nin, p->key, NULL, p->cell_start, p->cell_count,
-			p->x[s], p->y[s], p->z[s], p->qx[s], p->qy[s], p->qz[s], p->id[s],
-			p->x[d], p->y[d], p->z[d], p->qx[d], p->qy[d], p->qz[d], p->id[d]);
-		KERNEL_CHECK(c);
+		GEVB_TRY((small_window ? launch_window<false, 512> : launch_window<false, 1024>)(c, n_in, p, s, d));
 	}
 	else if (n_in > 0)
 	{

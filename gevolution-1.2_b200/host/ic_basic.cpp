@@ -71,7 +71,6 @@ public:
 struct Spline
 {
 	std::vector<double> x, y, c;                                   // knots, values, c_i = y''(x_i) / 2
-	size_t size() const { return x.size(); }
 	void init(const double * xa, const double * ya, size_t n)
 	{
 		x.assign(xa, xa + n); y.assign(ya, ya + n); c.assign(n, 0.);
@@ -477,7 +476,6 @@ int generate(gevb_sim * s, const gevb_settings & st)
 	// displacement: -3 phi / k^2 - delta (GR) or N-body gauge shift - delta (Newton); velocity potential: -a theta   (:1812 ...)
 	auto gauge = [&](size_t i) { return gr > 0 ? -3. * pkspline.y[i] / pkspline.x[i] / pkspline.x[i] : nbspline.y[i]; };
 	const double Ocb = cosmo.Omega_cdm + cosmo.Omega_b;
-	bool have_b_splines = false;
 	if (baryon_flag == 2)                                                                              // blend: weighted average (:1808-1842)
 	{
 		for (size_t i = 0; i < n; i++)
@@ -498,7 +496,7 @@ int generate(gevb_sim * s, const gevb_settings & st)
 			temp2[i] = -a * wt * prim(k[i], st, h);
 		}
 		if (many_b) { tk_d1.init(k.data(), temp1.data(), n); tk_t1.init(k.data(), temp2.data(), n); }
-		else { tk_d2.init(k.data(), temp1.data(), n); tk_t2.init(k.data(), temp2.data(), n); have_b_splines = true; }
+		else { tk_d2.init(k.data(), temp1.data(), n); tk_t2.init(k.data(), temp2.data(), n); }
 	}
 	if (baryon_flag == 1 || (baryon_flag == 3 && 8. * cosmo.Omega_b / Ocb > 1.))                       // baryonic displacement & velocity (:1919-1946)
 	{
@@ -507,7 +505,7 @@ int generate(gevb_sim * s, const gevb_settings & st)
 			temp1[i] = gauge(i) - d2[i] * prim(k[i], st, h);
 			temp2[i] = -a * t2[i] * prim(k[i], st, h);
 		}
-		tk_d2.init(k.data(), temp1.data(), n); tk_t2.init(k.data(), temp2.data(), n); have_b_splines = true;
+		tk_d2.init(k.data(), temp1.data(), n); tk_t2.init(k.data(), temp2.data(), n);
 	}
 	if (baryon_flag < 2 || (baryon_flag == 3 && 8. * cosmo.Omega_b / Ocb <= 1.))                       // CDM displacement & velocity (:1948-1975)
 	{
@@ -518,7 +516,6 @@ int generate(gevb_sim * s, const gevb_settings & st)
 		}
 		tk_d1.init(k.data(), temp1.data(), n); tk_t1.init(k.data(), temp2.data(), n);
 	}
-	(void) have_b_splines;
 	if ((baryon_flag == 1 && !st.correct_displacement) || baryon_flag == 3)                            // :1977-1984
 	{
 		G.displacement_field(0., tk_d2);

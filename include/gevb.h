@@ -59,10 +59,17 @@ typedef struct gevb_pcls gevb_pcls;     /* Particles_gevolution<part_simple,...>
 const char * gevb_last_error(void);
 const char * gevb_version(void);
 
-/* kernel-variant knobs for ablation runs ("geodesic_variant": block shape / prefetch of the kick-drift kernel, see geodesic.cu; "fft_exchange": 1 = transposes pushed
- * over peer memory, 0 = NCCL all-to-all + local transpose; "fft_overlap": 1 = the push of component k overlaps the local transform of
- * component k+1; "fft_decomposed": 1 = single-rank transforms as 2-D per plane + 1-D along z, 0 = cuFFT 3-D plans);
- * results do not depend on them */
+/* kernel-variant knobs for ablation runs; results do not depend on them (first value = default):
+ *   "geodesic_variant"  block shape / prefetch of the kick-drift kernel, see geodesic.cu
+ *   "fft_exchange"      1 = transposes pushed over peer memory, 0 = NCCL all-to-all + local transpose
+ *   "fft_overlap"       2 = pushes overlap the local transforms piece by piece, 1 = component by component, 0 = not at all
+ *   "fft_decomposed"    1 = single-rank transforms as 2-D per plane + 1-D along z, 0 = cuFFT 3-D plans
+ *   "fft_l2_planes"     0 = off, n = 2-D passes of a component in chunks of n planes
+ *   "deposit_variant"   4 = site tile flushed by bulk reductions, 0 = by one RED per site, 1 = per-cell accumulators in shared
+ *                       memory, 2 = thread per cell with register accumulators (deposit.cu)
+ *   "rebin_variant"     2 = re-bin move through a shared-memory window, 0 = direct scattered stores; +1 = slots from ranks the
+ *                       drift kernel recorded instead of counting the histogram down (particles.cu)
+ *   "peer_comm"         1 = halo / fold / migration over peer memory with flag barriers, 0 = NCCL point-to-point */
 int gevb_tuning(const char * knob, int value);
 
 /* ---- context: lattice geometry + device + communicator --------------------
