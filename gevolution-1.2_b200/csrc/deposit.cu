@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 	double pv[6] = {0., 0., 0., 0., 0., 0.};
 	if (first + threadIdx.x < last) load_particle(D, first + threadIdx.x, pv);
 	int cur = 0;
+	bool pending = false;                                   // DEPF_TMA: the unit is still reading the tile of the previous brick
 	while (brick < G.nbricks)
 	{
 		const uint32_t nbrick = brick + gridDim.x;
@@ -450,6 +451,16 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 				}
 				// shuffle steps of the segmented sum are a warp-uniform property of the batch: 0 when no two lanes share a cell;
 				// a warp without particles (tail of the brick) only keeps the barriers company
+				if ((FLAGS & DEPF_TMA) && pending)
+				{
+					// the read-out of the previous brick's tile ran behind the set-up of this batch; clear the tile before the first update
+					if (threadIdx.x < NCOMP) bulk_wait_read();
+					__syncthreads();
+					double2 * t2 = (double2 *) tile;
+					for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
+					__syncthreads();
+					pending = false;
+				}
 				int spilled;
 				if ((FLAGS & DEPF_LOOP) && last - base <= 32)
 				{
@@ -513,10 +524,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 						if (plane <= G.nzl + 1 && v != 0.) atomicAdd(D.out[k] + (size_t) plane * G.N * G.N + x0 + tx, v);
 					}
 				}
-				if (threadIdx.x < NCOMP) bulk_wait_read();
-				__syncthreads();
-				double2 * t2 = (double2 *) tile;
-				for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
+				pending = true;                                     // completed before the first update of the next brick
 			}
 			else if ((FLAGS & DEPF_BULK) && x0 + GEVB_BX <= G.N)
 			{
@@ -565,6 +573,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 		brick = nbrick; cur ^= 1;
 		first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast;
 	}
+	if ((FLAGS & DEPF_TMA) && pending && threadIdx.x < NCOMP) bulk_wait_read();      // the tile must outlive the read-out
 }
 
 // =====================================================================================================================

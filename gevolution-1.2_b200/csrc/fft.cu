@@ -452,7 +452,11 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		double2 * Xl = (double2 *) c->xchg[buf][c->rank];
 		// component pipeline: the push of component k (xstream) overlaps the local transform of component k+1 (stream);
 		// the time the main stream then still waits for the exchange is what CLS_FFT_A2A measures
-		const int chunks = gevb_tune(TUNE_FFT_OVERLAP) >= 2 ? (direction == GEVB_FFT_FORWARD ? p->chunks : p->chunks_bwd) : 1;   // fft_overlap: 0 off, 1 component pipeline, 2 (default) also pieces inside a component
+		// fft_overlap: 0 off, 1 component pipeline, 2 (default) also pieces inside a component for forward transforms, 3 for backward ones
+		// too (measured at 8 ranks: pieces gain 0.13 ms per cycle forward and lose 0.17 ms backward, where the z-pass comes first and its
+		// pieces leave too little behind them to hide a push -- profiles/round2_v10_multi/ablations_8.jsonl)
+		const int ov = gevb_tune(TUNE_FFT_OVERLAP);
+		const int chunks = direction == GEVB_FFT_FORWARD ? (ov >= 2 ? p->chunks : 1) : (ov >= 3 ? p->chunks_bwd : 1);
 		const bool overlap = gevb_tune(TUNE_FFT_OVERLAP) != 0 && (nc > 1 || chunks > 1) && nc <= 7;
 		cudaStream_t xs = overlap ? c->xstream : c->stream;
 		// resident blocks of the exchange: two per SM when it shares the machine with a local transform, else eight

@@ -458,8 +458,11 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		// which of the offered particles are filed in this rank's slab is decided by the same floor(pos/dx) the device uses; counting
 		// them on the host first (a few threads over the z coordinates) sizes the arrays once, so that the upload below runs
 		// chunk after chunk at PCIe speed without a count-and-synchronise round trip per chunk
-		const int nthreads = n > (1 << 20) ? 4 : 1;
-		std::vector<int64_t> part(nthreads, 0);
+		// When the arrays already hold all n offered particles (a refill of the same container, as in a restart or an
+		// end-to-end step), nothing needs sizing and the count is skipped.
+		const bool roomy = p->cap >= p->n + n;
+		const int nthreads = roomy ? 0 : n > (1 << 20) ? 4 : 1;
+		std::vector<int64_t> part(nthreads > 0 ? nthreads : 1, 0);
 		auto count = [&](int t)
 		{
 			int64_t mine = 0;
@@ -472,15 +475,19 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 			part[t] = mine;
 		};
 		if (nthreads == 1) count(0);
-		else
+		else if (nthreads > 1)
 		{
 			std::vector<std::thread> pool;
 			for (int t = 0; t < nthreads; t++) pool.emplace_back(count, t);
 			for (std::thread & th : pool) th.join();
 		}
 		for (int t = 0; t < nthreads; t++) nloc_host += part[t];
-		if (nloc_host == 0) return 0;
-		GEVB_TRY(gevb_pcls_reserve(p, p->n + nloc_host));
+		if (roomy) nloc_host = -1;                                                    // not counted
+		else
+		{
+			if (nloc_host == 0) return 0;
+			GEVB_TRY(gevb_pcls_reserve(p, p->n + nloc_host));
+		}
 		c->h_red[8] = 0.;
 		unsigned long long start = (unsigned long long) p->n;
 		memcpy(c->h_red + 8, &start, sizeof(start));                                  // pinned: stays valid while the copy is in flight
@@ -517,7 +524,8 @@ extern "C" int gevb_pcls_add(gevb_pcls * p, int64_t n, const int64_t * id, const
 		unsigned long long total = 0;
 		CUDA_TRY(cudaMemcpyAsync(&total, counter, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		GEVB_CHECK_ARG((int64_t) total == n_before + nloc_host, "gevb_pcls_add: the device kept %llu particles, the host counted %lld", total, (long long) (n_before + nloc_host));
+		GEVB_CHECK_ARG(nloc_host < 0 ? (int64_t) total <= p->cap : (int64_t) total == n_before + nloc_host,
+			"gevb_pcls_add: the device kept %llu particles, the host counted %lld (capacity %lld)", total, (long long) (n_before + nloc_host), (long long) p->cap);
 		p->n = (int64_t) total;
 	}
 	if (p->n == n_before) return 0;

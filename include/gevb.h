@@ -62,7 +62,8 @@ const char * gevb_version(void);
 /* kernel-variant knobs for ablation runs; results do not depend on them (first value = default):
  *   "geodesic_variant"  block shape / prefetch of the kick-drift kernel, see geodesic.cu
  *   "fft_exchange"      1 = transposes pushed over peer memory, 0 = NCCL all-to-all + local transpose
- *   "fft_overlap"       2 = pushes overlap the local transforms piece by piece, 1 = component by component, 0 = not at all
+ *   "fft_overlap"       pushes overlap the local transforms: 2 = piece by piece forward and component by component backward,
+ *                       3 = piece by piece both ways, 1 = component by component, 0 = not at all
  *   "fft_decomposed"    1 = single-rank transforms as 2-D per plane + 1-D along z, 0 = cuFFT 3-D plans
  *   "fft_l2_planes"     0 = off, n = 2-D passes of a component in chunks of n planes
  *   "deposit_variant"   4 = site tile flushed by bulk reductions, 0 = by one RED per site, 1 = per-cell accumulators in shared
