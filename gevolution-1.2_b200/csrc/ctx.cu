@@ -34,8 +34,8 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
-static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused", "peer_comm"};
-static int tune_values[GEVB_NTUNE] = {6, 1, 2, 1, 18, 0, 2, 1, 1};
+static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused", "peer_comm", "geodesic_tma", "tma_l2_promotion"};
+static int tune_values[GEVB_NTUNE] = {6, 1, 2, 1, 18, 0, 2, 1, 1, 1, 0};
 static bool tune_env_read = false;
 static void tune_read_env()
 {
@@ -50,6 +50,29 @@ static void tune_read_env()
 	}
 }
 int gevb_tune(int knob) { tune_read_env(); return tune_values[knob]; }
+typedef CUresult (* EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int gevb_tensor_map_3d(gevb_ctx * c, CUtensorMap * map, const double * base, int box_x, int box_y, int box_z)
+{
+	static EncodeTiled encode = []() -> EncodeTiled
+	{
+		void * p = NULL;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return NULL;
+		return (EncodeTiled) p;
+	}();
+	GEVB_CHECK_ARG(encode != NULL, "the driver does not provide cuTensorMapEncodeTiled");
+	const cuuint64_t dims[3] = {(cuuint64_t) c->N, (cuuint64_t) c->N, (cuuint64_t) c->nzl + 2};
+	const cuuint64_t strides[2] = {(cuuint64_t) c->N * sizeof(double), (cuuint64_t) c->N * c->N * sizeof(double)};
+	const cuuint32_t box[3] = {(cuuint32_t) box_x, (cuuint32_t) box_y, (cuuint32_t) box_z};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+	const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *) base, dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo[tune_values[TUNE_TMA_L2_PROMOTION] & 3], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	GEVB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int) r);
+	return 0;
+}
+
 extern "C" int gevb_tuning(const char * knob, int value)
 {
 	GEVB_CHECK_ARG(knob != NULL, "gevb_tuning: NULL knob");

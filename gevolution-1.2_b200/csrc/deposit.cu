@@ -32,7 +32,6 @@
 // x and y wrap by index arithmetic at flush time; z+1 of the last local plane
 // lands in the upper ghost plane which gevb_projection_comm folds into the next rank.
 #include "gevb_internal.cuh"
-#include <cuda.h>                                          // CUtensorMap (the encoder is fetched from the driver at run time, nothing links libcuda)
 
 namespace {
 
@@ -1188,36 +1187,11 @@ int check_real(const gevb_field * f, int ncomp, const char * who, const char * n
 	return 0;
 }
 
-typedef CUresult (* EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiled tensor_map_encoder()
-{
-	static EncodeTiled fn = []() -> EncodeTiled
-	{
-		void * p = NULL;
-		cudaDriverEntryPointQueryResult q;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return NULL;
-		return (EncodeTiled) p;
-	}();
-	return fn;
-}
-
 // tensor maps over the target components: double [nzl + 2][N][N], box = one accumulator tile of a component
 template <int WHAT, int FLAGS>
 int make_maps(gevb_ctx * c, const DParams & D, DMaps & M)
 {
-	EncodeTiled encode = tensor_map_encoder();
-	GEVB_CHECK_ARG(encode != NULL, "deposit: the driver does not provide cuTensorMapEncodeTiled");
-	const cuuint64_t dims[3] = {(cuuint64_t) c->N, (cuuint64_t) c->N, (cuuint64_t) c->nzl + 2};
-	const cuuint64_t strides[2] = {(cuuint64_t) c->N * sizeof(double), (cuuint64_t) c->N * c->N * sizeof(double)};
-	const cuuint32_t box[3] = {(cuuint32_t) acc_ax(FLAGS), (cuuint32_t) acc_ay(FLAGS), DZ};
-	const cuuint32_t estr[3] = {1, 1, 1};
-	for (int k = 0; k < dep_ncomp(WHAT); k++)
-	{
-		const CUresult r = encode(&M.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, D.out[k], dims, strides, box, estr,
-			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-		GEVB_CHECK_ARG(r == CUDA_SUCCESS, "deposit: cuTensorMapEncodeTiled failed (%d)", (int) r);
-	}
+	for (int k = 0; k < dep_ncomp(WHAT); k++) GEVB_TRY(gevb_tensor_map_3d(c, &M.m[k], D.out[k], acc_ax(FLAGS), acc_ay(FLAGS), DZ));
 	return 0;
 }
 

@@ -20,10 +20,14 @@
 
 namespace {
 
-#define TX (GEVB_BX + 2)
+#define TXO 2                                            // tile column of the brick's first cell: the tile starts at x0 - 2, an even
+                                                         // site, because a TMA tensor load wants its box 16-byte aligned in x (x0 - 1 is
+                                                         // odd: illegal instruction); column 0 and the last one are never read
+#define TX (GEVB_BX + 2 + TXO)
 #define TY (GEVB_BY + 2)
 #define TZ (GEVB_BZ + 2)
-#define TILE_SITES (TX * TY * TZ)
+#define TILE_BOX (TX * TY * TZ)                          // 20 x 10 x 6 sites
+#define TILE_SITES ((TILE_BOX + 15) / 16 * 16)           // component stride: a component starts on a 128-byte boundary (TMA destination)
 
 struct GParams
 {
@@ -34,6 +38,7 @@ struct GParams
 	double binv_kick, binv_drift;   // 1 / params[1] (the a^2 N that un-scales the stored B, main.cpp:772)
 	const double * phi, * chi, * B;
 	int nfmax;                 // how many of {phi, chi, B} the tile needs
+	int tma;                   // tiles of bricks away from the lattice edge are fetched by the TMA unit (tensor maps in GMaps)
 	// kick
 	int fn, nf_kick; double dtau_kick, a_kick, bscale_kick;
 	// drift
@@ -48,6 +53,8 @@ struct GParams
 	unsigned long long * nsend;          // [2]: down, up
 	double * sendbuf[2]; int64_t sendcap;
 };
+
+struct GMaps { CUtensorMap m[5]; };                      // phi, chi, B0, B1, B2 as 3-D tensors [nzl + 2][N][N], box = one tile
 
 // scaled coordinate pos/dx (LATfield2 drivers use pos/dx; the product is bit-identical for power-of-two N)
 __device__ __forceinline__ double scaled(const GParams & P, double p) { return P.pow2 ? p * P.rN : p / P.dx; }
@@ -249,8 +256,47 @@ __device__ __forceinline__ void cp_async8(double * smem_dst, const double * gmem
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long * bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long * bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long * bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA tensor load: the box of the tensor map at (x, y, z) -> dense box at smem_dst (128-byte aligned), completion on the mbarrier
+__device__ __forceinline__ void tensor_load_3d(double * smem_dst, const CUtensorMap * map, int x, int y, int z, unsigned long long * bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+		:: "r"(smem_u32(smem_dst)), "l"((unsigned long long) map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// does the tile of the brick at (x0, y0) lie inside the lattice in x and y (no periodic wrap)?  Planes past the top of the slab
+// are out of the tensor's bounds and arrive as zeros; they belong to a partial brick and are never read.
+__device__ __forceinline__ bool tile_inside(const BrickGeom & G, int x0, int y0)
+{
+	return x0 >= TXO && x0 - TXO + TX <= G.N && y0 >= 1 && y0 + GEVB_BY + 1 <= G.N;
+}
+
+// the same tile by tensor loads of the TMA unit (UTMALDG): one instruction per component, issued by one thread
+__device__ __forceinline__ void stage_tile_tma(const GParams & P, const GMaps & maps, int x0, int y0, int zl0, double * tile, unsigned long long * bar)
+{
+	if (threadIdx.x != 0) return;
+	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
+	mbar_expect(bar, (uint32_t) (ncomp * TILE_BOX * sizeof(double)));
+	for (int f = 0; f < ncomp; f++) tensor_load_3d(tile + f * TILE_SITES, &maps.m[f], x0 - TXO, y0 - 1, zl0, bar);
+}
+
 // asynchronous copy (LDGSTS) of one brick's field tile into shared memory: site (lx, ly, lz) of the tile is
-// lattice site (x0 - 1 + lx, y0 - 1 + ly, local z = zl0 - 1 + lz); a thread keeps its (lx, ly) column and
+// lattice site (x0 - TXO + lx, y0 - 1 + ly, local z = zl0 - 1 + lz); a thread keeps its (lx, ly) column and
 // walks z, so the periodic wrap is resolved once per thread and all copies of a thread are in flight together
 template <int THREADS>
 __device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, double * tile)
@@ -258,10 +304,10 @@ __device__ __forceinline__ void stage_tile(const GParams & P, uint32_t brick, do
 	const BrickGeom & G = P.G;
 	int x0, y0, zl0;
 	brick_origin(G, brick, x0, y0, zl0);
-	for (int col_id = threadIdx.x; col_id < TX * TY; col_id += THREADS)
+	for (int col_id = threadIdx.x; col_id < (GEVB_BX + 2) * TY; col_id += THREADS)
 	{
-	const int lx = col_id % TX, ly = col_id / TX;
-	const size_t col = (size_t) wrap_index(y0 - 1 + ly, G.N) * G.N + wrap_index(x0 - 1 + lx, G.N);
+	const int lx = col_id % (GEVB_BX + 2) + TXO - 1, ly = col_id / (GEVB_BX + 2);
+	const size_t col = (size_t) wrap_index(y0 - 1 + ly, G.N) * G.N + wrap_index(x0 - TXO + lx, G.N);
 	const int ncomp = P.nfmax >= 3 ? 5 : P.nfmax;
 	#pragma unroll
 	for (int lz = 0; lz < TZ; lz++)
@@ -299,18 +345,30 @@ __device__ __forceinline__ void brick_range(const GParams & P, uint32_t b, uint3
 // the bottom of the loop is consumed immediately at its top and hides nothing within the warp.  PREF 2: the same
 // through a second set of registers, loaded at the top of the iteration.
 template <int MODE, int THREADS, int NBUF, int MINB, int PREF>
-__global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
+__global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P, const __grid_constant__ GMaps maps)
 {
-	extern __shared__ double smem[];
+	extern __shared__ __align__(128) double smem[];
 	const BrickGeom & G = P.G;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
 	const int tile_doubles = ncomp * TILE_SITES;
 	double * slot = smem + NBUF * tile_doubles + threadIdx.x;           // [6][THREADS] staging of the prefetched particle (PREF)
+	// TMA staging (single tile buffer only): completion barrier behind everything else; `landed` = parity of the next completion
+	unsigned long long * bar = (unsigned long long *) (smem + NBUF * tile_doubles + (PREF == 1 ? 6 * THREADS : 0));
+	const bool tma = NBUF == 1 && P.tma;
+	uint32_t landed = 0;
+	bool by_tma = false;                                                // how the current brick's tile was requested
+	if (tma) { if (threadIdx.x == 0) mbar_init(bar, 1); __syncthreads(); }
 	uint32_t first, last, nfirst, nlast, nnfirst, nnlast;
 	uint32_t brick = blockIdx.x;
 	brick_range(P, brick, first, last);
 	brick_range(P, brick + gridDim.x, nfirst, nlast);
-	if (first != last) stage_tile<THREADS>(P, brick, smem);
+	if (first != last)
+	{
+		int x0, y0, zl0;
+		brick_origin(G, brick, x0, y0, zl0);
+		by_tma = tma && tile_inside(G, x0, y0);
+		if (by_tma) stage_tile_tma(P, maps, x0, y0, zl0, smem, bar); else stage_tile<THREADS>(P, brick, smem);
+	}
 	cp_async_commit();
 	int cur = 0;
 	double vmax = 0.;
@@ -332,8 +390,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 		{
 			int x0, y0, zl0;
 			brick_origin(G, brick, x0, y0, zl0);
-			if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();  // this brick's tile has landed
-			__syncthreads();
+			if (by_tma) { mbar_wait(bar, landed); landed ^= 1; }         // this brick's tile has landed (TMA: the barrier's completion makes it visible)
+			else
+			{
+				if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+				__syncthreads();
+			}
 			const double * tile = smem + (NBUF == 2 ? cur * tile_doubles : 0);
 			while (i < last)
 			{
@@ -367,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 					const double sx = scaled(P, pos[0]), sy = scaled(P, pos[1]), sz = scaled(P, pos[2]);
 					const int cx = cell_scaled(sx, G.N), cy = cell_scaled(sy, G.N), cz = cell_scaled(sz, G.N);
 					r[0] = sx - floor(sx); r[1] = sy - floor(sy); r[2] = sz - floor(sz);      // modf(pos/dx) for pos >= 0
-					t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + 1);
+					t = tile + ((cz - G.z0 - zl0 + 1) * TY + (cy - y0 + 1)) * TX + (cx - x0 + TXO);
 				}
 				const int64_t pid = P.fn >= GEVB_DISPLACE_PCLS_IC_BASIC ? P.id[i] : 0;      // only the IC callbacks look at the ID
 				if (MODE == 0 || MODE == 2)
@@ -439,7 +501,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_geodesic(GParams P)
 		if (first != last) __syncthreads();                      // the tile is free again
 		if (NBUF == 1)
 		{
-			if (nfirst != nlast) stage_tile<THREADS>(P, nbrick, smem);
+			if (nfirst != nlast)
+			{
+				int x0, y0, zl0;
+				brick_origin(G, nbrick, x0, y0, zl0);
+				by_tma = tma && tile_inside(G, x0, y0);
+				if (by_tma) stage_tile_tma(P, maps, x0, y0, zl0, smem, bar); else stage_tile<THREADS>(P, nbrick, smem);
+			}
 			cp_async_commit();
 		}
 		brick = nbrick; first = nfirst; last = nlast; nfirst = nnfirst; nlast = nnlast; cur ^= 1;
@@ -512,6 +580,7 @@ void base_params(GParams & P, gevb_pcls * p, gevb_field * const * fields, int nf
 	P.B = nfields >= 3 ? fields[2]->data : NULL;
 	P.csB = nfields >= 3 ? fields[2]->comp_stride : 0;
 	P.nfmax = nfields;
+	P.tma = gevb_tune(TUNE_GEODESIC_TMA) != 0 && nfields > 0;
 	P.n = p->n;
 	P.x = p->x[b]; P.y = p->y[b]; P.z = p->z[b]; P.qx = p->qx[b]; P.qy = p->qy[b]; P.qz = p->qz[b]; P.id = p->id[b]; P.key = p->key;
 	P.cell_start = p->cell_start; P.cell_count = p->cell_count;
@@ -525,10 +594,17 @@ int launch_variant(gevb_pcls * p, const GParams & P)
 {
 	gevb_ctx * c = p->ctx;
 	const int ncomp = P.nfmax >= 3 ? 5 : (P.nfmax > 0 ? P.nfmax : 1);
-	const size_t smem = ((size_t) NBUF * ncomp * TILE_SITES + (PREF == 1 ? 6 * THREADS : 0)) * sizeof(double);
+	const size_t smem = ((size_t) NBUF * ncomp * TILE_SITES + (PREF == 1 ? 6 * THREADS : 0)) * sizeof(double) + 16;
+	GMaps M;
+	memset(&M, 0, sizeof(M));
+	if (P.tma && NBUF == 1)
+	{
+		const double * base[5] = {P.phi, P.chi, P.B, P.B + P.csB, P.B + 2 * P.csB};
+		for (int f = 0; f < (P.nfmax >= 3 ? 5 : P.nfmax); f++) GEVB_TRY(gevb_tensor_map_3d(c, &M.m[f], base[f], TX, TY, TZ));
+	}
 	CUDA_TRY(cudaFuncSetAttribute(k_geodesic<MODE, THREADS, NBUF, MINB, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	const uint32_t persistent = (uint32_t) c->num_sms * MINB;
-	k_geodesic<MODE, THREADS, NBUF, MINB, PREF><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P);
+	k_geodesic<MODE, THREADS, NBUF, MINB, PREF><<<P.G.nbricks < persistent ? P.G.nbricks : persistent, THREADS, smem, c->stream>>>(P, M);
 	KERNEL_CHECK(c);
 	return 0;
 }

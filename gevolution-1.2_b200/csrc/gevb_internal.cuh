@@ -1,6 +1,7 @@
 // gevb_internal.cuh -- shared definitions of libgevb.so (sm_100a only)
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>                 // CUtensorMap; the encoder is fetched from the driver at run time, nothing links libcuda
 #include <cufft.h>
 #include <nccl.h>
 #include <stdint.h>
@@ -11,9 +12,12 @@
 
 // ---------------------------------------------------------------- errors -----
 void gevb_set_error(const char * fmt, ...);
+// 3-D tensor map (TMA) over one component of a real field, double [nzl + 2][N][N], with the given box; returns non-zero with the error set
+struct gevb_ctx;
+int gevb_tensor_map_3d(gevb_ctx * c, CUtensorMap * map, const double * base, int box_x, int box_y, int box_z);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, TUNE_PEER_COMM, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, TUNE_PEER_COMM, TUNE_GEODESIC_TMA, TUNE_TMA_L2_PROMOTION, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)

@@ -70,7 +70,9 @@ const char * gevb_version(void);
  *                       memory, 2 = thread per cell with register accumulators (deposit.cu)
  *   "rebin_variant"     2 = re-bin move through a shared-memory window, 0 = direct scattered stores; +1 = slots from ranks the
  *                       drift kernel recorded instead of counting the histogram down (particles.cu)
- *   "peer_comm"         1 = halo / fold / migration over peer memory with flag barriers, 0 = NCCL point-to-point */
+ *   "peer_comm"         1 = halo / fold / migration over peer memory with flag barriers, 0 = NCCL point-to-point
+ *   "geodesic_tma"      1 = field tiles of the kick/drift kernel by TMA tensor loads (bricks away from the lattice edge), 0 = LDGSTS
+ *   "tma_l2_promotion"  L2 promotion of the tensor maps: 0 = none, 1 / 2 / 3 = 64 / 128 / 256 bytes */
 int gevb_tuning(const char * knob, int value);
 
 /* ---- context: lattice geometry + device + communicator --------------------
