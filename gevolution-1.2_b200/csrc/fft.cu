@@ -354,7 +354,7 @@ extern "C" int gevb_plan_destroy(gevb_plan * p)
 	if (p == NULL) return 0;
 	cudaSetDevice(p->ctx->device);
 	cudaStreamSynchronize(p->ctx->stream);
-	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); } }
+	if (!p->multi) { cufftDestroy(p->fwd); cufftDestroy(p->bwd); cufftDestroy(p->f2d); cufftDestroy(p->bz1d); cufftDestroy(p->b2d); if (p->chunk_planes) { cufftDestroy(p->f2d_c); cufftDestroy(p->b2d_c); } if (p->yz2d) cufftDestroy(p->yz2d); }
 	else { cufftDestroy(p->fwd2d); cufftDestroy(p->bwd2d); cufftDestroy(p->z1d); cufftDestroy(p->z1d_one); if (p->chunks > 1) cufftDestroy(p->fwd2d_c); if (p->chunks_bwd > 1) cufftDestroy(p->z1d_c); }
 	delete p;
 	return 0;
@@ -385,6 +385,7 @@ extern "C" int gevb_plan_execute(gevb_plan * p, int direction)
 		if (direction == GEVB_FFT_FORWARD)
 		{
 			if (!decomposed) { CUFFT_TRY(cufftExecD2Z(p->fwd, rbulk, (cufftDoubleComplex *) cf->data)); c->launches++; return 0; }
+			if (gevb_xpass_available(p)) return gevb_xpass_forward(p, 0, NULL, NULL, 0., 0., 0., 0., NULL);   // own x-pass + one strided 2-D pass (xpass.cu)
 			const int L = chunked_planes(p);
 			for (int k = 0; k < nc; k++)
 			{

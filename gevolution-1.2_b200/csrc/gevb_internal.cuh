@@ -17,7 +17,7 @@ struct gevb_ctx;
 int gevb_tensor_map_3d(gevb_ctx * c, CUtensorMap * map, const double * base, int box_x, int box_y, int box_z);
 
 // ---------------------------------------------------------------- tuning knobs (ctx.cu)
-enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, TUNE_PEER_COMM, TUNE_GEODESIC_TMA, TUNE_TMA_L2_PROMOTION, GEVB_NTUNE };
+enum { TUNE_GEODESIC_VARIANT = 0, TUNE_FFT_EXCHANGE, TUNE_FFT_OVERLAP, TUNE_FFT_DECOMPOSED, TUNE_DEPOSIT_VARIANT, TUNE_FFT_L2_PLANES, TUNE_REBIN_VARIANT, TUNE_FFT_FUSED, TUNE_PEER_COMM, TUNE_GEODESIC_TMA, TUNE_TMA_L2_PROMOTION, TUNE_FFT_XPASS, GEVB_NTUNE };
 int gevb_tune(int knob);
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed, see nccl_dl.cu)
@@ -163,10 +163,15 @@ struct gevb_plan
 	cufftHandle fwd2d_c, z1d_c;      // nranks > 1: the same for one piece of a component (chunks > 1)
 	int chunks, chunks_bwd;          // pieces per component of the exchange pipeline (forward: planes, backward: rows)
 	cufftHandle f2d_c, b2d_c;        // nranks == 1: the 2-D transforms of `chunk_planes` planes at a time (tuning knob fft_l2_planes)
+	cufftHandle yz2d;                // nranks == 1, own x-pass (xpass.cu): y- and z-pass as one strided 2-D Z2Z over (z, y), batched along kx; 0: not created
 	int chunk_planes;                // 0: not created
 	bool multi;
 	bool preserve;             // backward execute keeps the Fourier field intact (default)
 };
+
+// own x-pass of the forward transform with the source preparation fused into its load (xpass.cu)
+bool gevb_xpass_available(const gevb_plan * p);
+int gevb_xpass_forward(gevb_plan * p, int mode, const double * phi, const double * chi, double bgmodel, double coeff, double coeff2, double coeff3, double * sum_dev);
 
 // ---------------------------------------------------------------- particles --
 // Particle order: "brick-major cell order".  The local slab is cut into bricks of 16 x 8 x 4 cells (x, y, z);

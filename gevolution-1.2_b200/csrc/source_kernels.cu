@@ -208,3 +208,47 @@ extern "C" int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, g
 	KERNEL_CHECK(c);
 	return 0;
 }
+
+// fused with the forward transform (xpass.cu) where that applies
+extern "C" int gevb_prepareFTsource_scalar_fft(gevb_field * phi, gevb_field * chi, gevb_plan * plan, double bgmodel, double coeff, double coeff2, double coeff3, double * sum_source)
+{
+	GEVB_CHECK_ARG(plan != NULL, "prepareFTsource: NULL plan");
+	gevb_field * source = plan->real_field;
+	if (!gevb_xpass_available(plan))
+	{
+		GEVB_TRY(prepare_scalar(phi, chi, source, bgmodel, source, coeff, coeff2, coeff3, sum_source));
+		return gevb_plan_execute(plan, GEVB_FFT_FORWARD);
+	}
+	GEVB_TRY(check_real(phi, 1, "prepareFTsource", "phi"));
+	GEVB_TRY(check_real(chi, 1, "prepareFTsource", "chi"));
+	GEVB_TRY(check_real(source, 1, "prepareFTsource", "source"));
+	GEVB_CHECK_ARG(source != phi && source != chi, "prepareFTsource: result must not alias phi or chi");
+	gevb_ctx * c = phi->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FFT_FWD);
+	GEVB_TRY(gevb_xpass_forward(plan, 1, phi->data, chi->data, bgmodel, coeff, coeff2, coeff3, sum_source ? c->d_red + 2048 : NULL));
+	if (sum_source)
+	{
+		CUDA_TRY(cudaMemcpyAsync(c->h_red, c->d_red + 2048, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		*sum_source = c->h_red[0];
+	}
+	return 0;
+}
+
+extern "C" int gevb_prepareFTsource_tensor_fft(gevb_field * phi, gevb_plan * plan, double coeff)
+{
+	GEVB_CHECK_ARG(plan != NULL, "prepareFTsource: NULL plan");
+	gevb_field * Sij = plan->real_field;
+	if (!gevb_xpass_available(plan))
+	{
+		GEVB_TRY(gevb_prepareFTsource_tensor(phi, Sij, Sij, coeff));
+		return gevb_plan_execute(plan, GEVB_FFT_FORWARD);
+	}
+	GEVB_TRY(check_real(phi, 1, "prepareFTsource", "phi"));
+	GEVB_TRY(check_real(Sij, 6, "prepareFTsource", "Tij"));
+	gevb_ctx * c = phi->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	Timed timed_(c, CLS_FFT_FWD);
+	return gevb_xpass_forward(plan, 2, phi->data, NULL, 0., coeff, 0., 0., NULL);
+}

@@ -35,7 +35,7 @@ SYMBOLS = [
     "gevb_pcls_destroy", "gevb_pcls_reset", "gevb_pcls_add", "gevb_pcls_count", "gevb_pcls_download", "gevb_pcls_cell_counts", "gevb_pcls_mass", "gevb_brick_dims",
     "gevb_projection_T00_project", "gevb_projection_T0i_project", "gevb_projection_Tij_project",
     "gevb_scalarProjectionCIC_project", "gevb_projection_T00_Tij_project", "gevb_prepareFTsource_scalar",
-    "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
+    "gevb_prepareFTsource_scalar_sum", "gevb_prepareFTsource_tensor", "gevb_prepareFTsource_scalar_fft", "gevb_prepareFTsource_tensor_fft", "gevb_solveModifiedPoissonFT", "gevb_projectFTscalar", "gevb_evolveFTvector",
     "gevb_projectFTscalar_evolveFTvector", "gevb_projectFTvector", "gevb_projectFTtensor", "gevb_updateVel", "gevb_moveParticles", "gevb_moveParticles_max", "gevb_kick_drift",
     "gevb_extractPowerSpectrum", "gevb_writePowerSpectrum", "gevb_pcls_saveGadget2", "gevb_pcls_gadget2_arrays", "gevb_pcls_ctx", "gevb_ctx_ranks",
     "gevb_sim_write_spectra", "gevb_sim_save_gadget2", "gevb_sim_write_field_snapshot", "gevb_sim_hibernate", "gevb_sim_restore", "gevb_sim_run", "gevb_background_eval", "gevb_sim_create", "gevb_sim_destroy", "gevb_sim_set_ncdm", "gevb_sim_set_ncdm_maxvel", "gevb_sim_get_ncdm_state", "gevb_sim_set_particles", "gevb_sim_set_field",
@@ -107,6 +107,7 @@ def _declare(L):
         "gevb_projection_Tij_project": [vp, vp, d, vp, d], "gevb_scalarProjectionCIC_project": [vp, vp],
         "gevb_projection_T00_Tij_project": [vp, vp, vp, d, vp, d],
         "gevb_prepareFTsource_scalar": [vp, vp, vp, d, vp, d, d, d], "gevb_prepareFTsource_scalar_sum": [vp, vp, vp, d, vp, d, d, d, C.POINTER(C.c_double)], "gevb_prepareFTsource_tensor": [vp, vp, vp, d],
+        "gevb_prepareFTsource_scalar_fft": [vp, vp, vp, d, d, d, d, C.POINTER(C.c_double)], "gevb_prepareFTsource_tensor_fft": [vp, vp, d],
         "gevb_solveModifiedPoissonFT": [vp, vp, d, d], "gevb_projectFTscalar": [vp, vp, i],
         "gevb_evolveFTvector": [vp, vp, d], "gevb_projectFTscalar_evolveFTvector": [vp, vp, vp, d], "gevb_projectFTvector": [vp, vp, d, d], "gevb_projectFTtensor": [vp, vp],
         "gevb_updateVel": [vp, i, d, C.POINTER(vp), i, pd, pd],
@@ -422,6 +423,17 @@ def prepareFTsource_scalar(phi, chi, source, bgmodel, result, coeff, coeff2, coe
 
 def prepareFTsource_tensor(phi, Tij, Sij, coeff):
     _ck(lib().gevb_prepareFTsource_tensor(phi.h, Tij.h, Sij.h, coeff), "prepareFTsource")
+
+
+def prepareFTsource_scalar_fft(phi, chi, plan_source, bgmodel, coeff, coeff2, coeff3, want_sum=False):
+    """prepareFTsource + plan.execute(FFT_FORWARD) in one call; returns the sum of the incoming source if asked for"""
+    out = C.c_double(0.0)
+    _ck(lib().gevb_prepareFTsource_scalar_fft(phi.h, chi.h, plan_source.h, bgmodel, coeff, coeff2, coeff3, C.byref(out) if want_sum else None), "prepareFTsource")
+    return out.value if want_sum else None
+
+
+def prepareFTsource_tensor_fft(phi, plan_Sij, coeff):
+    _ck(lib().gevb_prepareFTsource_tensor_fft(phi.h, plan_Sij.h, coeff), "prepareFTsource")
 
 
 def solveModifiedPoissonFT(sourceFT, potFT, coeff, modif=0.0):

@@ -665,11 +665,13 @@ static int sim_solve(gevb_sim * s)
 
 		if (dtau_old > 0.)
 		{
-			if (fuse_sum)
-				prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx, T00hom);
+			if (fuse)                                                                         // :472 + :477 in one pass where the own x-pass applies
+				prepareFTsource_execute(phi, chi, s->plan_source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx, fuse_sum ? &T00hom : NULL);
 			else
-			prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx);   // :472
-			s->plan_source.execute(FFT_FORWARD);                                              // :477
+			{
+				prepareFTsource<Real>(phi, chi, source, cosmo.Omega_cdm + cosmo.Omega_b + bg_ncdm(a, cosmo), source, 3. * Hconf(a, fourpiG, cosmo) * dx * dx / dtau_old, fourpiG * dx * dx / a, 3. * Hconf(a, fourpiG, cosmo) * Hconf(a, fourpiG, cosmo) * dx * dx);   // :472
+				s->plan_source.execute(FFT_FORWARD);                                          // :477
+			}
 			solveModifiedPoissonFT(scalarFT, scalarFT, 1. / (dx * dx), 3. * Hconf(a, fourpiG, cosmo) / dtau_old);   // :483
 			s->plan_phi.execute(FFT_BACKWARD);                                                // :488
 		}
@@ -685,8 +687,12 @@ static int sim_solve(gevb_sim * s)
 
 	phi.updateHalo();                                                                         // :518
 
-	prepareFTsource<Real>(phi, Sij, Sij, 2. * fourpiG * dx * dx / a);                         // :539
-	s->plan_Sij.execute(FFT_FORWARD);                                                         // :544
+	if (fuse) prepareFTsource_execute(phi, s->plan_Sij, 2. * fourpiG * dx * dx / a);          // :539 + :544
+	else
+	{
+		prepareFTsource<Real>(phi, Sij, Sij, 2. * fourpiG * dx * dx / a);                     // :539
+		s->plan_Sij.execute(FFT_FORWARD);                                                     // :544
+	}
 	// parabolic B: :558 and :586 both read SijFT and nothing in between writes it, so one pass over it serves both
 	const bool fuse_chi_B = fuse && s->vector_flag != VECTOR_ELLIPTIC;
 	if (fuse_chi_B) projectFTscalar_evolveFTvector(SijFT, scalarFT, BiFT, a * a * dtau_old);  // :558 + :586

@@ -72,7 +72,9 @@ const char * gevb_version(void);
  *                       drift kernel recorded instead of counting the histogram down (particles.cu)
  *   "peer_comm"         1 = halo / fold / migration over peer memory with flag barriers, 0 = NCCL point-to-point
  *   "geodesic_tma"      1 = field tiles of the kick/drift kernel by TMA tensor loads (bricks away from the lattice edge), 0 = LDGSTS
- *   "tma_l2_promotion"  L2 promotion of the tensor maps: 0 = none, 1 / 2 / 3 = 64 / 128 / 256 bytes */
+ *   "tma_l2_promotion"  L2 promotion of the tensor maps: 0 = none, 1 / 2 / 3 = 64 / 128 / 256 bytes
+ *   "fft_xpass"         0 = cuFFT only, 1 = forward transforms at N = 512 on one rank through the own x-pass (xpass.cu, prepareFTsource
+ *                       fused into its load) + one strided 2-D cuFFT pass -- correct, measured slower */
 int gevb_tuning(const char * knob, int value);
 
 /* ---- context: lattice geometry + device + communicator --------------------
@@ -181,6 +183,13 @@ int gevb_prepareFTsource_scalar(gevb_field * phi, gevb_field * chi, gevb_field *
  * (local sum + parallel.sum) without its own pass over the field                     */
 int gevb_prepareFTsource_scalar_sum(gevb_field * phi, gevb_field * chi, gevb_field * source, double bgmodel, gevb_field * result, double coeff, double coeff2, double coeff3, double * sum_source);
 int gevb_prepareFTsource_tensor(gevb_field * phi, gevb_field * Tij, gevb_field * Sij, double coeff);
+/* fused forms of main.cpp:472+477 and :539+544: prepareFTsource(...) in place on the plan's real field followed by
+ * plan.execute(FFT_FORWARD).  Where the own x-pass is switched on (knob fft_xpass; one rank, N = 512) the preparation rides on the load of
+ * the transform's first pass and the prepared values are never stored: on return the plan's Fourier field holds the transform of
+ * the prepared source, the real field still holds the incoming one.  Elsewhere: the two calls one after the other.
+ * sum_source may be NULL.                                                          */
+int gevb_prepareFTsource_scalar_fft(gevb_field * phi, gevb_field * chi, gevb_plan * plan_source, double bgmodel, double coeff, double coeff2, double coeff3, double * sum_source);
+int gevb_prepareFTsource_tensor_fft(gevb_field * phi, gevb_plan * plan_Sij, double coeff);
 
 /* ---- Fourier-space kernels (gevolution.hpp:211,284,350,411,501); outputs may alias inputs */
 int gevb_solveModifiedPoissonFT(gevb_field * sourceFT, gevb_field * potFT, double coeff, double modif);

@@ -235,6 +235,13 @@ inline void projectFTscalar_evolveFTvector(Field<Cplx> & SijFT, Field<Cplx> & ch
 template <class FieldType>
 inline void prepareFTsource(Field<FieldType> & phi, Field<FieldType> & chi, Field<FieldType> & source, const FieldType bgmodel, Field<FieldType> & result, const double coeff, const double coeff2, const double coeff3, double & sum_source)
 { check(gevb_prepareFTsource_scalar_sum(phi.handle(), chi.handle(), source.handle(), bgmodel, result.handle(), coeff, coeff2, coeff3, &sum_source), "prepareFTsource"); }
+// prepareFTsource + plan.execute(FFT_FORWARD) in one call (one pass over HBM where the own x-pass applies)
+template <class T>
+inline void prepareFTsource_execute(Field<Real> & phi, Field<Real> & chi, PlanFFT<T> & plan_source, const Real bgmodel, const double coeff, const double coeff2, const double coeff3, double * sum_source = NULL)
+{ check(gevb_prepareFTsource_scalar_fft(phi.handle(), chi.handle(), plan_source.handle(), bgmodel, coeff, coeff2, coeff3, sum_source), "prepareFTsource"); }
+template <class T>
+inline void prepareFTsource_execute(Field<Real> & phi, PlanFFT<T> & plan_Sij, const double coeff)
+{ check(gevb_prepareFTsource_tensor_fft(phi.handle(), plan_Sij.handle(), coeff), "prepareFTsource"); }
 inline void projectFTvector(Field<Cplx> & SiFT, Field<Cplx> & BiFT, const Real coeff = 1., const Real modif = 0.) { check(gevb_projectFTvector(SiFT.handle(), BiFT.handle(), coeff, modif), "projectFTvector"); }
 inline void projectFTtensor(Field<Cplx> & SijFT, Field<Cplx> & hijFT) { check(gevb_projectFTtensor(SijFT.handle(), hijFT.handle()), "projectFTtensor"); }
 inline void solveModifiedPoissonFT(Field<Cplx> & sourceFT, Field<Cplx> & potFT, Real coeff, const Real modif = 0.) { check(gevb_solveModifiedPoissonFT(sourceFT.handle(), potFT.handle(), coeff, modif), "solveModifiedPoissonFT"); }

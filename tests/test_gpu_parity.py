@@ -339,6 +339,66 @@ def test_full_size_properties(gevb, ctx, N):
     assert np.array_equal(p0.cell_counts(), counts)
 
 
+# ---- the own x-pass of the forward transform (N = 512 only) with the source preparation fused into its load --------------------
+def test_own_xpass_512(gevb, ctx):
+    """csrc/xpass.cu against numpy (the transform itself, a few planes and lines of the 512^3 spectrum) and against the
+    cuFFT path with the separate prepareFTsource kernels (both oracle-checked at small N): same spectrum to 1e-12 of its
+    largest coefficient, same T00hom sum."""
+    N = 512
+    rng = np.random.default_rng(21)
+    c = ctx(N)
+    f = rng.standard_normal((N, N, N))
+    R, K = gevb.Field(c, gevb.REAL, 1, data=f[None]), gevb.Field(c, gevb.CPLX, 1)
+    plan = gevb.PlanFFT(R, K)
+    gevb.tuning("fft_xpass", 1)
+    plan.execute(gevb.FFT_FORWARD)
+    cplx = lambda a: a[..., 0] + 1j * a[..., 1] if a.shape[-1] == 2 and not np.iscomplexobj(a) else a
+    own = cplx(K.download()[0])                                # [kz][ky][kx]
+    gevb.tuning("fft_xpass", 0)
+    plan.execute(gevb.FFT_FORWARD)
+    lib = cplx(K.download()[0])
+    scale = np.abs(lib).max()
+    assert np.abs(own - lib).max() < 1e-12 * scale
+    # numpy on the part it can do quickly: the full transform of three x-lines' worth of modes through separable passes
+    fx = np.fft.rfft(f[:, :, :], axis=2)[:, :, [0, 1, 37, 255, 256]]      # x-pass (all rows), five kx columns
+    ref = np.fft.fft(np.fft.fft(fx, axis=1), axis=0)
+    assert np.abs(own[:, :, [0, 1, 37, 255, 256]] - ref).max() < 1e-12 * scale
+    gevb.tuning("fft_xpass", 0)
+    plan.close(); R.close(); K.close()
+    del own, lib, fx, ref
+
+    # fused scalar and tensor preparation against the separate kernels + cuFFT
+    phi = gevb.Field(c, gevb.REAL, 1, data=1e-5 * rng.standard_normal((1, N, N, N))); phi.updateHalo()
+    chi = gevb.Field(c, gevb.REAL, 1, data=1e-7 * rng.standard_normal((1, N, N, N))); chi.updateHalo()
+    src0 = 1.0 + 0.1 * rng.standard_normal((1, N, N, N))
+    coeffs = (0.3, 1.7e-3, 2.2e-3, 4.1e-3)
+    out = {}
+    for knob in (1, 0):
+        gevb.tuning("fft_xpass", knob)
+        S, SF = gevb.Field(c, gevb.REAL, 1, data=src0), gevb.Field(c, gevb.CPLX, 1)
+        pl = gevb.PlanFFT(S, SF)
+        total = gevb.prepareFTsource_scalar_fft(phi, chi, pl, *coeffs, want_sum=True)
+        out[knob] = (cplx(SF.download()[0]), total)
+        pl.close(); S.close(); SF.close()
+    scale = np.abs(out[0][0]).max()
+    assert np.abs(out[1][0] - out[0][0]).max() < 1e-12 * scale
+    assert abs(out[1][1] - out[0][1]) < 1e-12 * abs(out[0][1]) and abs(out[0][1] - src0.sum()) < 1e-10 * abs(src0.sum())
+    del out, src0
+    T0 = 1e-3 * rng.standard_normal((6, N, N, N))
+    res = {}
+    for knob in (1, 0):
+        gevb.tuning("fft_xpass", knob)
+        T, TF = gevb.Field(c, gevb.REAL, 6, data=T0), gevb.Field(c, gevb.CPLX, 6)
+        pl = gevb.PlanFFT(T, TF)
+        gevb.prepareFTsource_tensor_fft(phi, pl, 0.37)
+        res[knob] = cplx(TF.download())
+        pl.close(); T.close(); TF.close()
+    gevb.tuning("fft_xpass", 0)
+    for k in range(6):
+        scale = np.abs(res[0][k]).max()
+        assert np.abs(res[1][k] - res[0][k]).max() < 1e-12 * scale, f"component {k}"
+
+
 # ---- outputs the parity metrics are defined on (SURVEY 8f: f1 spectra files, f3 Gadget-2 snapshot) --------------------
 def _read_gadget2(path):
     """minimal Gadget-2 reader (format 1, int64 IDs): header dict, pos[n][3] float32, vel[n][3] float32, ids[n]"""
