@@ -35,7 +35,7 @@ extern "C" int gevb_nccl_unique_id(void * out128)
 // ---- tuning knobs: kernel variants kept side by side for ablation runs (bench.py --ablate); the defaults are the
 //      measured best.  Environment variables GEVB_<KNOB> (upper case) preset them.
 static const char * const tune_names[GEVB_NTUNE] = {"geodesic_variant", "fft_exchange", "fft_overlap", "fft_decomposed", "deposit_variant", "fft_l2_planes", "rebin_variant", "fft_fused", "peer_comm", "geodesic_tma", "tma_l2_promotion", "fft_xpass"};
-static int tune_values[GEVB_NTUNE] = {6, 1, 2, 1, 18, 0, 2, 1, 1, 1, 0, 0};
+static int tune_values[GEVB_NTUNE] = {5, 1, 2, 1, 18, 0, 2, 1, 1, 1, 0, 0};
 static bool tune_env_read = false;
 static void tune_read_env()
 {

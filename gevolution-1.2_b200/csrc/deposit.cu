@@ -52,7 +52,7 @@ enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
 //               eight phases in the instruction stream instead of four (0, 1, 2, 5 steps)
 //   DEPF_SPILL  (deposit_variant 8 with DEPF_BULK, 10 with both) no shared-memory atomics inside the phases.  The only lanes that could
 //               meet another warp on a site are those whose cell began in the previous warp of the batch; they accumulate into a
-//               spare "cell" of their warp in two extra rows of the tile (y = 9, 10 of planes 0 and 1) with the same plain
+//               spare "cell" of their warp in front of the tile of every component (acc_base) with the same plain
 //               read-add-write as everyone else, and one extra step per batch merges the spare cells into the real ones
 //   DEPF_TMA    (deposit_variant 18, with the three above) the whole tile of a component is flushed by ONE tensor reduction of the TMA unit
 //               (cp.reduce.async.bulk.tensor.3d ... add, UTMAREDG) through a 3-D tensor map over the field [nzl+2][N][N]: 7 per brick
@@ -62,8 +62,15 @@ enum { DEP_T00 = 0, DEP_TIJ = 1, DEP_T00_TIJ = 2, DEP_T0I = 3 };
 enum { DEPF_BULK = 1, DEPF_LOOP = 2, DEPF_SPILL = 4, DEPF_TMA = 8 };
 struct DMaps { CUtensorMap m[7]; };                      // one tensor map per target component
 __host__ __device__ constexpr int acc_ax(int flags) { return (flags & DEPF_BULK) ? DX + 1 : DX; }
-__host__ __device__ constexpr int acc_ay(int flags) { return (flags & DEPF_SPILL) ? DY + 2 : DY; }            // rows of a plane of the accumulator tile         // row stride of the accumulator tile
-__host__ __device__ constexpr int acc_sites(int flags) { return (flags & DEPF_TMA) ? (acc_ax(flags) * acc_ay(flags) * DZ + 15) / 16 * 16 : acc_ax(flags) * acc_ay(flags) * DZ; }   // TMA: a component starts on a 128-byte boundary
+__host__ __device__ constexpr int acc_ay(int flags) { return DY; }                                              // rows of a plane of the accumulator tile
+// DEPF_SPILL: every component is preceded by 208 doubles that hold the warps' spare cells.  The spare cell of warp w starts 2 w doubles
+// into them and uses the strides of the tile (1, 18, 162), so its corners lie at 2w + {0, 1, 18, 19, 162, 163, 180, 181}: inside the 208,
+// disjoint between warps, and outside the dense 18 x 9 x 5 box that the TMA unit reads (which starts 1664 bytes = 13 x 128 in)
+__host__ __device__ constexpr int acc_base(int flags) { return (flags & DEPF_SPILL) ? 208 : 0; }
+__host__ __device__ constexpr int acc_sites(int flags)                                                          // component stride
+{
+	return (flags & (DEPF_TMA | DEPF_SPILL)) ? (acc_base(flags) + acc_ax(flags) * acc_ay(flags) * DZ + 15) / 16 * 16 : acc_ax(flags) * acc_ay(flags) * DZ;
+}
 __host__ __device__ constexpr int acc_corner(int flags, int k) { return ((k >> 2) & 1) + ((k >> 1) & 1) * acc_ax(flags) + (k & 1) * acc_ax(flags) * acc_ay(flags); }
 
 // tile components per projection; Tij components follow the field order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 	constexpr int AX = acc_ax(FLAGS), AY = acc_ay(FLAGS), ASITES = acc_sites(FLAGS);
 	extern __shared__ __align__(128) double site_smem[];
 	double * smem = site_smem;
-	double * tile = smem;                                   // [NCOMP][ASITES] accumulators
+	double * tile = smem + acc_base(FLAGS);                 // [NCOMP][ASITES] accumulators (behind the spare cells of component 0)
 	double * stages = smem + NCOMP * ASITES;                // [2][DEP_STAGE_DOUBLES]
 
 	const BrickGeom & G = D.G;
@@ -432,9 +439,9 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 					W.tile = tile + asite; ph = tphi + site;
 					if (FLAGS & DEPF_SPILL)
 					{
-						// the cell began in the previous warp of this batch: accumulate in the warp's spare cell (rows 9 and 10, x = 2 warp)
+						// the cell began in the previous warp of this batch: accumulate in the warp's spare cell
 						spill = valid && cfirst < warp_lo && (threadIdx.x >> 5) != 0;
-						if (spill) W.tile = tile + (DY * AX + 2 * (threadIdx.x >> 5));
+						if (spill) W.tile = smem + 2 * (threadIdx.x >> 5);
 						spill_to = __shfl_sync(0xffffffffu, spill ? asite : -1, 0);
 					}
 					W.after = (int) (seg_hi - 1 - i);
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 					// the read-out of the previous brick's tile ran behind the set-up of this batch; clear the tile before the first update
 					if (threadIdx.x < NCOMP) bulk_wait_read();
 					__syncthreads();
-					double2 * t2 = (double2 *) tile;
+					double2 * t2 = (double2 *) smem;
 					for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
 					__syncthreads();
 					pending = false;
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 					if (spill_to >= 0)
 					{
 						double * real = tile + spill_to;
-						double * spare = tile + (DY * AX + 2 * (threadIdx.x >> 5));
+						double * spare = smem + 2 * (threadIdx.x >> 5);
 						for (int e = lane; e < 8 * NCOMP; e += 32)
 						{
 							const int k = e / NCOMP, comp = e - k * NCOMP;
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(DEP_THREADS, 3) k_deposit(DParams D, const __g
 				bulk_commit();
 				bulk_wait_read();                                   // the rows have been read: the tile may be cleared
 				__syncthreads();
-				double2 * t2 = (double2 *) tile;
+				double2 * t2 = (double2 *) smem;
 				for (int idx = threadIdx.x; idx < NCOMP * ASITES / 2; idx += DEP_THREADS) t2[idx] = make_double2(0., 0.);
 			}
 			else

@@ -609,9 +609,11 @@ int launch_variant(gevb_pcls * p, const GParams & P)
 	return 0;
 }
 
-// tuning knob geodesic_variant (default 6, measured in profiles/r2c): 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 = 128 threads, single
-// tile buffer, 4 blocks per SM; 4 = the same with the next particle fetched by cp.async into shared memory (measured slower:
-// 10.4 vs 7.7 ms at 512^3, profiles/r1q); 5 / 6 = the next particle in a second set of registers, 4 / 3 blocks per SM; 2 = 256 threads, single buffer, 2 blocks per SM
+// tuning knob geodesic_variant: 0 = 256 threads, double-buffered tile, 2 blocks per SM; 1 = 128 threads, single tile buffer, 4 blocks per
+// SM; 4 = the same with the next particle fetched by cp.async into shared memory (measured slower: 10.4 vs 7.7 ms at 512^3,
+// profiles/r1q); 5 / 6 = the next particle in a second set of registers, 4 / 3 blocks per SM; 7 = 96 threads, 4 blocks; 2 = 256 threads,
+// single buffer, 2 blocks per SM.  Default 5: with the tiles fetched by TMA the staging code no longer needs the registers that made 6
+// (3 blocks, 164 registers) the better choice in round 1 -- 6.3 vs 6.7 ms per cycle (profiles/round2_v15)
 template <int MODE>
 int launch_geodesic(gevb_pcls * p, const GParams & P)
 {
@@ -620,10 +622,10 @@ int launch_geodesic(gevb_pcls * p, const GParams & P)
 		case 0: return launch_variant<MODE, 256, 2, 2, 0>(p, P);
 		case 2: return launch_variant<MODE, 256, 1, 2, 0>(p, P);
 		case 4: return launch_variant<MODE, 128, 1, 4, 1>(p, P);
-		case 5: return launch_variant<MODE, 128, 1, 4, 2>(p, P);
 		case 1: return launch_variant<MODE, 128, 1, 4, 0>(p, P);
 		case 7: return launch_variant<MODE, 96, 1, 4, 2>(p, P);
-		default: return launch_variant<MODE, 128, 1, 3, 2>(p, P);     // 6
+		case 6: return launch_variant<MODE, 128, 1, 3, 2>(p, P);
+		default: return launch_variant<MODE, 128, 1, 4, 2>(p, P);     // 5
 	}
 }
 
