@@ -5,7 +5,7 @@ TAG=${1:-r2n}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest_gpu.log | cut -c1-300
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?"; tail -1 $OUT/smoke.log
-timeout 1200 python bench.py --steps 20 --warmup 5 --ablate deposit_variant=18:10:4:0:18:10:4:0 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; tail -c 300 $OUT/bench.err
+timeout 1200 python bench.py --steps 20 --warmup 5 --ablate deposit_variant=18:10:4:0,geodesic_variant=5:6,rebin_variant=2:0 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; tail -c 300 $OUT/bench.err
 grep -h ablate $OUT/bench.err | python -c "
 import sys,json
 for l in sys.stdin:
