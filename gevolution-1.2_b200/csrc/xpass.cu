@@ -4,8 +4,13 @@
 //
 // Separately, prepareFTsource reads and writes every component once (2 x 8 B per site) and cuFFT's x-pass reads it again
 // and writes the half spectrum (2 x 8 B per site): 32 B per site and component.  Fused, the prepared values never travel:
-// 16 B per site and component (the phi stencil comes from L1 / L2).  The y- and z-passes stay with cuFFT, as ONE strided
-// 2-D complex transform over (z, y) batched along kx.
+// 16 B per site and component (the phi stencil comes from L1 / L2).  cuFFT cannot run the y-pass alone on the [z][y][kx]
+// layout in one call (as a strided 2-D (z, y) transform its passes take 1.1 ms instead of 0.43 ms), so the y-pass is an own
+// kernel too (k_ypass: eight kx columns per block, two 256-point FFTs + a radix-2 step per column); the z-pass is cuFFT's.
+//
+// STATUS: correct (1e-12 against cuFFT and numpy at 512^3), traffic ideal, but both kernels are latency-bound (no load /
+// compute overlap inside a warp or block): x-pass 0.85 ms (scalar, with preparation) and 0.95 ms per tensor component, y-pass
+// 0.87 ms, against cuFFT's 0.52 and 0.43 ms + 0.45 ms of separate preparation.  Off by default (knob fft_xpass); DESIGN.md 5.2.
 //
 // One warp transforms one row of N = 512 reals.  The row is read as 256 complex numbers z[n] = x[2n] + i x[2n+1] (which is
 // how it lies in memory), transformed by a 256-point complex FFT and un-packed into the 257 coefficients of the real
@@ -31,7 +36,7 @@ namespace {
 #define XP_WS 288                         // double2 per warp of exchange space: max(8 x 36, 4 x 66, 256)
 #define XP_TAB (256 + 36 + 256)           // w256^(b c) as [c][b]; w32^(f g) as [f][9]; w512^k
 #define XP_WARPS_PLAIN 8
-#define XP_WARPS_TENSOR 12                // two rows x six components
+#define XP_WARPS_TENSOR 6                 // one row x six components
 
 struct XParams
 {
@@ -74,10 +79,10 @@ __device__ __forceinline__ void dft8(double2 * a)
 	a[3] = cadd(e3, w3); a[7] = csub(e3, w3);
 }
 
-// z[m] = packed row element lane + 32 m on entry; X[k] for k = lane + 32 m (and X[256] by lane 0) stored to `out` on exit
-__device__ __forceinline__ void row_fft_store(double2 * z, double2 * ws, const double2 * tab, double2 * out, int lane)
+// 256-point forward FFT of a warp: z[m] = element lane + 32 m on entry, Z[lane + 32 m] on exit; ws = the warp's exchange space
+__device__ __forceinline__ void fft256(double2 * z, double2 * ws, const double2 * tab, int lane)
 {
-	const double2 * T1 = tab, * T2 = tab + 256, * T3 = tab + 256 + 36;
+	const double2 * T1 = tab, * T2 = tab + 256;
 	// ---- stage 1
 	dft8(z);
 	#pragma unroll
@@ -110,6 +115,13 @@ __device__ __forceinline__ void row_fft_store(double2 * z, double2 * ws, const d
 		#pragma unroll
 		for (int h = 0; h < 4; h++) z[j + 2 * h] = u[j][h];
 	}
+}
+
+// z[m] = packed row element lane + 32 m on entry; X[k] for k = lane + 32 m (and X[256] by lane 0) stored to `out` on exit
+__device__ __forceinline__ void row_fft_store(double2 * z, double2 * ws, const double2 * tab, double2 * out, int lane)
+{
+	const double2 * T3 = tab + 256 + 36;
+	fft256(z, ws, tab, lane);
 	// ---- un-packing: X[k] = (Z[k] + conj Z[256-k]) / 2 - i w512^k (Z[k] - conj Z[256-k]) / 2
 	#pragma unroll
 	for (int m = 0; m < 8; m++) ws[m * 32 + lane] = z[m];
@@ -146,7 +158,7 @@ __device__ __forceinline__ double scalar_site(double src, double p, double chi, 
 // MODE 0: transform src as it is; MODE 1: scalar prepareFTsource on load; MODE 2: tensor prepareFTsource on load, one warp per
 // (row, component) -- the six warps of a row read the same phi stencil at the same time, so L1 serves five of the six
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? XP_WARPS_TENSOR * 32 : XP_WARPS_PLAIN * 32) k_xpass(XParams P)
+__global__ void __launch_bounds__(MODE == 2 ? XP_WARPS_TENSOR * 32 : XP_WARPS_PLAIN * 32, MODE == 2 ? 5 : 4) k_xpass(XParams P)
 {
 	extern __shared__ __align__(16) double2 xp_smem[];
 	constexpr int WARPS = MODE == 2 ? XP_WARPS_TENSOR : XP_WARPS_PLAIN;
@@ -251,6 +263,64 @@ __global__ void __launch_bounds__(MODE == 2 ? XP_WARPS_TENSOR * 32 : XP_WARPS_PL
 	}
 }
 
+// y-pass of the forward transform, in place on [z][y][kx]: 512-point complex FFTs along y for eight adjacent kx columns per block.
+// The tile (512 rows x 128 bytes) is brought in with the even and the odd rows of a column split (so that a warp reads its two
+// 256-point halves contiguously), every warp transforms one column as two 256-point FFTs and the radix-2 step
+// X[k] = E[k] + w512^k O[k], X[k + 256] = E[k] - w512^k O[k] (the un-packing table again), and the tile goes back row by row.
+#define YP_COLS 8
+#define YP_PITCH 521                                   // double2 per column in shared memory: 521 = 1 mod 8, so the eight columns of a row land in eight different 16-byte bank groups
+__global__ void __launch_bounds__(YP_COLS * 32, 2) k_ypass(double2 * f, int nplanes, const double2 * __restrict__ gtab)
+{
+	extern __shared__ __align__(16) double2 xp_smem[];
+	double2 * tab = xp_smem;
+	double2 * cols = xp_smem + XP_TAB;
+	for (int i = threadIdx.x; i < XP_TAB; i += YP_COLS * 32) tab[i] = gtab[i];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int kxl = threadIdx.x & (YP_COLS - 1), ys = threadIdx.x >> 3;          // tile traffic: 8 columns x 32 rows per step
+	const int groups = (XP_NH + YP_COLS - 1) / YP_COLS;                             // 33: the last group holds the single column kx = 256
+	const double2 * T3 = tab + 256 + 36;
+	for (int t = blockIdx.x; t < nplanes * groups; t += gridDim.x)
+	{
+		const int zp = t / groups, kx0 = (t - zp * groups) * YP_COLS;
+		const bool have = kx0 + kxl < XP_NH;
+		double2 * plane = f + (size_t) zp * XP_N * XP_NH;
+		__syncthreads();                                                            // the previous tile has been written out (and the tables are in)
+		#pragma unroll 4
+		for (int it = 0; it < XP_N / 32; it++)
+		{
+			const int y = it * 32 + ys;
+			if (have) cols[kxl * YP_PITCH + (y & 1) * 256 + (y >> 1)] = __ldcs(plane + (size_t) y * XP_NH + kx0 + kxl);
+		}
+		__syncthreads();
+		if (kx0 + warp < XP_NH)
+		{
+			double2 * col = cols + warp * YP_PITCH;
+			double2 e[8], o[8];
+			#pragma unroll
+			for (int m = 0; m < 8; m++) { e[m] = col[lane + 32 * m]; o[m] = col[256 + lane + 32 * m]; }
+			__syncwarp();
+			fft256(e, col, tab, lane);
+			__syncwarp();
+			fft256(o, col, tab, lane);
+			__syncwarp();
+			#pragma unroll
+			for (int m = 0; m < 8; m++)
+			{
+				const int k = lane + 32 * m;
+				const double2 wo = cmul(T3[k], o[m]);
+				col[k] = cadd(e[m], wo); col[k + 256] = csub(e[m], wo);
+			}
+		}
+		__syncthreads();
+		#pragma unroll 4
+		for (int it = 0; it < XP_N / 32; it++)
+		{
+			const int y = it * 32 + ys;
+			if (have) plane[(size_t) y * XP_NH + kx0 + kxl] = cols[kxl * YP_PITCH + y];
+		}
+	}
+}
+
 __global__ void k_sum_rows(const double * __restrict__ partial, int n, double * out)
 {
 	__shared__ double sh[1024];
@@ -312,13 +382,6 @@ int gevb_xpass_forward(gevb_plan * p, int mode, const double * phi, const double
 	gevb_ctx * c = p->ctx;
 	gevb_field * rf = p->real_field, * cf = p->cplx_field;
 	const int N = c->N, nh = c->nh, nc = rf->ncomp;
-	if (p->yz2d == 0)
-	{
-		// y- and z-pass as one strided 2-D complex transform over (z, y), batched along kx: element (kx, z, y) at kx + (z N + y) nh
-		int n2[2] = {N, N}, e2[2] = {N, N};
-		CUFFT_TRY(cufftPlanMany(&p->yz2d, 2, n2, e2, nh, 1, e2, nh, 1, CUFFT_Z2Z, nh));
-		CUFFT_TRY(cufftSetStream(p->yz2d, c->stream));
-	}
 	XParams P;
 	memset(&P, 0, sizeof(P));
 	P.nzl = c->nzl; P.phi = phi; P.chi = chi; P.bgmodel = bgmodel; P.coeff = coeff; P.coeff2 = coeff2; P.coeff3 = coeff3;
@@ -345,11 +408,19 @@ int gevb_xpass_forward(gevb_plan * p, int mode, const double * phi, const double
 			P.out = (double2 *) cf->data + k * cf->comp_stride;
 			GEVB_TRY(launch_xpass<0>(c, P));
 		}
-	for (int k = 0; k < nc; k++)
 	{
-		cufftDoubleComplex * f = (cufftDoubleComplex *) cf->data + k * cf->comp_stride;
-		CUFFT_TRY(cufftExecZ2Z(p->yz2d, f, f, CUFFT_FORWARD));
+		// y-pass: own kernel, in place; z-pass: cuFFT's 1-D transform along z (the plan the cuFFT path uses too)
+		const size_t smem = (XP_TAB + (size_t) YP_COLS * YP_PITCH) * sizeof(double2);
+		CUDA_TRY(cudaFuncSetAttribute(k_ypass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		const int tiles = c->nzl * ((XP_NH + YP_COLS - 1) / YP_COLS), persistent = c->num_sms * 2;
+		for (int k = 0; k < nc; k++)
+		{
+			double2 * f = (double2 *) cf->data + k * cf->comp_stride;
+			k_ypass<<<tiles < persistent ? tiles : persistent, YP_COLS * 32, smem, c->stream>>>(f, c->nzl, P.tab);
+			KERNEL_CHECK(c);
+			CUFFT_TRY(cufftExecZ2Z(p->bz1d, (cufftDoubleComplex *) f, (cufftDoubleComplex *) f, CUFFT_FORWARD));
+		}
 	}
-	c->launches += 2 * nc;
+	c->launches += 3 * nc;
 	return 0;
 }
