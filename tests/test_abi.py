@@ -39,6 +39,23 @@ def test_argument_validation_needs_no_device(gevb):
     assert L.gevb_ctx_create(ctypes.byref(h), 16, 0, 1, 2, None) != 0       # nccl id missing
 
 
+def test_documented_knobs_exist(gevb):
+    """every tuning knob include/gevb.h documents is known to the library (no device needed), anything else is refused"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "gevb.h")).read()
+    block = hdr[hdr.index("kernel-variant knobs"):hdr.index("int gevb_tuning")]
+    knobs = re.findall(r'^ \*   "([a-z0-9_]+)"', block, flags=re.M)
+    assert len(knobs) >= 10 and "deposit_variant" in knobs and "geodesic_tma" in knobs
+    lib = gevb.lib()
+    for k in knobs:
+        assert lib.gevb_tuning(k.encode(), 0) == 0, k
+    assert lib.gevb_tuning(b"no_such_knob", 1) != 0 and b"unknown knob" in lib.gevb_last_error()
+    # back to the defaults for whatever runs next in this process
+    for k, v in (("geodesic_variant", 5), ("fft_exchange", 1), ("fft_overlap", 2), ("fft_decomposed", 1), ("deposit_variant", 18), ("fft_l2_planes", 0),
+                 ("rebin_variant", 2), ("peer_comm", 1), ("geodesic_tma", 1), ("tma_l2_promotion", 0), ("fft_xpass", 0)):
+        assert lib.gevb_tuning(k.encode(), v) == 0
+
+
 def test_no_cpu_fallback(gevb):
     """without a CUDA device context creation must fail loudly, not fall back"""
     import torch
