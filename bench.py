@@ -116,7 +116,7 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.lines, self.t0 = device, None, [], None
 
     def start(self):
         try:
@@ -129,7 +129,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """the timed region starts now: only samples taken from here on count (the sampler itself is started during the warm-up, so
+        that a short timed region still sees one)"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -141,7 +146,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if self.t0 is None or t >= self.t0]
+        where = "timed region"
+        if not inside and self.lines:                               # region shorter than the sampling period: the last sample before it
+            inside, where = [self.lines[-1][1]], "last sample of the warm-up (timed region shorter than the 200 ms sampling period)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -153,7 +162,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": where}
 
 
 # ----------------------------------------------------------------------------- roofline bookkeeping
@@ -466,17 +475,20 @@ def run_ours(args, rank, world, local_rank):
     t_setup = time.perf_counter() - t_setup
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    for _ in range(args.warmup):
+    clocks = ClockSampler(local_rank)
+    for w in range(args.warmup):
+        if rank == 0 and w == args.warmup - 1:
+            clocks.start()                                      # streaming before the timed region begins
         sim.step()
     ctx.sync()
     ctx.timing(True)
     ctx.timing_read()
     launches0 = ctx.launches
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and clocks.proc is None:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); ctx.sync(); torch.cuda.synchronize()
+    clocks.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         sim.step()
