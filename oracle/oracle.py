@@ -78,6 +78,7 @@ _SIGS = {
     "generateCICKernel": (None, [_i, _l, _vp, _i, _dp]),
     "generateDisplacementField": (None, [_i, _dp, _d, _i, _dp, _dp, C.c_uint, _i, _i]),
     "dump_shipped_files": (_l, [C.c_char_p, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS"), _l]),
+    "parse_settings": (C.c_int, [C.c_char_p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]),
 }
 
 FIELD_IDS = {"phi": 0, "chi": 1, "Bi": 2, "source": 3, "Sij": 4, "scalarFT": 10, "BiFT": 11, "SijFT": 12}
@@ -269,6 +270,22 @@ class Oracle:
         buf = np.zeros((4096, 3), dtype=np.float32)
         n = self.fn["dump_shipped_files"](str(directory).encode(), buf, len(buf))
         return buf[:n].copy()
+
+    def parse_settings(self, text):
+        """the reference's parser (parser.hpp:122,759) on a settings text (compiled reference only): dict of what it derives"""
+        ints, dbl = np.zeros(16, dtype=np.int32), np.zeros(84)
+        n = self.fn["parse_settings"](text.encode(), ints, dbl)
+        if n <= 0:
+            raise RuntimeError("reference parser read no parameters")
+        names = ("ngrid gr_flag vector_flag baryon_flag seed ksphere correct_displacement tiling0 tiling1 tracer0 tracer1 numbins "
+                 "pk_mask snapshot_mask num_pk num_snapshot").split()
+        out = {k: int(v) for k, v in zip(names, ints)}
+        for k, v in zip("boxsize Cf steplimit movelimit z_in z_relax A_s n_s k_pivot".split(), dbl[:9]):
+            out[k] = float(v)
+        out["cosmo"] = dbl[9:20].copy()
+        out["z_pk"] = dbl[20:20 + out["num_pk"]].copy()
+        out["z_snapshot"] = dbl[52:52 + out["num_snapshot"]].copy()
+        return out
 
     # ---- stateful simulation -----------------------------------------------------------
     def sim(self, N, gr_flag, vector_flag, dsettings, cosmo):

@@ -497,6 +497,38 @@ static std::string apply_overrides(const std::string & text, const char * overri
 	return out;
 }
 
+// the reference's own parser (loadParameterFile + parseMetadata, parser.hpp:122,759) on a settings text: what the product's
+// gevb_settings_read is compared with.  ints[16]: numpts, gr_flag, vector_flag, baryon_flag, seed, ksphere, correct_displacement,
+// numtile[0], numtile[1], tracer_factor[0], tracer_factor[1], numbins, out_pk, out_snapshot, num_pk, num_snapshot;
+// dbl[9 + 11 + 2 x 32]: boxsize, Cf, steplimit, movelimit, z_in, z_relax, A_s, n_s, k_pivot, the cosmology in gevb_settings' order,
+// z_pk[32], z_snapshot[32].  Returns the number of parameters read (<= 0: failure).
+int ref_parse_settings(const char * text, int * ints, double * dbl)
+{
+	char tmpl[] = "/tmp/gevref_XXXXXX";
+	if (mkdtemp(tmpl) == NULL) return -1;
+	const std::string dir(tmpl);
+	const std::string settings = write_embedded(dir, "settings.ini", (const unsigned char *) text, strlen(text));
+	metadata sim;
+	icsettings ic;
+	cosmology cosmo;
+	parameter * params = NULL;
+	const int numparam = loadParameterFile(settings.c_str(), params);
+	if (numparam <= 0) return numparam;
+	std::streambuf * quiet = std::cout.rdbuf(NULL);
+	parseMetadata(params, numparam, sim, cosmo, ic);
+	std::cout.rdbuf(quiet);
+	free(params);
+	remove(settings.c_str()); rmdir(dir.c_str());
+	const int iv[16] = {sim.numpts, sim.gr_flag, sim.vector_flag, sim.baryon_flag, ic.seed, (ic.flags & ICFLAG_KSPHERE) ? 1 : 0, (ic.flags & ICFLAG_CORRECT_DISPLACEMENT) ? 1 : 0,
+		ic.numtile[0], ic.numtile[1], sim.tracer_factor[0], sim.tracer_factor[1], sim.numbins, sim.out_pk, sim.out_snapshot, sim.num_pk, sim.num_snapshot};
+	for (int i = 0; i < 16; i++) ints[i] = iv[i];
+	const double dv[20] = {sim.boxsize, sim.Cf, sim.steplimit, sim.movelimit, sim.z_in, ic.z_relax, ic.A_s, ic.n_s, ic.k_pivot,
+		cosmo.Omega_cdm, cosmo.Omega_b, cosmo.Omega_m, cosmo.Omega_Lambda, cosmo.Omega_fld, cosmo.w0_fld, cosmo.wa_fld, cosmo.Omega_g, cosmo.Omega_ur, cosmo.Omega_rad, cosmo.h};
+	for (int i = 0; i < 20; i++) dbl[i] = dv[i];
+	for (int i = 0; i < 32; i++) { dbl[20 + i] = i < sim.num_pk ? sim.z_pk[i] : 0.; dbl[52 + i] = i < sim.num_snapshot ? sim.z_snapshot[i] : 0.; }
+	return numparam;
+}
+
 void * ref_sim_create_from_settings(int ngrid, int tiling, int seed, const char * overrides)
 {
 	char tmpl[] = "/tmp/gevref_XXXXXX";

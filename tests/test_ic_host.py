@@ -82,3 +82,57 @@ def test_settings_reader(gevb_host, shipped):
             gevb_host.settings_read(d / "settings.ini", bad)
     with pytest.raises(gevb_host.GevbError):
         gevb_host.settings_read(d / "no_such_file.ini")
+
+
+# ---- the product's settings reader against the reference's own parser on variants of the shipped file -----------------------------
+_BASE = """
+template file = sc1_crystal.dat
+Tk file = class_tk.dat
+IC generator = basic
+boxsize = 320.0
+Ngrid = 64
+tiling factor = 16
+initial redshift = 100.0
+Courant factor = 48.0
+time step limit = 0.04
+seed = 42
+"""
+
+_VARIANTS = {
+    "minimal: parser defaults everywhere": _BASE,
+    "comments, blank lines, odd spacing": "# a comment line\n\n   boxsize=200.5   # trailing comment\nNgrid   =   32\n" + _BASE.replace("boxsize = 320.0", "").replace("Ngrid = 64", "")
+                                          + "\ngravity theory = Newton   # N-body gauge\n",
+    "first match wins": _BASE + "seed = 7\nNgrid = 128\n",
+    "physical densities and radiation": _BASE + "h = 0.7\nomega_b = 0.0224\nomega_cdm = 0.12\nT_cmb = 2.7255\nN_ur = 2.0328\n",
+    "fractional densities": _BASE + "h = 0.6774\nOmega_b = 0.0486\nOmega_cdm = 0.2589\nOmega_g = 5.4e-5\nOmega_ur = 3.7e-5\n",
+    "N_eff alias": _BASE + "N_eff = 3.5\n",
+    "dark-energy fluid": _BASE + "Omega_fld = 0.65\nw0_fld = -0.9\nwa_fld = 0.1\n",
+    "elliptic, sample, outputs": _BASE + "vector method = elliptic\nbaryon treatment = sample\nsnapshot redshifts = 0, 3, 30, 10\nsnapshot outputs = phi, B, Gadget2, chi, hij, T00\n"
+                                 "Pk redshifts = 1, 50, 0\nPk outputs = phi, chi, hij, B, T00, delta\nPk bins = 512\ntracer factor = 4\n",
+    "hybrid baryons, relaxation, k-domain": _BASE + "baryon treatment = hybrid\nrelaxation redshift = 50\nk-domain = cube\ncorrect displacement = no\nmove limit = 8\n"
+                                            "A_s = 2.1e-9\nn_s = 0.965\nk_pivot = 0.002\n",
+    "two tiling factors and templates": _BASE.replace("tiling factor = 16", "tiling factor = 16, 8").replace("template file = sc1_crystal.dat", "template file = sc1_crystal.dat, sc1_crystal.dat")
+                                        + "baryon treatment = sample\n",
+}
+
+
+@pytest.mark.parametrize("name", list(_VARIANTS))
+def test_settings_reader_matches_the_reference_parser(gevb_host, ref, tmp_path, name):
+    """gevb_settings_read (host/settings.cpp) against loadParameterFile + parseMetadata of the compiled reference (parser.hpp:122,759)
+    on the same text: every value a basic run consults, bit for bit (the derived cosmology included)."""
+    text = _VARIANTS[name]
+    f = tmp_path / "settings.ini"
+    f.write_text(text)
+    want = ref.parse_settings(text)
+    st = gevb_host.settings_read(f)
+    got = {"ngrid": st.ngrid, "gr_flag": st.gr_flag, "vector_flag": st.vector_flag, "baryon_flag": st.baryon_flag, "seed": st.seed, "ksphere": st.ksphere,
+           "correct_displacement": st.correct_displacement, "tiling0": st.tiling[0], "tracer0": st.tracer_factor[0], "numbins": st.numbins,
+           "pk_mask": st.pk_mask, "snapshot_mask": st.snapshot_mask, "num_pk": st.num_pk, "num_snapshot": st.num_snapshot}
+    if st.baryon_flag in (1, 3):                                     # the second species exists: its tiling and tracer factors count
+        got["tiling1"], got["tracer1"] = st.tiling[1], st.tracer_factor[1]
+    for k, v in got.items():
+        assert v == want[k], (name, k, v, want[k])
+    for k in "boxsize Cf steplimit movelimit z_in z_relax A_s n_s k_pivot".split():
+        assert getattr(st, k) == want[k], (name, k, getattr(st, k), want[k])
+    assert np.array_equal(np.array(st.cosmo), want["cosmo"]), (name, np.array(st.cosmo) - want["cosmo"])
+    assert np.array_equal(np.array(st.z_pk)[:st.num_pk], want["z_pk"]) and np.array_equal(np.array(st.z_snapshot)[:st.num_snapshot], want["z_snapshot"]), name
